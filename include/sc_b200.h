@@ -1,0 +1,128 @@
+/* sc_b200.h — C ABI of the B200-native ORT / ACORT captioning hot path.
+ *
+ * The reference (jiahuei/sparse-image-captioning) is pure Python/PyTorch and has no FFI of its own; its
+ * boundary for this path is the Python class surface.  Each entry point below replaces
+ * the ATen op sequence of the cited reference lines (paths relative to the reference checkout) and is what
+ * the drop-in Python classes in sparse-image-captioning_b200/ bind through ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated; the caller owns all memory; the library never allocates.
+ *  - all work is enqueued on `stream` (CUDA-graph capturable); no host synchronisation inside.
+ *  - return 0 on success, <0 for argument errors (codes below), >0 = cudaError_t of the failed launch.
+ *    sc_last_error() returns a thread-local description.  No exceptions, no aborts.
+ *  - dtype codes: SC_F32 = 0, SC_BF16 = 1.  Matrices are row-major.
+ */
+#ifndef SC_B200_H
+#define SC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sc_stream_t; /* == cudaStream_t */
+
+#define SC_F32 0
+#define SC_BF16 1
+
+#define SC_OK 0
+#define SC_ERR_SHAPE (-1)
+#define SC_ERR_ALIGN (-2)
+#define SC_ERR_DTYPE (-3)
+#define SC_ERR_WORKSPACE (-4)
+#define SC_ERR_UNSUPPORTED (-5)
+#define SC_ERR_DRIVER (-6)
+
+/* mask modes of the supermask layers (pruning/masked_layer.py:84-110, pruning/sampler.py:43-66) */
+#define SC_MASK_NONE 0      /* weight used as is                                             */
+#define SC_MASK_ROUND 1     /* eval:  W * rint(sigmoid(S))   (bit-exact: S > 1.5*2^-24)      */
+#define SC_MASK_BERNOULLI 2 /* train: W * Bernoulli(sigmoid(S)), Philox4x32-10(seed, stream_id, element) */
+#define SC_MASK_RAW 3       /* snip / mag_* / lottery_* / mask_freeze: W * S                 */
+#define SC_MASK_UNIFORM 4   /* train with caller-provided uniforms: W * (u < sigmoid(S))     */
+
+const char* sc_last_error(void);
+int sc_version(void);
+
+/* K1 / K3a — MaskedLinear.forward / nn.Linear on densified weights
+ * (pruning/masked_layer.py:134-135; models/transformer.py:315-325 FFN ReLU; :345-358 residual).
+ *   y[M,N] = epilogue( x[M,K] * (w (.) mask)[N,K]^T )      epilogue: +bias[N], ReLU, +residual[M,N] (fp32)
+ * x_dtype = SC_BF16: tcgen05/TMEM tensor-core kernel; w is either bf16 (pre-masked, TMA-fed) or fp32 master
+ *           weights + fp32 mask (mask applied in the operand-load prologue).  K % 8 == 0.
+ * x_dtype = SC_F32 : fp32-FMA verification kernel (1e-5 parity mode); w fp32.
+ * tile_n: 0 = auto, or 64/128/256 (tensor path).  residual may alias y. */
+int sc_linear(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
+              const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
+              const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
+              sc_stream_t stream);
+
+/* K3b — the same product from CSR weights (rows = output features, 16-bit column indices, values in x's dtype).
+ * The reference only stores the sparse form (pruning/prune.py:200-221). */
+int sc_csr_spmm(const void* x, int dtype, const int* row_ptr, const unsigned short* col_idx, const void* vals,
+                const float* bias, const float* residual, void* y, int y_dtype, int M, int N, int K, int relu,
+                sc_stream_t stream);
+
+/* K9 — LayerNorm a*(x-mean)/(std_unbiased+eps)+b (models/transformer.py:329-341).  x fp32 [rows,D]. */
+int sc_layernorm(const float* x, const float* a, const float* b, void* y, int y_dtype, int rows, int D, float eps,
+                 sc_stream_t stream);
+
+/* K9 — MaskedEmbedding + InputEmbedding + PositionalEncoding:
+ * out[r] = (table (.) mask)[tokens[r]] * scale + pe[pos0 + r % T]
+ * (pruning/masked_layer.py:160-169; models/transformer.py:383-401). tokens int32. */
+int sc_embed_pe(const int* tokens, const float* table, const float* mask, int mask_mode, const float* uniforms,
+                unsigned long long seed, unsigned long long stream_id, const float* pe, void* out, int out_dtype,
+                int rows, int D, int V, int T, int pos0, float scale, sc_stream_t stream);
+
+/* prune_weights / densify: out = w (.) mask  (pruning/prune.py:165-174) */
+int sc_apply_mask(const float* w, const float* mask, int mask_mode, const float* uniforms, unsigned long long seed,
+                  unsigned long long stream_id, void* out, int out_dtype, size_t n, sc_stream_t stream);
+
+/* sum rint(sigmoid(S)) accumulated into *count_out (calculate_sparsities, pruning/prune.py:124-144, 249-252) */
+int sc_mask_count(const float* logits, size_t n, unsigned long long* count_out, sc_stream_t stream);
+
+int sc_cast_f32_bf16(const float* x, void* y, size_t n, sc_stream_t stream);
+
+/* pack_wrapper zero-padding of padded regions (utils/model_utils.py:149-168): x[r,:] *= (mask[r] != 0) */
+int sc_mask_rows(float* x, const float* row_mask, int rows, int D, sc_stream_t stream);
+
+/* K4 — BoxRelationalEmbedding + WG + ReLU + log + softmax attention + PV, fused
+ * (models/relation_transformer.py:148-191, 196-256, 258-293).
+ * q/k/v: element (row=b*N+i, head, d) at ptr[row*ld + head*dk + d]; boxes fp32 [B,N,4];
+ * wg_w fp32 [h, 64 (trig) | 4], wg_b fp32 [h]; att_mask fp32 [B,N] or NULL. */
+int sc_box_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype,
+                         const float* boxes, const float* wg_w, const float* wg_b, const float* att_mask, void* out,
+                         int ldo, int B, int N, int h, int dk, int trig, float wave_len, sc_stream_t stream);
+
+/* K5 — decoder self-attention, one new token per row, append-to-cache + attention
+ * (models/transformer.py:230-295 incremental branch).  cache_[kv]: [slots][R][D]; anc: int32 [R, anc_ld]
+ * ancestor row of slot s is anc[r][s / slot_div].  Attends slots [0,n_prev) + the new token; the new k,v are
+ * stored in slot write_slot (skip with -1: reference quirk Q1). */
+int sc_decode_self_attn_step(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype,
+                             void* cache_k, void* cache_v, const int* anc, int anc_ld, int slot_div, void* out, int ldo,
+                             int R, int D, int h, int n_prev, int write_slot, sc_stream_t stream);
+
+/* K6 — decoder cross-attention step over the per-image memory K/V [B*N, ldm] (models/transformer.py:255-256). */
+int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const void* mem_v, int ldm, int dtype,
+                              const float* att_mask, void* out, int ldo, int B, int beam, int N, int D, int h,
+                              sc_stream_t stream);
+
+/* K7 — log-softmax + beam_step + finished-beam handling of batch_beam_search, group_size 1
+ * (models/caption_model.py:56-111, 151-226; utils/model_utils.py:121-146).
+ * penalty_kind: 0 "", 1 "wu_<alpha>", 2 "avg_<alpha>".  seq/lp/anc are ping-pong buffers [B*beam, L]. */
+int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
+                 int decoding_constraint, int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out,
+                 const float* lp_in, float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out,
+                 int* done_seq, float* done_lp, double* done_p, int* done_count, sc_stream_t stream);
+
+/* greedy branch of _generate_captions (models/transformer.py:507-561) */
+int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, int* seq,
+                   float* seq_lp, int* tokens, int* unfinished, int* live_count, sc_stream_t stream);
+
+/* K8 — state[i][:, state_ix] (models/caption_model.py:106-110): dst[r] = src[idx[r]], rows of row_bytes */
+int sc_cache_reorder(const void* src, void* dst, const int* idx, long rows, long row_bytes, sc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SC_B200_H */

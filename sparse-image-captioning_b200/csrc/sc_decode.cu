@@ -1,0 +1,552 @@
+// Incremental decoding kernels (K5, K6, K7, K8).
+// Reference behaviour:
+//   K5 self-attention step with growing cache  : sparse_caption/models/transformer.py:230-295 (cat(cache,k), softmax, PV)
+//   K6 cross-attention step, cache re-use       : transformer.py:255-256,276
+//   K7 beam step + finished-beam bookkeeping    : sparse_caption/models/caption_model.py:56-111,151-226
+//      greedy step                              : transformer.py:507-561
+//   K8 state reorder state[i][:, state_ix]      : caption_model.py:106-110
+//
+// Layout: rows r = image*beam + slot.  Self K/V caches are [slot s][row][D], written once and never moved; a
+// beam's history is found through the ancestor table anc[row][s] (row that wrote slot s for this beam), which
+// K7 rewrites each step (a [R,L] int gather) instead of gathering 24 cache tensors like the reference does.
+// Cross K/V are per IMAGE ([B*N, D]) and shared by the beams of that image.
+#include "sc_common.cuh"
+
+namespace {
+
+template <typename T> struct Vec8;  // 8 consecutive elements
+template <> struct Vec8<float> {
+  float v[8];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 a = *(const float4*)p, b = *(const float4*)(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *(float4*)p = make_float4(v[0], v[1], v[2], v[3]);
+    *(float4*)(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    uint4 u = *(const uint4*)p;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *(uint32_t*)&t;
+    }
+    *(uint4*)p = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float group_sum(float x, int lanes) {
+  for (int o = lanes >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: thread = (row, 8-dim chunk); dk/8 adjacent lanes form a head.  Appends k_t,v_t to slot n_prev and attends over
+// slots 0..n_prev with an online softmax (keys stream through registers, 16-byte loads, 1 KB coalesced per row).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) self_attn_step_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                             const T* __restrict__ v, int ldq, int ldk, int ldv,
+                                                             T* __restrict__ cache_k, T* __restrict__ cache_v,
+                                                             const int* __restrict__ anc, int anc_ld, int slot_div,
+                                                             T* __restrict__ out, int ldo, int R, int D, int dk,
+                                                             int n_prev, int write_slot) {
+  const int chunks = D / 8;
+  const int lanes = dk / 8;
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = g < (long)R * chunks;
+  const int r = active ? (int)(g / chunks) : R - 1;
+  const int c = active ? (int)(g % chunks) : 0;
+  const float scale_div = sqrtf((float)dk);
+  Vec8<T> qv, kv, vv;
+  qv.load(q + (size_t)r * ldq + c * 8);
+  kv.load(k + (size_t)r * ldk + c * 8);
+  vv.load(v + (size_t)r * ldv + c * 8);
+  if (active && write_slot >= 0) {
+    kv.store(cache_k + ((size_t)write_slot * R + r) * D + c * 8);
+    vv.store(cache_v + ((size_t)write_slot * R + r) * D + c * 8);
+  }
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int s = 0; s <= n_prev; ++s) {
+    Vec8<T> kk, vs;
+    if (s < n_prev) {
+      const int src = anc[(size_t)r * anc_ld + s / slot_div];
+      kk.load(cache_k + ((size_t)s * R + src) * D + c * 8);
+      vs.load(cache_v + ((size_t)s * R + src) * D + c * 8);
+    } else {
+      kk = kv; vs = vv;
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dot = fmaf(qv.v[i], kk.v[i], dot);
+    dot = group_sum(dot, lanes) / scale_div;
+    const float mn = fmaxf(m, dot);
+    const float corr = expf(m - mn);
+    const float p = expf(dot - mn);
+    l = l * corr + p;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = acc[i] * corr + p * vs.v[i];
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  Vec8<T> o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.v[i] = acc[i] * inv;
+  if (active) o.store(out + (size_t)r * ldo + c * 8);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K6: thread = (image, 8-dim chunk), handles the NB beam rows of that image together so each memory K/V element is
+// loaded once per image instead of once per beam.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int NB>
+__global__ void __launch_bounds__(128) cross_attn_step_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ mk,
+                                                              const T* __restrict__ mv, int ldm,
+                                                              const float* __restrict__ att_mask, T* __restrict__ out,
+                                                              int ldo, int B, int N, int D, int dk) {
+  const int chunks = D / 8;
+  const int lanes = dk / 8;
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = g < (long)B * chunks;
+  const int b = active ? (int)(g / chunks) : B - 1;
+  const int c = active ? (int)(g % chunks) : 0;
+  const float scale_div = sqrtf((float)dk);
+  Vec8<T> qv[NB];
+  float m[NB], l[NB], acc[NB][8];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    qv[n].load(q + ((size_t)b * NB + n) * ldq + c * 8);
+    m[n] = -INFINITY; l[n] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[n][i] = 0.f;
+  }
+  for (int j = 0; j < N; ++j) {
+    Vec8<T> kk, vs;
+    const size_t row = (size_t)b * N + j;
+    kk.load(mk + row * ldm + c * 8);
+    vs.load(mv + row * ldm + c * 8);
+    const bool masked = att_mask && att_mask[row] == 0.f;
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(qv[n].v[i], kk.v[i], dot);
+      dot = group_sum(dot, lanes) / scale_div;
+      if (masked) dot = -1e9f;
+      const float mn = fmaxf(m[n], dot);
+      const float corr = expf(m[n] - mn);
+      const float p = expf(dot - mn);
+      l[n] = l[n] * corr + p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[n][i] = acc[n][i] * corr + p * vs.v[i];
+      m[n] = mn;
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    const float inv = 1.f / l[n];
+    Vec8<T> o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = acc[n][i] * inv;
+    if (active) o.store(out + ((size_t)b * NB + n) * ldo + c * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K7 beam step.  One CTA per image.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxBeam = 8;
+
+struct Cand {
+  float s;
+  int idx;  // flat index beam*V + word; smaller index wins ties (== stable descending sort)
+};
+__device__ __forceinline__ bool better(const Cand& a, const Cand& b) { return a.s > b.s || (a.s == b.s && a.idx < b.idx); }
+
+template <int NB>
+__device__ __forceinline__ void topk_insert(Cand (&top)[NB], Cand c) {
+  if (!better(c, top[NB - 1])) return;
+  top[NB - 1] = c;
+#pragma unroll
+  for (int i = NB - 1; i > 0; --i) {
+    if (better(top[i], top[i - 1])) { Cand t = top[i]; top[i] = top[i - 1]; top[i - 1] = t; }
+  }
+}
+
+struct BeamArgs {
+  const float* logits;  // [B*beam, V] raw generator output (bias included)
+  int B, beam, V, L, t;
+  int eos, pad;
+  float temperature;
+  int constraint;      // decoding_constraint: forbid repeating the previous token
+  int penalty_kind;    // 0 none, 1 wu, 2 avg
+  float penalty_alpha;
+  // beam state, ping-pong (in -> out)
+  const int* seq_in; int* seq_out;        // [B*beam, L]
+  const float* lp_in; float* lp_out;      // [B*beam, L] log-prob of each chosen token
+  float* sum;                             // [B*beam] running joint log-prob (in/out)
+  const int* anc_in; int* anc_out;        // [B*beam, L]
+  int* tokens_out;                        // [B*beam] token fed at step t+1
+  // finished beams: running top-`beam` per image
+  int* done_seq; float* done_lp; double* done_p; int* done_count;  // [B,beam,L] [B,beam,L] [B,beam] [B]
+};
+
+template <int NB>
+__global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = a.V;
+  const int rows = (a.t == 0) ? 1 : NB;  // first step: every beam holds BOS, only beam 0 is expanded
+  __shared__ float s_red[8];
+  __shared__ float s_mx[NB], s_ls[NB], s_mx2[NB], s_ls2[NB], s_sum[NB];
+  // init_logprobs (t == 0) are never temperature-scaled (caption_model.py:135, 218)
+  const float T = (a.t == 0) ? 1.0f : a.temperature;
+  __shared__ int s_prev[NB];
+  __shared__ Cand s_top[8][NB];
+  __shared__ Cand s_final[NB];
+
+  // ---- log-softmax statistics per row (twice when temperature != 1: log_softmax(log_softmax(x)/T)) ----
+  for (int k = 0; k < rows; ++k) {
+    const float* x = a.logits + ((size_t)b * NB + k) * V;
+    float mx = -INFINITY;
+    for (int i = tid; i < V; i += 256) mx = fmaxf(mx, x[i]);
+    mx = sc::warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+    __syncthreads();
+    float se = 0.f;
+    for (int i = tid; i < V; i += 256) se += expf(x[i] - mx);
+    se = sc::warp_sum(se);
+    if (lane == 0) s_red[warp] = se;
+    __syncthreads();
+    se = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) se += s_red[w];
+    __syncthreads();
+    // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
+    float ls = logf(se), mx2 = 0.f, ls2 = 0.f;
+    if (T != 1.0f) {
+      // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
+      mx2 = (0.f - ls) / T;
+      float se2 = 0.f;
+      for (int i = tid; i < V; i += 256) se2 += expf(((x[i] - mx) - ls) / T - mx2);
+      se2 = sc::warp_sum(se2);
+      if (lane == 0) s_red[warp] = se2;
+      __syncthreads();
+      se2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) se2 += s_red[w];
+      __syncthreads();
+      ls2 = logf(se2);
+    }
+    if (tid == 0) {
+      s_mx[k] = mx; s_ls[k] = ls; s_mx2[k] = mx2; s_ls2[k] = ls2;
+      s_sum[k] = a.sum[b * NB + k];
+      s_prev[k] = (a.constraint && a.t > 0) ? a.seq_in[((size_t)b * NB + k) * a.L + a.t - 1] : -1;
+    }
+  }
+  __syncthreads();
+
+  // ---- per-thread top-NB over the rows*V candidates ----
+  Cand top[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
+  for (int k = 0; k < rows; ++k) {
+    const float* x = a.logits + ((size_t)b * NB + k) * V;
+    const float mx = s_mx[k], ls = s_ls[k], mx2 = s_mx2[k], ls2 = s_ls2[k], base = s_sum[k];
+    const int prev = s_prev[k];
+    for (int i = tid; i < V; i += 256) {
+      float lp = (x[i] - mx) - ls;
+      if (T != 1.0f) lp = (lp / T - mx2) - ls2;
+      if (i == prev) lp = -INFINITY;
+      Cand c; c.s = base + lp; c.idx = k * V + i;
+      topk_insert<NB>(top, c);
+    }
+  }
+  // warp merge: every lane offers its sorted list; NB rounds of arg-best over the heads
+  {
+    int head = 0;
+    Cand mine[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) mine[i] = top[i];
+#pragma unroll
+    for (int rnd = 0; rnd < NB; ++rnd) {
+      Cand c;
+      c.s = -INFINITY; c.idx = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < NB; ++i) if (i == head) c = mine[i];
+      Cand best = c;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Cand other;
+        other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
+        other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+        if (better(other, best)) best = other;
+      }
+      if (head < NB && c.idx == best.idx && c.s == best.s) head++;
+      if (lane == 0) s_top[warp][rnd] = best;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int heads[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int rnd = 0; rnd < NB; ++rnd) {
+      int bw = -1;
+      Cand best; best.s = -INFINITY; best.idx = 0x7fffffff;
+      for (int w = 0; w < 8; ++w) {
+        if (heads[w] < NB) {
+          Cand c = s_top[w][heads[w]];
+          if (bw < 0 || better(c, best)) { best = c; bw = w; }
+        }
+      }
+      heads[bw]++;
+      s_final[rnd] = best;
+    }
+  }
+  __syncthreads();
+
+  // ---- bookkeeping (caption_model.py:84-110, 195-210) ----
+  const int L = a.L, t = a.t;
+  // history gathers: NB rows x L entries, spread over the CTA
+  for (int e = tid; e < NB * L; e += 256) {
+    const int j = e / L, s = e - j * L;
+    const int parent = s_final[j].idx / V;
+    const size_t src = ((size_t)b * NB + parent) * L + s, dst = ((size_t)b * NB + j) * L + s;
+    if (s < t) {
+      a.seq_out[dst] = a.seq_in[src];
+      a.lp_out[dst] = a.lp_in[src];
+      a.anc_out[dst] = a.anc_in[src];
+    } else if (s == t) {
+      const int word = s_final[j].idx - parent * V;
+      a.seq_out[dst] = word;
+      const float x = a.logits[((size_t)b * NB + parent) * V + word];
+      float lp = (x - s_mx[parent]) - s_ls[parent];
+      if (T != 1.0f) lp = (lp / T - s_mx2[parent]) - s_ls2[parent];
+      a.lp_out[dst] = lp;
+      a.anc_out[dst] = b * NB + parent;
+    } else {
+      a.seq_out[dst] = a.pad;
+      a.lp_out[dst] = 0.f;
+      a.anc_out[dst] = b * NB + j;  // slots of future steps are written by the row itself
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int cnt = a.done_count[b];
+    for (int j = 0; j < NB; ++j) {
+      const int parent = s_final[j].idx / V;
+      const int word = s_final[j].idx - parent * V;
+      float ys = s_final[j].s;
+      a.tokens_out[b * NB + j] = word;
+      const bool is_end = (word == a.eos) || (t == L - 1);
+      if (is_end) {
+        // the reference scores finished beams in Python floats (double): model_utils.py:121-146
+        double p = (double)ys;
+        const double len = (double)(t + 1);
+        if (a.penalty_kind == 1) p = p / (pow(5.0 + len, (double)a.penalty_alpha) / pow(6.0, (double)a.penalty_alpha));
+        else if (a.penalty_kind == 2) p = p / len;
+        // stable insertion into the running top-NB (python's sorted() is stable, entries arrive chronologically)
+        int pos = cnt < NB ? cnt : NB;
+        while (pos > 0 && a.done_p[b * NB + pos - 1] < p) --pos;
+        if (pos < NB) {
+          const int last = (cnt < NB ? cnt : NB - 1);
+          for (int m = last; m > pos; --m) {
+            a.done_p[b * NB + m] = a.done_p[b * NB + m - 1];
+            for (int s = 0; s < L; ++s) {
+              a.done_seq[((size_t)b * NB + m) * L + s] = a.done_seq[((size_t)b * NB + m - 1) * L + s];
+              a.done_lp[((size_t)b * NB + m) * L + s] = a.done_lp[((size_t)b * NB + m - 1) * L + s];
+            }
+          }
+          a.done_p[b * NB + pos] = p;
+          for (int s = 0; s < L; ++s) {
+            const size_t src = ((size_t)b * NB + j) * L + s;
+            a.done_seq[((size_t)b * NB + pos) * L + s] = s <= t ? a.seq_out[src] : a.pad;
+            a.done_lp[((size_t)b * NB + pos) * L + s] = s <= t ? a.lp_out[src] : 0.f;
+          }
+          if (cnt < NB) cnt++;
+        }
+        ys -= 1000.f;
+      }
+      a.sum[b * NB + j] = ys;
+    }
+    a.done_count[b] = cnt;
+  }
+}
+
+// greedy step (beam_size == 1): one warp per row
+__global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restrict__ logits, int R, int V, int L, int t,
+                                                          int eos, int constraint, int* __restrict__ seq,
+                                                          float* __restrict__ seq_lp, int* __restrict__ tokens,
+                                                          int* __restrict__ unfinished, int* __restrict__ live_count) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  // reference loop breaks once every row has finished (transformer.py:550-552): later columns stay pad/0
+  if (t > 0 && live_count[t - 1] == 0) return;
+  const float* x = logits + (size_t)r * V;
+  const int prev = (constraint && t > 0) ? seq[(size_t)r * L + t - 1] : -1;  // transformer.py:523-526 uses seq[:, t-1]
+  float mx = -INFINITY; int arg = 0x7fffffff;
+  for (int i = lane; i < V; i += 32) {
+    const float v = (i == prev) ? -INFINITY : x[i];
+    if (v > mx) { mx = v; arg = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  // log-softmax over the unconstrained row
+  float rmx = -INFINITY;
+  for (int i = lane; i < V; i += 32) rmx = fmaxf(rmx, x[i]);
+  rmx = sc::warp_max(rmx);
+  float se = 0.f;
+  for (int i = lane; i < V; i += 32) se += expf(x[i] - rmx);
+  se = sc::warp_sum(se);
+  if (lane == 0) {
+    const int unf = unfinished[r];
+    seq[(size_t)r * L + t] = unf ? arg : 0;
+    seq_lp[(size_t)r * L + t] = mx - (rmx + logf(se));
+    const int still = unf && (arg != eos);
+    unfinished[r] = still;
+    tokens[r] = arg;
+    if (still) atomicAdd(&live_count[t], 1);
+  }
+}
+
+// K8: dst[r] = src[idx[r]] for rows of row_bytes (16-byte vectorised)
+__global__ void __launch_bounds__(256) reorder_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                           const int* __restrict__ idx, long rows, long vec_per_row) {
+  const long total = rows * vec_per_row;
+  for (long g = (long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long)gridDim.x * blockDim.x) {
+    const long r = g / vec_per_row, c = g - r * vec_per_row;
+    dst[g] = src[(long)idx[r] * vec_per_row + c];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_decode_self_attn_step(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype,
+                             void* cache_k, void* cache_v, const int* anc, int anc_ld, int slot_div, void* out, int ldo,
+                             int R, int D, int h, int n_prev, int write_slot, cudaStream_t stream) {
+  SC_CHECK(R > 0 && D > 0 && h > 0 && D % h == 0, SC_ERR_SHAPE, "sc_decode_self_attn_step: R=%d D=%d h=%d", R, D, h);
+  const int dk = D / h;
+  SC_CHECK(dk % 8 == 0 && dk <= 256 && (dk & (dk - 1)) == 0, SC_ERR_UNSUPPORTED,
+           "sc_decode_self_attn_step: d_k=%d must be a power of two in [8,256]", dk);
+  SC_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, SC_ERR_ALIGN, "sc_decode_self_attn_step: ld %% 8");
+  SC_CHECK(n_prev >= 0 && slot_div >= 1, SC_ERR_SHAPE, "sc_decode_self_attn_step: n_prev=%d slot_div=%d", n_prev, slot_div);
+  SC_CHECK(n_prev == 0 || anc != nullptr, SC_ERR_SHAPE, "sc_decode_self_attn_step: ancestor table missing");
+  const long threads = (long)R * (D / 8);
+  const int blocks = (int)((threads + 255) / 256);
+  if (dtype == SC_F32)
+    self_attn_step_kernel<float><<<blocks, 256, 0, stream>>>((const float*)q, (const float*)k, (const float*)v, ldq, ldk, ldv,
+                                                             (float*)cache_k, (float*)cache_v, anc, anc_ld, slot_div,
+                                                             (float*)out, ldo, R, D, dk, n_prev, write_slot);
+  else if (dtype == SC_BF16)
+    self_attn_step_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldq, ldk, ldv, (__nv_bfloat16*)cache_k,
+        (__nv_bfloat16*)cache_v, anc, anc_ld, slot_div, (__nv_bfloat16*)out, ldo, R, D, dk, n_prev, write_slot);
+  else
+    SC_CHECK(false, SC_ERR_DTYPE, "sc_decode_self_attn_step: bad dtype %d", dtype);
+  SC_LAUNCH_CHECK("sc_decode_self_attn_step");
+  return SC_OK;
+}
+
+int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const void* mem_v, int ldm, int dtype,
+                              const float* att_mask, void* out, int ldo, int B, int beam, int N, int D, int h,
+                              cudaStream_t stream) {
+  SC_CHECK(B > 0 && beam > 0 && N > 0 && D % h == 0, SC_ERR_SHAPE, "sc_decode_cross_attn_step: bad shape");
+  const int dk = D / h;
+  SC_CHECK(dk % 8 == 0 && dk <= 256 && (dk & (dk - 1)) == 0, SC_ERR_UNSUPPORTED,
+           "sc_decode_cross_attn_step: d_k=%d must be a power of two in [8,256]", dk);
+  SC_CHECK(ldq % 8 == 0 && ldm % 8 == 0 && ldo % 8 == 0, SC_ERR_ALIGN, "sc_decode_cross_attn_step: ld %% 8");
+  SC_CHECK(beam <= kMaxBeam, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: beam=%d > %d", beam, kMaxBeam);
+  const long threads = (long)B * (D / 8);
+  const int blocks = (int)((threads + 127) / 128);
+#define XATT(T, NBV)                                                                                               \
+  cross_attn_step_kernel<T, NBV><<<blocks, 128, 0, stream>>>((const T*)q, ldq, (const T*)mem_k, (const T*)mem_v, ldm, \
+                                                             att_mask, (T*)out, ldo, B, N, D, dk)
+#define XATT_NB(T)                                          \
+  switch (beam) {                                           \
+    case 1: XATT(T, 1); break; case 2: XATT(T, 2); break;   \
+    case 3: XATT(T, 3); break; case 4: XATT(T, 4); break;   \
+    case 5: XATT(T, 5); break; case 6: XATT(T, 6); break;   \
+    case 7: XATT(T, 7); break; default: XATT(T, 8); break;  \
+  }
+  if (dtype == SC_F32) { XATT_NB(float) }
+  else if (dtype == SC_BF16) { XATT_NB(__nv_bfloat16) }
+  else SC_CHECK(false, SC_ERR_DTYPE, "sc_decode_cross_attn_step: bad dtype %d", dtype);
+#undef XATT_NB
+#undef XATT
+  SC_LAUNCH_CHECK("sc_decode_cross_attn_step");
+  return SC_OK;
+}
+
+int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
+                 int decoding_constraint, int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out,
+                 const float* lp_in, float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out,
+                 int* done_seq, float* done_lp, double* done_p, int* done_count, cudaStream_t stream) {
+  SC_CHECK(B > 0 && beam >= 1 && beam <= kMaxBeam, SC_ERR_UNSUPPORTED, "sc_beam_step: beam=%d not in [1,%d]", beam, kMaxBeam);
+  SC_CHECK(V >= beam && L > 0 && t >= 0 && t < L, SC_ERR_SHAPE, "sc_beam_step: V=%d L=%d t=%d", V, L, t);
+  SC_CHECK(temperature > 0.f, SC_ERR_SHAPE, "sc_beam_step: temperature must be > 0");
+  BeamArgs a;
+  a.logits = logits; a.B = B; a.beam = beam; a.V = V; a.L = L; a.t = t; a.eos = eos; a.pad = pad;
+  a.temperature = temperature; a.constraint = decoding_constraint; a.penalty_kind = penalty_kind;
+  a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
+  a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
+  a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
+  switch (beam) {
+    case 1: beam_step_kernel<1><<<B, 256, 0, stream>>>(a); break;
+    case 2: beam_step_kernel<2><<<B, 256, 0, stream>>>(a); break;
+    case 3: beam_step_kernel<3><<<B, 256, 0, stream>>>(a); break;
+    case 4: beam_step_kernel<4><<<B, 256, 0, stream>>>(a); break;
+    case 5: beam_step_kernel<5><<<B, 256, 0, stream>>>(a); break;
+    case 6: beam_step_kernel<6><<<B, 256, 0, stream>>>(a); break;
+    case 7: beam_step_kernel<7><<<B, 256, 0, stream>>>(a); break;
+    default: beam_step_kernel<8><<<B, 256, 0, stream>>>(a); break;
+  }
+  SC_LAUNCH_CHECK("sc_beam_step");
+  return SC_OK;
+}
+
+int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, int* seq,
+                   float* seq_lp, int* tokens, int* unfinished, int* live_count, cudaStream_t stream) {
+  SC_CHECK(R > 0 && V > 0 && t >= 0 && t < L, SC_ERR_SHAPE, "sc_greedy_step: R=%d V=%d t=%d L=%d", R, V, t, L);
+  greedy_step_kernel<<<(R * 32 + 255) / 256, 256, 0, stream>>>(logits, R, V, L, t, eos, decoding_constraint, seq, seq_lp,
+                                                              tokens, unfinished, live_count);
+  SC_LAUNCH_CHECK("sc_greedy_step");
+  return SC_OK;
+}
+
+int sc_cache_reorder(const void* src, void* dst, const int* idx, long rows, long row_bytes, cudaStream_t stream) {
+  SC_CHECK(rows > 0 && row_bytes > 0 && row_bytes % 16 == 0, SC_ERR_ALIGN, "sc_cache_reorder: row_bytes=%ld must be a multiple of 16", row_bytes);
+  SC_CHECK(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && src != dst, SC_ERR_ALIGN, "sc_cache_reorder: alignment / in-place");
+  const long vec = row_bytes / 16;
+  long blocks = (rows * vec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  reorder_rows_kernel<<<(int)blocks, 256, 0, stream>>>((const uint4*)src, (uint4*)dst, idx, rows, vec);
+  SC_LAUNCH_CHECK("sc_cache_reorder");
+  return SC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+"""Inference engine for the ORT / ACORT captioner: encoder, KV-cached incremental decoding, beam / greedy search.
+
+Host-side orchestration only — every arithmetic step is one of the sm_100a kernels behind include/sc_b200.h.
+The whole encoder and the whole L-step decode loop are each captured into ONE CUDA graph per (batch, boxes, beam)
+configuration, so a batch costs two graph launches and no host synchronisation (the reference does B*beam
+``bool(tensor)`` syncs per step, sparse_caption/models/caption_model.py:195-210).
+
+Reference call stack replaced:
+  RelationTransformerModel._sample          sparse_caption/models/relation_transformer.py:390-396
+  CachedTransformerBase._generate_captions  sparse_caption/models/transformer.py:471-561
+  CaptionModel.batch_beam_search            sparse_caption/models/caption_model.py:30-226
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import kernels as K
+from . import lib
+
+
+class ModelCfg:
+    """Hyper-parameters the model reads from the reference Config (models/transformer.py:418-437)."""
+
+    FIELDS = ("d_model", "dim_feedforward", "num_layers", "num_heads", "max_seq_length", "att_feat_size", "vocab_size",
+              "eos_token_id", "bos_token_id", "unk_token_id", "pad_token_id", "share_att_encoder", "share_att_decoder",
+              "share_layer_encoder", "share_layer_decoder", "no_box_trigonometric_embedding")
+    DEFAULTS = dict(d_model=512, dim_feedforward=2048, num_layers=6, num_heads=8, max_seq_length=16, att_feat_size=2048,
+                    eos_token_id=3, bos_token_id=2, unk_token_id=1, pad_token_id=0, share_att_encoder=None,
+                    share_att_decoder=None, share_layer_encoder=None, share_layer_decoder=None,
+                    no_box_trigonometric_embedding=False)
+
+    def __init__(self, config=None, **kw):
+        for f in self.FIELDS:
+            if f in kw:
+                v = kw[f]
+            elif config is not None and hasattr(config, f):
+                v = getattr(config, f)
+            elif config is not None and isinstance(config, dict) and f in config:
+                v = config[f]
+            elif f in self.DEFAULTS:
+                v = self.DEFAULTS[f]
+            else:
+                raise ValueError(f"missing config field `{f}`")
+            setattr(self, f, v)
+        assert self.d_model % self.num_heads == 0
+
+    def uids(self, which):
+        share = self.share_layer_encoder if which == "enc" else self.share_layer_decoder
+        return list(share) if share else list(range(self.num_layers))
+
+
+def _att_parts(share_att):
+    """(q, k, v, out) linear indices per share mode (relation_transformer.py:162-176, transformer.py:256-263)."""
+    if share_att is None:
+        return 0, 1, 2, 3
+    if share_att == "kv":
+        return 0, 1, 1, 2
+    if share_att == "qk":
+        return 0, 0, 1, 2
+    raise ValueError(f"Invalid `share_att`: {share_att}")
+
+
+class _Lin:
+    """One packed linear: dense weight in the activation dtype and/or CSR, fp32 bias."""
+
+    def __init__(self, w, b, adt, backend, csr_threshold):
+        w = w.detach().float().contiguous()
+        self.N, self.K = w.shape
+        self.bias = None if b is None else b.detach().float().contiguous()
+        self.sparsity = float((w == 0).sum()) / w.numel()
+        use_csr = backend == "csr" or (backend == "auto" and self.sparsity >= csr_threshold)
+        self.csr = K.CsrWeight(w, adt) if use_csr else None
+        self.w = None
+        if not use_csr:
+            self.w = K.cast_bf16(w) if adt == torch.bfloat16 else w
+
+    def __call__(self, x, out, residual=None, relu=False):
+        if self.csr is not None:
+            return K.csr_spmm(x, self.csr, self.bias, residual=residual, relu=relu, out=out)
+        return K.linear(x, self.w, self.bias, residual=residual, relu=relu, out=out)
+
+
+class _Norm:
+    def __init__(self, sd, prefix):
+        self.a = sd[prefix + ".a_2"].detach().float().contiguous()
+        self.b = sd[prefix + ".b_2"].detach().float().contiguous()
+
+    def __call__(self, x, out):
+        return K.layernorm(x, self.a, self.b, out=out)
+
+
+class BeamState:
+    def __init__(self, B, beam, L, dev):
+        R = B * beam
+        i32, f32 = dict(dtype=torch.int32, device=dev), dict(dtype=torch.float32, device=dev)
+        self.seq = [torch.zeros(R, L, **i32) for _ in range(2)]
+        self.lp = [torch.zeros(R, L, **f32) for _ in range(2)]
+        self.anc = [torch.zeros(R, L, **i32) for _ in range(2)]
+        self.sum = torch.zeros(R, **f32)
+        self.tokens = torch.zeros(R, **i32)
+        self.done_seq = torch.zeros(B, beam, L, **i32)
+        self.done_lp = torch.zeros(B, beam, L, **f32)
+        self.done_p = torch.zeros(B, beam, dtype=torch.float64, device=dev)
+        self.done_count = torch.zeros(B, **i32)
+        self.rows = torch.arange(R, **i32).unsqueeze(1).expand(R, L).contiguous()
+
+    def reset(self, bos, pad):
+        self.anc[0].copy_(self.rows)
+        self.sum.zero_()
+        self.tokens.fill_(bos)
+        self.done_count.zero_()
+        self.done_seq.fill_(pad)
+        self.done_lp.zero_()
+        self.done_p.zero_()
+
+
+class GreedyState:
+    def __init__(self, R, L, dev):
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.seq = torch.zeros(R, L, **i32)
+        self.lp = torch.zeros(R, L, dtype=torch.float32, device=dev)
+        self.tokens = torch.zeros(R, **i32)
+        self.unfinished = torch.ones(R, **i32)
+        self.live = torch.zeros(L, **i32)
+        self.anc = torch.arange(R, **i32).unsqueeze(1).expand(R, L).contiguous()
+
+    def reset(self, bos, pad):
+        self.seq.fill_(pad)
+        self.lp.zero_()
+        self.tokens.fill_(bos)
+        self.unfinished.fill_(1)
+        self.live.zero_()
+
+
+class OrtEngine:
+    """Packed weights + workspaces + CUDA graphs for one model.
+
+    ``state_dict``: dense-class parameter names (``relation_transformer``); masked weights must already be folded
+    (``prune.fold_masks`` does that on device).  ``precision``: "bf16" (tcgen05 tensor-core GEMMs, bf16 activations)
+    or "fp32" (fp32 verification kernels).  ``sparse_backend``: "dense" | "csr" | "auto" for the decoder linears
+    (K3a vs K3b); the encoder always runs the dense tensor path (M = B*N rows is large).
+    """
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, precision="bf16", sparse_backend="dense",
+                 csr_threshold=0.97, device="cuda", use_graphs=True, no_history=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("OrtEngine needs a CUDA device: the B200 path has no CPU fallback")
+        lib.load()
+        assert precision in ("bf16", "fp32")
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.precision = precision
+        self.use_graphs = use_graphs
+        self.no_history = no_history  # reference quirk Q1 (relation_transformer_prune never enables its KV cache)
+        self.sparse_backend = sparse_backend
+        sd = {k: v.to(self.dev) for k, v in state_dict.items() if torch.is_tensor(v) and not v.is_sparse}
+        sd.update({k: v.to(self.dev).to_dense() for k, v in state_dict.items() if torch.is_tensor(v) and v.is_sparse})
+        d, adt = cfg.d_model, self.adt
+
+        def lin(prefixes, backend="dense"):
+            ws = torch.cat([sd[p + ".weight"].float() for p in prefixes], 0)
+            bs = torch.cat([sd[p + ".bias"].float() for p in prefixes], 0)
+            return _Lin(ws, bs, adt, backend, csr_threshold)
+
+        self.att_embed = lin(["att_embed.0"])
+        # ---- encoder (unique modules only; shared layers re-use the pack) ----
+        self.enc_uids = cfg.uids("enc")
+        self.enc = {}
+        qi, ki, vi, oi = _att_parts(cfg.share_att_encoder)
+        for pos, u in enumerate(self.enc_uids):
+            if u in self.enc:
+                continue
+            p = f"model.encoder.layers.{pos}"
+            parts = sorted(set((qi, ki, vi)))
+            e = {
+                "qkv": lin([f"{p}.self_attn.linears.{j}" for j in parts]),
+                "offs": tuple(parts.index(j) * d for j in (qi, ki, vi)),
+                "ld": len(parts) * d,
+                "o": lin([f"{p}.self_attn.linears.{oi}"]),
+                "wg_w": torch.cat([sd[f"{p}.self_attn.WGs.{j}.weight"].float() for j in range(cfg.num_heads)], 0).contiguous(),
+                "wg_b": torch.cat([sd[f"{p}.self_attn.WGs.{j}.bias"].float() for j in range(cfg.num_heads)], 0).contiguous(),
+                "ff1": lin([f"{p}.feed_forward.w_1"]),
+                "ff2": lin([f"{p}.feed_forward.w_2"]),
+                "n0": _Norm(sd, f"{p}.sublayer.0.norm"),
+                "n1": _Norm(sd, f"{p}.sublayer.1.norm"),
+            }
+            self.enc[u] = e
+        self.enc_norm = _Norm(sd, "model.encoder.norm")
+        # ---- decoder ----
+        self.dec_uids = cfg.uids("dec")
+        self.dec = {}
+        qi, ki, vi, oi = _att_parts(cfg.share_att_decoder)
+        be = sparse_backend
+        for pos, u in enumerate(self.dec_uids):
+            if u in self.dec:
+                continue
+            p = f"model.decoder.layers.{pos}"
+            parts = sorted(set((qi, ki, vi)))
+            kv_parts = sorted(set((ki, vi)))
+            if cfg.share_att_decoder == "qk":
+                # cross-attention: key = linears.0(memory), value = linears.1(memory)
+                kv_parts = [0, 1]
+            e = {
+                "qkv": lin([f"{p}.self_attn.linears.{j}" for j in parts], be),
+                "offs": tuple(parts.index(j) * d for j in (qi, ki, vi)),
+                "ld": len(parts) * d,
+                "o": lin([f"{p}.self_attn.linears.{oi}"], be),
+                "cq": lin([f"{p}.src_attn.linears.{qi}"], be),
+                "ckv": lin([f"{p}.src_attn.linears.{j}" for j in kv_parts]),
+                "ckv_offs": tuple(kv_parts.index(j) * d for j in (ki, vi)),
+                "ckv_ld": len(kv_parts) * d,
+                "co": lin([f"{p}.src_attn.linears.{oi}"], be),
+                "ff1": lin([f"{p}.feed_forward.w_1"], be),
+                "ff2": lin([f"{p}.feed_forward.w_2"], be),
+                "n0": _Norm(sd, f"{p}.sublayer.0.norm"),
+                "n1": _Norm(sd, f"{p}.sublayer.1.norm"),
+                "n2": _Norm(sd, f"{p}.sublayer.2.norm"),
+                "apps": self.dec_uids.count(u),
+            }
+            self.dec[u] = e
+        self.dec_norm = _Norm(sd, "model.decoder.norm")
+        self.table = sd["model.tgt_embed.0.lut.weight"].float().contiguous()
+        L = cfg.max_seq_length
+        pe = sd.get("model.tgt_embed.1.pe")
+        self.pe = (pe[0, : L + 2] if pe is not None else _positional_encoding(d, L + 2, self.dev)).float().contiguous()
+        self.generator = lin(["model.generator.proj"], be)
+        self._enc_ws = {}
+        self._dec_ws = {}
+        torch.cuda.synchronize(self.dev)
+
+    # ------------------------------------------------------------------------------------------------
+    def _get_enc_ws(self, B, N, masked):
+        key = (B, N, masked)
+        if key in self._enc_ws:
+            return self._enc_ws[key]
+        c, dev, adt = self.cfg, self.dev, self.adt
+        d, ff, M = c.d_model, c.dim_feedforward, B * N
+        ws = type("EncWs", (), {})()
+        ws.B, ws.N, ws.masked = B, N, masked
+        ws.att_in = torch.zeros(M, c.att_feat_size, device=dev)
+        ws.att_a = torch.zeros(M, c.att_feat_size, device=dev, dtype=adt) if adt != torch.float32 else ws.att_in
+        ws.boxes = torch.zeros(B, N, 4, device=dev)
+        ws.att_mask = torch.ones(B, N, device=dev) if masked else None
+        ws.x = torch.zeros(M, d, device=dev)
+        ws.xn = torch.zeros(M, d, device=dev, dtype=adt)
+        ws.qkv = torch.zeros(M, 3 * d, device=dev, dtype=adt)
+        ws.att = torch.zeros(M, d, device=dev, dtype=adt)
+        ws.hid = torch.zeros(M, ff, device=dev, dtype=adt)
+        ws.mem = torch.zeros(M, d, device=dev, dtype=adt)
+        ws.memkv = {u: torch.zeros(M, e["ckv_ld"], device=dev, dtype=adt) for u, e in self.dec.items()}
+        ws.graph = None
+        self._enc_ws[key] = ws
+        return ws
+
+    def _encode_body(self, ws):
+        c = self.cfg
+        B, N, d, h = ws.B, ws.N, c.d_model, c.num_heads
+        dk = d // h
+        if ws.att_a is not ws.att_in:
+            K.cast_bf16(ws.att_in, out=ws.att_a)
+        self.att_embed(ws.att_a, ws.x, relu=True)
+        if ws.att_mask is not None:
+            K.mask_rows(ws.x, ws.att_mask.view(-1))
+        for u in self.enc_uids:
+            e = self.enc[u]
+            e["n0"](ws.x, ws.xn)
+            ld = e["ld"]
+            qkv = ws.qkv.view(-1)[: B * N * ld].view(B * N, ld)
+            e["qkv"](ws.xn, qkv)
+            qo, ko, vo = e["offs"]
+            K.box_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.boxes, e["wg_w"], e["wg_b"], ws.att_mask, ws.att,
+                            B=B, N=N, h=h, dk=dk, ldq=ld, ldk=ld, ldv=ld, ldo=d,
+                            trig=not c.no_box_trigonometric_embedding)
+            e["o"](ws.att, ws.x, residual=ws.x)
+            e["n1"](ws.x, ws.xn)
+            e["ff1"](ws.xn, ws.hid, relu=True)
+            e["ff2"](ws.hid, ws.x, residual=ws.x)
+        self.enc_norm(ws.x, ws.mem)
+        for u, e in self.dec.items():
+            e["ckv"](ws.mem, ws.memkv[u])
+
+    def encode(self, att_feats, boxes, att_masks=None):
+        """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V."""
+        B, N, F = att_feats.shape
+        ws = self._get_enc_ws(B, N, att_masks is not None)
+        ws.att_in.copy_(att_feats.reshape(B * N, F), non_blocking=True)
+        ws.boxes.copy_(boxes, non_blocking=True)
+        if att_masks is not None:
+            ws.att_mask.copy_(att_masks.float(), non_blocking=True)
+        self.run_encoder(ws)
+        return ws
+
+    def run_encoder(self, ws):
+        if not self.use_graphs:
+            self._encode_body(ws)
+            return
+        if ws.graph is None:
+            self._warm_and_capture(ws, lambda: self._encode_body(ws))
+        ws.graph.replay()
+
+    def _warm_and_capture(self, ws, body):
+        # warm-up on a side stream (lazy module loading, cudaFuncSetAttribute) before capture
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        before = lib.launch_count
+        with torch.cuda.graph(g):
+            body()
+        ws.graph = g
+        ws.launches = lib.launch_count - before
+
+    # ------------------------------------------------------------------------------------------------
+    def _get_dec_ws(self, B, beam, N, greedy):
+        key = (B, beam, N, greedy)
+        if key in self._dec_ws:
+            return self._dec_ws[key]
+        c, dev, adt = self.cfg, self.dev, self.adt
+        d, ff, L, V = c.d_model, c.dim_feedforward, c.max_seq_length, c.vocab_size
+        R = B * beam
+        ws = type("DecWs", (), {})()
+        ws.B, ws.beam, ws.N, ws.R, ws.greedy = B, beam, N, R, greedy
+        ws.x = torch.zeros(R, d, device=dev)
+        ws.xn = torch.zeros(R, d, device=dev, dtype=adt)
+        ws.qkv = torch.zeros(R, 3 * d, device=dev, dtype=adt)
+        ws.att = torch.zeros(R, d, device=dev, dtype=adt)
+        ws.qc = torch.zeros(R, d, device=dev, dtype=adt)
+        ws.hid = torch.zeros(R, ff, device=dev, dtype=adt)
+        ws.logits = torch.zeros(R, V, device=dev)
+        ws.cache = {u: (torch.zeros(L * e["apps"], R, d, device=dev, dtype=adt),
+                        torch.zeros(L * e["apps"], R, d, device=dev, dtype=adt)) for u, e in self.dec.items()}
+        ws.state = GreedyState(R, L, dev) if greedy else BeamState(B, beam, L, dev)
+        ws.graph = None
+        ws.opt_key = None
+        self._dec_ws[key] = ws
+        return ws
+
+    def _decode_step(self, ws, enc, t, anc):
+        c = self.cfg
+        R, d, h, N = ws.R, c.d_model, c.num_heads, ws.N
+        K.embed_pe(ws.state.tokens, self.table, self.pe, T=1, pos0=t, out=ws.x)
+        used = {u: 0 for u in self.dec}
+        for u in self.dec_uids:
+            e = self.dec[u]
+            e["n0"](ws.x, ws.xn)
+            ld = e["ld"]
+            qkv = ws.qkv.view(-1)[: R * ld].view(R, ld)
+            e["qkv"](ws.xn, qkv)
+            qo, ko, vo = e["offs"]
+            apps = e["apps"]
+            slot = t * apps + used[u]
+            used[u] += 1
+            ck, cv = ws.cache[u]
+            K.self_attn_step(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ck, cv, anc, ws.att, R=R, D=d, h=h,
+                             n_prev=0 if self.no_history else slot, write_slot=-1 if self.no_history else slot,
+                             ldq=ld, ldk=ld, ldv=ld, ldo=d, anc_ld=anc.shape[1], slot_div=apps)
+            e["o"](ws.att, ws.x, residual=ws.x)
+            e["n1"](ws.x, ws.xn)
+            e["cq"](ws.xn, ws.qc)
+            mkv = enc.memkv[u]
+            ko2, vo2 = e["ckv_offs"]
+            K.cross_attn_step(ws.qc, mkv[:, ko2:], mkv[:, vo2:], enc.att_mask, ws.att, B=ws.B, beam=ws.beam, N=N, D=d, h=h,
+                              ldq=d, ldm=e["ckv_ld"], ldo=d)
+            e["co"](ws.att, ws.x, residual=ws.x)
+            e["n2"](ws.x, ws.xn)
+            e["ff1"](ws.xn, ws.hid, relu=True)
+            e["ff2"](ws.hid, ws.x, residual=ws.x)
+        self.dec_norm(ws.x, ws.xn)
+        self.generator(ws.xn, ws.logits)
+
+    def _beam_body(self, ws, enc, opt):
+        c = self.cfg
+        L, V = c.max_seq_length, c.vocab_size
+        st = ws.state
+        st.reset(c.bos_token_id, c.pad_token_id)
+        kind, alpha = _parse_penalty(opt.get("length_penalty", ""))
+        for t in range(L):
+            self._decode_step(ws, enc, t, st.anc[t & 1])
+            K.beam_step(ws.logits, st, t, B=ws.B, beam=ws.beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id,
+                        temperature=opt.get("temperature", 1.0), constraint=opt.get("decoding_constraint", 0),
+                        penalty_kind=kind, penalty_alpha=alpha)
+
+    def _greedy_body(self, ws, enc, opt):
+        c = self.cfg
+        L, V = c.max_seq_length, c.vocab_size
+        st = ws.state
+        st.reset(c.bos_token_id, c.pad_token_id)
+        for t in range(L):
+            self._decode_step(ws, enc, t, st.anc)
+            K.greedy_step(ws.logits, st, t, R=ws.R, V=V, L=L, eos=c.eos_token_id,
+                          constraint=opt.get("decoding_constraint", 0))
+
+    def decode(self, enc, opt):
+        """Beam (beam_size > 1) or greedy search over an encoded batch.  Returns (seq int32 [B,b,L], lp [B,b,L])."""
+        beam = int(opt.get("beam_size", 1))
+        if opt.get("num_random_sample", 0) > 0:
+            raise NotImplementedError("multinomial sampling is not part of the B200 hot path yet")
+        if opt.get("group_size", 1) != 1:
+            raise NotImplementedError("diverse beam search (group_size > 1) is out of scope (SURVEY.md section 2.1 #6)")
+        greedy = beam == 1
+        assert beam <= self.cfg.vocab_size
+        ws = self._get_dec_ws(enc.B, beam, enc.N, greedy)
+        body = (lambda: self._greedy_body(ws, enc, opt)) if greedy else (lambda: self._beam_body(ws, enc, opt))
+        opt_key = (id(enc), tuple(sorted((k, str(v)) for k, v in opt.items())))
+        if not self.use_graphs:
+            body()
+        else:
+            if ws.graph is None or ws.opt_key != opt_key:
+                self._warm_and_capture(ws, body)
+                ws.opt_key = opt_key
+            ws.graph.replay()
+        st = ws.state
+        if greedy:
+            return st.seq.view(enc.B, 1, -1), st.lp.view(enc.B, 1, -1)
+        return st.done_seq, st.done_lp
+
+    def sample(self, att_feats, boxes, att_masks=None, opt=None):
+        """Drop-in for ``model(att_feats=..., boxes=..., att_masks=..., opt=..., mode="sample")``:
+        returns (seq int64 [B,b,L], seq_logprobs fp32 [B,b,L]) on the device."""
+        opt = dict(opt or {})
+        if att_masks is not None:
+            # clip_att (relation_transformer.py:398-405): host-side length, no device sync for CPU masks
+            max_len = int(att_masks.long().sum(1).max())
+            att_feats, boxes, att_masks = att_feats[:, :max_len], boxes[:, :max_len], att_masks[:, :max_len]
+        enc = self.encode(att_feats, boxes, att_masks)
+        seq, lp = self.decode(enc, opt)
+        return seq.long(), lp.clone()
+
+
+def _parse_penalty(s):
+    if not s:
+        return 0, 0.0
+    kind, alpha = s.split("_")
+    return {"wu": 1, "avg": 2}[kind], float(alpha)
+
+
+def _positional_encoding(d_model, max_len, dev):
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len).unsqueeze(1).float()
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.to(dev)

@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI in include/sc_b200.h (built as csrc/libsc_b200.so).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads libcudart into the process before our library)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsc_b200.so")
+
+F32, BF16 = 0, 1
+MASK_NONE, MASK_ROUND, MASK_BERNOULLI, MASK_RAW, MASK_UNIFORM = 0, 1, 2, 3, 4
+
+_p, _i, _f, _u64, _sz, _l = C.c_void_p, C.c_int, C.c_float, C.c_ulonglong, C.c_size_t, C.c_long
+
+# name -> argtypes (mirrors include/sc_b200.h; tests/test_abi.py checks header and table agree)
+SIGNATURES = {
+    "sc_linear": [_p, _i, _p, _i, _p, _i, _p, _u64, _u64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "sc_csr_spmm": [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sc_layernorm": [_p, _p, _p, _p, _i, _i, _i, _f, _p],
+    "sc_embed_pe": [_p, _p, _p, _i, _p, _u64, _u64, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p],
+    "sc_apply_mask": [_p, _p, _i, _p, _u64, _u64, _p, _i, _sz, _p],
+    "sc_mask_count": [_p, _sz, _p, _p],
+    "sc_cast_f32_bf16": [_p, _p, _sz, _p],
+    "sc_mask_rows": [_p, _p, _i, _i, _p],
+    "sc_box_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p],
+    "sc_decode_self_attn_step": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "sc_decode_cross_attn_step": [_p, _i, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "sc_beam_step": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "sc_greedy_step": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "sc_cache_reorder": [_p, _p, _p, _l, _l, _p],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or `make -C {os.path.dirname(LIB_PATH)}`).  There is no CPU/PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.sc_last_error.restype = C.c_char_p
+    lib.sc_last_error.argtypes = []
+    lib.sc_version.restype = C.c_int
+    lib.sc_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {dt}")
+
+
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+def call(name, *args):
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (status {rc}): {lib.sc_last_error().decode()}")
+    launch_count += 1

@@ -1,0 +1,313 @@
+"""Kernel-level parity: every C-ABI entry point against the CPU oracle / plain torch fp32 on the same inputs.
+GPU tier (`-m gpu`).  Tolerances: fp32 kernels 1e-5 relative (north_star), bf16 tensor path 2e-2;
+integer / index / mask results bit-exact."""
+import math
+
+import pytest
+import torch
+
+from oracle import ort_oracle as O
+from tests import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import sparse_caption_b200.kernels as k
+    return k
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _mk(M, N, Kd, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(M, Kd, generator=g)
+    w = torch.randn(N, Kd, generator=g) / math.sqrt(Kd)
+    s = torch.randn(N, Kd, generator=g) * 2
+    s.view(-1)[:4] = torch.tensor([0.0, 5e-8, 1e-7, -0.0])
+    u = torch.rand(N, Kd, generator=g)
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g)
+    return x, w, s, u, b, r
+
+
+def _ref_linear(x, w, s, u, b, r, mode, relu):
+    if mode == 1:
+        w = w * O.binarize_logits(s)
+    elif mode == 3:
+        w = w * s
+    elif mode == 4:
+        w = w * O.bernoulli_from_uniform(s, u)
+    y = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    if relu:
+        y = torch.relu(y)
+    return y + r.double()
+
+
+@pytest.mark.parametrize("shape", [(7, 5, 8), (64, 64, 16), (130, 70, 96), (300, 771, 512), (50, 1, 64)])
+@pytest.mark.parametrize("mode", [0, 1, 3, 4])
+def test_linear_fp32(K, shape, mode):
+    M, N, Kd = shape
+    x, w, s, u, b, r = _mk(M, N, Kd)
+    dev = "cuda"
+    y = K.linear(x.to(dev), w.to(dev), b.to(dev), mask=s.to(dev), mask_mode=mode, uniforms=u.to(dev), residual=r.to(dev),
+                 relu=True)
+    assert rel_err(y, _ref_linear(x, w, s, u, b, r, mode, True)) < 1e-5
+
+
+@pytest.mark.parametrize("tile_n", [64, 128, 256])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (128, 256, 512), (300, 200, 512), (1536, 512, 512), (1800, 2048, 512),
+                                   (257, 1000, 2048), (100, 771, 512), (36, 64, 96)])
+def test_linear_bf16_dense(K, shape, tile_n):
+    """tcgen05 GEMM, bf16 operands via TMA.  Checked against a float64 product of the SAME bf16-rounded operands,
+    so the tolerance only covers fp32 accumulation order (tight), not quantisation."""
+    M, N, Kd = shape
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=1)
+    xb, wb = x.bfloat16(), w.bfloat16()
+    dev = "cuda"
+    y = K.linear(xb.to(dev), wb.to(dev), b.to(dev), residual=r.to(dev), relu=False, tile_n=tile_n)
+    ref = torch.nn.functional.linear(xb.double(), wb.double(), b.double()) + r.double()
+    assert rel_err(y, ref) < 2e-5, shape
+    yb = K.linear(xb.to(dev), wb.to(dev), b.to(dev), relu=True, out_dtype=torch.bfloat16, tile_n=tile_n)
+    ref = torch.relu(torch.nn.functional.linear(xb.double(), wb.double(), b.double()))
+    assert rel_err(yb.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("mode", [0, 1, 3, 4])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (300, 200, 512), (1536, 512, 2048), (100, 771, 512)])
+def test_linear_bf16_masked_prologue(K, shape, mode):
+    """fp32 master weights + fp32 mask logits, mask applied while building the UMMA operand tile."""
+    M, N, Kd = shape
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=2)
+    xb = x.bfloat16()
+    dev = "cuda"
+    y = K.linear(xb.to(dev), w.to(dev), b.to(dev), mask=s.to(dev), mask_mode=mode, uniforms=u.to(dev), residual=r.to(dev))
+    if mode == 1:
+        wm = w * O.binarize_logits(s)
+    elif mode == 3:
+        wm = w * s
+    elif mode == 4:
+        wm = w * O.bernoulli_from_uniform(s, u)
+    else:
+        wm = w
+    ref = torch.nn.functional.linear(xb.double(), wm.bfloat16().double(), b.double()) + r.double()
+    assert rel_err(y, ref) < 2e-5, (shape, mode)
+
+
+def test_bernoulli_mask_consistency(K):
+    """Philox masks: the tensor-core prologue, the fp32 kernel and sc_apply_mask regenerate the SAME mask from
+    (seed, stream_id, element); the keep-rate matches sigmoid(S)."""
+    M, N, Kd = 256, 384, 512
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=3)
+    s = s * 0 + 1.0  # p = sigmoid(1) = 0.731
+    dev = "cuda"
+    wm = K.apply_mask(w.to(dev), s.to(dev), K.MASK_BERNOULLI, seed=1234, stream_id=7)
+    keep = float((wm != 0).float().mean())
+    assert abs(keep - 0.7311) < 0.01
+    wm2 = K.apply_mask(w.to(dev), s.to(dev), K.MASK_BERNOULLI, seed=1234, stream_id=8)
+    assert float(((wm != 0) != (wm2 != 0)).float().mean()) > 0.2  # different stream -> different mask
+    y32 = K.linear(x.to(dev), w.to(dev), b.to(dev), mask=s.to(dev), mask_mode=K.MASK_BERNOULLI, seed=1234, stream_id=7)
+    ref = torch.nn.functional.linear(x.double(), wm.cpu().double(), b.double())
+    assert rel_err(y32, ref) < 1e-5
+    xb = x.bfloat16()
+    yb = K.linear(xb.to(dev), w.to(dev), b.to(dev), mask=s.to(dev), mask_mode=K.MASK_BERNOULLI, seed=1234, stream_id=7)
+    ref = torch.nn.functional.linear(xb.double(), wm.cpu().bfloat16().double(), b.double())
+    assert rel_err(yb, ref) < 2e-5
+
+
+def test_binarize_bit_exact(K):
+    z = golden_io.load("binarize")
+    s = z["s"].cuda()
+    m = K.apply_mask(torch.ones_like(s), s, K.MASK_ROUND)
+    assert torch.equal(m.cpu(), z["m"])
+    assert int(K.mask_count([s])) == int(z["m"].sum())
+    big = torch.randn(1_000_003) * 3
+    assert int(K.mask_count([big.cuda()])) == int(O.binarize_logits(big).sum())
+
+
+@pytest.mark.parametrize("D", [64, 512, 2048])
+def test_layernorm(K, D):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(77, D, generator=g) * 3 + 1
+    a, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    y = K.layernorm(x.cuda(), a.cuda(), b.cuda())
+    assert rel_err(y, O.layer_norm(x.double(), a.double(), b.double())) < 1e-5
+    yb = K.layernorm(x.cuda(), a.cuda(), b.cuda(), out_dtype=torch.bfloat16)
+    assert rel_err(yb.float(), O.layer_norm(x, a, b)) < 1e-2
+
+
+def test_embed_pe(K):
+    g = torch.Generator().manual_seed(0)
+    V, D, T, R = 50, 64, 7, 5
+    table = torch.randn(V, D, generator=g)
+    s = torch.randn(V, D, generator=g)
+    pe = O.positional_encoding(D, 20)
+    tok = torch.randint(0, V, (R, T), generator=g)
+    out = K.embed_pe(tok.int().cuda().view(-1), table.cuda(), pe.cuda(), T=T, pos0=0, mask=s.cuda(), mask_mode=K.MASK_ROUND)
+    ref = (table * O.binarize_logits(s))[tok] * math.sqrt(D) + pe[:T]
+    assert rel_err(out.view(R, T, D), ref) < 1e-6
+    out = K.embed_pe(tok[:, 0].int().cuda().contiguous(), table.cuda(), pe.cuda(), T=1, pos0=3)
+    assert rel_err(out, table[tok[:, 0]] * math.sqrt(D) + pe[3]) < 1e-6
+
+
+@pytest.mark.parametrize("cfg", [(2, 9, 4, 16), (3, 36, 8, 64), (2, 47, 8, 64), (1, 100, 8, 64)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_box_attention(K, cfg, dt):
+    B, N, h, dk = cfg
+    g = torch.Generator().manual_seed(5)
+    D = h * dk
+    data = O.synthetic_inputs(B, N, 8, seed=11)
+    boxes = data["boxes"]
+    mask = torch.ones(B, N)
+    if N > 10:
+        mask[0, N - 3:] = 0
+        boxes[0, N - 3:] = 0
+    qkv = (torch.randn(B * N, 3 * D, generator=g)).to(dt)
+    wg_w = torch.randn(h, 64, generator=g) * 0.3
+    wg_b = torch.randn(h, generator=g) * 0.3
+    out = torch.zeros(B * N, D, dtype=dt, device="cuda")
+    qkv_d = qkv.cuda()
+    K.box_attention(qkv_d[:, 0:], qkv_d[:, D:], qkv_d[:, 2 * D:], boxes.cuda(), wg_w.cuda(), wg_b.cuda(), mask.cuda(), out,
+                    B=B, N=N, h=h, dk=dk, ldq=3 * D, ldk=3 * D, ldv=3 * D, ldo=D)
+    emb = O.box_relational_embedding(boxes)
+    q, k, v = (qkv.float()[:, i * D:(i + 1) * D].view(B, N, h, dk).transpose(1, 2) for i in range(3))
+    gw = torch.relu(torch.einsum("bijf,hf->bhij", emb, wg_w) + wg_b.view(1, h, 1, 1))
+    scores = (q @ k.transpose(-2, -1)) / math.sqrt(dk)
+    scores = scores.masked_fill(mask.view(B, 1, 1, N) == 0, -1e9)
+    ref = torch.softmax(torch.log(torch.clamp(gw, min=1e-6)) + scores, -1) @ v
+    ref = ref.transpose(1, 2).reshape(B * N, D)
+    tol = 3e-4 if dt == torch.float32 else 2e-2  # fp32: logf/sincosf ulp differences are amplified by 100x angles (SURVEY Q-notes)
+    assert rel_err(out.float(), ref) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_decode_attention_steps(K, dt):
+    g = torch.Generator().manual_seed(9)
+    B, beam, N, h, dk, L = 3, 3, 11, 4, 16, 6
+    D, R = h * dk, B * beam
+    dev = "cuda"
+    ck = torch.zeros(L, R, D, dtype=dt, device=dev)
+    cv = torch.zeros(L, R, D, dtype=dt, device=dev)
+    hist_k, hist_v = [], []
+    anc = torch.arange(R, dtype=torch.int32).unsqueeze(1).expand(R, L).contiguous()
+    for t in range(4):
+        qkv = torch.randn(R, 3 * D, generator=g).to(dt)
+        if t > 0:  # shuffle beams inside each image like a beam step would
+            perm = torch.cat([torch.randperm(beam, generator=g) + b * beam for b in range(B)])
+            anc = anc[perm].clone()
+            anc[:, t:] = torch.arange(R, dtype=torch.int32).unsqueeze(1)
+            hist_k = [x[perm] for x in hist_k]
+            hist_v = [x[perm] for x in hist_v]
+        out = torch.zeros(R, D, dtype=dt, device=dev)
+        qd = qkv.to(dev)
+        K.self_attn_step(qd[:, 0:], qd[:, D:], qd[:, 2 * D:], ck, cv, anc.to(dev), out, R=R, D=D, h=h, n_prev=t, write_slot=t,
+                         ldq=3 * D, ldk=3 * D, ldv=3 * D, ldo=D, anc_ld=L)
+        q, k, v = (qkv.float()[:, i * D:(i + 1) * D] for i in range(3))
+        hist_k.append(k)
+        hist_v.append(v)
+        kk = torch.stack(hist_k, 1).view(R, t + 1, h, dk).transpose(1, 2)
+        vv = torch.stack(hist_v, 1).view(R, t + 1, h, dk).transpose(1, 2)
+        ref = O.attention(q.view(R, 1, h, dk).transpose(1, 2), kk, vv, None).transpose(1, 2).reshape(R, D)
+        assert rel_err(out.float(), ref) < (1e-5 if dt == torch.float32 else 2e-2), t
+    # cross attention
+    mem = torch.randn(B * N, 2 * D, generator=g).to(dt)
+    qc = torch.randn(R, D, generator=g).to(dt)
+    mask = torch.ones(B, N)
+    mask[1, 7:] = 0
+    out = torch.zeros(R, D, dtype=dt, device=dev)
+    md = mem.to(dev)
+    K.cross_attn_step(qc.to(dev), md[:, 0:], md[:, D:], mask.to(dev), out, B=B, beam=beam, N=N, D=D, h=h, ldq=D, ldm=2 * D, ldo=D)
+    kk = mem.float()[:, :D].view(B, N, h, dk).transpose(1, 2).repeat_interleave(beam, 0)
+    vv = mem.float()[:, D:].view(B, N, h, dk).transpose(1, 2).repeat_interleave(beam, 0)
+    m4 = mask.view(B, 1, 1, N).repeat_interleave(beam, 0)
+    ref = O.attention(qc.float().view(R, 1, h, dk).transpose(1, 2), kk, vv, m4).transpose(1, 2).reshape(R, D)
+    assert rel_err(out.float(), ref) < (1e-5 if dt == torch.float32 else 2e-2)
+
+
+def test_cache_reorder(K):
+    src = torch.randn(12, 4, 5, 8).cuda()
+    idx = torch.tensor([3, 3, 0, 11, 7, 1, 2, 2, 2, 9, 10, 4], dtype=torch.int32).cuda()
+    assert torch.equal(K.cache_reorder(src, idx), src[idx.long()])
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1536, 512, 512, 0.95), (100, 771, 512, 0.99), (300, 512, 2048, 0.9), (20, 64, 96, 0.5)])
+def test_csr_spmm(K, dt, shape):
+    M, N, Kd, sp = shape
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=4)
+    w = w * (torch.rand(N, Kd) >= sp)
+    w[min(3, N - 1)] = 0  # an empty row
+    dev = "cuda"
+    csr = K.CsrWeight(w.to(dev), dt)
+    y = K.csr_spmm(x.to(dt).to(dev), csr, b.to(dev), residual=r.to(dev), relu=True)
+    ref = torch.relu(torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double(), b.double())) + r.double()
+    assert rel_err(y, ref) < 2e-5
+
+
+def _beam_ref(logits, B, beam, V, L, eos, opt):
+    """Drive oracle.beam_select + the bookkeeping of oracle.beam_search on a fixed logits sequence."""
+    pen = O.length_penalty(opt.get("length_penalty", ""))
+    T = opt.get("temperature", 1.0)
+    beam_seq = torch.zeros(B, beam, 0, dtype=torch.long)
+    beam_lp = torch.zeros(B, beam, 0)
+    beam_sum = torch.zeros(B, beam)
+    done = [[] for _ in range(B)]
+    for t in range(L):
+        lp = torch.log_softmax(logits[t], -1)
+        if t > 0:  # caption_model.py:218 (init_logprobs at t == 0 are used as returned by the model)
+            lp = torch.log_softmax(lp / T, -1)
+        if t == 0:
+            lp = lp.view(B, beam, V)[:, 0]
+        if opt.get("decoding_constraint", 0) and t > 0:
+            lp = lp.clone()
+            lp.scatter_(1, beam_seq[:, :, t - 1].reshape(-1, 1), float("-inf"))
+        parent, word, new_sum = O.beam_select(lp, beam_sum, beam, first=(t == 0))
+        nb = lp.size(0) // B
+        chosen = lp.view(B, nb, V).gather(1, parent.unsqueeze(-1).expand(-1, -1, V)).gather(2, word.unsqueeze(-1)).squeeze(-1)
+        if t > 0:
+            beam_seq = beam_seq.gather(1, parent.unsqueeze(-1).expand_as(beam_seq))
+            beam_lp = beam_lp.gather(1, parent.unsqueeze(-1).expand_as(beam_lp))
+        beam_seq = torch.cat([beam_seq, word.unsqueeze(-1)], -1)
+        beam_lp = torch.cat([beam_lp, chosen.unsqueeze(-1)], -1)
+        beam_sum = new_sum.clone()
+        for b in range(B):
+            is_end = beam_seq[b, :, t] == eos
+            if t == L - 1:
+                is_end = torch.ones_like(is_end)
+            for v in range(beam):
+                if is_end[v]:
+                    done[b].append({"seq": beam_seq[b, v].clone(), "lp": beam_lp[b, v].clone(), "p": pen(t + 1, float(beam_sum[b, v]))})
+            beam_sum[b, is_end] -= 1000
+    seq = torch.zeros(B, beam, L, dtype=torch.long)
+    slp = torch.zeros(B, beam, L)
+    for b in range(B):
+        for v, d in enumerate(sorted(done[b], key=lambda d: -d["p"])[:beam]):
+            seq[b, v, : d["seq"].numel()] = d["seq"]
+            slp[b, v, : d["lp"].numel()] = d["lp"]
+    return seq, slp
+
+
+@pytest.mark.parametrize("beam,V", [(3, 10000), (5, 771), (2, 37), (8, 300)])
+@pytest.mark.parametrize("opt", [{}, {"decoding_constraint": 1, "length_penalty": "wu_0.7"}, {"temperature": 0.8, "length_penalty": "avg_0"}])
+def test_beam_step(K, beam, V, opt):
+    """K7 against the oracle's beam bookkeeping on a fixed sequence of logits (EOS made likely so beams finish)."""
+    from sparse_caption_b200.engine import BeamState, _parse_penalty
+    B, L, eos = 7, 9, 3
+    g = torch.Generator().manual_seed(beam * 1000 + V)
+    logits = [torch.randn(B * beam, V, generator=g) * 2 for _ in range(L)]
+    for t in range(L):
+        logits[t][:, eos] += 2.5
+        logits[t][::2, 5] = logits[t][::2, 6]  # exact ties inside a row
+    ref_seq, ref_lp = _beam_ref(logits, B, beam, V, L, eos, opt)
+    st = BeamState(B, beam, L, torch.device("cuda"))
+    st.reset(2, 0)
+    kind, alpha = _parse_penalty(opt.get("length_penalty", ""))
+    for t in range(L):
+        K.beam_step(logits[t].cuda(), st, t, B=B, beam=beam, V=V, L=L, eos=eos, pad=0, temperature=opt.get("temperature", 1.0),
+                    constraint=opt.get("decoding_constraint", 0), penalty_kind=kind, penalty_alpha=alpha)
+    assert torch.equal(st.done_seq.cpu().long(), ref_seq)
+    torch.testing.assert_close(st.done_lp.cpu(), ref_lp, rtol=1e-5, atol=1e-5)
