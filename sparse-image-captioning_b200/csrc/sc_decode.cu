@@ -111,59 +111,105 @@ __global__ void __launch_bounds__(256) self_attn_step_kernel(const T* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K6: thread = (image, 8-dim chunk), handles the NB beam rows of that image together so each memory K/V element is
-// loaded once per image instead of once per beam.
+// K6: one warp per (image, head) serves the NB beam rows of that image together, so each memory K/V element is
+// loaded once per image instead of once per beam.  Scores: lane = key (16-byte loads of that key's d_k slice, q
+// broadcast from shared memory); softmax by warp shuffles; PV: lane = output dims, V rows read coalesced.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxKeyPass = 4;  // N <= 128 memory slots
+
 template <typename T, int NB>
-__global__ void __launch_bounds__(128) cross_attn_step_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ mk,
+__global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ mk,
                                                               const T* __restrict__ mv, int ldm,
                                                               const float* __restrict__ att_mask, T* __restrict__ out,
-                                                              int ldo, int B, int N, int D, int dk) {
-  const int chunks = D / 8;
-  const int lanes = dk / 8;
-  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = g < (long)B * chunks;
-  const int b = active ? (int)(g / chunks) : B - 1;
-  const int c = active ? (int)(g % chunks) : 0;
+                                                              int ldo, int B, int N, int h, int dk) {
+  extern __shared__ float s_q[];  // [8 warps][NB][dk]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + warp;
+  if (w >= B * h) return;
+  const int b = w / h, hh = w - b * h;
+  float* sq = s_q + warp * NB * dk;
+  for (int e = lane; e < NB * dk; e += 32) {
+    const int n = e / dk, d = e - n * dk;
+    sq[e] = sc::to_f32<T>(q[((size_t)b * NB + n) * ldq + hh * dk + d]);
+  }
+  __syncwarp();
   const float scale_div = sqrtf((float)dk);
-  Vec8<T> qv[NB];
-  float m[NB], l[NB], acc[NB][8];
+  float sc_[kMaxKeyPass][NB];
+  float mx[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) mx[n] = -INFINITY;
+#pragma unroll
+  for (int ps = 0; ps < kMaxKeyPass; ++ps) {
+    const int j = ps * 32 + lane;
+    float dot[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) dot[n] = 0.f;
+    if (ps * 32 < N && j < N) {
+      const T* kr = mk + ((size_t)b * N + j) * ldm + hh * dk;
+      for (int c = 0; c < dk; c += 8) {
+        Vec8<T> kk;
+        kk.load(kr + c);
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+          const float4 q0 = *(const float4*)(sq + n * dk + c), q1 = *(const float4*)(sq + n * dk + c + 4);
+          dot[n] = fmaf(q0.x, kk.v[0], dot[n]); dot[n] = fmaf(q0.y, kk.v[1], dot[n]);
+          dot[n] = fmaf(q0.z, kk.v[2], dot[n]); dot[n] = fmaf(q0.w, kk.v[3], dot[n]);
+          dot[n] = fmaf(q1.x, kk.v[4], dot[n]); dot[n] = fmaf(q1.y, kk.v[5], dot[n]);
+          dot[n] = fmaf(q1.z, kk.v[6], dot[n]); dot[n] = fmaf(q1.w, kk.v[7], dot[n]);
+        }
+      }
+      const bool masked = att_mask && att_mask[(size_t)b * N + j] == 0.f;
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        float sv = dot[n] / scale_div;
+        if (masked) sv = -1e9f;
+        sc_[ps][n] = sv;
+        mx[n] = fmaxf(mx[n], sv);
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NB; ++n) sc_[ps][n] = -INFINITY;
+    }
+  }
+  float inv[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
-    qv[n].load(q + ((size_t)b * NB + n) * ldq + c * 8);
-    m[n] = -INFINITY; l[n] = 0.f;
+    const float m = sc::warp_max(mx[n]);
+    float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[n][i] = 0.f;
+    for (int ps = 0; ps < kMaxKeyPass; ++ps) {
+      const float e = (ps * 32 + lane < N) ? expf(sc_[ps][n] - m) : 0.f;
+      sc_[ps][n] = e;
+      sum += e;
+    }
+    inv[n] = 1.f / sc::warp_sum(sum);
   }
-  for (int j = 0; j < N; ++j) {
-    Vec8<T> kk, vs;
-    const size_t row = (size_t)b * N + j;
-    kk.load(mk + row * ldm + c * 8);
-    vs.load(mv + row * ldm + c * 8);
-    const bool masked = att_mask && att_mask[row] == 0.f;
+  // PV: lane owns dims lane, lane+32 (d_k <= 64)
+  float o0[NB], o1[NB];
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      float dot = 0.f;
+  for (int n = 0; n < NB; ++n) { o0[n] = 0.f; o1[n] = 0.f; }
+  const bool d0 = lane < dk, d1 = lane + 32 < dk;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dot = fmaf(qv[n].v[i], kk.v[i], dot);
-      dot = group_sum(dot, lanes) / scale_div;
-      if (masked) dot = -1e9f;
-      const float mn = fmaxf(m[n], dot);
-      const float corr = expf(m[n] - mn);
-      const float p = expf(dot - mn);
-      l[n] = l[n] * corr + p;
+  for (int ps = 0; ps < kMaxKeyPass; ++ps) {
+    if (ps * 32 >= N) break;
+    const int lim = min(32, N - ps * 32);
+    for (int l = 0; l < lim; ++l) {
+      const T* vr = mv + ((size_t)b * N + ps * 32 + l) * ldm + hh * dk;
+      const float v0 = d0 ? sc::to_f32<T>(vr[lane]) : 0.f;
+      const float v1 = d1 ? sc::to_f32<T>(vr[lane + 32]) : 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[n][i] = acc[n][i] * corr + p * vs.v[i];
-      m[n] = mn;
+      for (int n = 0; n < NB; ++n) {
+        const float p = __shfl_sync(0xffffffffu, sc_[ps][n], l);
+        o0[n] = fmaf(p, v0, o0[n]);
+        o1[n] = fmaf(p, v1, o1[n]);
+      }
     }
   }
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
-    const float inv = 1.f / l[n];
-    Vec8<T> o;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o.v[i] = acc[n][i] * inv;
-    if (active) o.store(out + ((size_t)b * NB + n) * ldo + c * 8);
+    T* orow = out + ((size_t)b * NB + n) * ldo + hh * dk;
+    if (d0) orow[lane] = sc::from_f32<T>(o0[n] * inv[n]);
+    if (d1) orow[lane + 32] = sc::from_f32<T>(o1[n] * inv[n]);
   }
 }
 
@@ -171,6 +217,8 @@ __global__ void __launch_bounds__(128) cross_attn_step_kernel(const T* __restric
 // K7 beam step.  One CTA per image.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kMaxBeam = 8;
+constexpr int kBeamThreads = 1024;
+constexpr int kBeamWarps = kBeamThreads / 32;
 
 struct Cand {
   float s;
@@ -207,39 +255,39 @@ struct BeamArgs {
 };
 
 template <int NB>
-__global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
+__global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs a) {
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V;
   const int rows = (a.t == 0) ? 1 : NB;  // first step: every beam holds BOS, only beam 0 is expanded
-  __shared__ float s_red[8];
+  __shared__ float s_red[kBeamWarps];
   __shared__ float s_mx[NB], s_ls[NB], s_mx2[NB], s_ls2[NB], s_sum[NB];
   // init_logprobs (t == 0) are never temperature-scaled (caption_model.py:135, 218)
   const float T = (a.t == 0) ? 1.0f : a.temperature;
   __shared__ int s_prev[NB];
-  __shared__ Cand s_top[8][NB];
+  __shared__ Cand s_top[kBeamWarps][NB];
   __shared__ Cand s_final[NB];
 
   // ---- log-softmax statistics per row (twice when temperature != 1: log_softmax(log_softmax(x)/T)) ----
   for (int k = 0; k < rows; ++k) {
     const float* x = a.logits + ((size_t)b * NB + k) * V;
     float mx = -INFINITY;
-    for (int i = tid; i < V; i += 256) mx = fmaxf(mx, x[i]);
+    for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
     mx = sc::warp_max(mx);
     if (lane == 0) s_red[warp] = mx;
     __syncthreads();
     mx = s_red[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w]);
+    for (int w = 1; w < kBeamWarps; ++w) mx = fmaxf(mx, s_red[w]);
     __syncthreads();
     float se = 0.f;
-    for (int i = tid; i < V; i += 256) se += expf(x[i] - mx);
+    for (int i = tid; i < V; i += kBeamThreads) se += expf(x[i] - mx);
     se = sc::warp_sum(se);
     if (lane == 0) s_red[warp] = se;
     __syncthreads();
     se = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) se += s_red[w];
+    for (int w = 0; w < kBeamWarps; ++w) se += s_red[w];
     __syncthreads();
     // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
     float ls = logf(se), mx2 = 0.f, ls2 = 0.f;
@@ -247,13 +295,13 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
       // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
       mx2 = (0.f - ls) / T;
       float se2 = 0.f;
-      for (int i = tid; i < V; i += 256) se2 += expf(((x[i] - mx) - ls) / T - mx2);
+      for (int i = tid; i < V; i += kBeamThreads) se2 += expf(((x[i] - mx) - ls) / T - mx2);
       se2 = sc::warp_sum(se2);
       if (lane == 0) s_red[warp] = se2;
       __syncthreads();
       se2 = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) se2 += s_red[w];
+      for (int w = 0; w < kBeamWarps; ++w) se2 += s_red[w];
       __syncthreads();
       ls2 = logf(se2);
     }
@@ -273,7 +321,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
     const float* x = a.logits + ((size_t)b * NB + k) * V;
     const float mx = s_mx[k], ls = s_ls[k], mx2 = s_mx2[k], ls2 = s_ls2[k], base = s_sum[k];
     const int prev = s_prev[k];
-    for (int i = tid; i < V; i += 256) {
+    for (int i = tid; i < V; i += kBeamThreads) {
       float lp = (x[i] - mx) - ls;
       if (T != 1.0f) lp = (lp / T - mx2) - ls2;
       if (i == prev) lp = -INFINITY;
@@ -307,11 +355,12 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
   }
   __syncthreads();
   if (tid == 0) {
-    int heads[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int heads[kBeamWarps];
+    for (int w = 0; w < kBeamWarps; ++w) heads[w] = 0;
     for (int rnd = 0; rnd < NB; ++rnd) {
       int bw = -1;
       Cand best; best.s = -INFINITY; best.idx = 0x7fffffff;
-      for (int w = 0; w < 8; ++w) {
+      for (int w = 0; w < kBeamWarps; ++w) {
         if (heads[w] < NB) {
           Cand c = s_top[w][heads[w]];
           if (bw < 0 || better(c, best)) { best = c; bw = w; }
@@ -326,7 +375,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamArgs a) {
   // ---- bookkeeping (caption_model.py:84-110, 195-210) ----
   const int L = a.L, t = a.t;
   // history gathers: NB rows x L entries, spread over the CTA
-  for (int e = tid; e < NB * L; e += 256) {
+  for (int e = tid; e < NB * L; e += kBeamThreads) {
     const int j = e / L, s = e - j * L;
     const int parent = s_final[j].idx / V;
     const size_t src = ((size_t)b * NB + parent) * L + s, dst = ((size_t)b * NB + j) * L + s;
@@ -481,11 +530,13 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
            "sc_decode_cross_attn_step: d_k=%d must be a power of two in [8,256]", dk);
   SC_CHECK(ldq % 8 == 0 && ldm % 8 == 0 && ldo % 8 == 0, SC_ERR_ALIGN, "sc_decode_cross_attn_step: ld %% 8");
   SC_CHECK(beam <= kMaxBeam, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: beam=%d > %d", beam, kMaxBeam);
-  const long threads = (long)B * (D / 8);
-  const int blocks = (int)((threads + 127) / 128);
-#define XATT(T, NBV)                                                                                               \
-  cross_attn_step_kernel<T, NBV><<<blocks, 128, 0, stream>>>((const T*)q, ldq, (const T*)mem_k, (const T*)mem_v, ldm, \
-                                                             att_mask, (T*)out, ldo, B, N, D, dk)
+  SC_CHECK(N <= 32 * kMaxKeyPass, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: N=%d > %d memory slots", N, 32 * kMaxKeyPass);
+  SC_CHECK(dk <= 64, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: d_k=%d > 64", dk);
+  const int blocks = (B * h + 7) / 8;
+  const size_t smem = (size_t)8 * beam * dk * sizeof(float);
+#define XATT(T, NBV)                                                                                                  \
+  cross_attn_step_kernel<T, NBV><<<blocks, 256, smem, stream>>>((const T*)q, ldq, (const T*)mem_k, (const T*)mem_v, ldm, \
+                                                                att_mask, (T*)out, ldo, B, N, h, dk)
 #define XATT_NB(T)                                          \
   switch (beam) {                                           \
     case 1: XATT(T, 1); break; case 2: XATT(T, 2); break;   \
@@ -516,14 +567,14 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
   a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
   switch (beam) {
-    case 1: beam_step_kernel<1><<<B, 256, 0, stream>>>(a); break;
-    case 2: beam_step_kernel<2><<<B, 256, 0, stream>>>(a); break;
-    case 3: beam_step_kernel<3><<<B, 256, 0, stream>>>(a); break;
-    case 4: beam_step_kernel<4><<<B, 256, 0, stream>>>(a); break;
-    case 5: beam_step_kernel<5><<<B, 256, 0, stream>>>(a); break;
-    case 6: beam_step_kernel<6><<<B, 256, 0, stream>>>(a); break;
-    case 7: beam_step_kernel<7><<<B, 256, 0, stream>>>(a); break;
-    default: beam_step_kernel<8><<<B, 256, 0, stream>>>(a); break;
+    case 1: beam_step_kernel<1><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 2: beam_step_kernel<2><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 3: beam_step_kernel<3><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 4: beam_step_kernel<4><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 5: beam_step_kernel<5><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 6: beam_step_kernel<6><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 7: beam_step_kernel<7><<<B, kBeamThreads, 0, stream>>>(a); break;
+    default: beam_step_kernel<8><<<B, kBeamThreads, 0, stream>>>(a); break;
   }
   SC_LAUNCH_CHECK("sc_beam_step");
   return SC_OK;

@@ -68,6 +68,93 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(const SpmmArgs a) {
   }
 }
 
+// K larger than one shared-memory tile (fp32 verification mode with K = dim_feedforward): the CTA walks K in
+// chunks of KC columns; each warp keeps a cursor and fp32 accumulators for its <= 8 CSR rows across chunks
+// (columns are sorted inside a CSR row, so the entries of one chunk form a prefix of what is left).
+template <typename T, int MPL>
+__global__ void __launch_bounds__(256) csr_spmm_chunked_kernel(const SpmmArgs a, int KC) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* xs = (T*)smem_raw;  // [KC][M_T]
+  constexpr int M_T = 32 * MPL;
+  constexpr int RPW = 8;  // CSR rows per warp (n_per_cta == 64)
+  const int m0 = blockIdx.x * M_T;
+  const int nb = blockIdx.y * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* x = (const T*)a.x;
+  const T* vals = (const T*)a.val;
+  float acc[RPW][MPL];
+  int cur[RPW], end[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int n = nb + warp + 8 * i;
+    cur[i] = n < a.N ? a.row_ptr[n] : 0;
+    end[i] = n < a.N ? a.row_ptr[n + 1] : 0;
+#pragma unroll
+    for (int j = 0; j < MPL; ++j) acc[i][j] = 0.f;
+  }
+  for (int k0 = 0; k0 < a.K; k0 += KC) {
+    const int kw = min(KC, a.K - k0);
+    __syncthreads();
+    for (int e = tid; e < M_T * kw; e += 256) {
+      const int m = e / kw, k = e - m * kw;
+      xs[(size_t)k * M_T + m] = (m0 + m < a.M) ? x[(size_t)(m0 + m) * a.K + k0 + k] : sc::from_f32<T>(0.f);
+    }
+    __syncthreads();
+    const int kend = k0 + kw;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      while (cur[i] < end[i]) {
+        const int p = cur[i] + lane;
+        int c = 0x7fffffff; float v = 0.f;
+        if (p < end[i]) { c = a.col[p]; v = sc::to_f32<T>(vals[p]); }
+        const int cnt = __popc(__ballot_sync(0xffffffffu, c < kend));
+        for (int l = 0; l < cnt; ++l) {
+          const int cc = __shfl_sync(0xffffffffu, c, l) - k0;
+          const float vv = __shfl_sync(0xffffffffu, v, l);
+          const T* xr = xs + (size_t)cc * M_T + lane * MPL;
+#pragma unroll
+          for (int j = 0; j < MPL; ++j) acc[i][j] = fmaf(vv, sc::to_f32<T>(xr[j]), acc[i][j]);
+        }
+        cur[i] += cnt;
+        if (cnt < 32) break;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int n = nb + warp + 8 * i;
+    if (n >= a.N) continue;
+    const float bz = a.bias ? a.bias[n] : 0.f;
+#pragma unroll
+    for (int j = 0; j < MPL; ++j) {
+      const int m = m0 + lane * MPL + j;
+      if (m >= a.M) continue;
+      float r = acc[i][j] + bz;
+      if (a.relu) r = fmaxf(r, 0.f);
+      if (a.residual) r += a.residual[(size_t)m * a.N + n];
+      if (a.y_bf16) ((__nv_bfloat16*)a.y)[(size_t)m * a.N + n] = __float2bfloat16_rn(r);
+      else ((float*)a.y)[(size_t)m * a.N + n] = r;
+    }
+  }
+}
+
+template <typename T, int MPL>
+int launch_chunked(const SpmmArgs& a, cudaStream_t stream) {
+  constexpr int M_T = 32 * MPL;
+  const int KC = (int)((160 * 1024) / (M_T * sizeof(T)));
+  const size_t smem = (size_t)KC * M_T * sizeof(T);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(csr_spmm_chunked_kernel<T, MPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    SC_CHECK(e == cudaSuccess, (int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((a.M + M_T - 1) / M_T, (a.N + 63) / 64);
+  csr_spmm_chunked_kernel<T, MPL><<<grid, 256, smem, stream>>>(a, KC);
+  SC_LAUNCH_CHECK("sc_csr_spmm(chunked)");
+  return SC_OK;
+}
+
 template <typename T, int MPL>
 int launch(const SpmmArgs& a0, cudaStream_t stream) {
   SpmmArgs a = a0;
@@ -108,12 +195,12 @@ extern "C" int sc_csr_spmm(const void* x, int dtype, const int* row_ptr, const u
   if (dtype == SC_BF16) {
     if ((size_t)K * 128 * 2 <= budget && M > 64) return launch<__nv_bfloat16, 4>(a, stream);
     if ((size_t)K * 64 * 2 <= budget && M > 32) return launch<__nv_bfloat16, 2>(a, stream);
-    SC_CHECK((size_t)K * 32 * 2 <= budget, SC_ERR_UNSUPPORTED, "sc_csr_spmm: K=%d too large for the shared-memory tile", K);
-    return launch<__nv_bfloat16, 1>(a, stream);
+    if ((size_t)K * 32 * 2 <= budget) return launch<__nv_bfloat16, 1>(a, stream);
+    return launch_chunked<__nv_bfloat16, 2>(a, stream);
   } else if (dtype == SC_F32) {
     if ((size_t)K * 64 * 4 <= budget && M > 32) return launch<float, 2>(a, stream);
-    SC_CHECK((size_t)K * 32 * 4 <= budget, SC_ERR_UNSUPPORTED, "sc_csr_spmm: K=%d too large for the shared-memory tile", K);
-    return launch<float, 1>(a, stream);
+    if ((size_t)K * 32 * 4 <= budget) return launch<float, 1>(a, stream);
+    return launch_chunked<float, 2>(a, stream);
   }
   SC_CHECK(false, SC_ERR_DTYPE, "sc_csr_spmm: bad dtype %d", dtype);
   return SC_OK;

@@ -33,7 +33,9 @@ def linear(x, w, bias=None, *, mask=None, mask_mode=MASK_NONE, uniforms=None, se
         mask_mode = MASK_NONE
     lib.call("sc_linear", lib.ptr(x), lib.dtype_code(x.dtype), lib.ptr(w), lib.dtype_code(w.dtype), lib.ptr(mask),
              mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(bias), lib.ptr(residual), lib.ptr(out),
-             lib.dtype_code(out.dtype), M, N, K, int(relu), tile_n, lib.stream())
+             lib.dtype_code(out.dtype), M, N, K, int(relu), tile_n, lib.stream(),
+             meta=("gemm_bf16" if x.dtype == torch.bfloat16 else "gemm_f32", M, N, K, x.element_size(), w.element_size(),
+                   out.element_size(), mask is not None))
     return out
 
 
@@ -71,7 +73,8 @@ def csr_spmm(x, csr, bias=None, *, residual=None, relu=False, out=None, out_dtyp
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=out_dtype or torch.float32)
     lib.call("sc_csr_spmm", lib.ptr(x), lib.dtype_code(x.dtype), lib.ptr(csr.row_ptr), lib.ptr(csr.col), lib.ptr(csr.val),
-             lib.ptr(bias), lib.ptr(residual), lib.ptr(out), lib.dtype_code(out.dtype), M, N, K, int(relu), lib.stream())
+             lib.ptr(bias), lib.ptr(residual), lib.ptr(out), lib.dtype_code(out.dtype), M, N, K, int(relu), lib.stream(),
+             meta=("csr_spmm", M, N, K, x.element_size(), csr.nnz, out.element_size()))
     return out
 
 

@@ -76,12 +76,19 @@ def dtype_code(dt):
 
 
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+profile = None    # set to a list to record (name, meta, start_event, end_event) per launch (bench.py roofline leg)
 
 
-def call(name, *args):
+def call(name, *args, meta=None):
     global launch_count
     lib = load()
+    if profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (status {rc}): {lib.sc_last_error().decode()}")
+    if profile is not None:
+        ev1.record()
+        profile.append((name, meta, ev0, ev1))
     launch_count += 1
