@@ -13,10 +13,25 @@ void sc_set_error(const char* fmt, ...) {
 
 int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* mask, int mask_mode, const float* uniforms,
                         unsigned long long seed, unsigned long long stream_id, const float* bias, const float* residual,
-                        void* y, int y_dtype, int M, int N, int K, int relu, int block_n, cudaStream_t stream);
+                        void* y, int y_dtype, int M, int N, int K, int relu, int block_n, const ScGemmExtra* ex,
+                        cudaStream_t stream);
 int sc_gemm_f32_launch(const float* x, const float* w, const float* mask, int mask_mode, const float* uniforms,
                        unsigned long long seed, unsigned long long stream_id, const float* bias, const float* residual,
-                       void* y, int y_dtype, int M, int N, int K, int relu, cudaStream_t stream);
+                       void* y, int y_dtype, int M, int N, int K, int relu, const ScGemmExtra* ex, cudaStream_t stream);
+
+static int linear_dispatch(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
+                           const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
+                           const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
+                           const ScGemmExtra* ex, cudaStream_t stream) {
+  SC_CHECK(mask_mode >= SC_MASK_NONE && mask_mode <= SC_MASK_UNIFORM, SC_ERR_UNSUPPORTED, "sc_linear: mask_mode %d", mask_mode);
+  if (x_dtype == SC_BF16)
+    return sc_gemm_bf16_launch(x, w, w_dtype, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y, y_dtype, M, N, K,
+                               relu, tile_n, ex, stream);
+  SC_CHECK(x_dtype == SC_F32, SC_ERR_DTYPE, "sc_linear: bad x dtype %d", x_dtype);
+  SC_CHECK(w_dtype == SC_F32, SC_ERR_DTYPE, "sc_linear: fp32 activations need fp32 weights");
+  return sc_gemm_f32_launch((const float*)x, (const float*)w, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y,
+                            y_dtype, M, N, K, relu, ex, stream);
+}
 
 extern "C" {
 
@@ -27,14 +42,39 @@ int sc_linear(const void* x, int x_dtype, const void* w, int w_dtype, const floa
               const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
               const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
               cudaStream_t stream) {
-  SC_CHECK(mask_mode >= SC_MASK_NONE && mask_mode <= SC_MASK_UNIFORM, SC_ERR_UNSUPPORTED, "sc_linear: mask_mode %d", mask_mode);
-  if (x_dtype == SC_BF16)
-    return sc_gemm_bf16_launch(x, w, w_dtype, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y, y_dtype, M, N, K,
-                               relu, tile_n, stream);
-  SC_CHECK(x_dtype == SC_F32, SC_ERR_DTYPE, "sc_linear: bad x dtype %d", x_dtype);
-  SC_CHECK(w_dtype == SC_F32, SC_ERR_DTYPE, "sc_linear: fp32 activations need fp32 weights");
-  return sc_gemm_f32_launch((const float*)x, (const float*)w, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y,
-                            y_dtype, M, N, K, relu, stream);
+  return linear_dispatch(x, x_dtype, w, w_dtype, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y, y_dtype, M, N,
+                         K, relu, tile_n, nullptr, stream);
+}
+
+// training forward: y = dropout(act(x (W.m)^T + b), p) + residual, dropout mask = Philox(drop_seed, drop_stream, element)
+int sc_linear_dropout(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
+                      const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
+                      const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
+                      float dropout_p, unsigned long long drop_seed, unsigned long long drop_stream, cudaStream_t stream) {
+  SC_CHECK(dropout_p >= 0.f && dropout_p < 1.f, SC_ERR_SHAPE, "sc_linear_dropout: p=%f", dropout_p);
+  ScGemmExtra ex = {};
+  ex.dropout_p = dropout_p; ex.drop_seed = drop_seed; ex.drop_stream = drop_stream;
+  return linear_dispatch(x, x_dtype, w, w_dtype, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y, y_dtype, M, N,
+                         K, relu, tile_n, &ex, stream);
+}
+
+// K2 weight gradient: dWm[N,K] = dyT[N,M] * xT[K,M]^T with the straight-through epilogue
+//   dW (+)= dWm (.) m ;  dS (+)= dWm (.) W (.) sigmoid'(S) [(.) 1 when bypass / raw] + sparsity_coeff * sigmoid'(S)
+// dyT, xT: transposed activations in `dtype`; w, mask: the fp32 weight and its logits (mask regenerated from
+// (mask_mode, seed, stream_id, element) exactly as the forward drew it); dw / ds may be NULL.
+int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, const float* mask, int mask_mode,
+                    const float* uniforms, unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad,
+                    float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K, int M, int tile_n,
+                    cudaStream_t stream) {
+  SC_CHECK(w != nullptr && (dw != nullptr || ds != nullptr), SC_ERR_SHAPE, "sc_linear_wgrad: w and one of dw/ds are required");
+  SC_CHECK(mask_mode == SC_MASK_NONE || mask != nullptr, SC_ERR_SHAPE, "sc_linear_wgrad: mask missing");
+  ScGemmExtra ex = {};
+  ex.wgrad = 1; ex.bypass = bypass_sigmoid_grad; ex.sp_coeff = sparsity_coeff; ex.accumulate = accumulate;
+  ex.wg_w = w; ex.wg_s = mask; ex.wg_u = uniforms; ex.dw = dw; ex.ds = ds;
+  // GEMM view: rows = N (weight rows), cols = K (weight cols), contraction = M tokens; y unused (dw stands in for alignment checks)
+  void* ydummy = dw ? (void*)dw : (void*)ds;
+  return linear_dispatch(dyT, dtype, xT, dtype, nullptr, mask_mode, nullptr, seed, stream_id, nullptr, nullptr, ydummy, SC_F32, N,
+                         K, M, 0, tile_n, &ex, stream);
 }
 
 }  // extern "C"

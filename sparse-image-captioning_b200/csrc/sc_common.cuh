@@ -39,6 +39,13 @@ void sc_set_error(const char* fmt, ...);
     }                                                                     \
   } while (0)
 
+// optional GEMM epilogue extensions (training): dropout, or the weight-gradient epilogue
+struct ScGemmExtra {
+  float dropout_p; unsigned long long drop_seed, drop_stream;
+  int wgrad, bypass; float sp_coeff; int accumulate;
+  const float* wg_w; const float* wg_s; const float* wg_u; float* dw; float* ds;
+};
+
 namespace sc {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -104,6 +111,43 @@ __device__ __forceinline__ void bernoulli4(const Philox& ph, uint64_t e4, uint64
   m[1] = u24(r.y) < sigmoidf_(s[1]) ? 1.f : 0.f;
   m[2] = u24(r.z) < sigmoidf_(s[2]) ? 1.f : 0.f;
   m[3] = u24(r.w) < sigmoidf_(s[3]) ? 1.f : 0.f;
+}
+
+// mask value of element e under `mode` (shared by forward prologues and backward epilogues so that both see the
+// same sample): s = logit / raw mask, u = injected uniform.
+__device__ __forceinline__ float mask_value(int mode, float s, float u, const Philox& ph, size_t e, unsigned long long stream) {
+  switch (mode) {
+    case SC_MASK_NONE: return 1.f;
+    case SC_MASK_ROUND: return mask_round(s);
+    case SC_MASK_RAW: return s;
+    case SC_MASK_UNIFORM: return u < sigmoidf_(s) ? 1.f : 0.f;
+    default: {
+      uint4 rr = ph(e >> 2, stream);
+      const uint32_t bits = (e & 3) == 0 ? rr.x : (e & 3) == 1 ? rr.y : (e & 3) == 2 ? rr.z : rr.w;
+      return u24(bits) < sigmoidf_(s) ? 1.f : 0.f;
+    }
+  }
+}
+
+// inverted-dropout factor of element e: 0 (dropped, probability p) or 1/(1-p)
+__device__ __forceinline__ float keep_scale(const Philox& ph, size_t e, unsigned long long stream, float p) {
+  if (p <= 0.f) return 1.f;
+  uint4 rr = ph(e >> 2, stream);
+  const uint32_t bits = (e & 3) == 0 ? rr.x : (e & 3) == 1 ? rr.y : (e & 3) == 2 ? rr.z : rr.w;
+  return u24(bits) >= p ? 1.f / (1.f - p) : 0.f;
+}
+
+// straight-through gradient of one masked weight element (sampler.py:15-17,32-34; prune.py:249-258):
+//   dW = g*m ; dS = g*W*sigmoid'(S) [* 1 when bypass / raw] + sp_coeff*sigmoid'(S)
+__device__ __forceinline__ void mask_grad_elem(int mode, float g, float w, float s, float m, int bypass, float sp_coeff,
+                                               float& dw, float& ds) {
+  dw = g * m;
+  float d = g * w;
+  float dsig = 1.f;
+  if (mode != SC_MASK_RAW && mode != SC_MASK_NONE) { const float sig = sigmoidf_(s); dsig = sig * (1.f - sig); }
+  if (!(bypass || mode == SC_MASK_RAW)) d *= dsig;
+  if (sp_coeff != 0.f) d += sp_coeff * dsig;
+  ds = d;
 }
 
 }  // namespace sc

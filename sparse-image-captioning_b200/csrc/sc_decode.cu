@@ -117,17 +117,51 @@ __global__ void __launch_bounds__(256) self_attn_step_kernel(const T* __restrict
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kMaxKeyPass = 4;  // N <= 128 memory slots
 
+// 16-byte global -> shared copies of one (image, head) K or V slice: rows of dk elements, row stride in smem = rb bytes
+template <typename T>
+__device__ __forceinline__ void stage_rows(const T* __restrict__ src, int ld, unsigned char* dst, int rb, int N, int dk, int lane) {
+  const int vec_per_row = dk * (int)sizeof(T) / 16;
+  const int total = N * vec_per_row;
+  for (int e0 = 0; e0 < total; e0 += 32 * 4) {
+    uint4 tmp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // 4 loads in flight per lane
+      const int e = e0 + u * 32 + lane;
+      if (e < total) {
+        const int j = e / vec_per_row, c = e - j * vec_per_row;
+        tmp[u] = *(const uint4*)((const unsigned char*)(src + (size_t)j * ld) + c * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 32 + lane;
+      if (e < total) {
+        const int j = e / vec_per_row, c = e - j * vec_per_row;
+        *(uint4*)(dst + (size_t)j * rb + c * 16) = tmp[u];
+      }
+    }
+  }
+}
+
 template <typename T, int NB>
 __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ mk,
                                                               const T* __restrict__ mv, int ldm,
                                                               const float* __restrict__ att_mask, T* __restrict__ out,
-                                                              int ldo, int B, int N, int h, int dk) {
-  extern __shared__ float s_q[];  // [8 warps][NB][dk]
+                                                              int ldo, int B, int N, int h, int dk, int warps) {
+  extern __shared__ __align__(16) unsigned char smem_x[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * 8 + warp;
+  const int w = blockIdx.x * warps + warp;
   if (w >= B * h) return;
   const int b = w / h, hh = w - b * h;
-  float* sq = s_q + warp * NB * dk;
+  const int rbk = dk * (int)sizeof(T) + 16;  // padded K rows: lane=key 16-byte reads are bank-conflict free
+  const int rbv = dk * (int)sizeof(T);
+  const int per_warp = N * (rbk + rbv) + NB * dk * 4;
+  unsigned char* base = smem_x + (size_t)warp * per_warp;
+  unsigned char* sk = base;
+  unsigned char* sv = base + (size_t)N * rbk;
+  float* sq = (float*)(sv + (size_t)N * rbv);
+  stage_rows<T>(mk + (size_t)b * N * ldm + hh * dk, ldm, sk, rbk, N, dk, lane);
+  stage_rows<T>(mv + (size_t)b * N * ldm + hh * dk, ldm, sv, rbv, N, dk, lane);
   for (int e = lane; e < NB * dk; e += 32) {
     const int n = e / dk, d = e - n * dk;
     sq[e] = sc::to_f32<T>(q[((size_t)b * NB + n) * ldq + hh * dk + d]);
@@ -145,7 +179,7 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restric
 #pragma unroll
     for (int n = 0; n < NB; ++n) dot[n] = 0.f;
     if (ps * 32 < N && j < N) {
-      const T* kr = mk + ((size_t)b * N + j) * ldm + hh * dk;
+      const T* kr = (const T*)(sk + (size_t)j * rbk);
       for (int c = 0; c < dk; c += 8) {
         Vec8<T> kk;
         kk.load(kr + c);
@@ -161,10 +195,10 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restric
       const bool masked = att_mask && att_mask[(size_t)b * N + j] == 0.f;
 #pragma unroll
       for (int n = 0; n < NB; ++n) {
-        float sv = dot[n] / scale_div;
-        if (masked) sv = -1e9f;
-        sc_[ps][n] = sv;
-        mx[n] = fmaxf(mx[n], sv);
+        float sv_ = dot[n] / scale_div;
+        if (masked) sv_ = -1e9f;
+        sc_[ps][n] = sv_;
+        mx[n] = fmaxf(mx[n], sv_);
       }
     } else {
 #pragma unroll
@@ -184,7 +218,7 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restric
     }
     inv[n] = 1.f / sc::warp_sum(sum);
   }
-  // PV: lane owns dims lane, lane+32 (d_k <= 64)
+  // PV: lane owns dims lane, lane+32 (d_k <= 64); V rows come from shared memory
   float o0[NB], o1[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) { o0[n] = 0.f; o1[n] = 0.f; }
@@ -194,7 +228,7 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restric
     if (ps * 32 >= N) break;
     const int lim = min(32, N - ps * 32);
     for (int l = 0; l < lim; ++l) {
-      const T* vr = mv + ((size_t)b * N + ps * 32 + l) * ldm + hh * dk;
+      const T* vr = (const T*)(sv + (size_t)(ps * 32 + l) * rbv);
       const float v0 = d0 ? sc::to_f32<T>(vr[lane]) : 0.f;
       const float v1 = d1 ? sc::to_f32<T>(vr[lane + 32]) : 0.f;
 #pragma unroll
@@ -217,8 +251,9 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restric
 // K7 beam step.  One CTA per image.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kMaxBeam = 8;
-constexpr int kBeamThreads = 1024;
+constexpr int kBeamThreads = 256;
 constexpr int kBeamWarps = kBeamThreads / 32;
+constexpr int kBeamRegs = 40;  // logits of one row live in registers when V <= 256*40 = 10240
 
 struct Cand {
   float s;
@@ -254,93 +289,119 @@ struct BeamArgs {
   int* done_seq; float* done_lp; double* done_p; int* done_count;  // [B,beam,L] [B,beam,L] [B,beam] [B]
 };
 
-template <int NB>
+__device__ __forceinline__ float block_max(float v, float* s_red) {
+  v = sc::warp_max(v);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kBeamWarps; ++w) r = fmaxf(r, s_red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = sc::warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < kBeamWarps; ++w) r += s_red[w];
+  __syncthreads();
+  return r;
+}
+
+// kRegs: the row is read from HBM exactly once into registers (V <= 256*40); otherwise it is re-read (L2 hits).
+template <int NB, bool kRegs>
 __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs a) {
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V;
   const int rows = (a.t == 0) ? 1 : NB;  // first step: every beam holds BOS, only beam 0 is expanded
   __shared__ float s_red[kBeamWarps];
-  __shared__ float s_mx[NB], s_ls[NB], s_mx2[NB], s_ls2[NB], s_sum[NB];
-  // init_logprobs (t == 0) are never temperature-scaled (caption_model.py:135, 218)
-  const float T = (a.t == 0) ? 1.0f : a.temperature;
-  __shared__ int s_prev[NB];
+  __shared__ float s_mx[NB], s_ls[NB], s_mx2[NB], s_ls2[NB];
   __shared__ Cand s_top[kBeamWarps][NB];
   __shared__ Cand s_final[NB];
+  __shared__ int s_pos, s_last;
+  // init_logprobs (t == 0) are never temperature-scaled (caption_model.py:135, 218)
+  const float T = (a.t == 0) ? 1.0f : a.temperature;
 
-  // ---- log-softmax statistics per row (twice when temperature != 1: log_softmax(log_softmax(x)/T)) ----
+  Cand top[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
+
   for (int k = 0; k < rows; ++k) {
     const float* x = a.logits + ((size_t)b * NB + k) * V;
+    float xr[kRegs ? kBeamRegs : 1];
     float mx = -INFINITY;
-    for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
-    mx = sc::warp_max(mx);
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    mx = s_red[0];
+    if (kRegs) {
 #pragma unroll
-    for (int w = 1; w < kBeamWarps; ++w) mx = fmaxf(mx, s_red[w]);
-    __syncthreads();
+      for (int i = 0; i < kBeamRegs; ++i) {
+        const int c = tid + i * kBeamThreads;
+        xr[i] = c < V ? __ldg(x + c) : -INFINITY;
+      }
+#pragma unroll
+      for (int i = 0; i < kBeamRegs; ++i) mx = fmaxf(mx, xr[i]);
+    } else {
+      for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
+    }
+    mx = block_max(mx, s_red);
     float se = 0.f;
-    for (int i = tid; i < V; i += kBeamThreads) se += expf(x[i] - mx);
-    se = sc::warp_sum(se);
-    if (lane == 0) s_red[warp] = se;
-    __syncthreads();
-    se = 0.f;
+    if (kRegs) {
 #pragma unroll
-    for (int w = 0; w < kBeamWarps; ++w) se += s_red[w];
-    __syncthreads();
+      for (int i = 0; i < kBeamRegs; ++i) se += expf(xr[i] - mx);  // exp(-inf) = 0 for the padding lanes
+    } else {
+      for (int i = tid; i < V; i += kBeamThreads) se += expf(x[i] - mx);
+    }
+    se = block_sum(se, s_red);
     // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
-    float ls = logf(se), mx2 = 0.f, ls2 = 0.f;
+    const float ls = logf(se);
+    float mx2 = 0.f, ls2 = 0.f;
     if (T != 1.0f) {
       // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
       mx2 = (0.f - ls) / T;
       float se2 = 0.f;
-      for (int i = tid; i < V; i += kBeamThreads) se2 += expf(((x[i] - mx) - ls) / T - mx2);
-      se2 = sc::warp_sum(se2);
-      if (lane == 0) s_red[warp] = se2;
-      __syncthreads();
-      se2 = 0.f;
+      if (kRegs) {
 #pragma unroll
-      for (int w = 0; w < kBeamWarps; ++w) se2 += s_red[w];
-      __syncthreads();
-      ls2 = logf(se2);
+        for (int i = 0; i < kBeamRegs; ++i) se2 += expf(((xr[i] - mx) - ls) / T - mx2);
+      } else {
+        for (int i = tid; i < V; i += kBeamThreads) se2 += expf(((x[i] - mx) - ls) / T - mx2);
+      }
+      ls2 = logf(block_sum(se2, s_red));
     }
-    if (tid == 0) {
-      s_mx[k] = mx; s_ls[k] = ls; s_mx2[k] = mx2; s_ls2[k] = ls2;
-      s_sum[k] = a.sum[b * NB + k];
-      s_prev[k] = (a.constraint && a.t > 0) ? a.seq_in[((size_t)b * NB + k) * a.L + a.t - 1] : -1;
-    }
-  }
-  __syncthreads();
-
-  // ---- per-thread top-NB over the rows*V candidates ----
-  Cand top[NB];
+    if (tid == 0) { s_mx[k] = mx; s_ls[k] = ls; s_mx2[k] = mx2; s_ls2[k] = ls2; }
+    const float base = a.sum[b * NB + k];
+    const int prev = (a.constraint && a.t > 0) ? a.seq_in[((size_t)b * NB + k) * a.L + a.t - 1] : -1;
+    if (kRegs) {
 #pragma unroll
-  for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
-  for (int k = 0; k < rows; ++k) {
-    const float* x = a.logits + ((size_t)b * NB + k) * V;
-    const float mx = s_mx[k], ls = s_ls[k], mx2 = s_mx2[k], ls2 = s_ls2[k], base = s_sum[k];
-    const int prev = s_prev[k];
-    for (int i = tid; i < V; i += kBeamThreads) {
-      float lp = (x[i] - mx) - ls;
-      if (T != 1.0f) lp = (lp / T - mx2) - ls2;
-      if (i == prev) lp = -INFINITY;
-      Cand c; c.s = base + lp; c.idx = k * V + i;
-      topk_insert<NB>(top, c);
+      for (int i = 0; i < kBeamRegs; ++i) {
+        const int c = tid + i * kBeamThreads;
+        if (c < V) {
+          float lp = (xr[i] - mx) - ls;
+          if (T != 1.0f) lp = (lp / T - mx2) - ls2;
+          if (c == prev) lp = -INFINITY;
+          Cand cd; cd.s = base + lp; cd.idx = k * V + c;
+          topk_insert<NB>(top, cd);
+        }
+      }
+    } else {
+      for (int i = tid; i < V; i += kBeamThreads) {
+        float lp = (x[i] - mx) - ls;
+        if (T != 1.0f) lp = (lp / T - mx2) - ls2;
+        if (i == prev) lp = -INFINITY;
+        Cand cd; cd.s = base + lp; cd.idx = k * V + i;
+        topk_insert<NB>(top, cd);
+      }
     }
   }
   // warp merge: every lane offers its sorted list; NB rounds of arg-best over the heads
   {
     int head = 0;
-    Cand mine[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) mine[i] = top[i];
 #pragma unroll
     for (int rnd = 0; rnd < NB; ++rnd) {
       Cand c;
       c.s = -INFINITY; c.idx = 0x7fffffff;
 #pragma unroll
-      for (int i = 0; i < NB; ++i) if (i == head) c = mine[i];
+      for (int i = 0; i < NB; ++i) if (i == head) c = top[i];
       Cand best = c;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -356,17 +417,19 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs 
   __syncthreads();
   if (tid == 0) {
     int heads[kBeamWarps];
+#pragma unroll
     for (int w = 0; w < kBeamWarps; ++w) heads[w] = 0;
     for (int rnd = 0; rnd < NB; ++rnd) {
-      int bw = -1;
+      int bw = 0;
       Cand best; best.s = -INFINITY; best.idx = 0x7fffffff;
+#pragma unroll
       for (int w = 0; w < kBeamWarps; ++w) {
-        if (heads[w] < NB) {
-          Cand c = s_top[w][heads[w]];
-          if (bw < 0 || better(c, best)) { best = c; bw = w; }
-        }
+        Cand c; c.s = -INFINITY; c.idx = 0x7fffffff;
+        if (heads[w] < NB) c = s_top[w][heads[w]];
+        if (better(c, best)) { best = c; bw = w; }
       }
-      heads[bw]++;
+#pragma unroll
+      for (int w = 0; w < kBeamWarps; ++w) if (w == bw) heads[w]++;
       s_final[rnd] = best;
     }
   }
@@ -374,7 +437,6 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs 
 
   // ---- bookkeeping (caption_model.py:84-110, 195-210) ----
   const int L = a.L, t = a.t;
-  // history gathers: NB rows x L entries, spread over the CTA
   for (int e = tid; e < NB * L; e += kBeamThreads) {
     const int j = e / L, s = e - j * L;
     const int parent = s_final[j].idx / V;
@@ -398,46 +460,53 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs 
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    int cnt = a.done_count[b];
-    for (int j = 0; j < NB; ++j) {
-      const int parent = s_final[j].idx / V;
-      const int word = s_final[j].idx - parent * V;
-      float ys = s_final[j].s;
-      a.tokens_out[b * NB + j] = word;
-      const bool is_end = (word == a.eos) || (t == L - 1);
-      if (is_end) {
+  // finished beams: stable insertion into the running top-NB (python's sorted() is stable and entries arrive
+  // chronologically); thread 0 picks the slot, L threads move the rows.
+  int cnt = a.done_count[b];
+  for (int j = 0; j < NB; ++j) {
+    const int parent = s_final[j].idx / V;
+    const int word = s_final[j].idx - parent * V;
+    float ys = s_final[j].s;
+    const bool is_end = (word == a.eos) || (t == L - 1);
+    if (is_end) {
+      if (tid == 0) {
         // the reference scores finished beams in Python floats (double): model_utils.py:121-146
         double p = (double)ys;
         const double len = (double)(t + 1);
         if (a.penalty_kind == 1) p = p / (pow(5.0 + len, (double)a.penalty_alpha) / pow(6.0, (double)a.penalty_alpha));
         else if (a.penalty_kind == 2) p = p / len;
-        // stable insertion into the running top-NB (python's sorted() is stable, entries arrive chronologically)
         int pos = cnt < NB ? cnt : NB;
         while (pos > 0 && a.done_p[b * NB + pos - 1] < p) --pos;
+        const int last = (cnt < NB ? cnt : NB - 1);
         if (pos < NB) {
-          const int last = (cnt < NB ? cnt : NB - 1);
-          for (int m = last; m > pos; --m) {
-            a.done_p[b * NB + m] = a.done_p[b * NB + m - 1];
-            for (int s = 0; s < L; ++s) {
-              a.done_seq[((size_t)b * NB + m) * L + s] = a.done_seq[((size_t)b * NB + m - 1) * L + s];
-              a.done_lp[((size_t)b * NB + m) * L + s] = a.done_lp[((size_t)b * NB + m - 1) * L + s];
-            }
-          }
+          for (int m = last; m > pos; --m) a.done_p[b * NB + m] = a.done_p[b * NB + m - 1];
           a.done_p[b * NB + pos] = p;
-          for (int s = 0; s < L; ++s) {
-            const size_t src = ((size_t)b * NB + j) * L + s;
-            a.done_seq[((size_t)b * NB + pos) * L + s] = s <= t ? a.seq_out[src] : a.pad;
-            a.done_lp[((size_t)b * NB + pos) * L + s] = s <= t ? a.lp_out[src] : 0.f;
-          }
-          if (cnt < NB) cnt++;
         }
-        ys -= 1000.f;
+        s_pos = pos; s_last = last;
       }
+      __syncthreads();
+      const int pos = s_pos, last = s_last;
+      if (pos < NB) {
+        for (int s = tid; s < L; s += kBeamThreads) {
+          for (int m = last; m > pos; --m) {
+            a.done_seq[((size_t)b * NB + m) * L + s] = a.done_seq[((size_t)b * NB + m - 1) * L + s];
+            a.done_lp[((size_t)b * NB + m) * L + s] = a.done_lp[((size_t)b * NB + m - 1) * L + s];
+          }
+          const size_t src = ((size_t)b * NB + j) * L + s;
+          a.done_seq[((size_t)b * NB + pos) * L + s] = s <= t ? a.seq_out[src] : a.pad;
+          a.done_lp[((size_t)b * NB + pos) * L + s] = s <= t ? a.lp_out[src] : 0.f;
+        }
+        if (cnt < NB) cnt++;
+      }
+      __syncthreads();
+      ys -= 1000.f;
+    }
+    if (tid == 0) {
+      a.tokens_out[b * NB + j] = word;
       a.sum[b * NB + j] = ys;
     }
-    a.done_count[b] = cnt;
   }
+  if (tid == 0) a.done_count[b] = cnt;
 }
 
 // greedy step (beam_size == 1): one warp per row
@@ -532,11 +601,25 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
   SC_CHECK(beam <= kMaxBeam, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: beam=%d > %d", beam, kMaxBeam);
   SC_CHECK(N <= 32 * kMaxKeyPass, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: N=%d > %d memory slots", N, 32 * kMaxKeyPass);
   SC_CHECK(dk <= 64, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: d_k=%d > 64", dk);
-  const int blocks = (B * h + 7) / 8;
-  const size_t smem = (size_t)8 * beam * dk * sizeof(float);
-#define XATT(T, NBV)                                                                                                  \
-  cross_attn_step_kernel<T, NBV><<<blocks, 256, smem, stream>>>((const T*)q, ldq, (const T*)mem_k, (const T*)mem_v, ldm, \
-                                                                att_mask, (T*)out, ldo, B, N, h, dk)
+  const int esz = dtype == SC_F32 ? 4 : 2;
+  const size_t per_warp = (size_t)N * (2 * dk * esz + 16) + (size_t)beam * dk * 4;
+  int warps = (int)((96 * 1024) / per_warp);
+  if (warps > 8) warps = 8;
+  SC_CHECK(warps >= 1, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: N=%d too large for shared memory", N);
+  const int blocks = (B * h + warps - 1) / warps;
+  const size_t smem = per_warp * warps;
+  SC_CHECK(ldm * esz % 16 == 0 && dk * esz % 16 == 0, SC_ERR_ALIGN, "sc_decode_cross_attn_step: 16-byte rows needed");
+#define XATT(T, NBV)                                                                                                    \
+  do {                                                                                                                  \
+    static bool attr_##NBV = false;                                                                                     \
+    if (!attr_##NBV) {                                                                                                  \
+      cudaFuncSetAttribute(cross_attn_step_kernel<T, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);    \
+      attr_##NBV = true;                                                                                                \
+    }                                                                                                                   \
+    cross_attn_step_kernel<T, NBV><<<blocks, 32 * warps, smem, stream>>>((const T*)q, ldq, (const T*)mem_k,             \
+                                                                         (const T*)mem_v, ldm, att_mask, (T*)out, ldo,  \
+                                                                         B, N, h, dk, warps);                           \
+  } while (0)
 #define XATT_NB(T)                                          \
   switch (beam) {                                           \
     case 1: XATT(T, 1); break; case 2: XATT(T, 2); break;   \
@@ -566,15 +649,21 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
   a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
   a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
+#define BEAM_LAUNCH(NBV)                                                              \
+  do {                                                                                 \
+    if (regs) beam_step_kernel<NBV, true><<<B, kBeamThreads, 0, stream>>>(a);           \
+    else beam_step_kernel<NBV, false><<<B, kBeamThreads, 0, stream>>>(a);               \
+  } while (0)
+  const bool regs = V <= kBeamThreads * kBeamRegs;
   switch (beam) {
-    case 1: beam_step_kernel<1><<<B, kBeamThreads, 0, stream>>>(a); break;
-    case 2: beam_step_kernel<2><<<B, kBeamThreads, 0, stream>>>(a); break;
-    case 3: beam_step_kernel<3><<<B, kBeamThreads, 0, stream>>>(a); break;
-    case 4: beam_step_kernel<4><<<B, kBeamThreads, 0, stream>>>(a); break;
-    case 5: beam_step_kernel<5><<<B, kBeamThreads, 0, stream>>>(a); break;
-    case 6: beam_step_kernel<6><<<B, kBeamThreads, 0, stream>>>(a); break;
-    case 7: beam_step_kernel<7><<<B, kBeamThreads, 0, stream>>>(a); break;
-    default: beam_step_kernel<8><<<B, kBeamThreads, 0, stream>>>(a); break;
+    case 1: BEAM_LAUNCH(1); break;
+    case 2: BEAM_LAUNCH(2); break;
+    case 3: BEAM_LAUNCH(3); break;
+    case 4: BEAM_LAUNCH(4); break;
+    case 5: BEAM_LAUNCH(5); break;
+    case 6: BEAM_LAUNCH(6); break;
+    case 7: BEAM_LAUNCH(7); break;
+    default: BEAM_LAUNCH(8); break;
   }
   SC_LAUNCH_CHECK("sc_beam_step");
   return SC_OK;

@@ -21,7 +21,6 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kNumTransformWarps = 4;
 
 struct GemmArgs {
@@ -36,6 +35,11 @@ struct GemmArgs {
   void* y;
   int y_bf16;
   int relu;
+  // forward training: y = dropout(act(acc + bias)) + residual
+  float dropout_p; unsigned long long drop_seed, drop_stream;
+  // weight-gradient mode: the accumulator tile is dWm[n,k]; the epilogue emits dW and dS (straight-through)
+  int wgrad; int bypass; float sp_coeff; int accumulate;
+  const float* wg_w; const float* wg_s; const float* wg_u; float* dw; float* ds;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,19 +116,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int kStages>
 struct Smem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 128 + 1024;  // barriers + tmem ptr + alignment slack
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
-template <int BLOCK_N, bool kMasked>
+// kStages: depth of the TMA->MMA ring.  Rings are kept shallow enough (64x4: 96 KB, 128x3: 96 KB) for two CTAs to
+// share an SM, so one CTA's epilogue overlaps the other's main loop (scripts/gemm_sweep.py: deeper rings with one
+// CTA per SM measured slower for every shape of this model).
+template <int BLOCK_N, bool kMasked, int kStages>
 __global__ void __launch_bounds__(kMasked ? 384 : 256, 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
-  using L = Smem<BLOCK_N>;
+  using L = Smem<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
@@ -211,6 +218,39 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (args.wgrad) {
+        // K2: dW = dWm (.) m ; dS = dWm (.) W (.) sigmoid'(S) (+ sparsity term), mask regenerated from (seed, stream, element)
+        const sc::Philox wph(args.seed);
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col >= args.N) break;
+          const size_t e = (size_t)row * args.N + col;
+          const float sv = args.wg_s ? __ldg(args.wg_s + e) : 0.f;
+          const float m = sc::mask_value(args.mask_mode, sv, args.wg_u ? __ldg(args.wg_u + e) : 0.f, wph, e, args.stream_id);
+          float gw, gs;
+          sc::mask_grad_elem(args.mask_mode, f[j], __ldg(args.wg_w + e), sv, m, args.bypass, args.sp_coeff, gw, gs);
+          if (args.dw) args.dw[e] = (args.accumulate ? args.dw[e] : 0.f) + gw;
+          if (args.ds) args.ds[e] = (args.accumulate ? args.ds[e] : 0.f) + gs;
+        }
+        continue;
+      }
+      if (args.dropout_p > 0.f) {
+        // training forward epilogue with dropout: scalar path (bias, act, dropout, residual)
+        const sc::Philox dph(args.drop_seed);
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          if (col >= args.N) break;
+          const size_t e = (size_t)row * args.N + col;
+          float x = f[j];
+          if (args.bias) x += __ldg(args.bias + col);
+          if (args.relu) x = fmaxf(x, 0.f);
+          x *= sc::keep_scale(dph, e, args.drop_stream, args.dropout_p);
+          if (args.residual) x += __ldg(args.residual + e);
+          if (args.y_bf16) ((__nv_bfloat16*)args.y)[e] = __float2bfloat16_rn(x);
+          else ((float*)args.y)[e] = x;
+        }
+        continue;
+      }
       if (vec_ok && col0 + 32 <= args.N) {
         if (args.bias) {
           const float4* bp = (const float4*)(args.bias + col0);
@@ -359,10 +399,10 @@ int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int box_row
   return SC_OK;
 }
 
-template <int BLOCK_N, bool kMasked>
+template <int BLOCK_N, bool kMasked, int kStages>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked>;
-  constexpr int smem = Smem<BLOCK_N>::kTotal;
+  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages>;
+  constexpr int smem = Smem<BLOCK_N, kStages>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -380,24 +420,32 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cuda
 // Internal entry used by sc_linear (sc_api.cu).
 int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* mask, int mask_mode, const float* uniforms,
                         unsigned long long seed, unsigned long long stream_id, const float* bias, const float* residual,
-                        void* y, int y_dtype, int M, int N, int K, int relu, int block_n, cudaStream_t stream) {
+                        void* y, int y_dtype, int M, int N, int K, int relu, int block_n, const ScGemmExtra* ex,
+                        cudaStream_t stream) {
   SC_CHECK(M > 0 && N > 0 && K > 0, SC_ERR_SHAPE, "sc_linear: empty problem M=%d N=%d K=%d", M, N, K);
   SC_CHECK(K % 8 == 0, SC_ERR_SHAPE, "sc_linear(bf16): K=%d must be a multiple of 8 (16-byte TMA rows)", K);
   SC_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0, SC_ERR_ALIGN,
            "sc_linear(bf16): x, w, y must be 16-byte aligned");
   SC_CHECK(y_dtype == SC_F32 || y_dtype == SC_BF16, SC_ERR_DTYPE, "sc_linear: bad y dtype %d", y_dtype);
+  const bool wgrad = ex && ex->wgrad;
   const bool masked = (w_dtype == SC_F32);
-  SC_CHECK(masked || mask_mode == SC_MASK_NONE, SC_ERR_DTYPE,
+  SC_CHECK(masked || mask_mode == SC_MASK_NONE || wgrad, SC_ERR_DTYPE,
            "sc_linear(bf16): mask modes need fp32 master weights (bf16 weights are expected pre-masked)");
   if (masked && mask_mode != SC_MASK_NONE) {
     SC_CHECK(mask != nullptr && ((uintptr_t)mask & 15) == 0, SC_ERR_ALIGN, "sc_linear: mask must be 16-byte aligned");
     SC_CHECK(mask_mode != SC_MASK_UNIFORM || uniforms != nullptr, SC_ERR_SHAPE, "sc_linear: uniforms missing");
     SC_CHECK(K % 4 == 0, SC_ERR_SHAPE, "K %% 4");
   }
+  const long tiles128 = (long)((N + 127) / 128) * ((M + 127) / 128);
+  int force_stages = 0;
+  if (block_n >= 1000) {  // tuning hook: tile_n = 1000 * stages + block_n
+    force_stages = block_n / 1000;
+    block_n %= 1000;
+  }
   if (block_n == 0) {
     // fill the 148 SMs: prefer the widest tile that still yields >= ~1 wave
-    const long tiles128 = (long)((N + 127) / 128) * ((M + 127) / 128);
-    block_n = (tiles128 >= 120) ? 128 : 64;
+    // measured with scripts/gemm_sweep.py (in-graph, L2-warm): 128-wide tiles win once they fill the 148 SMs
+    block_n = (tiles128 >= 148) ? 128 : 64;
     if (N <= 64) block_n = 64;
   }
   CUtensorMap ta, tb;
@@ -415,11 +463,21 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   a.mask = mask; a.uniforms = uniforms; a.mask_mode = mask_mode;
   a.seed = seed; a.stream_id = stream_id;
   a.bias = bias; a.residual = residual; a.y = y; a.y_bf16 = (y_dtype == SC_BF16); a.relu = relu;
-  switch (block_n) {
-    case 64: return masked ? launch<64, true>(ta, tb, a, stream) : launch<64, false>(ta, tb, a, stream);
-    case 128: return masked ? launch<128, true>(ta, tb, a, stream) : launch<128, false>(ta, tb, a, stream);
-    case 256: return masked ? launch<256, true>(ta, tb, a, stream) : launch<256, false>(ta, tb, a, stream);
-    default: SC_CHECK(false, SC_ERR_UNSUPPORTED, "sc_linear(bf16): block_n=%d not in {64,128,256}", block_n);
+  a.dropout_p = 0.f; a.drop_seed = 0; a.drop_stream = 0; a.wgrad = 0; a.bypass = 0; a.sp_coeff = 0.f; a.accumulate = 0;
+  a.wg_w = nullptr; a.wg_s = nullptr; a.wg_u = nullptr; a.dw = nullptr; a.ds = nullptr;
+  if (ex) {
+    a.dropout_p = ex->dropout_p; a.drop_seed = ex->drop_seed; a.drop_stream = ex->drop_stream;
+    a.wgrad = ex->wgrad; a.bypass = ex->bypass; a.sp_coeff = ex->sp_coeff; a.accumulate = ex->accumulate;
+    a.wg_w = ex->wg_w; a.wg_s = ex->wg_s; a.wg_u = ex->wg_u; a.dw = ex->dw; a.ds = ex->ds;
   }
+#define SC_GEMM_CASE(BN, ST) \
+  if (block_n == BN && stages == ST) return masked ? launch<BN, true, ST>(ta, tb, a, stream) : launch<BN, false, ST>(ta, tb, a, stream)
+  int stages = force_stages;
+  if (stages == 0) stages = block_n == 64 ? 4 : block_n == 256 ? 4 : 3;
+  SC_GEMM_CASE(64, 4); SC_GEMM_CASE(64, 8);
+  SC_GEMM_CASE(128, 3); SC_GEMM_CASE(128, 4); SC_GEMM_CASE(128, 6);
+  SC_GEMM_CASE(256, 4);
+#undef SC_GEMM_CASE
+  SC_CHECK(false, SC_ERR_UNSUPPORTED, "sc_linear(bf16): tile %d x %d stages not instantiated", block_n, stages);
   return SC_OK;
 }

@@ -182,3 +182,131 @@ def cache_reorder(src, idx, out=None):
     assert idx.dtype == torch.int32
     lib.call("sc_cache_reorder", lib.ptr(src), lib.ptr(out), lib.ptr(idx), rows, row_bytes, lib.stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training-side wrappers
+# ------------------------------------------------------------------------------------------------------------------
+def pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def linear_dropout(x, w, bias=None, *, mask=None, mask_mode=MASK_NONE, uniforms=None, seed=0, stream_id=0, residual=None,
+                   relu=False, out=None, out_dtype=None, p=0.0, drop_seed=0, drop_stream=0, tile_n=0):
+    """Training forward of a (masked) linear: y = dropout(act(x (W.m)^T + b), p) + residual."""
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype or torch.float32)
+    if mask is None:
+        mask_mode = MASK_NONE
+    lib.call("sc_linear_dropout", lib.ptr(x), lib.dtype_code(x.dtype), lib.ptr(w), lib.dtype_code(w.dtype), lib.ptr(mask),
+             mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(bias), lib.ptr(residual), lib.ptr(out),
+             lib.dtype_code(out.dtype), M, N, K, int(relu), tile_n, float(p), drop_seed, drop_stream, lib.stream(),
+             meta=("gemm_bf16" if x.dtype == torch.bfloat16 else "gemm_f32", M, N, K, x.element_size(), w.element_size(),
+                   out.element_size(), mask is not None))
+    return out
+
+
+def linear_wgrad(dyT, xT, w, mask, mask_mode, dw, ds, *, M, uniforms=None, seed=0, stream_id=0, bypass=False, sp_coeff=0.0,
+                 accumulate=False, tile_n=0):
+    """dWm = dyT[N,Mp] @ xT[K,Mp]^T with the fused straight-through epilogue into dw / ds (either may be None).
+    ``M`` = padded token count (columns of dyT / xT, multiple of 8 in bf16)."""
+    N, K = w.shape
+    assert dyT.shape[0] == N and xT.shape[0] == K and dyT.shape[1] == xT.shape[1] == M
+    if mask is None:
+        mask_mode = MASK_NONE
+    lib.call("sc_linear_wgrad", lib.ptr(dyT), lib.ptr(xT), lib.dtype_code(dyT.dtype), lib.ptr(w), lib.ptr(mask), mask_mode,
+             lib.ptr(uniforms), seed, stream_id, int(bypass), float(sp_coeff), lib.ptr(dw), lib.ptr(ds), int(accumulate), N, K,
+             M, tile_n, lib.stream(),
+             meta=("gemm_bf16" if dyT.dtype == torch.bfloat16 else "gemm_f32", N, K, M, dyT.element_size(), xT.element_size(), 4, False))
+
+
+def prep_grad(g, *, h=None, out=None, outT=None, scale=1.0, p=0.0, seed=0, stream_id=0):
+    """out = g * keep * scale (cast), outT = its transpose with leading dim outT.shape[1] (zero padded)."""
+    rows, cols = g.shape
+    assert g.dtype == torch.float32
+    ref = out if out is not None else outT
+    ldT = outT.shape[1] if outT is not None else rows
+    lib.call("sc_prep_grad", lib.ptr(g), lib.ptr(h), lib.dtype_code(h.dtype) if h is not None else F32, lib.ptr(out),
+             lib.ptr(outT), ldT, lib.dtype_code(ref.dtype), rows, cols, float(scale), float(p), seed, stream_id, lib.stream())
+
+
+def transpose(x, outT):
+    rows, cols = x.shape
+    lib.call("sc_transpose", lib.ptr(x), lib.dtype_code(x.dtype), lib.ptr(outT), outT.shape[1], lib.dtype_code(outT.dtype), rows,
+             cols, lib.stream())
+    return outT
+
+
+def apply_mask_transposed(w, mask, mask_mode, outT, *, uniforms=None, seed=0, stream_id=0):
+    N, K = w.shape
+    assert tuple(outT.shape) == (K, N)
+    if mask is None:
+        mask_mode = MASK_NONE
+    lib.call("sc_apply_mask_transposed", lib.ptr(w), lib.ptr(mask), mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(outT),
+             lib.dtype_code(outT.dtype), N, K, lib.stream())
+    return outT
+
+
+def mask_grad(dwm, w, mask, mask_mode, dw, ds, *, uniforms=None, seed=0, stream_id=0, bypass=False, sp_coeff=0.0,
+              accumulate=False):
+    if mask is None:
+        mask_mode = MASK_NONE
+    lib.call("sc_mask_grad", lib.ptr(dwm), lib.ptr(w), lib.ptr(mask), mask_mode, lib.ptr(uniforms), seed, stream_id, int(bypass),
+             float(sp_coeff), lib.ptr(dw), lib.ptr(ds), int(accumulate), w.numel(), lib.stream())
+
+
+def colsum(x, out, accumulate=False):
+    rows, cols = x.shape
+    lib.call("sc_colsum", lib.ptr(x), lib.dtype_code(x.dtype), lib.ptr(out), rows, cols, int(accumulate), lib.stream())
+    return out
+
+
+def layernorm_bwd(x, a, dy, dx, da, db, *, dres=None, eps=1e-6):
+    rows, D = x.shape
+    lib.call("sc_layernorm_bwd", lib.ptr(x), lib.ptr(a), lib.ptr(dy), lib.dtype_code(dy.dtype), lib.ptr(dres), lib.ptr(dx),
+             lib.ptr(da), lib.ptr(db), rows, D, eps, lib.stream())
+    return dx
+
+
+def logsoftmax_nll(logits, target=None, weight=None, inv_norm=None, loss_sum=None, dlogits=None, logprobs=None):
+    rows, V = logits.shape
+    lib.call("sc_logsoftmax_nll", lib.ptr(logits), lib.ptr(target), lib.ptr(weight), lib.ptr(inv_norm), lib.ptr(loss_sum),
+             lib.ptr(dlogits), lib.dtype_code(dlogits.dtype) if dlogits is not None else F32, lib.ptr(logprobs), rows, V,
+             lib.stream())
+
+
+def embedding_bwd(tokens, dy, dtable, scale):
+    rows, D = dy.shape
+    lib.call("sc_embedding_bwd", lib.ptr(tokens), lib.ptr(dy), lib.ptr(dtable), rows, D, dtable.shape[0], float(scale), lib.stream())
+
+
+def adam_clip(param, grad, m, v, *, lr, betas, eps, weight_decay, clip, grad_scale, step):
+    lib.call("sc_adam_clip", lib.ptr(param), lib.ptr(grad), lib.ptr(m), lib.ptr(v), param.numel(), float(lr), float(betas[0]),
+             float(betas[1]), float(eps), float(weight_decay), float(clip), float(grad_scale), int(step), lib.stream())
+
+
+def attention_fwd(q, k, v, out, probs, *, G, Tq, Tk, h, dk, ldq, ldk, ldv, ldo, key_valid=None, bias=None, causal_T=0, p=0.0,
+                  seed=0, stream_id=0):
+    lib.call("sc_attention_fwd", lib.ptr(q), lib.ptr(k), lib.ptr(v), ldq, ldk, ldv, lib.dtype_code(out.dtype), lib.ptr(key_valid),
+             lib.ptr(bias), lib.ptr(probs), lib.ptr(out), ldo, G, Tq, Tk, h, dk, causal_T, float(p), seed, stream_id, lib.stream())
+    return out
+
+
+def attention_bwd(q, k, v, probs, d_out, dq, dk_, dv, *, dtype, G, Tq, Tk, h, dk, ldq, ldk, ldv, ldd, ldgq, ldgk, ldgv, dbias=None,
+                  p=0.0, seed=0, stream_id=0):
+    lib.call("sc_attention_bwd", lib.ptr(q), lib.ptr(k), lib.ptr(v), ldq, ldk, ldv, lib.dtype_code(dtype), lib.ptr(probs),
+             lib.ptr(d_out), ldd, lib.ptr(dq), lib.ptr(dk_), lib.ptr(dv), ldgq, ldgk, ldgv, lib.ptr(dbias), G, Tq, Tk, h, dk,
+             float(p), seed, stream_id, lib.stream())
+
+
+def box_bias_fwd(boxes, wg_w, wg_b, bias, *, B, N, h, trig=True, wave_len=1000.0):
+    lib.call("sc_box_bias_fwd", lib.ptr(boxes), lib.ptr(wg_w), lib.ptr(wg_b), lib.ptr(bias), B, N, h, int(trig), wave_len,
+             lib.stream())
+    return bias
+
+
+def box_bias_bwd(boxes, bias, dbias, dwg_w, dwg_b, *, B, N, h, trig=True, wave_len=1000.0):
+    lib.call("sc_box_bias_bwd", lib.ptr(boxes), lib.ptr(bias), lib.ptr(dbias), lib.ptr(dwg_w), lib.ptr(dwg_b), B, N, h, int(trig),
+             wave_len, lib.stream())
