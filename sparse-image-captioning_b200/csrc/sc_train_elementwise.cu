@@ -260,11 +260,15 @@ __global__ void __launch_bounds__(128) embedding_bwd_kernel(const int* __restric
 // bias-corrected moments, eps added outside the sqrt).  grad_scale: e.g. 1/world after a sum all-reduce.
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
-                                                        float wd, float clip, float grad_scale, float bc1, float bc2_sqrt) {
+                                                        float wd, float clip, float grad_scale, float bc1, float bc2_sqrt,
+                                                        const float* __restrict__ sig_coeff) {
+  // sig_coeff (mask-logit group only): gradient of the sparsity loss, coeff * sigmoid'(S), with S = the parameter itself
+  const float sc_ = sig_coeff ? *sig_coeff : 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
-    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
     const float pi = p[i];
+    if (sc_ != 0.f) { const float sg = sc::sigmoidf_(pi); gi += sc_ * sg * (1.f - sg); }
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
     if (wd != 0.f) gi += wd * pi;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -272,6 +276,16 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = pi - (lr / bc1) * (mi / denom);
   }
+}
+
+// PruningMixin.compute_sparsity_loss (pruning/prune.py:228-269) from the binarized-mask count:
+//   out[0] = |target - sparsity| ; out[1] = d(scaled loss)/d(nnz) = sign(target - sparsity) / total * scale ; out[2] = sparsity
+__global__ void sparsity_coeff_kernel(const unsigned long long* count, double total, float target, float scale, float* out) {
+  const double sparsity = 1.0 - (double)(*count) / total;
+  const double diff = (double)target - sparsity;
+  out[0] = (float)fabs(diff);
+  out[1] = (float)((diff >= 0 ? 1.0 : -1.0) / total * (double)scale);
+  out[2] = (float)sparsity;
 }
 
 int grid_for(size_t n, int block) {
@@ -375,13 +389,21 @@ int sc_embedding_bwd(const int* tokens, const float* dy, float* dtable, int rows
   return SC_OK;
 }
 
+int sc_sparsity_coeff(const unsigned long long* count, double total, float target, float scale, float* out3, cudaStream_t stream) {
+  SC_CHECK(count && out3 && total > 0, SC_ERR_SHAPE, "sc_sparsity_coeff: bad args");
+  sparsity_coeff_kernel<<<1, 1, 0, stream>>>(count, total, target, scale, out3);
+  SC_LAUNCH_CHECK("sc_sparsity_coeff");
+  return SC_OK;
+}
+
 int sc_adam_clip(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
-                 float eps, float weight_decay, float clip_value, float grad_scale, int step, cudaStream_t stream) {
+                 float eps, float weight_decay, float clip_value, float grad_scale, int step, const float* sigmoid_grad_coeff,
+                 cudaStream_t stream) {
   SC_CHECK(n > 0 && step >= 1, SC_ERR_SHAPE, "sc_adam_clip: n=%zu step=%d", n, step);
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
   adam_clip_kernel<<<grid_for(n, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                         clip_value, grad_scale, bc1, bc2);
+                                                         clip_value, grad_scale, bc1, bc2, sigmoid_grad_coeff);
   SC_LAUNCH_CHECK("sc_adam_clip");
   return SC_OK;
 }

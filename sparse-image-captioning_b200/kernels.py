@@ -282,9 +282,16 @@ def embedding_bwd(tokens, dy, dtable, scale):
     lib.call("sc_embedding_bwd", lib.ptr(tokens), lib.ptr(dy), lib.ptr(dtable), rows, D, dtable.shape[0], float(scale), lib.stream())
 
 
-def adam_clip(param, grad, m, v, *, lr, betas, eps, weight_decay, clip, grad_scale, step):
+def adam_clip(param, grad, m, v, *, lr, betas, eps, weight_decay, clip, grad_scale, step, sigmoid_grad_coeff=None):
     lib.call("sc_adam_clip", lib.ptr(param), lib.ptr(grad), lib.ptr(m), lib.ptr(v), param.numel(), float(lr), float(betas[0]),
-             float(betas[1]), float(eps), float(weight_decay), float(clip), float(grad_scale), int(step), lib.stream())
+             float(betas[1]), float(eps), float(weight_decay), float(clip), float(grad_scale), int(step),
+             lib.ptr(sigmoid_grad_coeff), lib.stream())
+
+
+def sparsity_coeff(count, total, target, scale, out3):
+    """out3 = [|target - sparsity|, d(scaled loss)/d(nnz), sparsity] from the device-side binarized-mask count."""
+    lib.call("sc_sparsity_coeff", lib.ptr(count), float(total), float(target), float(scale), lib.ptr(out3), lib.stream())
+    return out3
 
 
 def attention_fwd(q, k, v, out, probs, *, G, Tq, Tk, h, dk, ldq, ldk, ldv, ldo, key_valid=None, bias=None, causal_T=0, p=0.0,

@@ -42,7 +42,8 @@ SIGNATURES = {
     "sc_layernorm_bwd": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p],
     "sc_logsoftmax_nll": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p],
     "sc_embedding_bwd": [_p, _p, _p, _i, _i, _i, _f, _p],
-    "sc_adam_clip": [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _i, _p],
+    "sc_adam_clip": [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _i, _p, _p],
+    "sc_sparsity_coeff": [_p, C.c_double, _f, _f, _p, _p],
     "sc_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_attention_bwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_box_bias_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p],

@@ -1,0 +1,520 @@
+"""Supermask (SMP) training step of the ORT captioner on the B200 kernels.
+
+Replaces the reference's hot loop body (scripts/train_n_prune_transformer.py:132-156):
+    model(**data) -> LanguageModelCriterion -> + compute_sparsity_loss -> backward -> clip_gradient(0.1) -> Adam
+for `relation_transformer_prune` (sparse_caption/models/relation_transformer_prune.py) and, with mask_type=None, for the
+dense `relation_transformer`.  The encoder runs once per image; the S captions of an image share its memory K/V
+(the reference repeats the memory S times before the cross K/V projections, relation_transformer.py:63-66).
+
+All parameters live in two flat fp32 buffers (weights+biases+norms | mask logits) with views per reference parameter
+name, so the optimizer is two fused kernels and the data-parallel gradient exchange is an NCCL all-reduce over flat
+gradient buffers (mask-logit gradients included).  Forward and backward are explicit sequences of kernel launches;
+no autograd graph is built.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import kernels as K
+from .engine import ModelCfg
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class OrtTrainer:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, mask_type: Optional[str] = "supermask",
+                 precision="bf16", device="cuda", dropout=0.1 / 3, drop_prob_src=0.5, bypass_sigmoid_grad=False, seed=0,
+                 mask_init_value=5.0, uniforms: Optional[Dict[str, torch.Tensor]] = None):
+        assert cfg.share_att_encoder is None and cfg.share_att_decoder is None and not cfg.share_layer_encoder \
+            and not cfg.share_layer_decoder, "ACORT weight sharing is an inference-side feature in this round"
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.mask_type = mask_type
+        self.p_drop, self.p_src = float(dropout), float(drop_prob_src)
+        self.bypass = bool(bypass_sigmoid_grad)
+        self.seed = int(seed)
+        self.step_id = 0
+        self.training = True
+        d, L = cfg.d_model, cfg.num_layers
+        sd = state_dict
+        # ---- parameter layout: fused groups are contiguous so that [q;k;v] / [k;v] / WG blocks are single views ----
+        order = ["att_embed.0.weight", "att_embed.0.bias"]
+        for i in range(L):
+            p = f"model.encoder.layers.{i}"
+            order += [f"{p}.self_attn.linears.{j}.weight" for j in range(3)] + [f"{p}.self_attn.linears.{j}.bias" for j in range(3)]
+            order += [f"{p}.self_attn.linears.3.weight", f"{p}.self_attn.linears.3.bias"]
+            order += [f"{p}.self_attn.WGs.{j}.weight" for j in range(cfg.num_heads)] + [f"{p}.self_attn.WGs.{j}.bias" for j in range(cfg.num_heads)]
+            order += [f"{p}.feed_forward.w_1.weight", f"{p}.feed_forward.w_1.bias", f"{p}.feed_forward.w_2.weight", f"{p}.feed_forward.w_2.bias"]
+            order += [f"{p}.sublayer.{j}.norm.{ab}" for j in range(2) for ab in ("a_2", "b_2")]
+        order += ["model.encoder.norm.a_2", "model.encoder.norm.b_2"]
+        for i in range(L):
+            p = f"model.decoder.layers.{i}"
+            for att in ("self_attn", "src_attn"):
+                order += [f"{p}.{att}.linears.{j}.weight" for j in range(3)] + [f"{p}.{att}.linears.{j}.bias" for j in range(3)]
+                order += [f"{p}.{att}.linears.3.weight", f"{p}.{att}.linears.3.bias"]
+            order += [f"{p}.feed_forward.w_1.weight", f"{p}.feed_forward.w_1.bias", f"{p}.feed_forward.w_2.weight", f"{p}.feed_forward.w_2.bias"]
+            order += [f"{p}.sublayer.{j}.norm.{ab}" for j in range(3) for ab in ("a_2", "b_2")]
+        order += ["model.decoder.norm.a_2", "model.decoder.norm.b_2", "model.tgt_embed.0.lut.weight",
+                  "model.generator.proj.weight", "model.generator.proj.bias"]
+        self.names = order
+        # the generator is stored with its vocabulary padded to a multiple of 8 rows (zero weights, bias -1e9, masked
+        # out) so that dlogits can be a 16-byte-aligned bf16 GEMM operand for any V (e.g. the 771-token radix vocab)
+        V = cfg.vocab_size
+        self.Vp = K.pad8(V)
+        self._pad_rows = {"model.generator.proj.weight": self.Vp, "model.generator.proj.bias": self.Vp}
+
+        def alloc(k):
+            if k in self._pad_rows:
+                return sd[k].numel() // V * self.Vp
+            return sd[k].numel()
+
+        def layout(keys):
+            # every view 16-byte aligned, except that the h one-element WG biases of a layer are packed into one [h] block
+            offs, n = {}, 0
+            for k in keys:
+                offs[k] = n
+                n += alloc(k)
+                if not (".WGs." in k and k.endswith(".bias") and not k.endswith(f".WGs.{cfg.num_heads - 1}.bias")):
+                    n = _round_up(n, 4)
+            return offs, n
+
+        offs, n = layout(order)
+        self.flat_w = torch.zeros(n, device=self.dev)
+        self.flat_gw = torch.zeros(n, device=self.dev)
+        self.p = {k: self.flat_w[offs[k]: offs[k] + sd[k].numel()].view(sd[k].shape) for k in order}
+        self.g = {k: self.flat_gw[offs[k]: offs[k] + sd[k].numel()].view(sd[k].shape) for k in order}
+        for k in order:
+            self.p[k].copy_(sd[k])
+        self._offs_w = offs
+        if self.Vp != V:
+            ob = offs["model.generator.proj.bias"]
+            self.flat_w[ob + V: ob + self.Vp] = -1e9
+        # mask logits for every 2-D weight
+        self.masked = [k for k in order if k.endswith(".weight") and sd[k].dim() == 2] if mask_type else []
+        offs_s, n = layout(self.masked)
+        self.flat_s = torch.zeros(max(n, 4), device=self.dev)
+        self.flat_gs = torch.zeros(max(n, 4), device=self.dev)
+        self.n_logits = sum(sd[k].numel() for k in self.masked)
+        self.s = {k: self.flat_s[offs_s[k]: offs_s[k] + sd[k].numel()].view(sd[k].shape) for k in self.masked}
+        self.gs = {k: self.flat_gs[offs_s[k]: offs_s[k] + sd[k].numel()].view(sd[k].shape) for k in self.masked}
+        for k in self.masked:
+            mk = k + "_pruning_mask"
+            if mk in sd:
+                self.s[k].copy_(sd[mk])
+            else:
+                self.s[k].fill_(mask_init_value)
+        self._offs_s = offs_s
+        # padding elements of flat_s must never count as "kept" in the sparsity statistics
+        pad = torch.ones_like(self.flat_s, dtype=torch.bool)
+        for k in self.masked:
+            pad[offs_s[k]: offs_s[k] + sd[k].numel()] = False
+        self.flat_s[pad] = -1.0
+        self._s_pad_mask = pad
+        self.stream_of = {k: i + 1 for i, k in enumerate(order)}
+        # injected uniforms (parity tests): same layout as flat_s
+        self.flat_u = None
+        if uniforms is not None:
+            self.flat_u = torch.zeros_like(self.flat_s)
+            for k in self.masked:
+                self.flat_u[offs_s[k]: offs_s[k] + sd[k].numel()].view(sd[k].shape).copy_(uniforms[k])
+        pe = sd.get("model.tgt_embed.1.pe")
+        from .engine import _positional_encoding
+        self.pe = (pe[0, : cfg.max_seq_length + 2].to(self.dev) if pe is not None
+                   else _positional_encoding(d, cfg.max_seq_length + 2, self.dev)).float().contiguous()
+        # optimizer state
+        self.m_w, self.v_w = torch.zeros_like(self.flat_w), torch.zeros_like(self.flat_w)
+        self.m_s, self.v_s = torch.zeros_like(self.flat_s), torch.zeros_like(self.flat_s)
+        self.opt_step = 0
+        self.sp_out = torch.zeros(3, device=self.dev)
+        self.sp_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._ws = {}
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _group(self, table, first, count):
+        """Contiguous view over `count` consecutive same-shape parameters starting at `first` (e.g. [q;k;v])."""
+        shp = table[first].shape
+        offs = self._offs_w if table is self.p or table is self.g else self._offs_s
+        flat = {id(self.p): self.flat_w, id(self.g): self.flat_gw, id(self.s): self.flat_s, id(self.gs): self.flat_gs}[id(table)]
+        n = table[first].numel()
+        if first in self._pad_rows and count == 1:
+            rows = self._pad_rows[first]
+            return flat[offs[first]: offs[first] + n // shp[0] * rows].view((rows,) + tuple(shp[1:]))
+        return flat[offs[first]: offs[first] + n * count].view((shp[0] * count,) + tuple(shp[1:]))
+
+    def _u(self, first, count=1):
+        if self.flat_u is None:
+            return None
+        n = self.s[first].numel()
+        shp = self.s[first].shape
+        if first in self._pad_rows and count == 1:
+            rows = self._pad_rows[first]
+            return self.flat_u[self._offs_s[first]: self._offs_s[first] + n // shp[0] * rows].view((rows,) + tuple(shp[1:]))
+        return self.flat_u[self._offs_s[first]: self._offs_s[first] + n * count].view((shp[0] * count,) + tuple(shp[1:]))
+
+    def mask_mode(self):
+        if not self.mask_type:
+            return K.MASK_NONE
+        if self.mask_type == "supermask":
+            if not self.training:
+                return K.MASK_ROUND
+            return K.MASK_UNIFORM if self.flat_u is not None else K.MASK_BERNOULLI
+        return K.MASK_RAW
+
+    def _mask_args(self, wname, count=1):
+        """(weight view, logits view, mode, uniforms view, seed, stream) of a (fused) masked weight."""
+        W = self._group(self.p, wname, count)
+        if not self.mask_type:
+            return W, None, K.MASK_NONE, None, 0, 0
+        return (W, self._group(self.s, wname, count), self.mask_mode(), self._u(wname, count), self.seed,
+                self.step_id * 4096 + self.stream_of[wname])
+
+    def _drop_stream(self, site):
+        return self.step_id * 4096 + 2048 + site
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _get_ws(self, B, N, S, T, masked):
+        key = (B, N, S, T, masked)
+        if key in self._ws:
+            return self._ws[key]
+        c, dev, adt = self.cfg, self.dev, self.adt
+        d, ff, V, L, h, F = c.d_model, c.dim_feedforward, c.vocab_size, c.num_layers, c.num_heads, c.att_feat_size
+        ME, R = B * N, B * S
+        MD = R * T
+        Mp = K.pad8(max(ME, MD))
+        f32 = dict(device=dev, dtype=torch.float32)
+        a = dict(device=dev, dtype=adt)
+        ws = type("TrainWs", (), {})()
+        ws.B, ws.N, ws.S, ws.T, ws.ME, ws.MD, ws.R, ws.Mp = B, N, S, T, ME, MD, R, Mp
+        ws.att_in = torch.zeros(ME, F, **f32)
+        ws.att_a = torch.zeros(ME, F, **a) if adt != torch.float32 else ws.att_in
+        ws.boxes = torch.zeros(B, N, 4, **f32)
+        ws.att_mask = torch.ones(B, N, **f32) if masked else None
+        ws.tokens = torch.zeros(MD, device=dev, dtype=torch.int32)
+        ws.targets = torch.zeros(MD, device=dev, dtype=torch.int32)
+        ws.tok_w = torch.zeros(MD, **f32)
+        ws.key_valid = torch.zeros(R, T, **f32)
+        ws.inv_norm = torch.zeros(1, **f32)
+        ws.loss_sum = torch.zeros(1, **f32)
+        ws.xe = [torch.zeros(ME, d, **f32) for _ in range(2 * L + 1)]
+        ws.e_xn1 = [torch.zeros(ME, d, **a) for _ in range(L)]
+        ws.e_qkv = [torch.zeros(ME, 3 * d, **a) for _ in range(L)]
+        ws.e_bias = [torch.zeros(B, h, N, N, **f32) for _ in range(L)]
+        ws.e_probs = [torch.zeros(B, h, N, N, **f32) for _ in range(L)]
+        ws.e_att = [torch.zeros(ME, d, **a) for _ in range(L)]
+        ws.e_xn2 = [torch.zeros(ME, d, **a) for _ in range(L)]
+        ws.e_hid = [torch.zeros(ME, ff, **a) for _ in range(L)]
+        ws.wg_eff = [torch.zeros(h, 64 if not c.no_box_trigonometric_embedding else 4, **f32) for _ in range(L)]
+        ws.mem = torch.zeros(ME, d, **a)
+        ws.memkv = [torch.zeros(ME, 2 * d, **a) for _ in range(L)]
+        ws.y = [torch.zeros(MD, d, **f32) for _ in range(3 * L + 1)]
+        ws.d_yn1 = [torch.zeros(MD, d, **a) for _ in range(L)]
+        ws.d_qkv = [torch.zeros(MD, 3 * d, **a) for _ in range(L)]
+        ws.d_probs = [torch.zeros(R, h, T, T, **f32) for _ in range(L)]
+        ws.d_att = [torch.zeros(MD, d, **a) for _ in range(L)]
+        ws.d_yn2 = [torch.zeros(MD, d, **a) for _ in range(L)]
+        ws.d_qc = [torch.zeros(MD, d, **a) for _ in range(L)]
+        ws.c_probs = [torch.zeros(B, h, S * T, N, **f32) for _ in range(L)]
+        ws.d_catt = [torch.zeros(MD, d, **a) for _ in range(L)]
+        ws.d_yn3 = [torch.zeros(MD, d, **a) for _ in range(L)]
+        ws.d_hid = [torch.zeros(MD, ff, **a) for _ in range(L)]
+        ws.yf = torch.zeros(MD, d, **a)
+        ws.logits = torch.zeros(MD, self.Vp, **f32)
+        ws.dlogits = torch.zeros(MD, self.Vp, **a)
+        # backward scratch
+        nmax = max(self.Vp, ff, 3 * d, F)
+        ws.gb = torch.zeros(max(ME, MD) * max(ff, 3 * d), **a)         # grad operand [M, N]
+        ws.gT = torch.zeros(nmax * Mp, **a)                            # grad operand transposed [N, Mp]
+        ws.xT = torch.zeros(max(ff, F, d) * Mp, **a)                   # activation transposed [K, Mp]
+        ws.wT = torch.zeros(max(self.Vp * d, ff * d, F * d, 3 * d * d), **a)  # (W.m)^T [K, N]
+        ws.ga = torch.zeros(max(ME, MD), max(ff, 3 * d), **f32)        # fp32 activation gradient scratch
+        ws.gq = torch.zeros(max(ME, MD), 3 * d, **f32)                 # dq|dk|dv
+        ws.dres = [torch.zeros(max(ME, MD), d, **f32) for _ in range(2)]  # running residual-stream gradient (ping-pong)
+        ws.dmem = torch.zeros(ME, d, **f32)
+        ws.dmemkv = torch.zeros(ME, 2 * d, **f32)
+        ws.dbias = torch.zeros(B, h, N, N, **f32)
+        ws.dwg = torch.zeros(h, ws.wg_eff[0].shape[1], **f32)
+        ws.dtable = torch.zeros(V, d, **f32)
+        self._ws[key] = ws
+        return ws
+
+    # ---- linear forward / backward helpers ------------------------------------------------------------------
+    def _lin(self, wname, x, out, *, count=1, relu=False, residual=None, p=0.0, site=0, bias=True):
+        W, S, mode, U, seed, stream = self._mask_args(wname, count)
+        b = self._group(self.p, wname.replace(".weight", ".bias"), count) if bias else None
+        p = p if self.training else 0.0
+        K.linear_dropout(x, W, b, mask=S, mask_mode=mode, uniforms=U, seed=seed, stream_id=stream, residual=residual,
+                         relu=relu, out=out, p=p, drop_seed=self.seed + 1, drop_stream=self._drop_stream(site))
+        return out
+
+    def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None):
+        """Backward of y = drop(act(x W^T + b)).  g: fp32 [M,N] gradient wrt the layer output (after dropout);
+        h: saved post-activation output when the layer has ReLU (mask = h != 0, which also covers its dropout);
+        p/site: dropout to regenerate when h is None.  g_ready: (gb, None) when the gradient is already in the
+        activation dtype and needs no masking (generator).  dx (fp32 [M,K]) receives g' (W.m) [+ dx_residual]."""
+        W, S, mode, U, seed, stream = self._mask_args(wname, count)
+        N, Kd = W.shape
+        M = x_saved.shape[0]
+        Mp = K.pad8(M)
+        p = p if self.training else 0.0
+        gT = ws.gT[: N * Mp].view(N, Mp)
+        if g_ready is not None:
+            gb = g_ready
+            if Mp != M:
+                gT[:, M:].zero_()
+            K.transpose(gb, gT)
+        else:
+            gb = ws.gb[: M * N].view(M, N)
+            if Mp != M:
+                gT[:, M:].zero_()
+            K.prep_grad(g, h=h, out=gb, outT=gT, scale=(1.0 / (1.0 - p)) if (h is not None and p > 0) else 1.0,
+                        p=0.0 if h is not None else p, seed=self.seed + 1, stream_id=self._drop_stream(site))
+        bname = wname.replace(".weight", ".bias")
+        if bname in self.g:
+            K.colsum(gb, self._group(self.g, bname, count))
+        if dx is not None:
+            wT = ws.wT[: Kd * N].view(Kd, N)
+            K.apply_mask_transposed(W, S, mode, wT, uniforms=U, seed=seed, stream_id=stream)
+            K.linear(gb, wT, None, residual=dx_residual, out=dx)
+        xT = ws.xT[: Kd * Mp].view(Kd, Mp)
+        if Mp != M:
+            xT[:, M:].zero_()
+        K.transpose(x_saved, xT)
+        K.linear_wgrad(gT, xT, W, S, mode, self._group(self.g, wname, count),
+                       self._group(self.gs, wname, count) if S is not None else None, M=Mp, uniforms=U, seed=seed, stream_id=stream,
+                       bypass=self.bypass)
+
+    def _ln(self, name, x, out):
+        return K.layernorm(x, self.p[name + ".a_2"], self.p[name + ".b_2"], out=out)
+
+    def _ln_bwd(self, name, x, dy, dx, dres=None):
+        return K.layernorm_bwd(x, self.p[name + ".a_2"], dy, dx, self.g[name + ".a_2"], self.g[name + ".b_2"], dres=dres)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def load_batch(self, ws, att_feats, boxes, seqs, masks, att_masks=None, global_tokens=None):
+        c = self.cfg
+        B, N, S, T = ws.B, ws.N, ws.S, ws.T
+        ws.att_in.copy_(att_feats.reshape(B * N, -1), non_blocking=True)
+        ws.boxes.copy_(boxes, non_blocking=True)
+        if att_masks is not None:
+            ws.att_mask.copy_(att_masks.float(), non_blocking=True)
+        seqs = seqs.to(self.dev, non_blocking=True)
+        masks = masks.to(self.dev, non_blocking=True).float()
+        tok = seqs[:, :T].contiguous()
+        ws.tokens.copy_(tok.reshape(-1).int())
+        ws.targets.copy_(seqs[:, 1: T + 1].reshape(-1).int())
+        ws.tok_w.copy_(masks[:, 1: T + 1].reshape(-1))
+        ws.key_valid.copy_((tok != c.pad_token_id).float())
+        denom = masks[:, 1: T + 1].sum() if global_tokens is None else global_tokens
+        ws.inv_norm.copy_((1.0 / denom).reshape(1))
+
+    def forward(self, ws):
+        """Teacher-forcing forward; leaves logits in ws.logits and every activation the backward needs."""
+        c = self.cfg
+        B, N, S, T, ME, MD, R = ws.B, ws.N, ws.S, ws.T, ws.ME, ws.MD, ws.R
+        d, h, L = c.d_model, c.num_heads, c.num_layers
+        dk = d // h
+        pd = self.p_drop if self.training else 0.0
+        trig = not c.no_box_trigonometric_embedding
+        if ws.att_a is not ws.att_in:
+            K.cast_bf16(ws.att_in, out=ws.att_a)
+        self._lin("att_embed.0.weight", ws.att_a, ws.xe[0], relu=True, p=self.p_src, site=1)
+        if ws.att_mask is not None:
+            K.mask_rows(ws.xe[0], ws.att_mask.view(-1))
+        for l in range(L):
+            p = f"model.encoder.layers.{l}"
+            x0, x1, x2 = ws.xe[2 * l], ws.xe[2 * l + 1], ws.xe[2 * l + 2]
+            self._ln(f"{p}.sublayer.0.norm", x0, ws.e_xn1[l])
+            self._lin(f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], ws.e_qkv[l], count=3)
+            # effective (masked) WG weights, then the log-geometry bias for all heads
+            Wg, Sg, mode, U, seed, stream = self._mask_args(f"{p}.self_attn.WGs.0.weight", h)
+            if Sg is None:
+                ws.wg_eff[l].copy_(Wg)
+            else:
+                ws.wg_eff[l].copy_(K.apply_mask(Wg, Sg, mode, uniforms=U, seed=seed, stream_id=stream))
+            K.box_bias_fwd(ws.boxes, ws.wg_eff[l], self._group(self.p, f"{p}.self_attn.WGs.0.bias", h), ws.e_bias[l], B=B, N=N, h=h,
+                           trig=trig)
+            q = ws.e_qkv[l]
+            K.attention_fwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_att[l], ws.e_probs[l], G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d,
+                            ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.att_mask, bias=ws.e_bias[l], p=pd, seed=self.seed + 2,
+                            stream_id=self._drop_stream(10 + l))
+            self._lin(f"{p}.self_attn.linears.3.weight", ws.e_att[l], x1, residual=x0, p=pd, site=20 + l)
+            self._ln(f"{p}.sublayer.1.norm", x1, ws.e_xn2[l])
+            self._lin(f"{p}.feed_forward.w_1.weight", ws.e_xn2[l], ws.e_hid[l], relu=True, p=pd, site=30 + l)
+            self._lin(f"{p}.feed_forward.w_2.weight", ws.e_hid[l], x2, residual=x1, p=pd, site=40 + l)
+        self._ln("model.encoder.norm", ws.xe[2 * L], ws.mem)
+        for l in range(L):
+            self._lin(f"model.decoder.layers.{l}.src_attn.linears.1.weight", ws.mem, ws.memkv[l], count=2)
+        # ---- decoder ----
+        W, S_, mode, U, seed, stream = self._mask_args("model.tgt_embed.0.lut.weight")
+        K.embed_pe(ws.tokens, W, self.pe, T=T, pos0=0, mask=S_, mask_mode=mode, uniforms=U, seed=seed, stream_id=stream, out=ws.y[0])
+        if pd > 0:
+            K.prep_grad(ws.y[0], out=ws.y[0], p=pd, seed=self.seed + 1, stream_id=self._drop_stream(2))
+        for l in range(L):
+            p = f"model.decoder.layers.{l}"
+            y0, y1, y2, y3 = ws.y[3 * l], ws.y[3 * l + 1], ws.y[3 * l + 2], ws.y[3 * l + 3]
+            self._ln(f"{p}.sublayer.0.norm", y0, ws.d_yn1[l])
+            self._lin(f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], ws.d_qkv[l], count=3)
+            q = ws.d_qkv[l]
+            K.attention_fwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_att[l], ws.d_probs[l], G=R, Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d,
+                            ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.key_valid, causal_T=T, p=pd, seed=self.seed + 2,
+                            stream_id=self._drop_stream(50 + l))
+            self._lin(f"{p}.self_attn.linears.3.weight", ws.d_att[l], y1, residual=y0, p=pd, site=60 + l)
+            self._ln(f"{p}.sublayer.1.norm", y1, ws.d_yn2[l])
+            self._lin(f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], ws.d_qc[l])
+            kv = ws.memkv[l]
+            K.attention_fwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.d_catt[l], ws.c_probs[l], G=B, Tq=S * T, Tk=N, h=h, dk=dk, ldq=d,
+                            ldk=2 * d, ldv=2 * d, ldo=d, key_valid=ws.att_mask, p=pd, seed=self.seed + 2,
+                            stream_id=self._drop_stream(70 + l))
+            self._lin(f"{p}.src_attn.linears.3.weight", ws.d_catt[l], y2, residual=y1, p=pd, site=80 + l)
+            self._ln(f"{p}.sublayer.2.norm", y2, ws.d_yn3[l])
+            self._lin(f"{p}.feed_forward.w_1.weight", ws.d_yn3[l], ws.d_hid[l], relu=True, p=pd, site=90 + l)
+            self._lin(f"{p}.feed_forward.w_2.weight", ws.d_hid[l], y3, residual=y2, p=pd, site=100 + l)
+        self._ln("model.decoder.norm", ws.y[3 * L], ws.yf)
+        self._lin("model.generator.proj.weight", ws.yf, ws.logits)
+        return ws.logits
+
+    def loss_and_backward(self, ws):
+        """LanguageModelCriterion + full backward; gradients land in flat_gw / flat_gs (overwritten, not accumulated)."""
+        c = self.cfg
+        B, N, S, T, ME, MD, R = ws.B, ws.N, ws.S, ws.T, ws.ME, ws.MD, ws.R
+        d, h, L, ff = c.d_model, c.num_heads, c.num_layers, c.dim_feedforward
+        dk = d // h
+        pd = self.p_drop if self.training else 0.0
+        trig = not c.no_box_trigonometric_embedding
+        # norm gradients accumulate through atomics: zero them (everything else is overwritten)
+        for k in self.names:
+            if k.endswith("a_2") or k.endswith("b_2"):
+                self.g[k].zero_()
+        ws.loss_sum.zero_()
+        K.logsoftmax_nll(ws.logits, ws.targets, ws.tok_w, ws.inv_norm, ws.loss_sum, ws.dlogits)
+        ga_d = ws.ga.view(-1)[: MD * d].view(MD, d)
+        self._lin_bwd(ws, "model.generator.proj.weight", ws.yf, None, g_ready=ws.dlogits, dx=ga_d)
+        cur, nxt = ws.dres[0][:MD], ws.dres[1][:MD]
+        self._ln_bwd("model.decoder.norm", ws.y[3 * L], ga_d, cur)
+        ws.dmem.zero_()
+        for l in reversed(range(L)):
+            p = f"model.decoder.layers.{l}"
+            y0, y1, y2 = ws.y[3 * l], ws.y[3 * l + 1], ws.y[3 * l + 2]
+            ga_ff = ws.ga.view(-1)[: MD * ff].view(MD, ff)
+            # feed-forward sublayer
+            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.d_hid[l], cur, p=pd, site=100 + l, dx=ga_ff)
+            ga_dd = ws.gq.view(-1)[: MD * d].view(MD, d)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.d_yn3[l], ga_ff, h=ws.d_hid[l], p=pd, dx=ga_dd)
+            self._ln_bwd(f"{p}.sublayer.2.norm", y2, ga_dd, nxt, dres=cur)
+            cur, nxt = nxt, cur
+            # cross-attention sublayer
+            ga_c = ws.ga.view(-1)[: MD * d].view(MD, d)
+            self._lin_bwd(ws, f"{p}.src_attn.linears.3.weight", ws.d_catt[l], cur, p=pd, site=80 + l, dx=ga_c)
+            kv = ws.memkv[l]
+            dqc = ws.gq.view(-1)[: MD * d].view(MD, d)
+            K.attention_bwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.c_probs[l], ga_c, dqc, ws.dmemkv[:, 0:], ws.dmemkv[:, d:],
+                            dtype=self.adt, G=B, Tq=S * T, Tk=N, h=h, dk=dk, ldq=d, ldk=2 * d, ldv=2 * d, ldd=d, ldgq=d, ldgk=2 * d,
+                            ldgv=2 * d, p=pd, seed=self.seed + 2, stream_id=self._drop_stream(70 + l))
+            ga_c2 = ws.ga.view(-1)[: MD * d].view(MD, d)
+            self._lin_bwd(ws, f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], dqc, dx=ga_c2)
+            self._ln_bwd(f"{p}.sublayer.1.norm", y1, ga_c2, nxt, dres=cur)
+            cur, nxt = nxt, cur
+            self._lin_bwd(ws, f"{p}.src_attn.linears.1.weight", ws.mem, ws.dmemkv, count=2, dx=ws.dmem, dx_residual=ws.dmem)
+            # self-attention sublayer
+            ga_s = ws.ga.view(-1)[: MD * d].view(MD, d)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.d_att[l], cur, p=pd, site=60 + l, dx=ga_s)
+            q = ws.d_qkv[l]
+            gq = ws.gq[:MD]
+            K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_probs[l], ga_s, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
+                            G=R, Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
+                            p=pd, seed=self.seed + 2, stream_id=self._drop_stream(50 + l))
+            ga_s2 = ws.ga.view(-1)[: MD * d].view(MD, d)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], gq, count=3, dx=ga_s2)
+            self._ln_bwd(f"{p}.sublayer.0.norm", y0, ga_s2, nxt, dres=cur)
+            cur, nxt = nxt, cur
+        # embedding: dropout mask is recoverable from the saved output (dropped entries are exact zeros)
+        W, S_, mode, U, seed, stream = self._mask_args("model.tgt_embed.0.lut.weight")
+        emb_g = ws.ga.view(-1)[: MD * d].view(MD, d)
+        if pd > 0:
+            K.prep_grad(cur, h=ws.y[0], out=emb_g, scale=1.0 / (1.0 - pd))
+        else:
+            emb_g = cur
+        ws.dtable.zero_()
+        K.embedding_bwd(ws.tokens, emb_g, ws.dtable, math.sqrt(d))
+        K.mask_grad(ws.dtable, W, S_, mode, self.g["model.tgt_embed.0.lut.weight"],
+                    self.gs.get("model.tgt_embed.0.lut.weight"), uniforms=U, seed=seed, stream_id=stream, bypass=self.bypass)
+        # ---- encoder ----
+        cur, nxt = ws.dres[0][:ME], ws.dres[1][:ME]
+        self._ln_bwd("model.encoder.norm", ws.xe[2 * L], ws.dmem, cur)
+        for l in reversed(range(L)):
+            p = f"model.encoder.layers.{l}"
+            x0, x1 = ws.xe[2 * l], ws.xe[2 * l + 1]
+            ga_ff = ws.ga.view(-1)[: ME * ff].view(ME, ff)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.e_hid[l], cur, p=pd, site=40 + l, dx=ga_ff)
+            ga_dd = ws.gq.view(-1)[: ME * d].view(ME, d)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.e_xn2[l], ga_ff, h=ws.e_hid[l], p=pd, dx=ga_dd)
+            self._ln_bwd(f"{p}.sublayer.1.norm", x1, ga_dd, nxt, dres=cur)
+            cur, nxt = nxt, cur
+            ga_a = ws.ga.view(-1)[: ME * d].view(ME, d)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.e_att[l], cur, p=pd, site=20 + l, dx=ga_a)
+            q = ws.e_qkv[l]
+            gq = ws.gq[:ME]
+            K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
+                            G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
+                            dbias=ws.dbias, p=pd, seed=self.seed + 2, stream_id=self._drop_stream(10 + l))
+            ws.dwg.zero_()
+            gb_wg = self._group(self.g, f"{p}.self_attn.WGs.0.bias", h)
+            gb_wg.zero_()
+            K.box_bias_bwd(ws.boxes, ws.e_bias[l], ws.dbias, ws.dwg, gb_wg, B=B, N=N, h=h, trig=trig)
+            Wg, Sg, mode, U, seed, stream = self._mask_args(f"{p}.self_attn.WGs.0.weight", h)
+            K.mask_grad(ws.dwg, Wg, Sg, mode, self._group(self.g, f"{p}.self_attn.WGs.0.weight", h),
+                        self._group(self.gs, f"{p}.self_attn.WGs.0.weight", h) if Sg is not None else None, uniforms=U, seed=seed,
+                        stream_id=stream, bypass=self.bypass)
+            ga_a2 = ws.ga.view(-1)[: ME * d].view(ME, d)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], gq, count=3, dx=ga_a2)
+            self._ln_bwd(f"{p}.sublayer.0.norm", x0, ga_a2, nxt, dres=cur)
+            cur, nxt = nxt, cur
+        if ws.att_mask is not None:
+            K.mask_rows(cur, ws.att_mask.view(-1))
+        self._lin_bwd(ws, "att_embed.0.weight", ws.att_a, cur, h=ws.xe[0], p=self.p_src if self.training else 0.0)
+        return ws.loss_sum
+
+    # ---------------------------------------------------------------------------------------------------------
+    def optimizer_step(self, *, lr, mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0,
+                       grad_scale=1.0, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1):
+        """clip_gradient(0.1) + Adam for the two parameter groups of train_n_prune_transformer.py:67-82, with the
+        sparsity-loss gradient (prune.py:228-269) folded into the mask-logit update."""
+        self.opt_step += 1
+        K.adam_clip(self.flat_w, self.flat_gw, self.m_w, self.v_w, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip=clip,
+                    grad_scale=grad_scale, step=self.opt_step)
+        if self.masked and self.mask_type == "supermask":
+            coeff = None
+            if sparsity_target is not None and sparsity_weight:
+                anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
+                self.sp_count.zero_()
+                K.lib.call("sc_mask_count", K.lib.ptr(self.flat_s), self.flat_s.numel(), K.lib.ptr(self.sp_count), K.lib.stream())
+                K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out)
+                coeff = self.sp_out[1:2]
+            K.adam_clip(self.flat_s, self.flat_gs, self.m_s, self.v_s, lr=mask_lr, betas=betas, eps=mask_eps, weight_decay=0.0,
+                        clip=clip, grad_scale=grad_scale, step=self.opt_step, sigmoid_grad_coeff=coeff)
+            self.flat_s[self._s_pad_mask] = -1.0
+
+    def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None, **opt):
+        """One full SMP step.  ``all_reduce``: callable applied to the flat gradient buffers (NCCL sum) when data-parallel."""
+        B, N = att_feats.shape[:2]
+        T = seqs.shape[1] - 1
+        ws = self._get_ws(B, N, seq_per_img, T, att_masks is not None)
+        self.step_id += 1
+        self.load_batch(ws, att_feats, boxes, seqs, masks, att_masks, global_tokens)
+        self.forward(ws)
+        self.loss_and_backward(ws)
+        if all_reduce is not None:
+            all_reduce(self.flat_gw)
+            if self.masked:
+                all_reduce(self.flat_gs)
+        self.optimizer_step(lr=lr, **opt)
+        return ws.loss_sum * ws.inv_norm
+
+    def state_dict(self):
+        sd = {k: v.clone() for k, v in self.p.items()}
+        sd.update({k + "_pruning_mask": v.clone() for k, v in self.s.items()})
+        return sd
