@@ -99,6 +99,67 @@ def cpu_arm(steps, warmup, images):
     return images * steps / dt, dt / steps, cores
 
 
+def train_arm(args, dev, world, dist_mod=None, rank0_only=False):
+    """SMP training arm (BASELINE.json configs[1]): ORT supermask training, bf16 tensor-core GEMMs with fp32 master
+    weights + fp32 mask logits, 5 captions/image with the encoder run once, Bernoulli masks + dropout + sparsity
+    loss + clip + Adam inside the timed step.  Single-GPU here; the N-GPU variant adds the NCCL all-reduce of the
+    flat weight+logit gradient buffers (tests/test_ddp_cpu.py covers the sharding logic)."""
+    from sparse_caption_b200 import lib, synthetic
+    from sparse_caption_b200.engine import ModelCfg
+    from sparse_caption_b200.trainer import OrtTrainer
+    cfg = ModelCfg(dict(CFG, max_seq_length=17))
+    sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
+    tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888)
+    B, S, T = args.train_images, 5, 17
+    g = torch.Generator().manual_seed(8888)
+    att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888, pin=True)
+    R = B * S
+    seqs = torch.zeros(R, T + 1, dtype=torch.long)
+    masks = torch.zeros(R, T + 1)
+    lens = torch.randint(6, T - 1, (R,), generator=g)
+    for r in range(R):
+        n = int(lens[r])
+        seqs[r, 0] = 2
+        seqs[r, 1:1 + n] = torch.randint(4, CFG["vocab_size"], (n,), generator=g)
+        seqs[r, 1 + n] = 3
+        masks[r, :n + 2] = 1
+    seqs, masks = seqs.pin_memory(), masks.pin_memory()
+    opt = dict(lr=3e-4, sparsity_target=0.95, sparsity_weight=30.0, current_step=100, max_step=1000)
+
+    def step():
+        return tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    before = lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / args.train_steps
+    launches = (lib.launch_count - before) // args.train_steps
+    # GEMM share / tensor roofline from one instrumented step
+    lib.profile = []
+    step()
+    torch.cuda.synchronize(dev)
+    prof, lib.profile = lib.profile, None
+    gemm_ms = sum(a.elapsed_time(b) for n, m, a, b in prof if m and m[0] == "gemm_bf16")
+    gemm_fl = sum(2.0 * m[1] * m[2] * m[3] for n, m, a, b in prof if m and m[0] == "gemm_bf16")
+    tot_ms = sum(a.elapsed_time(b) for n, m, a, b in prof)
+    peaks = load_peaks()
+    tf = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else 0.0
+    return {"metric": "smp_train_images_per_sec", "value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+            "images_per_gpu_per_step": B, "captions_per_image": S, "positions": T, "dtype": "bf16 GEMM / fp32 master+logits",
+            "loss": float(loss), "gpu_launches_per_step": launches, "h2d_bytes_per_step": att.numel() * 4 + boxes.numel() * 4 + seqs.numel() * 8 + masks.numel() * 4,
+            "includes": "H2D of the batch, Bernoulli masks, dropout, sparsity loss, clip + Adam (2 groups)",
+            "algorithmic_gflop_per_step": gemm_fl / 1e9,
+            "roofline": {"kernel": "sc_gemm_bf16_kernel (fwd + dgrad + wgrad launches of one step)", "bound": "tensor", "achieved": tf,
+                         "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sus"], "share_of_step": gemm_ms / tot_ms if tot_ms else None}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -108,6 +169,9 @@ def main():
     ap.add_argument("--images", type=int, default=512, help="images per GPU per step")
     ap.add_argument("--backend", default="dense", choices=["dense", "csr", "auto"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the SMP training arm (BASELINE.json configs[1])")
+    ap.add_argument("--train-images", type=int, default=50, help="images per GPU per training step (5 captions each)")
+    ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--cpu-images", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -251,6 +315,10 @@ def main():
                 "share_of_step": g["ms"] / total_ms if total_ms else None,
                 "kernel_time_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}}
 
+    train = None
+    if not args.no_train:
+        train = train_arm(args, dev, world, dist_mod=None, rank0_only=True)
+
     cpu = None
     if not args.no_cpu_baseline:
         v, spp, cores = cpu_arm(1, 1, args.cpu_images)
@@ -263,7 +331,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "roofline": roofline,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "train": train}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

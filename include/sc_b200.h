@@ -122,6 +122,73 @@ int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int
 /* K8 — state[i][:, state_ix] (models/caption_model.py:106-110): dst[r] = src[idx[r]], rows of row_bytes */
 int sc_cache_reorder(const void* src, void* dst, const int* idx, long rows, long row_bytes, sc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training side (teacher forcing forward/backward; K2, K4/K9 backward, K10)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* sc_linear with inverted dropout in the epilogue: y = dropout(act(x (W.m)^T + b), p) + residual
+ * (nn.Dropout after the FFN ReLU / sublayer outputs / att_embed: models/transformer.py:325,356-358,
+ * relation_transformer.py:327-329).  Dropout mask = Philox(drop_seed, drop_stream, element). */
+int sc_linear_dropout(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
+                      const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
+                      const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
+                      float dropout_p, unsigned long long drop_seed, unsigned long long drop_stream, sc_stream_t stream);
+
+/* K2 — autograd of MaskedLinear (pruning/sampler.py:15-17,32-34): dWm[N,K] = dyT[N,M] * xT[K,M]^T with the fused
+ * straight-through epilogue  dW (+)= dWm.m ;  dS (+)= dWm.W.sigmoid'(S) [.1 if bypass or raw] + sparsity_coeff*sigmoid'(S).
+ * dyT/xT are transposed activations (M = padded token count, multiple of 8 for bf16). */
+int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, const float* mask, int mask_mode,
+                    const float* uniforms, unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad,
+                    float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K, int M, int tile_n,
+                    sc_stream_t stream);
+
+/* out = g*keep*scale (cast), outT = its transpose (leading dim ldT, caller zero-pads); keep = (h != 0) when the saved
+ * post-ReLU/dropout activation h is given, else the regenerated Philox dropout mask when dropout_p > 0. */
+int sc_prep_grad(const float* g, const void* h, int h_dtype, void* out, void* outT, int ldT, int out_dtype, int rows, int cols,
+                 float scale, float dropout_p, unsigned long long seed, unsigned long long stream_id, sc_stream_t stream);
+int sc_transpose(const void* x, int x_dtype, void* y, int ldT, int y_dtype, int rows, int cols, sc_stream_t stream);
+/* (W . mask)^T -> [K,N]: B operand of the dX GEMM */
+int sc_apply_mask_transposed(const float* w, const float* mask, int mask_mode, const float* uniforms, unsigned long long seed,
+                             unsigned long long stream_id, void* outT, int out_dtype, int N, int K, sc_stream_t stream);
+/* elementwise straight-through gradient from a dense dWm (embedding table, WG heads) */
+int sc_mask_grad(const float* dwm, const float* w, const float* mask, int mask_mode, const float* uniforms,
+                 unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad, float sparsity_coeff,
+                 float* dw, float* ds, int accumulate, size_t n, sc_stream_t stream);
+int sc_colsum(const void* x, int dtype, float* out, int rows, int cols, int accumulate, sc_stream_t stream);
+
+/* backward of the reference LayerNorm (models/transformer.py:329-341); dres (optional) is added to dx; da/db accumulate */
+int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
+                     float* db, int rows, int D, float eps, sc_stream_t stream);
+
+/* log_softmax (+ LanguageModelCriterion fwd/bwd when target != NULL): transformer.py:413, utils/losses.py:32-43 */
+int sc_logsoftmax_nll(const float* logits, const int* target, const float* weight, const float* inv_norm, float* loss_sum,
+                      void* dlogits, int d_dtype, float* logprobs, int rows, int V, sc_stream_t stream);
+int sc_embedding_bwd(const int* tokens, const float* dy, float* dtable, int rows, int D, int V, float scale, sc_stream_t stream);
+
+/* PruningMixin.compute_sparsity_loss from the binarized count (pruning/prune.py:228-269):
+ * out3 = { |target - sparsity|, d(scaled loss)/d(nnz), sparsity } */
+int sc_sparsity_coeff(const unsigned long long* count, double total, float target, float scale, float* out3, sc_stream_t stream);
+/* clip_grad_value_ + Adam on a flat buffer (utils/optim.py:116-126,187-191); sigmoid_grad_coeff (device scalar, optional)
+ * adds coeff*sigmoid'(param) to the gradient before clipping (sparsity loss on the mask-logit group) */
+int sc_adam_clip(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, float clip_value, float grad_scale, int step, const float* sigmoid_grad_coeff,
+                 sc_stream_t stream);
+
+/* teacher-forcing attention with saved probabilities + backward (decoder self: causal_T = T; cross: groups = images with
+ * S*T query rows; encoder box attention: additive bias): transformer.py:230-295, relation_transformer.py:258-293 */
+int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* key_valid,
+                     const float* bias, float* probs, void* out, int ldo, int G, int Tq, int Tk, int h, int dk, int causal_T,
+                     float dropout_p, unsigned long long seed, unsigned long long stream_id, sc_stream_t stream);
+int sc_attention_bwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* probs,
+                     const float* d_out, int ldd, float* dq, float* dk_, float* dv, int ldgq, int ldgk, int ldgv, float* dbias,
+                     int G, int Tq, int Tk, int h, int dk, float dropout_p, unsigned long long seed,
+                     unsigned long long stream_id, sc_stream_t stream);
+/* log(max(relu(WG_h . emb(i,j) + b_h), 1e-6)) for all heads, and its gradient to WG (relation_transformer.py:179-183,196-256) */
+int sc_box_bias_fwd(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int h, int trig,
+                    float wave_len, sc_stream_t stream);
+int sc_box_bias_bwd(const float* boxes, const float* bias, const float* dbias, float* dwg_w, float* dwg_b, int B, int N, int h,
+                    int trig, float wave_len, sc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

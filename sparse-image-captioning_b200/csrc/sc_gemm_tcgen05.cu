@@ -221,9 +221,10 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       if (args.wgrad) {
         // K2: dW = dWm (.) m ; dS = dWm (.) W (.) sigmoid'(S) (+ sparsity term), mask regenerated from (seed, stream, element)
         const sc::Philox wph(args.seed);
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          if (col >= args.N) break;
+          if (col >= args.N) continue;
           const size_t e = (size_t)row * args.N + col;
           const float sv = args.wg_s ? __ldg(args.wg_s + e) : 0.f;
           const float m = sc::mask_value(args.mask_mode, sv, args.wg_u ? __ldg(args.wg_u + e) : 0.f, wph, e, args.stream_id);
@@ -237,9 +238,10 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       if (args.dropout_p > 0.f) {
         // training forward epilogue with dropout: scalar path (bias, act, dropout, residual)
         const sc::Philox dph(args.drop_seed);
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          if (col >= args.N) break;
+          if (col >= args.N) continue;
           const size_t e = (size_t)row * args.N + col;
           float x = f[j];
           if (args.bias) x += __ldg(args.bias + col);
@@ -290,9 +292,10 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int j = 0; j < 8; ++j) yp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
       } else {
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = col0 + j;
-          if (col >= args.N) break;
+          if (col >= args.N) continue;
           float x = f[j];
           if (args.bias) x += __ldg(args.bias + col);
           if (args.relu) x = fmaxf(x, 0.f);

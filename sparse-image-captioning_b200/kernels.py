@@ -103,13 +103,14 @@ def embed_pe(tokens, table, pe, *, T=1, pos0=0, mask=None, mask_mode=MASK_NONE, 
     return out
 
 
-def apply_mask(w, mask, mask_mode, *, uniforms=None, seed=0, stream_id=0, out_dtype=torch.float32):
+def apply_mask(w, mask, mask_mode, *, uniforms=None, seed=0, stream_id=0, out_dtype=torch.float32, out=None):
     _chk(w, "w")
-    out = torch.empty(w.shape, device=w.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty(w.shape, device=w.device, dtype=out_dtype)
     if mask is None:
         mask_mode = MASK_NONE
     lib.call("sc_apply_mask", lib.ptr(w), lib.ptr(mask), mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(out),
-             lib.dtype_code(out_dtype), w.numel(), lib.stream())
+             lib.dtype_code(out.dtype), w.numel(), lib.stream())
     return out
 
 

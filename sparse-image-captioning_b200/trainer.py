@@ -132,6 +132,8 @@ class OrtTrainer:
         self.sp_out = torch.zeros(3, device=self.dev)
         self.sp_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._ws = {}
+        self.premask = True   # False: mask inside the GEMM operand prologue (K1 fused variant)
+        self._wm, self._wm_step = {}, {}
 
     # ---------------------------------------------------------------------------------------------------------
     def _group(self, table, first, count):
@@ -246,6 +248,19 @@ class OrtTrainer:
         W, S, mode, U, seed, stream = self._mask_args(wname, count)
         b = self._group(self.p, wname.replace(".weight", ".bias"), count) if bias else None
         p = p if self.training else 0.0
+        if self.adt == torch.bfloat16 and self.premask:
+            # bf16 training at M >= 1800 rows: W (.) m is materialised ONCE per step as a bf16 TMA operand; masking in
+            # the operand prologue would redo sigmoid + Philox for every 128-row tile ("K1: where to mask")
+            key = (wname, count)
+            wm = self._wm.get(key)
+            if wm is None:
+                wm = self._wm[key] = torch.empty(W.shape, device=self.dev, dtype=torch.bfloat16)
+            if self._wm_step.get(key) != (self.step_id, self.training):
+                K.apply_mask(W, S, mode, uniforms=U, seed=seed, stream_id=stream, out=wm)
+                self._wm_step[key] = (self.step_id, self.training)
+            K.linear_dropout(x, wm, b, residual=residual, relu=relu, out=out, p=p, drop_seed=self.seed + 1,
+                             drop_stream=self._drop_stream(site))
+            return out
         K.linear_dropout(x, W, b, mask=S, mask_mode=mode, uniforms=U, seed=seed, stream_id=stream, residual=residual,
                          relu=relu, out=out, p=p, drop_seed=self.seed + 1, drop_stream=self._drop_stream(site))
         return out

@@ -1,0 +1,77 @@
+"""CPU tier, world_size 2 over gloo: the data-parallel recipe of sparse_caption_b200/distributed.py reproduces the
+single-process gradient — images sharded by rank, each rank's loss normalised by the GLOBAL token count, SUM
+all-reduce of weight AND mask-logit gradients, same Bernoulli uniforms on every rank.  The per-rank compute is done
+with the CPU oracle (this tier has no GPU); the GPU trainer calls the same helpers."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _grads(z, img_lo, img_hi, denom, S=2):
+    from oracle import ort_oracle as O
+    cfg, full = z["cfg"], z["w"]
+    W = {k: v.clone().requires_grad_(True) for k, v in full.items()
+         if v.is_floating_point() and not k.endswith(".pe") and not k.endswith("_pruning_mask")}
+    Sg = {k: full[k + "_pruning_mask"].clone().requires_grad_(True) for k in z["u"]}
+    eff = dict(W)
+    for k in z["u"]:
+        p = torch.sigmoid(Sg[k])
+        m = (z["u"][k] < p).float()
+        eff[k] = (p + (m - p).detach()) * W[k]
+    eff["model.tgt_embed.1.pe"] = full["model.tgt_embed.1.pe"]
+    rows = slice(img_lo * S, img_hi * S)
+    lp = O.forward_tf(eff, cfg, z["att_feats"][img_lo:img_hi], z["boxes"][img_lo:img_hi], z["seqs"][rows], None)
+    tgt, msk = z["seqs"][rows, 1:], z["masks"][rows, 1:]
+    loss = -(lp.gather(2, tgt.unsqueeze(2)).squeeze(2) * msk).sum() / denom
+    loss.backward()
+    names = sorted(W)
+    flat_w = torch.cat([W[k].grad.reshape(-1) for k in names])
+    flat_s = torch.cat([Sg[k].grad.reshape(-1) for k in sorted(Sg)])
+    return flat_w, flat_s
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from sparse_caption_b200 import distributed as D
+    from tests import golden_io
+    z = golden_io.load("ort_prune_tiny")
+    B = z["att_feats"].shape[0]
+    lo, hi = D.shard_range(B, rank, world)
+    T = z["seqs"].shape[1] - 1
+    denom = D.global_token_count(z["masks"][lo * 2: hi * 2], T)
+    gw, gs = _grads(z, lo, hi, denom)
+    ar = D.make_all_reduce()
+    ar(gw)
+    ar(gs)
+    if rank == 0:
+        torch.save({"gw": gw, "gs": gs, "denom": denom}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gradients_equal_single_process(tmp_path):
+    sys.path.insert(0, ROOT)
+    from sparse_caption_b200 import distributed as D
+    assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert D.make_all_reduce() is None  # not initialised -> single process
+    out = str(tmp_path / "ddp.pt")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    from tests import golden_io
+    z = golden_io.load("ort_prune_tiny")
+    T = z["seqs"].shape[1] - 1
+    denom = z["masks"][:, 1: T + 1].sum()
+    assert float(got["denom"]) == float(denom)
+    gw, gs = _grads(z, 0, z["att_feats"].shape[0], denom)
+    torch.testing.assert_close(got["gw"], gw, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(got["gs"], gs, rtol=1e-4, atol=1e-7)

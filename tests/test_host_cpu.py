@@ -1,0 +1,151 @@
+"""CPU tier: host-side logic of the drop-in classes (no kernels run): parameter naming vs the reference, PruningMixin
+bookkeeping, mask schedulers, state-dict export, CSR packing, loud failure without CUDA."""
+import pytest
+import torch
+
+from oracle import ort_oracle as O
+from tests import golden_io
+
+
+def _cfg(**kw):
+    c = dict(d_model=64, dim_feedforward=128, num_layers=2, num_heads=4, drop_prob_src=0.5, max_seq_length=8, att_feat_size=96,
+             vocab_size=50, eos_token_id=3, bos_token_id=2, unk_token_id=1, pad_token_id=0, prune_type="supermask",
+             prune_mask_freeze_scope="", prune_supermask_init=5.0)
+    c.update(kw)
+    return c
+
+
+def test_reference_checkpoints_load_strict():
+    """Parameter names / shapes equal the reference's (fixtures store the reference's own state-dict keys)."""
+    import sparse_caption_b200.relation_transformer as R
+    for name, model in (("ort_tiny", "relation_transformer"), ("ort_prune_tiny", "relation_transformer_prune")):
+        z = golden_io.load(name)
+        m = R.get_model(model)(z["cfg_dict"])
+        m.load_state_dict(z["w"], strict=True)
+    z = golden_io.load("acort_tiny")
+    m = R.get_model("relation_transformer")(z["cfg_dict"])
+    m.load_state_dict(z["w"], strict=True)
+    assert m.model.encoder.layers[0] is m.model.encoder.layers[1]  # share_layer (0,0,1,1)
+    assert len(m.model.decoder.layers[0].self_attn.linears) == 3    # share_att 'kv'
+
+
+def test_registry_and_errors():
+    import sparse_caption_b200.relation_transformer as R
+    assert set(R.MODEL_REGISTRY) >= {"relation_transformer", "relation_transformer_prune"}
+    with pytest.raises(ValueError):
+        R.get_model("nope")
+    m = R.get_model("relation_transformer")(_cfg())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(att_feats=torch.zeros(1, 3, 96), boxes=torch.zeros(1, 3, 4), mode="sample", opt={})
+
+
+def test_pruning_mixin_bookkeeping():
+    import sparse_caption_b200.relation_transformer as R
+    z = golden_io.load("ort_prune_tiny")
+    m = R.get_model("relation_transformer_prune")(z["cfg_dict"])
+    m.load_state_dict(z["w"], strict=True)
+    masks = m.all_pruning_masks()
+    weights = m.all_pruned_weights()
+    assert len(masks) == len(weights) == len([k for k in z["w"] if k.endswith("_pruning_mask")])
+    assert m.total_mask_params == sum(p.numel() for _, p in masks)
+    sp, nnz, per, names = m.all_mask_sparsities
+    logits = [p for _, p in masks]
+    ref_nnz = sum(O.binarize_logits(p).sum() for p in logits)
+    assert float(nnz) == float(ref_nnz)
+    assert abs(float(sp) - (1 - float(ref_nnz) / m.total_mask_params)) < 1e-6
+    # sparsity loss value + straight-through gradient against the oracle
+    loss = m.compute_sparsity_loss(0.8, 7.5, 30, 100)
+    ref, _ = O.sparsity_loss(logits, 0.8, 7.5, 30, 100)
+    torch.testing.assert_close(loss.detach().float(), ref.float(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(loss.detach().float(), z["sparsity_loss"], rtol=1e-5, atol=1e-7)
+    loss.backward()
+    p0 = logits[0]
+    sig = torch.sigmoid(p0.detach())
+    import math
+    anneal = (1 + math.cos(0.3 * math.pi)) / 2
+    sign = 1.0 if 0.8 - float(sp) >= 0 else -1.0
+    expect = sign / m.total_mask_params * 7.5 * (1 - anneal) * sig * (1 - sig)
+    torch.testing.assert_close(p0.grad, expect, rtol=1e-4, atol=1e-12)
+    # dense / sparse export round trip (prune.py:176-226, model_utils.py:110-118)
+    dense = m.state_dict_dense(discard_pruning_mask=True, prune_weights=True)
+    assert not any(k.endswith("_pruning_mask") for k in dense)
+    eff = O.effective_state_dict(z["w"], "supermask")
+    for k in dense:
+        if k in eff:
+            torch.testing.assert_close(dense[k], eff[k])
+    sparse = m.state_dict_sparse()
+    from sparse_caption_b200.prune import densify_state_dict
+    back = densify_state_dict(sparse)
+    for k in dense:
+        torch.testing.assert_close(back[k], dense[k])
+    dm = R.get_model("relation_transformer")(z["cfg_dict"])
+    dm.load_state_dict(back, strict=True)  # eval_model.py:64-77 flow
+
+
+@pytest.mark.parametrize("mask_type", ["mag_blind", "mag_uniform", "mag_dist", "snip"])
+def test_one_shot_mask_updates(mask_type):
+    """update_masks_once hits the target sparsity (reference tests/test_prune.py:111-117 tolerance 0.05)."""
+    import sparse_caption_b200.relation_transformer as R
+    torch.manual_seed(8888)
+    m = R.get_model("relation_transformer_prune")(_cfg(prune_type=mask_type))
+    assert float(m.all_mask_sparsities[0]) == 0.0
+    if mask_type == "snip":
+        for p in m.all_pruning_masks(named=False):
+            p.grad = torch.rand_like(p)
+    m.update_masks_once(0.7)
+    assert abs(float(m.all_mask_sparsities[0]) - 0.7) < 0.05
+    if mask_type == "mag_uniform":
+        assert all(abs(float(s) - 0.7) < 0.05 for s in m.all_mask_sparsities[2])
+
+
+def test_gradual_schedule():
+    import sparse_caption_b200.relation_transformer as R
+    m = R.get_model("relation_transformer_prune")(_cfg(prune_type="mag_grad_uniform"))
+    seen = []
+    for step in range(0, 3001, 500):
+        m.update_masks_gradual(0.9, step, start_step=1000, prune_steps=2, prune_frequency=1000)
+        seen.append(round(float(m.all_mask_sparsities[0]), 2))
+    assert seen[0] == 0.0 and seen[2] == 0.0 and abs(seen[4] - 0.79) < 0.03 and abs(seen[6] - 0.9) < 0.03
+
+
+def test_csr_pack_matches_reference_sparse_export():
+    from sparse_caption_b200.kernels import CsrWeight
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(37, 64, generator=g) * (torch.rand(37, 64, generator=g) > 0.9)
+    w[5] = 0
+    csr = CsrWeight(w, torch.float32)
+    coo = w.to_sparse().coalesce()  # what state_dict_sparse stores
+    assert csr.nnz == coo.values().numel()
+    assert torch.equal(csr.val, coo.values())
+    assert torch.equal(csr.col.to(torch.int64) & 0xFFFF, coo.indices()[1])
+    rows = torch.repeat_interleave(torch.arange(37), (csr.row_ptr[1:] - csr.row_ptr[:-1]).long())
+    assert torch.equal(rows, coo.indices()[0])
+    assert CsrWeight(coo, torch.float32).nnz == csr.nnz  # accepts the reference's COO tensors directly
+
+
+def test_att_parts_and_cfg():
+    from sparse_caption_b200.engine import ModelCfg, _att_parts, _parse_penalty
+    assert _att_parts(None) == (0, 1, 2, 3) and _att_parts("kv") == (0, 1, 1, 2) and _att_parts("qk") == (0, 0, 1, 2)
+    c = ModelCfg(_cfg(share_layer_decoder=(0, 0, 1, 1), num_layers=4))
+    assert c.uids("dec") == [0, 0, 1, 1] and c.uids("enc") == [0, 1, 2, 3]
+    assert _parse_penalty("wu_0.5") == (1, 0.5) and _parse_penalty("") == (0, 0.0) and _parse_penalty("avg_0") == (2, 0.0)
+    with pytest.raises(ValueError):
+        ModelCfg(dict(d_model=64))
+
+
+def test_masked_layer_attributes_and_cpu_refusal():
+    from sparse_caption_b200.masked_layer import MaskedEmbedding, MaskedLinear
+    lin = MaskedLinear(16, 8, "supermask", 5.0)
+    assert lin.weight_pruning_mask.shape == lin.weight.shape and lin.weight_pruning_mask.requires_grad
+    assert float(lin.weight_pruning_mask.mean()) == 5.0 and lin.mask_trainable
+    assert set(dict(lin.named_parameters())) == {"weight", "bias", "weight_pruning_mask"}
+    frozen = MaskedLinear(16, 8, "mask_freeze", None)
+    assert not frozen.weight_pruning_mask.requires_grad and float(frozen.weight_pruning_mask.mean()) == 1.0
+    emb = MaskedEmbedding(10, 8, "snip", None)
+    assert emb.mask_trainable and emb.weight_pruning_mask.requires_grad
+    with pytest.raises(AssertionError):
+        MaskedLinear(4, 4, "bogus", 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lin(torch.zeros(2, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        emb(torch.zeros(2, dtype=torch.long))
