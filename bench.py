@@ -99,7 +99,7 @@ def cpu_arm(steps, warmup, images):
     return images * steps / dt, dt / steps, cores
 
 
-def train_arm(args, dev, world, dist_mod=None, rank0_only=False):
+def train_arm(args, dev, world, rank, dist_mod=None):
     """SMP training arm (BASELINE.json configs[1]): ORT supermask training, bf16 tensor-core GEMMs with fp32 master
     weights + fp32 mask logits, 5 captions/image with the encoder run once, Bernoulli masks + dropout + sparsity
     loss + clip + Adam inside the timed step.  Single-GPU here; the N-GPU variant adds the NCCL all-reduce of the
@@ -108,11 +108,12 @@ def train_arm(args, dev, world, dist_mod=None, rank0_only=False):
     from sparse_caption_b200.engine import ModelCfg
     from sparse_caption_b200.trainer import OrtTrainer
     cfg = ModelCfg(dict(CFG, max_seq_length=17))
+    from sparse_caption_b200 import distributed as D
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
-    tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888)
+    tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888)  # same mask seed on every rank
     B, S, T = args.train_images, 5, 17
-    g = torch.Generator().manual_seed(8888)
-    att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888, pin=True)
+    g = torch.Generator().manual_seed(8888 + rank)
+    att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank, pin=True)
     R = B * S
     seqs = torch.zeros(R, T + 1, dtype=torch.long)
     masks = torch.zeros(R, T + 1)
@@ -125,25 +126,37 @@ def train_arm(args, dev, world, dist_mod=None, rank0_only=False):
         masks[r, :n + 2] = 1
     seqs, masks = seqs.pin_memory(), masks.pin_memory()
     opt = dict(lr=3e-4, sparsity_target=0.95, sparsity_weight=30.0, current_step=100, max_step=1000)
+    all_reduce = D.make_all_reduce()  # NCCL SUM over the flat weight + mask-logit gradient buffers when world > 1
+    gtok = D.global_token_count(masks.to(dev), T)
 
     def step():
-        return tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt)
+        return tr.train_step(att, boxes, seqs, masks, seq_per_img=S, all_reduce=all_reduce, global_tokens=gtok, **opt)
+
+    def barrier():
+        if dist_mod is not None:
+            dist_mod.barrier()
+        torch.cuda.synchronize(dev)
 
     for _ in range(3):
         step()
-    torch.cuda.synchronize(dev)
+    barrier()
     before = lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.train_steps):
         loss = step()
     e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / args.train_steps
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist_mod is not None:
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+    ms = float(t[0]) / args.train_steps
     launches = (lib.launch_count - before) // args.train_steps
+    if rank != 0:
+        return None
     # GEMM share / tensor roofline from one instrumented step
     lib.profile = []
-    step()
+    tr.train_step(att, boxes, seqs, masks, seq_per_img=S, all_reduce=None, global_tokens=gtok, **opt)  # rank-local
     torch.cuda.synchronize(dev)
     prof, lib.profile = lib.profile, None
     gemm_ms = sum(a.elapsed_time(b) for n, m, a, b in prof if m and m[0] == "gemm_bf16")
@@ -151,7 +164,8 @@ def train_arm(args, dev, world, dist_mod=None, rank0_only=False):
     tot_ms = sum(a.elapsed_time(b) for n, m, a, b in prof)
     peaks = load_peaks()
     tf = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else 0.0
-    return {"metric": "smp_train_images_per_sec", "value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+    return {"metric": "smp_train_images_per_sec", "value": world * B / (ms / 1e3), "unit": "images/s", "n_gpus": world, "ms_per_step": ms,
+            "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce(sum) of flat fp32 weight+logit gradients after the backward, 2 calls/step",
             "images_per_gpu_per_step": B, "captions_per_image": S, "positions": T, "dtype": "bf16 GEMM / fp32 master+logits",
             "loss": float(loss), "gpu_launches_per_step": launches, "h2d_bytes_per_step": att.numel() * 4 + boxes.numel() * 4 + seqs.numel() * 8 + masks.numel() * 4,
             "includes": "H2D of the batch, Bernoulli masks, dropout, sparsity loss, clip + Adam (2 groups)",
@@ -274,6 +288,10 @@ def main():
     value = world * B * args.steps / (ms_dev / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
+    train = None
+    if not args.no_train:
+        train = train_arm(args, dev, world, rank, dist_mod=dist)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -314,10 +332,6 @@ def main():
                 "launches": g["n"], "avg_launch_us": 1e3 * g["ms"] / max(1, g["n"]),
                 "share_of_step": g["ms"] / total_ms if total_ms else None,
                 "kernel_time_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}}
-
-    train = None
-    if not args.no_train:
-        train = train_arm(args, dev, world, dist_mod=None, rank0_only=True)
 
     cpu = None
     if not args.no_cpu_baseline:
