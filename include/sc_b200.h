@@ -94,6 +94,20 @@ int sc_box_attention_fwd(const void* q, const void* k, const void* v, int ldq, i
                          const float* boxes, const float* wg_w, const float* wg_b, const float* att_mask, void* out,
                          int ldo, int B, int N, int h, int dk, int trig, float wave_len, sc_stream_t stream);
 
+/* K4 (inference split) — the geometry bias of EVERY encoder layer from one evaluation of the sin/cos embedding
+ * (models/relation_transformer.py:179-183, 196-256: the reference rebuilds emb[B,N,N,64] in each layer although it only
+ * depends on the boxes).  wg_w fp32 [layers*h, 64 (trig) | 4], wg_b fp32 [layers*h];
+ * bias fp32 [layers, B, h, N, N] = log(max(relu(WG . emb + b), 1e-6)). */
+int sc_box_bias_all(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int layers,
+                    int h, int trig, float wave_len, sc_stream_t stream);
+
+/* K4 (inference split) — box_attention given the bias of one layer (models/relation_transformer.py:258-293):
+ * out = softmax(bias + masked_fill(QK^T/sqrt(dk), mask==0, -1e9)) V.  bf16, d_k = 64, N <= 128; one warp per
+ * (image, head) on mma.sync tiles.  bias fp32 [B, h, N, N]; att_mask fp32 [B,N] or NULL. */
+int sc_bias_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype,
+                          const float* bias, const float* att_mask, void* out, int ldo, int B, int N, int h, int dk,
+                          sc_stream_t stream);
+
 /* K5 — decoder self-attention, one new token per row, append-to-cache + attention
  * (models/transformer.py:230-295 incremental branch).  cache_[kv]: [slots][R][D]; anc: int32 [R, anc_ld]
  * ancestor row of slot s is anc[r][s / slot_div].  Attends slots [0,n_prev) + the new token; the new k,v are
@@ -109,11 +123,16 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
 
 /* K7 — log-softmax + beam_step + finished-beam handling of batch_beam_search, group_size 1
  * (models/caption_model.py:56-111, 151-226; utils/model_utils.py:121-146).
- * penalty_kind: 0 "", 1 "wu_<alpha>", 2 "avg_<alpha>".  seq/lp/anc are ping-pong buffers [B*beam, L]. */
+ * penalty_kind: 0 "", 1 "wu_<alpha>", 2 "avg_<alpha>".  seq/lp/anc are ping-pong buffers [B*beam, L].
+ * Two launches: one CTA per (image, beam) row reads its logits row once (log-softmax statistics + the row's top-`beam`
+ * candidates by final score), then one small CTA per image merges the rows and does the bookkeeping.
+ * workspace: sc_beam_step_workspace_bytes(B, beam) bytes of device scratch, 16-byte aligned. */
+int sc_beam_step_workspace_bytes(int B, int beam);
 int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
                  int decoding_constraint, int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out,
                  const float* lp_in, float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out,
-                 int* done_seq, float* done_lp, double* done_p, int* done_count, sc_stream_t stream);
+                 int* done_seq, float* done_lp, double* done_p, int* done_count, void* workspace, size_t workspace_bytes,
+                 sc_stream_t stream);
 
 /* greedy branch of _generate_captions (models/transformer.py:507-561) */
 int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, int* seq,

@@ -310,87 +310,86 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
   return r;
 }
 
-// kRegs: the row is read from HBM exactly once into registers (V <= 256*40); otherwise it is re-read (L2 hits).
+// Phase A — one CTA per ROW (image, beam): the row is read from HBM exactly once into registers (kRegs: V <= 256*40;
+// otherwise re-read through L2), log-softmax statistics, then the row's top-NB candidates by FINAL score
+// (sum + log-prob, ties to the smaller flat index == stable descending sort) -> workspace.
 template <int NB, bool kRegs>
-__global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs a) {
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(kBeamThreads) beam_row_kernel(const BeamArgs a, float* __restrict__ ws_stats,
+                                                                Cand* __restrict__ ws_cand) {
+  const int r = blockIdx.x;            // row = b*NB + k
+  const int k = r % NB;
+  if (a.t == 0 && k != 0) return;      // first step: every beam holds BOS, only beam 0 is expanded
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V;
-  const int rows = (a.t == 0) ? 1 : NB;  // first step: every beam holds BOS, only beam 0 is expanded
   __shared__ float s_red[kBeamWarps];
-  __shared__ float s_mx[NB], s_ls[NB], s_mx2[NB], s_ls2[NB];
   __shared__ Cand s_top[kBeamWarps][NB];
-  __shared__ Cand s_final[NB];
-  __shared__ int s_pos, s_last;
   // init_logprobs (t == 0) are never temperature-scaled (caption_model.py:135, 218)
   const float T = (a.t == 0) ? 1.0f : a.temperature;
-
+  const float* x = a.logits + (size_t)r * V;
+  float xr[kRegs ? kBeamRegs : 1];
+  float mx = -INFINITY;
+  if (kRegs) {
+#pragma unroll
+    for (int i = 0; i < kBeamRegs; ++i) {
+      const int c = tid + i * kBeamThreads;
+      xr[i] = c < V ? __ldg(x + c) : -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < kBeamRegs; ++i) mx = fmaxf(mx, xr[i]);
+  } else {
+    for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
+  }
+  mx = block_max(mx, s_red);
+  float se = 0.f;
+  if (kRegs) {
+#pragma unroll
+    for (int i = 0; i < kBeamRegs; ++i) se += expf(xr[i] - mx);  // exp(-inf) = 0 for the padding lanes
+  } else {
+    for (int i = tid; i < V; i += kBeamThreads) se += expf(x[i] - mx);
+  }
+  se = block_sum(se, s_red);
+  // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
+  const float ls = logf(se);
+  float mx2 = 0.f, ls2 = 0.f;
+  if (T != 1.0f) {
+    // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
+    mx2 = (0.f - ls) / T;
+    float se2 = 0.f;
+    if (kRegs) {
+#pragma unroll
+      for (int i = 0; i < kBeamRegs; ++i) se2 += expf(((xr[i] - mx) - ls) / T - mx2);
+    } else {
+      for (int i = tid; i < V; i += kBeamThreads) se2 += expf(((x[i] - mx) - ls) / T - mx2);
+    }
+    ls2 = logf(block_sum(se2, s_red));
+  }
+  if (tid == 0) {
+    ws_stats[r * 4 + 0] = mx; ws_stats[r * 4 + 1] = ls; ws_stats[r * 4 + 2] = mx2; ws_stats[r * 4 + 3] = ls2;
+  }
   Cand top[NB];
 #pragma unroll
   for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
-
-  for (int k = 0; k < rows; ++k) {
-    const float* x = a.logits + ((size_t)b * NB + k) * V;
-    float xr[kRegs ? kBeamRegs : 1];
-    float mx = -INFINITY;
-    if (kRegs) {
+  const float base = a.sum[r];
+  const int prev = (a.constraint && a.t > 0) ? a.seq_in[(size_t)r * a.L + a.t - 1] : -1;
+  if (kRegs) {
 #pragma unroll
-      for (int i = 0; i < kBeamRegs; ++i) {
-        const int c = tid + i * kBeamThreads;
-        xr[i] = c < V ? __ldg(x + c) : -INFINITY;
-      }
-#pragma unroll
-      for (int i = 0; i < kBeamRegs; ++i) mx = fmaxf(mx, xr[i]);
-    } else {
-      for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
-    }
-    mx = block_max(mx, s_red);
-    float se = 0.f;
-    if (kRegs) {
-#pragma unroll
-      for (int i = 0; i < kBeamRegs; ++i) se += expf(xr[i] - mx);  // exp(-inf) = 0 for the padding lanes
-    } else {
-      for (int i = tid; i < V; i += kBeamThreads) se += expf(x[i] - mx);
-    }
-    se = block_sum(se, s_red);
-    // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
-    const float ls = logf(se);
-    float mx2 = 0.f, ls2 = 0.f;
-    if (T != 1.0f) {
-      // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
-      mx2 = (0.f - ls) / T;
-      float se2 = 0.f;
-      if (kRegs) {
-#pragma unroll
-        for (int i = 0; i < kBeamRegs; ++i) se2 += expf(((xr[i] - mx) - ls) / T - mx2);
-      } else {
-        for (int i = tid; i < V; i += kBeamThreads) se2 += expf(((x[i] - mx) - ls) / T - mx2);
-      }
-      ls2 = logf(block_sum(se2, s_red));
-    }
-    if (tid == 0) { s_mx[k] = mx; s_ls[k] = ls; s_mx2[k] = mx2; s_ls2[k] = ls2; }
-    const float base = a.sum[b * NB + k];
-    const int prev = (a.constraint && a.t > 0) ? a.seq_in[((size_t)b * NB + k) * a.L + a.t - 1] : -1;
-    if (kRegs) {
-#pragma unroll
-      for (int i = 0; i < kBeamRegs; ++i) {
-        const int c = tid + i * kBeamThreads;
-        if (c < V) {
-          float lp = (xr[i] - mx) - ls;
-          if (T != 1.0f) lp = (lp / T - mx2) - ls2;
-          if (c == prev) lp = -INFINITY;
-          Cand cd; cd.s = base + lp; cd.idx = k * V + c;
-          topk_insert<NB>(top, cd);
-        }
-      }
-    } else {
-      for (int i = tid; i < V; i += kBeamThreads) {
-        float lp = (x[i] - mx) - ls;
+    for (int i = 0; i < kBeamRegs; ++i) {
+      const int c = tid + i * kBeamThreads;
+      if (c < V) {
+        float lp = (xr[i] - mx) - ls;
         if (T != 1.0f) lp = (lp / T - mx2) - ls2;
-        if (i == prev) lp = -INFINITY;
-        Cand cd; cd.s = base + lp; cd.idx = k * V + i;
+        if (c == prev) lp = -INFINITY;
+        Cand cd; cd.s = base + lp; cd.idx = k * V + c;
         topk_insert<NB>(top, cd);
       }
+    }
+  } else {
+    for (int i = tid; i < V; i += kBeamThreads) {
+      float lp = (x[i] - mx) - ls;
+      if (T != 1.0f) lp = (lp / T - mx2) - ls2;
+      if (i == prev) lp = -INFINITY;
+      Cand cd; cd.s = base + lp; cd.idx = k * V + i;
+      topk_insert<NB>(top, cd);
     }
   }
   // warp merge: every lane offers its sorted list; NB rounds of arg-best over the heads
@@ -430,14 +429,46 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs 
       }
 #pragma unroll
       for (int w = 0; w < kBeamWarps; ++w) if (w == bw) heads[w]++;
+      ws_cand[(size_t)r * NB + rnd] = best;
+    }
+  }
+}
+
+// Phase B — one small CTA per image: NB-way merge of the rows' sorted candidate lists, then the beam bookkeeping
+// (caption_model.py:84-110, 195-210).
+constexpr int kMergeThreads = 64;
+template <int NB>
+__global__ void __launch_bounds__(kMergeThreads) beam_merge_kernel(const BeamArgs a, const float* __restrict__ ws_stats,
+                                                                   const Cand* __restrict__ ws_cand) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int V = a.V;
+  const int rows = (a.t == 0) ? 1 : NB;
+  __shared__ Cand s_final[NB];
+  __shared__ int s_pos, s_last;
+  const float T = (a.t == 0) ? 1.0f : a.temperature;
+  if (tid == 0) {
+    int heads[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) heads[k] = 0;
+    for (int rnd = 0; rnd < NB; ++rnd) {
+      int bk = 0;
+      Cand best; best.s = -INFINITY; best.idx = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        Cand c; c.s = -INFINITY; c.idx = 0x7fffffff;
+        if (k < rows && heads[k] < NB) c = ws_cand[((size_t)b * NB + k) * NB + heads[k]];
+        if (better(c, best)) { best = c; bk = k; }
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) if (k == bk) heads[k]++;
       s_final[rnd] = best;
     }
   }
   __syncthreads();
 
-  // ---- bookkeeping (caption_model.py:84-110, 195-210) ----
   const int L = a.L, t = a.t;
-  for (int e = tid; e < NB * L; e += kBeamThreads) {
+  for (int e = tid; e < NB * L; e += kMergeThreads) {
     const int j = e / L, s = e - j * L;
     const int parent = s_final[j].idx / V;
     const size_t src = ((size_t)b * NB + parent) * L + s, dst = ((size_t)b * NB + j) * L + s;
@@ -449,8 +480,9 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs 
       const int word = s_final[j].idx - parent * V;
       a.seq_out[dst] = word;
       const float x = a.logits[((size_t)b * NB + parent) * V + word];
-      float lp = (x - s_mx[parent]) - s_ls[parent];
-      if (T != 1.0f) lp = (lp / T - s_mx2[parent]) - s_ls2[parent];
+      const float* st = ws_stats + ((size_t)b * NB + parent) * 4;
+      float lp = (x - st[0]) - st[1];
+      if (T != 1.0f) lp = (lp / T - st[2]) - st[3];
       a.lp_out[dst] = lp;
       a.anc_out[dst] = b * NB + parent;
     } else {
@@ -487,7 +519,7 @@ __global__ void __launch_bounds__(kBeamThreads) beam_step_kernel(const BeamArgs 
       __syncthreads();
       const int pos = s_pos, last = s_last;
       if (pos < NB) {
-        for (int s = tid; s < L; s += kBeamThreads) {
+        for (int s = tid; s < L; s += kMergeThreads) {
           for (int m = last; m > pos; --m) {
             a.done_seq[((size_t)b * NB + m) * L + s] = a.done_seq[((size_t)b * NB + m - 1) * L + s];
             a.done_lp[((size_t)b * NB + m) * L + s] = a.done_lp[((size_t)b * NB + m - 1) * L + s];
@@ -562,6 +594,10 @@ __global__ void __launch_bounds__(256) reorder_rows_kernel(const uint4* __restri
 
 }  // namespace
 
+// tensor-path cross-attention (sc_mma_attention.cu); SC_ERR_UNSUPPORTED = shape not served, nothing launched
+int sc_cross_attn_mma_launch(const void* q, int ldq, const void* mem_k, const void* mem_v, int ldm, const float* att_mask,
+                             void* out, int ldo, int B, int beam, int N, int h, cudaStream_t stream);
+
 extern "C" {
 
 int sc_decode_self_attn_step(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype,
@@ -601,6 +637,10 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
   SC_CHECK(beam <= kMaxBeam, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: beam=%d > %d", beam, kMaxBeam);
   SC_CHECK(N <= 32 * kMaxKeyPass, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: N=%d > %d memory slots", N, 32 * kMaxKeyPass);
   SC_CHECK(dk <= 64, SC_ERR_UNSUPPORTED, "sc_decode_cross_attn_step: d_k=%d > 64", dk);
+  if (dtype == SC_BF16 && dk == 64) {
+    const int rc = sc_cross_attn_mma_launch(q, ldq, mem_k, mem_v, ldm, att_mask, out, ldo, B, beam, N, h, stream);
+    if (rc != SC_ERR_UNSUPPORTED) return rc;
+  }
   const int esz = dtype == SC_F32 ? 4 : 2;
   const size_t per_warp = (size_t)N * (2 * dk * esz + 16) + (size_t)beam * dk * 4;
   int warps = (int)((96 * 1024) / per_warp);
@@ -636,25 +676,36 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
   return SC_OK;
 }
 
+size_t sc_beam_step_workspace_bytes_impl(int B, int beam) {
+  return (size_t)B * beam * (4 * sizeof(float) + (size_t)beam * sizeof(Cand));
+}
+
 int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
                  int decoding_constraint, int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out,
                  const float* lp_in, float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out,
-                 int* done_seq, float* done_lp, double* done_p, int* done_count, cudaStream_t stream) {
+                 int* done_seq, float* done_lp, double* done_p, int* done_count, void* workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
   SC_CHECK(B > 0 && beam >= 1 && beam <= kMaxBeam, SC_ERR_UNSUPPORTED, "sc_beam_step: beam=%d not in [1,%d]", beam, kMaxBeam);
   SC_CHECK(V >= beam && L > 0 && t >= 0 && t < L, SC_ERR_SHAPE, "sc_beam_step: V=%d L=%d t=%d", V, L, t);
   SC_CHECK(temperature > 0.f, SC_ERR_SHAPE, "sc_beam_step: temperature must be > 0");
+  SC_CHECK(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= sc_beam_step_workspace_bytes_impl(B, beam),
+           SC_ERR_WORKSPACE, "sc_beam_step: workspace of %zu bytes (16-byte aligned) needed, got %zu",
+           sc_beam_step_workspace_bytes_impl(B, beam), workspace_bytes);
   BeamArgs a;
   a.logits = logits; a.B = B; a.beam = beam; a.V = V; a.L = L; a.t = t; a.eos = eos; a.pad = pad;
   a.temperature = temperature; a.constraint = decoding_constraint; a.penalty_kind = penalty_kind;
   a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
   a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
   a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
-#define BEAM_LAUNCH(NBV)                                                              \
-  do {                                                                                 \
-    if (regs) beam_step_kernel<NBV, true><<<B, kBeamThreads, 0, stream>>>(a);           \
-    else beam_step_kernel<NBV, false><<<B, kBeamThreads, 0, stream>>>(a);               \
-  } while (0)
+  float* ws_stats = (float*)workspace;
+  Cand* ws_cand = (Cand*)(ws_stats + (size_t)B * beam * 4);
   const bool regs = V <= kBeamThreads * kBeamRegs;
+#define BEAM_LAUNCH(NBV)                                                                                     \
+  do {                                                                                                        \
+    if (regs) beam_row_kernel<NBV, true><<<B * NBV, kBeamThreads, 0, stream>>>(a, ws_stats, ws_cand);          \
+    else beam_row_kernel<NBV, false><<<B * NBV, kBeamThreads, 0, stream>>>(a, ws_stats, ws_cand);              \
+    beam_merge_kernel<NBV><<<B, kMergeThreads, 0, stream>>>(a, ws_stats, ws_cand);                             \
+  } while (0)
   switch (beam) {
     case 1: BEAM_LAUNCH(1); break;
     case 2: BEAM_LAUNCH(2); break;
@@ -665,9 +716,12 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
     case 7: BEAM_LAUNCH(7); break;
     default: BEAM_LAUNCH(8); break;
   }
+#undef BEAM_LAUNCH
   SC_LAUNCH_CHECK("sc_beam_step");
   return SC_OK;
 }
+
+int sc_beam_step_workspace_bytes(int B, int beam) { return (int)sc_beam_step_workspace_bytes_impl(B, beam); }
 
 int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, int* seq,
                    float* seq_lp, int* tokens, int* unfinished, int* live_count, cudaStream_t stream) {

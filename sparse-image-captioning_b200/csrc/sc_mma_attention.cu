@@ -1,0 +1,384 @@
+// Warp-level tensor-core attention over SHORT key sets (36 boxes, <= 128), bf16 in / fp32 accumulate.
+//
+//   sc_box_bias_all        BoxRelationalEmbedding + WG + ReLU + log for EVERY encoder layer in one pass
+//                          (sparse_caption/models/relation_transformer.py:179-183,196-256).  The reference recomputes
+//                          the [B,N,N,64] sin/cos embedding in each of the 6 layers; the embedding only depends on the
+//                          boxes, so it is evaluated once per image pair and dotted with all L*h WG rows.
+//   sc_bias_attention_fwd  box_attention (relation_transformer.py:258-293) given that bias:
+//                          softmax(bias + mask(QK^T/sqrt(dk))) V, one WARP per (image, head).
+//   cross-attention step   (sparse_caption/models/transformer.py:255-256,276,285-295) one warp per (image, head), the
+//                          `beam` query rows of the image form the M dimension, so memory K/V are read once per image.
+//
+// The key sets are far too short for tcgen05 tiles (M=128/N>=8 with a TMEM round trip per 36x36 product); the products
+// run on mma.sync.m16n8k16 straight out of shared memory (cp.async -> padded rows -> ldmatrix), scores and
+// probabilities never leave registers.  These kernels are bound by the HBM bytes of Q,K,V,O (+ the bias tile).
+#include "sc_common.cuh"
+
+namespace {
+
+constexpr int kDk = 64;               // head dim served by the mma path
+constexpr int kPitch = (kDk + 8) * 2; // 144-byte rows: ldmatrix phases hit 8 distinct 16-byte bank groups
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&t;
+}
+
+// rows [0, rows_pad) of a [*, 64] bf16 slice (row stride ld elements) -> smem rows of kPitch bytes; rows >= n zeroed
+__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, size_t ld, int n, int rows_pad,
+                                           unsigned char* dst, int lane) {
+  for (int idx = lane; idx < rows_pad * 8; idx += 32) {
+    const int r = idx >> 3, c = idx & 7;
+    void* d = dst + r * kPitch + c * 16;
+    if (r < n) cp_async16(d, src + (size_t)r * ld + c * 8);
+    else *(uint4*)d = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// One m-tile (16 query rows starting at m0) of softmax(bias + mask(Q K^T / 8)) V for one warp.
+// sQ/sK/sV: this warp's staged tiles.  Result rows are written back over the Q rows of the m-tile (bf16, kPitch rows).
+template <int NT>
+__device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned char* sK, const unsigned char* sV, int m0,
+                                           int nq, int nk, const float* __restrict__ bias, int bias_ld,
+                                           const float* __restrict__ key_mask, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  // ---- S = Q K^T ----
+  float s[2 * NT][4];
+#pragma unroll
+  for (int n = 0; n < 2 * NT; ++n) { s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f; }
+  const uint32_t qbase = smem_u32(sQ) + (uint32_t)((m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 16);
+  const uint32_t kbase = smem_u32(sK) + (uint32_t)(((lane & 7) + (lane >> 4) * 8) * kPitch + ((lane >> 3) & 1) * 16);
+#pragma unroll
+  for (int ks = 0; ks < kDk / 16; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(qbase + ks * 32, a);
+#pragma unroll
+    for (int np = 0; np < NT; ++np) {
+      uint32_t b[4];
+      ldsm_x4(kbase + np * 16 * kPitch + ks * 32, b);
+      mma_bf16(s[2 * np], a, b[0], b[1]);
+      mma_bf16(s[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- scale, mask, bias, softmax (rows g and g+8 of the tile; a row lives in the 4 lanes of a quad) ----
+  const int r0 = m0 + g, r1 = r0 + 8;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 2 * NT; ++n) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int col = n * 8 + 2 * t + c;
+      float v0 = s[n][c] * 0.125f, v1 = s[n][2 + c] * 0.125f;  // / sqrt(64)
+      if (col < nk) {
+        if (key_mask && key_mask[col] == 0.f) { v0 = -1e9f; v1 = -1e9f; }
+        if (bias) {
+          if (r0 < nq) v0 += bias[(size_t)r0 * bias_ld + col];
+          if (r1 < nq) v1 += bias[(size_t)r1 * bias_ld + col];
+        }
+      } else {
+        v0 = -INFINITY; v1 = -INFINITY;
+      }
+      s[n][c] = v0; s[n][2 + c] = v1;
+      mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < 2 * NT; ++n) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float p0 = __expf(s[n][c] - mx0), p1 = __expf(s[n][2 + c] - mx1);
+      s[n][c] = p0; s[n][2 + c] = p1;
+      sum0 += p0; sum1 += p1;
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+  // ---- O = P V ----
+  float o[kDk / 8][4];
+#pragma unroll
+  for (int n = 0; n < kDk / 8; ++n) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
+  const uint32_t vbase = smem_u32(sV) + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 16);
+#pragma unroll
+  for (int kk = 0; kk < NT; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < kDk / 16; ++dp) {
+      uint32_t b[4];
+      ldsm_x4_trans(vbase + kk * 16 * kPitch + dp * 32, b);
+      mma_bf16(o[2 * dp], a, b[0], b[1]);
+      mma_bf16(o[2 * dp + 1], a, b[2], b[3]);
+    }
+  }
+  // ---- stage the output tile over this m-tile's Q rows (no longer needed) ----
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < kDk / 8; ++n) {
+    *(uint32_t*)(sQ + (m0 + g) * kPitch + (n * 8 + 2 * t) * 2) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
+    *(uint32_t*)(sQ + (m0 + g + 8) * kPitch + (n * 8 + 2 * t) * 2) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+  }
+}
+
+// 16-byte coalesced copy of rows [0, n) of the staged output to global
+__device__ __forceinline__ void store_rows(const unsigned char* sO, int n, __nv_bfloat16* __restrict__ dst, size_t ld, int lane) {
+  for (int idx = lane; idx < n * 8; idx += 32) {
+    const int r = idx >> 3, c = idx & 7;
+    *(uint4*)(dst + (size_t)r * ld + c * 8) = *(const uint4*)(sO + r * kPitch + c * 16);
+  }
+}
+
+struct EncAttnArgs {
+  const __nv_bfloat16* q; const __nv_bfloat16* k; const __nv_bfloat16* v; int ldq, ldk, ldv;
+  const float* bias;      // [B, h, N, N]
+  const float* att_mask;  // [B, N] or nullptr
+  __nv_bfloat16* out; int ldo;
+  int B, N, h, warps;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(128) enc_attn_mma_kernel(const EncAttnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_x[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * a.warps + warp;
+  if (w >= a.B * a.h) return;
+  const int b = w / a.h, hh = w - b * a.h;
+  constexpr int kRows = 16 * NT;
+  unsigned char* sQ = smem_x + (size_t)warp * 3 * kRows * kPitch;
+  unsigned char* sK = sQ + kRows * kPitch;
+  unsigned char* sV = sK + kRows * kPitch;
+  const int N = a.N;
+  const size_t row0 = (size_t)b * N;
+  stage_tile(a.q + row0 * a.ldq + hh * kDk, a.ldq, N, kRows, sQ, lane);
+  stage_tile(a.k + row0 * a.ldk + hh * kDk, a.ldk, N, kRows, sK, lane);
+  stage_tile(a.v + row0 * a.ldv + hh * kDk, a.ldv, N, kRows, sV, lane);
+  cp_async_wait_all();
+  __syncwarp();
+  const float* bias = a.bias + ((size_t)b * a.h + hh) * N * N;
+  const float* km = a.att_mask ? a.att_mask + (size_t)b * N : nullptr;
+  for (int m0 = 0; m0 < N; m0 += 16) attn_mtile<NT>(sQ, sK, sV, m0, N, N, bias, N, km, lane);
+  __syncwarp();
+  store_rows(sQ, N, a.out + row0 * a.ldo + hh * kDk, a.ldo, lane);
+}
+
+struct CrossAttnArgs {
+  const __nv_bfloat16* q; int ldq;
+  const __nv_bfloat16* mk; const __nv_bfloat16* mv; int ldm;
+  const float* att_mask;
+  __nv_bfloat16* out; int ldo;
+  int B, NB, N, h, warps;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256) cross_attn_mma_kernel(const CrossAttnArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_x[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * a.warps + warp;
+  if (w >= a.B * a.h) return;
+  const int b = w / a.h, hh = w - b * a.h;
+  constexpr int kRows = 16 * NT;
+  unsigned char* sQ = smem_x + (size_t)warp * (2 * kRows + 16) * kPitch;
+  unsigned char* sK = sQ + 16 * kPitch;
+  unsigned char* sV = sK + kRows * kPitch;
+  const int N = a.N;
+  stage_tile(a.q + (size_t)b * a.NB * a.ldq + hh * kDk, a.ldq, a.NB, 16, sQ, lane);
+  stage_tile(a.mk + (size_t)b * N * a.ldm + hh * kDk, a.ldm, N, kRows, sK, lane);
+  stage_tile(a.mv + (size_t)b * N * a.ldm + hh * kDk, a.ldm, N, kRows, sV, lane);
+  cp_async_wait_all();
+  __syncwarp();
+  const float* km = a.att_mask ? a.att_mask + (size_t)b * N : nullptr;
+  attn_mtile<NT>(sQ, sK, sV, 0, a.NB, N, nullptr, 0, km, lane);
+  __syncwarp();
+  store_rows(sQ, a.NB, a.out + (size_t)b * a.NB * a.ldo + hh * kDk, a.ldo, lane);
+}
+
+// ---- geometry bias for all layers: bias[l, b, hh, i, j] = log(max(relu(WG_{l,hh} . emb(i,j) + b_{l,hh}), 1e-6)) ----
+struct DimMat8 { float v[8]; };
+
+__global__ void __launch_bounds__(128) box_bias_all_kernel(const float* __restrict__ boxes, const float* __restrict__ wg_w,
+                                                           const float* __restrict__ wg_b, float* __restrict__ bias,
+                                                           int B, int N, int LH, int h, int trig, DimMat8 dm) {
+  extern __shared__ __align__(16) float s_w[];  // [LH][dim_g] + [LH]
+  const int dim_g = trig ? 64 : 4;
+  for (int i = threadIdx.x; i < LH * dim_g; i += blockDim.x) s_w[i] = wg_w[i];
+  for (int i = threadIdx.x; i < LH; i += blockDim.x) s_w[LH * dim_g + i] = wg_b[i];
+  __syncthreads();
+  const long pairs = (long)N * N;
+  const long total = (long)B * pairs;
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int b = (int)(p / pairs);
+  const int r = (int)(p - (long)b * pairs);
+  const int i = r / N, j = r - i * N;
+  const float4 bi = *(const float4*)(boxes + ((size_t)b * N + i) * 4);
+  const float4 bj = *(const float4*)(boxes + ((size_t)b * N + j) * 4);
+  const float cxi = (bi.x + bi.z) * 0.5f, cyi = (bi.y + bi.w) * 0.5f, wi = (bi.z - bi.x) + 1.0f, hi = (bi.w - bi.y) + 1.0f;
+  const float cxj = (bj.x + bj.z) * 0.5f, cyj = (bj.y + bj.w) * 0.5f, wj = (bj.z - bj.x) + 1.0f, hj = (bj.w - bj.y) + 1.0f;
+  float delta[4];
+  delta[0] = logf(fmaxf(fabsf((cxi - cxj) / wi), 1e-3f));
+  delta[1] = logf(fmaxf(fabsf((cyi - cyj) / hi), 1e-3f));
+  delta[2] = logf(wi / wj);
+  delta[3] = logf(hi / hj);
+  const int L = LH / h;
+  if (trig) {
+    float emb[64];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float p100 = 100.0f * delta[c];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) sincosf(p100 * dm.v[f], &emb[c * 8 + f], &emb[32 + c * 8 + f]);
+    }
+    for (int l = 0; l < L; ++l) {
+      for (int hh = 0; hh < h; ++hh) {
+        const int lh = l * h + hh;
+        const float4* wr = (const float4*)(s_w + lh * 64);
+        // same summation order as the per-layer kernel: for (c,f): acc += sin*w[c*8+f] + cos*w[32+c*8+f]
+        float acc = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 ws = wr[q4], wc = wr[8 + q4];
+          acc += emb[4 * q4 + 0] * ws.x + emb[32 + 4 * q4 + 0] * wc.x;
+          acc += emb[4 * q4 + 1] * ws.y + emb[32 + 4 * q4 + 1] * wc.y;
+          acc += emb[4 * q4 + 2] * ws.z + emb[32 + 4 * q4 + 2] * wc.z;
+          acc += emb[4 * q4 + 3] * ws.w + emb[32 + 4 * q4 + 3] * wc.w;
+        }
+        const float gg = fmaxf(acc + s_w[LH * 64 + lh], 0.f);
+        bias[((((size_t)l * B + b) * h + hh) * N + i) * N + j] = logf(fmaxf(gg, 1e-6f));
+      }
+    }
+  } else {
+    for (int l = 0; l < L; ++l)
+      for (int hh = 0; hh < h; ++hh) {
+        const int lh = l * h + hh;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc += delta[c] * s_w[lh * 4 + c];
+        const float gg = fmaxf(acc + s_w[LH * 4 + lh], 0.f);
+        bias[((((size_t)l * B + b) * h + hh) * N + i) * N + j] = logf(fmaxf(gg, 1e-6f));
+      }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sc_box_bias_all(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int layers, int h,
+                    int trig, float wave_len, cudaStream_t stream) {
+  SC_CHECK(B > 0 && N > 0 && layers >= 1 && h >= 1, SC_ERR_SHAPE, "sc_box_bias_all: B=%d N=%d layers=%d h=%d", B, N, layers, h);
+  SC_CHECK(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)wg_w & 15) == 0, SC_ERR_ALIGN, "sc_box_bias_all: boxes / wg_w must be 16-byte aligned");
+  const int LH = layers * h;
+  const int dim_g = trig ? 64 : 4;
+  const size_t smem = sizeof(float) * ((size_t)LH * dim_g + LH);
+  SC_CHECK(smem <= 200 * 1024, SC_ERR_UNSUPPORTED, "sc_box_bias_all: %d WG rows do not fit in shared memory", LH);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(box_bias_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  DimMat8 dm;
+  for (int f = 0; f < 8; ++f) dm.v[f] = 1.0f / powf(wave_len, (float)f / 8.0f);
+  const long total = (long)B * N * N;
+  box_bias_all_kernel<<<(unsigned)((total + 127) / 128), 128, smem, stream>>>(boxes, wg_w, wg_b, bias, B, N, LH, h, trig, dm);
+  SC_LAUNCH_CHECK("sc_box_bias_all");
+  return SC_OK;
+}
+
+int sc_bias_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* bias,
+                          const float* att_mask, void* out, int ldo, int B, int N, int h, int dk, cudaStream_t stream) {
+  SC_CHECK(B > 0 && N > 0 && h > 0, SC_ERR_SHAPE, "sc_bias_attention_fwd: B=%d N=%d h=%d", B, N, h);
+  SC_CHECK(dtype == SC_BF16, SC_ERR_DTYPE, "sc_bias_attention_fwd: bf16 only (fp32 runs sc_box_attention_fwd)");
+  SC_CHECK(dk == kDk, SC_ERR_UNSUPPORTED, "sc_bias_attention_fwd: d_k=%d (tensor path serves d_k=64)", dk);
+  SC_CHECK(N <= 128, SC_ERR_UNSUPPORTED, "sc_bias_attention_fwd: N=%d > 128", N);
+  SC_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, SC_ERR_ALIGN, "sc_bias_attention_fwd: ld %% 8");
+  SC_CHECK((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0, SC_ERR_ALIGN, "sc_bias_attention_fwd: 16-byte alignment");
+  SC_CHECK(bias != nullptr, SC_ERR_SHAPE, "sc_bias_attention_fwd: bias missing");
+  EncAttnArgs a;
+  a.q = (const __nv_bfloat16*)q; a.k = (const __nv_bfloat16*)k; a.v = (const __nv_bfloat16*)v;
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.bias = bias; a.att_mask = att_mask; a.out = (__nv_bfloat16*)out; a.ldo = ldo;
+  a.B = B; a.N = N; a.h = h;
+  const int NT = (N + 15) / 16;
+  const size_t per_warp = (size_t)3 * 16 * NT * kPitch;
+  int warps = (int)((200 * 1024) / per_warp);
+  if (warps > 4) warps = 4;
+  a.warps = warps;
+  const size_t smem = per_warp * warps;
+  const int blocks = (B * h + warps - 1) / warps;
+#define ENC_CASE(NTV)                                                                                              \
+  case NTV: {                                                                                                      \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      cudaFuncSetAttribute(enc_attn_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    enc_attn_mma_kernel<NTV><<<blocks, 32 * warps, smem, stream>>>(a);                                             \
+  } break
+  switch (NT) {
+    ENC_CASE(1); ENC_CASE(2); ENC_CASE(3); ENC_CASE(4); ENC_CASE(5); ENC_CASE(6); ENC_CASE(7); ENC_CASE(8);
+    default: SC_CHECK(false, SC_ERR_UNSUPPORTED, "sc_bias_attention_fwd: N=%d", N);
+  }
+#undef ENC_CASE
+  SC_LAUNCH_CHECK("sc_bias_attention_fwd");
+  return SC_OK;
+}
+
+}  // extern "C"
+
+// bf16, d_k = 64 cross-attention step on the tensor path; returns SC_ERR_UNSUPPORTED when the shape is not served
+// (sc_decode_cross_attn_step in sc_decode.cu then runs its generic kernel).
+int sc_cross_attn_mma_launch(const void* q, int ldq, const void* mem_k, const void* mem_v, int ldm, const float* att_mask,
+                             void* out, int ldo, int B, int beam, int N, int h, cudaStream_t stream) {
+  if (beam > 16 || N > 128) return SC_ERR_UNSUPPORTED;
+  if ((((uintptr_t)q | (uintptr_t)mem_k | (uintptr_t)mem_v | (uintptr_t)out) & 15) != 0) return SC_ERR_UNSUPPORTED;
+  CrossAttnArgs a;
+  a.q = (const __nv_bfloat16*)q; a.ldq = ldq; a.mk = (const __nv_bfloat16*)mem_k; a.mv = (const __nv_bfloat16*)mem_v; a.ldm = ldm;
+  a.att_mask = att_mask; a.out = (__nv_bfloat16*)out; a.ldo = ldo; a.B = B; a.NB = beam; a.N = N; a.h = h;
+  const int NT = (N + 15) / 16;
+  const size_t per_warp = (size_t)(2 * 16 * NT + 16) * kPitch;
+  int warps = (int)((100 * 1024) / per_warp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) return SC_ERR_UNSUPPORTED;
+  a.warps = warps;
+  const size_t smem = per_warp * warps;
+  const int blocks = (B * h + warps - 1) / warps;
+#define X_CASE(NTV)                                                                                                \
+  case NTV: {                                                                                                      \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      cudaFuncSetAttribute(cross_attn_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    cross_attn_mma_kernel<NTV><<<blocks, 32 * warps, smem, stream>>>(a);                                           \
+  } break
+  switch (NT) {
+    X_CASE(1); X_CASE(2); X_CASE(3); X_CASE(4); X_CASE(5); X_CASE(6); X_CASE(7); X_CASE(8);
+    default: return SC_ERR_UNSUPPORTED;
+  }
+#undef X_CASE
+  SC_LAUNCH_CHECK("sc_decode_cross_attn_step");
+  return SC_OK;
+}

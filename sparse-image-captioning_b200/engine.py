@@ -104,6 +104,7 @@ class BeamState:
         self.done_p = torch.zeros(B, beam, dtype=torch.float64, device=dev)
         self.done_count = torch.zeros(B, **i32)
         self.rows = torch.arange(R, **i32).unsqueeze(1).expand(R, L).contiguous()
+        self.ws = torch.zeros(K.beam_step_workspace_bytes(B, beam), dtype=torch.uint8, device=dev)  # sc_beam_step scratch
 
     def reset(self, bos, pad):
         self.anc[0].copy_(self.rows)
@@ -188,6 +189,12 @@ class OrtEngine:
             }
             self.enc[u] = e
         self.enc_norm = _Norm(sd, "model.encoder.norm")
+        # all unique encoder layers' WG rows stacked: the geometry bias of every layer comes from ONE pass over the boxes
+        self.enc_slot = {u: i for i, u in enumerate(self.enc)}
+        self.wg_w_all = torch.cat([self.enc[u]["wg_w"] for u in self.enc], 0).contiguous()
+        self.wg_b_all = torch.cat([self.enc[u]["wg_b"] for u in self.enc], 0).contiguous()
+        # tensor-path attention (mma tiles) serves bf16, d_k = 64, N <= 128; fp32 mode keeps the exact fused kernel
+        self.split_box_attn = (adt == torch.bfloat16 and d // cfg.num_heads == 64)
         # ---- decoder ----
         self.dec_uids = cfg.uids("dec")
         self.dec = {}
@@ -250,6 +257,8 @@ class OrtEngine:
         ws.hid = torch.zeros(M, ff, device=dev, dtype=adt)
         ws.mem = torch.zeros(M, d, device=dev, dtype=adt)
         ws.memkv = {u: torch.zeros(M, e["ckv_ld"], device=dev, dtype=adt) for u, e in self.dec.items()}
+        ws.box_bias = (torch.zeros(len(self.enc), B, c.num_heads, N, N, device=dev)
+                       if self.split_box_attn and N <= 128 else None)
         ws.graph = None
         self._enc_ws[key] = ws
         return ws
@@ -263,6 +272,9 @@ class OrtEngine:
         self.att_embed(ws.att_a, ws.x, relu=True)
         if ws.att_mask is not None:
             K.mask_rows(ws.x, ws.att_mask.view(-1))
+        trig = not c.no_box_trigonometric_embedding
+        if ws.box_bias is not None:
+            K.box_bias_all(ws.boxes, self.wg_w_all, self.wg_b_all, ws.box_bias, B=B, N=N, layers=len(self.enc), h=h, trig=trig)
         for u in self.enc_uids:
             e = self.enc[u]
             e["n0"](ws.x, ws.xn)
@@ -270,9 +282,12 @@ class OrtEngine:
             qkv = ws.qkv.view(-1)[: B * N * ld].view(B * N, ld)
             e["qkv"](ws.xn, qkv)
             qo, ko, vo = e["offs"]
-            K.box_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.boxes, e["wg_w"], e["wg_b"], ws.att_mask, ws.att,
-                            B=B, N=N, h=h, dk=dk, ldq=ld, ldk=ld, ldv=ld, ldo=d,
-                            trig=not c.no_box_trigonometric_embedding)
+            if ws.box_bias is not None:
+                K.bias_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.box_bias[self.enc_slot[u]], ws.att_mask, ws.att,
+                                 B=B, N=N, h=h, dk=dk, ldq=ld, ldk=ld, ldv=ld, ldo=d)
+            else:
+                K.box_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.boxes, e["wg_w"], e["wg_b"], ws.att_mask, ws.att,
+                                B=B, N=N, h=h, dk=dk, ldq=ld, ldk=ld, ldv=ld, ldo=d, trig=trig)
             e["o"](ws.att, ws.x, residual=ws.x)
             e["n1"](ws.x, ws.xn)
             e["ff1"](ws.xn, ws.hid, relu=True)

@@ -146,6 +146,20 @@ def box_attention(q, k, v, boxes, wg_w, wg_b, att_mask, out, *, B, N, h, dk, ldq
     return out
 
 
+def box_bias_all(boxes, wg_w, wg_b, out, *, B, N, layers, h, trig=True, wave_len=1000.0):
+    """Geometry bias of every encoder layer at once: out fp32 [layers, B, h, N, N] (sc_box_bias_all)."""
+    lib.call("sc_box_bias_all", lib.ptr(boxes), lib.ptr(wg_w), lib.ptr(wg_b), lib.ptr(out), B, N, layers, h, int(trig),
+             wave_len, lib.stream())
+    return out
+
+
+def bias_attention(q, k, v, bias, att_mask, out, *, B, N, h, dk, ldq, ldk, ldv, ldo):
+    """box_attention of one layer given its geometry bias [B,h,N,N] (bf16 tensor path, sc_bias_attention_fwd)."""
+    lib.call("sc_bias_attention_fwd", lib.ptr(q), lib.ptr(k), lib.ptr(v), ldq, ldk, ldv, lib.dtype_code(out.dtype),
+             lib.ptr(bias), lib.ptr(att_mask), lib.ptr(out), ldo, B, N, h, dk, lib.stream())
+    return out
+
+
 def self_attn_step(q, k, v, cache_k, cache_v, anc, out, *, R, D, h, n_prev, write_slot, ldq, ldk, ldv, ldo, anc_ld,
                    slot_div=1):
     lib.call("sc_decode_self_attn_step", lib.ptr(q), lib.ptr(k), lib.ptr(v), ldq, ldk, ldv, lib.dtype_code(out.dtype),
@@ -166,7 +180,12 @@ def beam_step(logits, st, t, *, B, beam, V, L, eos, pad, temperature=1.0, constr
     lib.call("sc_beam_step", lib.ptr(logits), B, beam, V, L, t, eos, pad, float(temperature), int(constraint),
              int(penalty_kind), float(penalty_alpha), lib.ptr(st.seq[i]), lib.ptr(st.seq[o]), lib.ptr(st.lp[i]),
              lib.ptr(st.lp[o]), lib.ptr(st.sum), lib.ptr(st.anc[i]), lib.ptr(st.anc[o]), lib.ptr(st.tokens),
-             lib.ptr(st.done_seq), lib.ptr(st.done_lp), lib.ptr(st.done_p), lib.ptr(st.done_count), lib.stream())
+             lib.ptr(st.done_seq), lib.ptr(st.done_lp), lib.ptr(st.done_p), lib.ptr(st.done_count), lib.ptr(st.ws),
+             st.ws.numel(), lib.stream())
+
+
+def beam_step_workspace_bytes(B, beam):
+    return int(lib.load().sc_beam_step_workspace_bytes(B, beam))
 
 
 def greedy_step(logits, st, t, *, R, V, L, eos, constraint=0):

@@ -228,6 +228,68 @@ def test_decode_attention_steps(K, dt):
     assert rel_err(out.float(), ref) < (1e-5 if dt == torch.float32 else 2e-2)
 
 
+@pytest.mark.parametrize("cfg", [(3, 36, 8, 2), (2, 47, 8, 3), (1, 100, 8, 1), (2, 17, 4, 2), (1, 128, 2, 1)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_box_bias_all_and_tensor_attention(K, cfg, masked):
+    """Inference split of K4: geometry bias of all layers in one pass (fp32, vs the oracle embedding), then the
+    mma.sync attention of each layer (bf16, d_k = 64) vs plain fp32 softmax attention with that bias."""
+    B, N, h, layers = cfg
+    dk = 64
+    g = torch.Generator().manual_seed(17)
+    D = h * dk
+    data = O.synthetic_inputs(B, N, 8, seed=13)
+    boxes = data["boxes"]
+    mask = torch.ones(B, N)
+    if masked and N > 10:
+        mask[0, N - 5:] = 0
+        boxes[0, N - 5:] = 0
+    wg_w = torch.randn(layers * h, 64, generator=g) * 0.3
+    wg_b = torch.randn(layers * h, generator=g) * 0.3
+    bias = torch.zeros(layers, B, h, N, N, device="cuda")
+    K.box_bias_all(boxes.cuda(), wg_w.cuda(), wg_b.cuda(), bias, B=B, N=N, layers=layers, h=h)
+    emb = O.box_relational_embedding(boxes)
+    gw = torch.relu(torch.einsum("bijf,lhf->lbhij", emb, wg_w.view(layers, h, 64)) + wg_b.view(layers, 1, h, 1, 1))
+    ref_bias = torch.log(torch.clamp(gw, min=1e-6))
+    # relu/log amplify fp32 rounding of the 100x angles where WG.emb crosses 0: compare g = exp(bias) (SURVEY hard parts)
+    assert float((bias.cpu().exp() - ref_bias.exp()).abs().max()) < 2e-4
+    for l in range(layers):
+        qkv = torch.randn(B * N, 3 * D, generator=g).bfloat16()
+        out = torch.zeros(B * N, D, dtype=torch.bfloat16, device="cuda")
+        qd = qkv.cuda()
+        K.bias_attention(qd[:, 0:], qd[:, D:], qd[:, 2 * D:], bias[l], mask.cuda() if masked else None, out, B=B, N=N, h=h,
+                         dk=dk, ldq=3 * D, ldk=3 * D, ldv=3 * D, ldo=D)
+        q, k, v = (qkv.float()[:, i * D:(i + 1) * D].view(B, N, h, dk).transpose(1, 2) for i in range(3))
+        scores = (q @ k.transpose(-2, -1)) / math.sqrt(dk)
+        if masked:
+            scores = scores.masked_fill(mask.view(B, 1, 1, N) == 0, -1e9)
+        ref = torch.softmax(bias[l].cpu() + scores, -1) @ v
+        ref = ref.transpose(1, 2).reshape(B * N, D)
+        assert rel_err(out.float(), ref) < 2e-2, l
+
+
+@pytest.mark.parametrize("cfg", [(5, 3, 36, 8), (3, 5, 47, 4), (2, 1, 100, 8), (4, 8, 7, 2)])
+def test_cross_attention_tensor_path(K, cfg):
+    """K6 on the mma.sync path (bf16, d_k = 64): the beam rows of an image share one read of its memory K/V."""
+    B, beam, N, h = cfg
+    dk = 64
+    D, R = h * dk, B * beam
+    g = torch.Generator().manual_seed(23)
+    mem = torch.randn(B * N, 2 * D, generator=g).bfloat16()
+    qc = torch.randn(R, D, generator=g).bfloat16()
+    mask = torch.ones(B, N)
+    mask[B - 1, N - 2:] = 0
+    for m in (None, mask):
+        out = torch.zeros(R, D, dtype=torch.bfloat16, device="cuda")
+        md = mem.cuda()
+        K.cross_attn_step(qc.cuda(), md[:, 0:], md[:, D:], None if m is None else m.cuda(), out, B=B, beam=beam, N=N, D=D, h=h,
+                          ldq=D, ldm=2 * D, ldo=D)
+        kk = mem.float()[:, :D].view(B, N, h, dk).transpose(1, 2).repeat_interleave(beam, 0)
+        vv = mem.float()[:, D:].view(B, N, h, dk).transpose(1, 2).repeat_interleave(beam, 0)
+        m4 = None if m is None else m.view(B, 1, 1, N).repeat_interleave(beam, 0)
+        ref = O.attention(qc.float().view(R, 1, h, dk).transpose(1, 2), kk, vv, m4).transpose(1, 2).reshape(R, D)
+        assert rel_err(out.float(), ref) < 2e-2
+
+
 def test_cache_reorder(K):
     src = torch.randn(12, 4, 5, 8).cuda()
     idx = torch.tensor([3, 3, 0, 11, 7, 1, 2, 2, 2, 9, 10, 4], dtype=torch.int32).cuda()
