@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--train-images", type=int, default=50, help="images per GPU per training step (5 captions each)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--cpu-images", type=int, default=64)
+    ap.add_argument("--slots", type=int, default=4, help="batches in flight (pipeline slots: stream + workspaces + graphs each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -195,6 +196,7 @@ def main():
                           f"({args.images} images/GPU/step) [BASELINE.json configs[2]]",
               "images_per_gpu_per_step": args.images, "beam": BEAM, "max_len": 16, "sparsity": SPARSITY,
               "sharding": f"images by rank x{world}, no data-path collective", "decoder_gemm_backend": args.backend,
+              "batches_in_flight": args.slots,
               "l2_policy": "inputs_larger_than_L2 (151 MB fresh fp32 features + ~0.7 GB of activations/KV per step vs 126 MB L2)"}
 
     if args.impl == "reference":
@@ -236,50 +238,75 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---------------- device-resident arm: inputs already in HBM ----------------
-    enc = eng.encode(host[0][0], host[0][1])
-    eng.decode(enc, opt)
+    # `slots` batches are in flight at once: slot s = its own stream, workspaces and CUDA graphs (engine.submit);
+    # every timed step is still one full batch (encoder + 16 decode steps + beam bookkeeping).
+    S = max(1, args.slots)
+    slots = list(range(1, S + 1))
+    cur = torch.cuda.current_stream(dev)
+    encs = {}
+    for s in slots:
+        eng.submit(host[s & 1][0], host[s & 1][1], None, opt, slot=s)
+        encs[s] = eng._get_enc_ws(B, N_BOX, False, s)
+    eng.wait(host=True)
     torch.cuda.synchronize(dev)
-    dws = eng._get_dec_ws(B, BEAM, N_BOX, False)
-    launches_per_step = enc.launches + dws.launches
-    for _ in range(args.warmup):
-        eng.run_encoder(enc)
-        eng.decode(enc, opt)
+    dws = eng._get_dec_ws(B, BEAM, N_BOX, False, slots[0])
+    launches_per_step = encs[slots[0]].launches + dws.launches
+
+    def dev_step(i):
+        s = slots[i % S]
+        with torch.cuda.stream(eng.stream(s)):
+            eng.run_encoder(encs[s])
+            eng.decode(encs[s], opt)
+
+    def fork():
+        for s in slots:
+            eng.stream(s).wait_stream(cur)
+
+    def join():
+        for s in slots:
+            cur.wait_stream(eng.stream(s))
+
+    fork()
+    for i in range(args.warmup):
+        dev_step(i)
+    join()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        eng.run_encoder(enc)
-        eng.decode(enc, opt)
+    fork()
+    for i in range(args.steps):
+        dev_step(i)
+    join()
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
 
     # ---------------- end-to-end arm: pinned host inputs -> tokens on the host ----------------
-    out_seq = torch.empty(B, BEAM, 16, dtype=torch.int32).pin_memory()
-    out_lp = torch.empty(B, BEAM, 16, dtype=torch.float32).pin_memory()
+    out_seq = [torch.empty(B, BEAM, 16, dtype=torch.int32).pin_memory() for _ in slots]
+    out_lp = [torch.empty(B, BEAM, 16, dtype=torch.float32).pin_memory() for _ in slots]
 
     def e2e_step(i):
         att, boxes = host[i & 1]
-        enc_ = eng.encode(att, boxes)
-        seq, lp = eng.decode(enc_, opt)
-        out_seq.copy_(seq, non_blocking=True)
-        out_lp.copy_(lp, non_blocking=True)
+        k = i % S
+        eng.submit(att, boxes, None, opt, slot=slots[k], out=(out_seq[k], out_lp[k]))
 
     for i in range(args.warmup):
         e2e_step(i)
+    eng.wait()
     barrier()
     e0.record()
     for i in range(args.steps):
         e2e_step(i)
+    eng.wait()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
-    d2h = out_seq.numel() * 4 + out_lp.numel() * 4
+    d2h = out_seq[0].numel() * 4 + out_lp[0].numel() * 4
 
     t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
     if dist is not None:

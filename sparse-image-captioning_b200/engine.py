@@ -235,17 +235,27 @@ class OrtEngine:
         self.generator = lin(["model.generator.proj"], be)
         self._enc_ws = {}
         self._dec_ws = {}
+        self._streams = {}
+        self._done = {}
         torch.cuda.synchronize(self.dev)
 
     # ------------------------------------------------------------------------------------------------
-    def _get_enc_ws(self, B, N, masked):
-        key = (B, N, masked)
+    def stream(self, slot):
+        """CUDA stream of pipeline slot `slot` (slot 0 = the caller's current stream)."""
+        if slot == 0:
+            return torch.cuda.current_stream(self.dev)
+        if slot not in self._streams:
+            self._streams[slot] = torch.cuda.Stream(self.dev)
+        return self._streams[slot]
+
+    def _get_enc_ws(self, B, N, masked, slot=0):
+        key = (B, N, masked, slot)
         if key in self._enc_ws:
             return self._enc_ws[key]
         c, dev, adt = self.cfg, self.dev, self.adt
         d, ff, M = c.d_model, c.dim_feedforward, B * N
         ws = type("EncWs", (), {})()
-        ws.B, ws.N, ws.masked = B, N, masked
+        ws.B, ws.N, ws.masked, ws.slot = B, N, masked, slot
         ws.att_in = torch.zeros(M, c.att_feat_size, device=dev)
         ws.att_a = torch.zeros(M, c.att_feat_size, device=dev, dtype=adt) if adt != torch.float32 else ws.att_in
         ws.boxes = torch.zeros(B, N, 4, device=dev)
@@ -296,10 +306,11 @@ class OrtEngine:
         for u, e in self.dec.items():
             e["ckv"](ws.mem, ws.memkv[u])
 
-    def encode(self, att_feats, boxes, att_masks=None):
-        """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V."""
+    def encode(self, att_feats, boxes, att_masks=None, slot=0):
+        """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V.
+        ``slot`` selects an independent set of workspaces/graphs so that several batches can be in flight."""
         B, N, F = att_feats.shape
-        ws = self._get_enc_ws(B, N, att_masks is not None)
+        ws = self._get_enc_ws(B, N, att_masks is not None, slot)
         ws.att_in.copy_(att_feats.reshape(B * N, F), non_blocking=True)
         ws.boxes.copy_(boxes, non_blocking=True)
         if att_masks is not None:
@@ -331,8 +342,8 @@ class OrtEngine:
         ws.launches = lib.launch_count - before
 
     # ------------------------------------------------------------------------------------------------
-    def _get_dec_ws(self, B, beam, N, greedy):
-        key = (B, beam, N, greedy)
+    def _get_dec_ws(self, B, beam, N, greedy, slot=0):
+        key = (B, beam, N, greedy, slot)
         if key in self._dec_ws:
             return self._dec_ws[key]
         c, dev, adt = self.cfg, self.dev, self.adt
@@ -419,7 +430,7 @@ class OrtEngine:
             raise NotImplementedError("diverse beam search (group_size > 1) is out of scope (SURVEY.md section 2.1 #6)")
         greedy = beam == 1
         assert beam <= self.cfg.vocab_size
-        ws = self._get_dec_ws(enc.B, beam, enc.N, greedy)
+        ws = self._get_dec_ws(enc.B, beam, enc.N, greedy, enc.slot)
         body = (lambda: self._greedy_body(ws, enc, opt)) if greedy else (lambda: self._beam_body(ws, enc, opt))
         opt_key = (id(enc), tuple(sorted((k, str(v)) for k, v in opt.items())))
         if not self.use_graphs:
@@ -433,6 +444,38 @@ class OrtEngine:
         if greedy:
             return st.seq.view(enc.B, 1, -1), st.lp.view(enc.B, 1, -1)
         return st.done_seq, st.done_lp
+
+    # ---- batch pipelining: slot s owns a stream + workspaces + graphs; batches in different slots overlap on the GPU
+    # (the decode loop is a chain of ~70 short dependent kernels per step that leaves most SMs idle; a second
+    # batch fills them, and its H2D copy hides behind the first batch's compute) ----
+    def submit(self, att_feats, boxes, att_masks=None, opt=None, slot=0, out=None):
+        """Enqueue encode + decode of one batch on slot `slot` without waiting.  ``out``: optional pinned host tensors
+        (seq int32 [B,b,L], lp fp32 [B,b,L]) that receive the result asynchronously.  Returns (seq, lp) device views
+        that are valid after ``wait(slot)``."""
+        opt = dict(opt or {})
+        cur = torch.cuda.current_stream(self.dev)
+        st = self.stream(slot)
+        if st is not cur:
+            st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            enc = self.encode(att_feats, boxes, att_masks, slot=slot)
+            seq, lp = self.decode(enc, opt)
+            if out is not None:
+                out[0].copy_(seq, non_blocking=True)
+                out[1].copy_(lp, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._done[slot] = ev
+        return seq, lp
+
+    def wait(self, slot=None, host=False):
+        """Make the current stream (or the host when ``host``) wait for slot `slot` (all slots when None)."""
+        for s, ev in list(self._done.items()):
+            if slot is None or s == slot:
+                if host:
+                    ev.synchronize()
+                else:
+                    torch.cuda.current_stream(self.dev).wait_event(ev)
 
     def sample(self, att_feats, boxes, att_masks=None, opt=None):
         """Drop-in for ``model(att_feats=..., boxes=..., att_masks=..., opt=..., mode="sample")``:

@@ -86,3 +86,24 @@ def test_no_history_quirk_q1():
     rseq, rlp = O.sample(z["w"], z["cfg"], z["att_feats"], z["boxes"], None, {"beam_size": 2}, no_history=True)
     assert torch.equal(seq.cpu(), rseq)
     torch.testing.assert_close(lp.cpu(), rlp, rtol=1e-4, atol=2e-5)
+
+
+def test_pipelined_slots_match_sequential():
+    """Batches in flight on different pipeline slots (stream + workspaces + graphs each) give the results of the
+    sequential call, token for token; pinned host outputs arrive through the async D2H copies."""
+    cfg, ocfg, sd = _medium(seed=7)
+    eng = _engine(sd, cfg, precision="fp32")
+    opt = {"beam_size": 3}
+    batches = [O.synthetic_inputs(6, 36, cfg["att_feat_size"], seed=20 + i) for i in range(5)]
+    want = [eng.sample(b["att_feats"], b["boxes"], None, opt) for b in batches]
+    want = [(s.cpu(), l.cpu()) for s, l in want]
+    L = cfg["max_seq_length"]
+    outs = [(torch.zeros(6, 3, L, dtype=torch.int32).pin_memory(), torch.zeros(6, 3, L).pin_memory()) for _ in batches]
+    for rep in range(2):
+        for i, b in enumerate(batches):
+            eng.submit(b["att_feats"].pin_memory(), b["boxes"].pin_memory(), None, opt, slot=1 + i % 3, out=outs[i])
+            if i % 3 == 2 or i == len(batches) - 1:
+                eng.wait(host=True)  # slots are reused: drain before their workspaces are overwritten
+                for j in range(i - i % 3, i + 1):
+                    assert torch.equal(outs[j][0].long(), want[j][0]), (rep, j)
+                    torch.testing.assert_close(outs[j][1], want[j][1], rtol=1e-5, atol=1e-6)
