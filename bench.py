@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--train-images", type=int, default=50, help="images per GPU per training step (5 captions each)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--cpu-images", type=int, default=64)
+    ap.add_argument("--ln-fold", action="store_true", help="LayerNorm folded into the consuming GEMMs (sc_linear_ln) instead of separate LayerNorm kernels")
+    ap.add_argument("--no-pdl", action="store_true", help="diagnostic: disable programmatic dependent launch")
     ap.add_argument("--slots", type=int, default=4, help="batches in flight (pipeline slots: stream + workspaces + graphs each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -224,9 +226,11 @@ def main():
     from sparse_caption_b200 import lib, synthetic
     from sparse_caption_b200.engine import ModelCfg, OrtEngine
     lib.load()
+    if args.no_pdl:
+        lib.load().sc_set_pdl(0)
     cfg = ModelCfg(CFG)
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=SPARSITY, device=dev)
-    eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev)
+    eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold)
     B = args.images
     # two distinct pinned host batches, alternated
     host = [synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
@@ -326,7 +330,8 @@ def main():
 
     # ---------------- roofline leg: one instrumented step without graphs ----------------
     peaks = load_peaks()
-    eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False)
+    eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False,
+                     ln_fold=args.ln_fold)
     enc2 = eng2.encode(host[0][0], host[0][1])
     eng2.decode(enc2, opt)
     torch.cuda.synchronize(dev)

@@ -57,6 +57,20 @@ int sc_linear(const void* x, int x_dtype, const void* w, int w_dtype, const floa
               const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
               sc_stream_t stream);
 
+/* K1 + K9 — LayerNorm folded around the tensor-core GEMM for inference (models/transformer.py:329-358:
+ * x + dropout(sublayer(norm(x)))).  x, w bf16.
+ *   consumer (ln_stats != NULL): w = (W (.) m) (.) a_2, ln_c[n] = sum_k w[n,k], bias = W b_2 + bias; x = bf16 copy of the
+ *     un-normalised residual stream;  y = rstd * (x w^T) - rstd * mean * ln_c + bias, row statistics (unbiased std,
+ *     1/(std+eps)) merged from ln_stats fp32 [M][K/32][2] = per 32-column chunk (sum, M2 about the chunk mean).
+ *   producer (stats_out and/or y_bf16_copy != NULL): after bias / ReLU / residual the result goes to y (fp32), its bf16
+ *     copy to y_bf16_copy and the chunk statistics of the stored rows to stats_out [M][N/32][2]. */
+int sc_linear_ln(const void* x, const void* w, const float* bias, const float* residual, void* y, int y_dtype, int M, int N,
+                 int K, int relu, int tile_n, const float* ln_stats, const float* ln_c, float ln_eps, void* y_bf16_copy,
+                 float* stats_out, sc_stream_t stream);
+
+/* Programmatic dependent launch (griddepcontrol) between consecutive kernels of a stream: 1 = on (default), 0 = off. */
+int sc_set_pdl(int enabled);
+
 /* K3b — the same product from CSR weights (rows = output features, 16-bit column indices, values in x's dtype).
  * The reference only stores the sparse form (pruning/prune.py:200-221). */
 int sc_csr_spmm(const void* x, int dtype, const int* row_ptr, const unsigned short* col_idx, const void* vals,
@@ -73,6 +87,11 @@ int sc_layernorm(const float* x, const float* a, const float* b, void* y, int y_
 int sc_embed_pe(const int* tokens, const float* table, const float* mask, int mask_mode, const float* uniforms,
                 unsigned long long seed, unsigned long long stream_id, const float* pe, void* out, int out_dtype,
                 int rows, int D, int V, int T, int pos0, float scale, sc_stream_t stream);
+
+/* K9 (LayerNorm-folded decode path) — the same embedding for pre-masked tables, emitting the fp32 residual stream, its
+ * bf16 copy and the per-32-column (sum, M2) row statistics that sc_linear_ln consumes.  D % 32 == 0. */
+int sc_embed_pe_stats(const int* tokens, const float* table, const float* pe, float* x32, void* x_bf16, float* stats, int rows,
+                      int D, int V, int T, int pos0, float scale, sc_stream_t stream);
 
 /* prune_weights / densify: out = w (.) mask  (pruning/prune.py:165-174) */
 int sc_apply_mask(const float* w, const float* mask, int mask_mode, const float* uniforms, unsigned long long seed,

@@ -3,6 +3,7 @@
 #include <cstring>
 
 static thread_local char g_err[512] = "";
+int g_sc_pdl = 1;  // programmatic dependent launch between consecutive kernels of a stream (sc_set_pdl)
 
 void sc_set_error(const char* fmt, ...) {
   va_list ap;
@@ -36,7 +37,8 @@ static int linear_dispatch(const void* x, int x_dtype, const void* w, int w_dtyp
 extern "C" {
 
 const char* sc_last_error(void) { return g_err; }
-int sc_version(void) { return 100; }  // round 1
+int sc_version(void) { return 101; }
+int sc_set_pdl(int enabled) { g_sc_pdl = enabled ? 1 : 0; return SC_OK; }
 
 int sc_linear(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
               const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
@@ -44,6 +46,20 @@ int sc_linear(const void* x, int x_dtype, const void* w, int w_dtype, const floa
               cudaStream_t stream) {
   return linear_dispatch(x, x_dtype, w, w_dtype, mask, mask_mode, uniforms, seed, stream_id, bias, residual, y, y_dtype, M, N,
                          K, relu, tile_n, nullptr, stream);
+}
+
+// Inference GEMM with a LayerNorm folded around it (models/transformer.py:329-358: x + sublayer(norm(x))).
+//   consumer (ln_stats != NULL): w holds W (.) a, ln_c[n] = sum_k w[n,k], bias = W b + bias; x is the bf16 copy of the
+//     un-normalised residual stream; y = rstd * (x w^T) - rstd * mean * ln_c + bias with the row statistics of ln_stats.
+//   producer (stats_out / y_bf16_copy != NULL): after bias / ReLU / residual the fp32 result is stored to y, its bf16
+//     copy to y_bf16_copy and per 32-column chunk (sum, M2) to stats_out [M][N/32][2].
+int sc_linear_ln(const void* x, const void* w, const float* bias, const float* residual, void* y, int y_dtype, int M, int N,
+                 int K, int relu, int tile_n, const float* ln_stats, const float* ln_c, float ln_eps, void* y_bf16_copy,
+                 float* stats_out, cudaStream_t stream) {
+  ScGemmExtra ex = {};
+  ex.ln_stats = ln_stats; ex.ln_c = ln_c; ex.ln_eps = ln_eps; ex.y2 = y_bf16_copy; ex.stats_out = stats_out;
+  return sc_gemm_bf16_launch(x, w, SC_BF16, nullptr, SC_MASK_NONE, nullptr, 0, 0, bias, residual, y, y_dtype, M, N, K, relu,
+                             tile_n, &ex, stream);
 }
 
 // training forward: y = dropout(act(x (W.m)^T + b), p) + residual, dropout mask = Philox(drop_seed, drop_stream, element)

@@ -39,14 +39,38 @@ void sc_set_error(const char* fmt, ...);
     }                                                                     \
   } while (0)
 
-// optional GEMM epilogue extensions (training): dropout, or the weight-gradient epilogue
+// optional GEMM epilogue extensions (training: dropout / weight-gradient epilogue; inference: folded LayerNorm)
 struct ScGemmExtra {
   float dropout_p; unsigned long long drop_seed, drop_stream;
   int wgrad, bypass; float sp_coeff; int accumulate;
   const float* wg_w; const float* wg_s; const float* wg_u; float* dw; float* ds;
+  // consumer of a LayerNorm folded into the weights (W' = W (.) a, ln_c[n] = sum_k W'[n,k], bias' = W b + bias):
+  //   y = rstd[row] * acc - rstd[row] * mean[row] * ln_c[col] + bias'[col], row statistics from ln_stats
+  //   ln_stats: fp32 [M][K/32][2] = per 32-column chunk (sum, M2 about the chunk mean) written by the producer
+  const float* ln_stats; const float* ln_c; float ln_eps;
+  // producer of the residual stream: also emit a bf16 copy of y (the next GEMM's TMA operand) and the row statistics
+  void* y2; float* stats_out;
 };
 
+// Programmatic dependent launch (griddepcontrol): kernels launched through sc::launch_pdl may start while their
+// predecessor in the stream drains; they must call sc::pdl_wait() before touching global memory.
+extern int g_sc_pdl;
+
 namespace sc {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_sc_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(256) self_attn_step_kernel(const T* __restrict
                                                              int n_prev, int write_slot) {
   const int chunks = D / 8;
   const int lanes = dk / 8;
+  sc::pdl_launch();
+  sc::pdl_wait();
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = g < (long)R * chunks;
   const int r = active ? (int)(g / chunks) : R - 1;
@@ -151,6 +153,8 @@ __global__ void __launch_bounds__(256) cross_attn_step_kernel(const T* __restric
   extern __shared__ __align__(16) unsigned char smem_x[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * warps + warp;
+  sc::pdl_launch();
+  sc::pdl_wait();
   if (w >= B * h) return;
   const int b = w / h, hh = w - b * h;
   const int rbk = dk * (int)sizeof(T) + 16;  // padded K rows: lane=key 16-byte reads are bank-conflict free
@@ -318,6 +322,8 @@ __global__ void __launch_bounds__(kBeamThreads) beam_row_kernel(const BeamArgs a
                                                                 Cand* __restrict__ ws_cand) {
   const int r = blockIdx.x;            // row = b*NB + k
   const int k = r % NB;
+  sc::pdl_launch();
+  sc::pdl_wait();
   if (a.t == 0 && k != 0) return;      // first step: every beam holds BOS, only beam 0 is expanded
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V;
@@ -443,6 +449,8 @@ __global__ void __launch_bounds__(kMergeThreads) beam_merge_kernel(const BeamArg
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int V = a.V;
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int rows = (a.t == 0) ? 1 : NB;
   __shared__ Cand s_final[NB];
   __shared__ int s_pos, s_last;
@@ -613,13 +621,13 @@ int sc_decode_self_attn_step(const void* q, const void* k, const void* v, int ld
   const long threads = (long)R * (D / 8);
   const int blocks = (int)((threads + 255) / 256);
   if (dtype == SC_F32)
-    self_attn_step_kernel<float><<<blocks, 256, 0, stream>>>((const float*)q, (const float*)k, (const float*)v, ldq, ldk, ldv,
-                                                             (float*)cache_k, (float*)cache_v, anc, anc_ld, slot_div,
-                                                             (float*)out, ldo, R, D, dk, n_prev, write_slot);
+    sc::launch_pdl(self_attn_step_kernel<float>, dim3(blocks), dim3(256), 0, stream, (const float*)q, (const float*)k,
+                   (const float*)v, ldq, ldk, ldv, (float*)cache_k, (float*)cache_v, anc, anc_ld, slot_div, (float*)out, ldo, R, D,
+                   dk, n_prev, write_slot);
   else if (dtype == SC_BF16)
-    self_attn_step_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
-        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldq, ldk, ldv, (__nv_bfloat16*)cache_k,
-        (__nv_bfloat16*)cache_v, anc, anc_ld, slot_div, (__nv_bfloat16*)out, ldo, R, D, dk, n_prev, write_slot);
+    sc::launch_pdl(self_attn_step_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, (const __nv_bfloat16*)q,
+                   (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldq, ldk, ldv, (__nv_bfloat16*)cache_k,
+                   (__nv_bfloat16*)cache_v, anc, anc_ld, slot_div, (__nv_bfloat16*)out, ldo, R, D, dk, n_prev, write_slot);
   else
     SC_CHECK(false, SC_ERR_DTYPE, "sc_decode_self_attn_step: bad dtype %d", dtype);
   SC_LAUNCH_CHECK("sc_decode_self_attn_step");
@@ -656,9 +664,8 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
       cudaFuncSetAttribute(cross_attn_step_kernel<T, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);    \
       attr_##NBV = true;                                                                                                \
     }                                                                                                                   \
-    cross_attn_step_kernel<T, NBV><<<blocks, 32 * warps, smem, stream>>>((const T*)q, ldq, (const T*)mem_k,             \
-                                                                         (const T*)mem_v, ldm, att_mask, (T*)out, ldo,  \
-                                                                         B, N, h, dk, warps);                           \
+    sc::launch_pdl(cross_attn_step_kernel<T, NBV>, dim3(blocks), dim3(32 * warps), smem, stream, (const T*)q, ldq,      \
+                   (const T*)mem_k, (const T*)mem_v, ldm, att_mask, (T*)out, ldo, B, N, h, dk, warps);                  \
   } while (0)
 #define XATT_NB(T)                                          \
   switch (beam) {                                           \
@@ -702,9 +709,9 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   const bool regs = V <= kBeamThreads * kBeamRegs;
 #define BEAM_LAUNCH(NBV)                                                                                     \
   do {                                                                                                        \
-    if (regs) beam_row_kernel<NBV, true><<<B * NBV, kBeamThreads, 0, stream>>>(a, ws_stats, ws_cand);          \
-    else beam_row_kernel<NBV, false><<<B * NBV, kBeamThreads, 0, stream>>>(a, ws_stats, ws_cand);              \
-    beam_merge_kernel<NBV><<<B, kMergeThreads, 0, stream>>>(a, ws_stats, ws_cand);                             \
+    if (regs) sc::launch_pdl(beam_row_kernel<NBV, true>, dim3(B * NBV), dim3(kBeamThreads), 0, stream, a, ws_stats, ws_cand);  \
+    else sc::launch_pdl(beam_row_kernel<NBV, false>, dim3(B * NBV), dim3(kBeamThreads), 0, stream, a, ws_stats, ws_cand);      \
+    sc::launch_pdl(beam_merge_kernel<NBV>, dim3(B), dim3(kMergeThreads), 0, stream, a, ws_stats, (const Cand*)ws_cand);         \
   } while (0)
   switch (beam) {
     case 1: BEAM_LAUNCH(1); break;

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  sc::pdl_launch();
+  sc::pdl_wait();
   if (warp >= rows) return;
   const float* xr = x + (size_t)warp * D;
   float v[kMaxPerLane];
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(128) embed_pe_kernel(const int* __restrict__ t
                                                        OutT* __restrict__ out, int rows, int D, int V, int T, int pos0,
                                                        float scale) {
   const int r = blockIdx.x;
+  sc::pdl_launch();
+  sc::pdl_wait();
   if (r >= rows) return;
   int tok = tokens[r];
   tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
@@ -68,6 +72,36 @@ __global__ void __launch_bounds__(128) embed_pe_kernel(const int* __restrict__ t
       w = (sc::u24(bits) < sc::sigmoidf_(__ldg(mask + e))) ? w : 0.f;
     }
     out[(size_t)r * D + c] = sc::from_f32<OutT>(w * scale + __ldg(pe + (size_t)pos * D + c));
+  }
+}
+
+// Decode-step embedding for the LayerNorm-folded path: one warp per row writes the fp32 residual stream, its bf16
+// copy (the next GEMM's TMA operand) and the per-32-column (sum, M2) statistics sc_linear_ln consumes.  D % 32 == 0.
+template <int kMaxPerLane>
+__global__ void __launch_bounds__(256) embed_pe_stats_kernel(const int* __restrict__ tokens, const float* __restrict__ table,
+                                                             const float* __restrict__ pe, float* __restrict__ x32,
+                                                             __nv_bfloat16* __restrict__ xb, float* __restrict__ stats,
+                                                             int rows, int D, int V, int T, int pos0, float scale) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  sc::pdl_launch();
+  sc::pdl_wait();
+  if (r >= rows) return;
+  int tok = tokens[r];
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  const int pos = pos0 + (r % T);
+  const int chunks = D >> 5;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    if (i >= chunks) break;
+    const int c = lane + i * 32;
+    const float v = __ldg(table + (size_t)tok * D + c) * scale + __ldg(pe + (size_t)pos * D + c);
+    x32[(size_t)r * D + c] = v;
+    xb[(size_t)r * D + c] = __float2bfloat16_rn(v);
+    const float s = sc::warp_sum(v);
+    const float dlt = v - s * (1.f / 32.f);
+    const float m2 = sc::warp_sum(dlt * dlt);
+    if (lane == 0) *(float2*)(stats + ((size_t)r * chunks + i) * 2) = make_float2(s, m2);
   }
 }
 
@@ -147,7 +181,7 @@ int sc_layernorm(const float* x, const float* a, const float* b, void* y, int y_
   SC_CHECK(rows > 0 && D > 1, SC_ERR_SHAPE, "sc_layernorm: rows=%d D=%d", rows, D);
   SC_CHECK(D <= 2048, SC_ERR_UNSUPPORTED, "sc_layernorm: D=%d > 2048", D);
   const int blocks = (rows + 7) / 8;
-#define LN_LAUNCH(T, P) layernorm_kernel<T, P><<<blocks, 256, 0, stream>>>(x, a, b, (T*)y, rows, D, eps)
+#define LN_LAUNCH(T, P) sc::launch_pdl(layernorm_kernel<T, P>, dim3(blocks), dim3(256), 0, stream, x, a, b, (T*)y, rows, D, eps)
   if (y_dtype == SC_F32) {
     if (D <= 128) LN_LAUNCH(float, 4); else if (D <= 512) LN_LAUNCH(float, 16); else LN_LAUNCH(float, 64);
   } else if (y_dtype == SC_BF16) {
@@ -166,14 +200,29 @@ int sc_embed_pe(const int* tokens, const float* table, const float* mask, int ma
   SC_CHECK(rows > 0 && D > 0 && V > 0 && T > 0, SC_ERR_SHAPE, "sc_embed_pe: rows=%d D=%d V=%d T=%d", rows, D, V, T);
   SC_CHECK(mask_mode == SC_MASK_NONE || mask != nullptr, SC_ERR_SHAPE, "sc_embed_pe: mask missing");
   if (out_dtype == SC_F32)
-    embed_pe_kernel<float><<<rows, 128, 0, stream>>>(tokens, table, mask, mask_mode, uniforms, seed, stream_id, pe,
-                                                     (float*)out, rows, D, V, T, pos0, scale);
+    sc::launch_pdl(embed_pe_kernel<float>, dim3(rows), dim3(128), 0, stream, tokens, table, mask, mask_mode, uniforms, seed,
+                   stream_id, pe, (float*)out, rows, D, V, T, pos0, scale);
   else if (out_dtype == SC_BF16)
-    embed_pe_kernel<__nv_bfloat16><<<rows, 128, 0, stream>>>(tokens, table, mask, mask_mode, uniforms, seed, stream_id, pe,
-                                                             (__nv_bfloat16*)out, rows, D, V, T, pos0, scale);
+    sc::launch_pdl(embed_pe_kernel<__nv_bfloat16>, dim3(rows), dim3(128), 0, stream, tokens, table, mask, mask_mode, uniforms,
+                   seed, stream_id, pe, (__nv_bfloat16*)out, rows, D, V, T, pos0, scale);
   else
     SC_CHECK(false, SC_ERR_DTYPE, "sc_embed_pe: bad dtype %d", out_dtype);
   SC_LAUNCH_CHECK("sc_embed_pe");
+  return SC_OK;
+}
+
+int sc_embed_pe_stats(const int* tokens, const float* table, const float* pe, float* x32, void* x_bf16, float* stats, int rows,
+                      int D, int V, int T, int pos0, float scale, cudaStream_t stream) {
+  SC_CHECK(rows > 0 && D > 0 && V > 0 && T > 0, SC_ERR_SHAPE, "sc_embed_pe_stats: rows=%d D=%d V=%d T=%d", rows, D, V, T);
+  SC_CHECK(D % 32 == 0 && D <= 2048, SC_ERR_UNSUPPORTED, "sc_embed_pe_stats: D=%d must be a multiple of 32, <= 2048", D);
+  const int blocks = (rows + 7) / 8;
+  if (D <= 512)
+    sc::launch_pdl(embed_pe_stats_kernel<16>, dim3(blocks), dim3(256), 0, stream, tokens, table, pe, x32, (__nv_bfloat16*)x_bf16,
+                   stats, rows, D, V, T, pos0, scale);
+  else
+    sc::launch_pdl(embed_pe_stats_kernel<64>, dim3(blocks), dim3(256), 0, stream, tokens, table, pe, x32, (__nv_bfloat16*)x_bf16,
+                   stats, rows, D, V, T, pos0, scale);
+  SC_LAUNCH_CHECK("sc_embed_pe_stats");
   return SC_OK;
 }
 

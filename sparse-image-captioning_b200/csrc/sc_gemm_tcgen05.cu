@@ -11,10 +11,12 @@
 //                 (the "operand-load prologue"); the masked weight never exists in HBM.
 //   D (fp32 [128 x BLOCK_N]) in TMEM; epilogue warps tcgen05.ld it, add bias / residual, ReLU, store.
 //
-// Warp roles (one CTA per output tile): w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM
-// allocator, w4-7 epilogue (TMEM lane quarter = warp%4), w8-11 B-transform (kMasked only).
+// Warp roles (persistent CTA, one per SM): w0 TMA producer, w1 MMA issuer (one elected lane), w2 TMEM allocator,
+// w4-11 epilogue (TMEM lane quarter = warp%4, two warps per quarter), w12-15 B-transform (kMasked only).
 #include "sc_common.cuh"
 #include <cuda.h>
+#include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -22,9 +24,12 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumTransformWarps = 4;
+constexpr int kNumEpilogueWarps = 8;   // two per TMEM lane quarter, splitting the tile's 32-column chunks
+constexpr int kFirstTransformWarp = 4 + kNumEpilogueWarps;
 
 struct GemmArgs {
   int M, N, K;
+  int tiles_n, num_tiles, splits, kb_per_split;  // persistent schedule: unit u -> (tile = u / splits, split = u % splits)
   const float* w32;      // kMasked: fp32 weights [N,K]
   const float* mask;     // kMasked: fp32 logits / raw mask / nullptr
   const float* uniforms; // SC_MASK_UNIFORM
@@ -40,6 +45,9 @@ struct GemmArgs {
   // weight-gradient mode: the accumulator tile is dWm[n,k]; the epilogue emits dW and dS (straight-through)
   int wgrad; int bypass; float sp_coeff; int accumulate;
   const float* wg_w; const float* wg_s; const float* wg_u; float* dw; float* ds;
+  // folded LayerNorm (consumer) / residual-stream producer (ScGemmExtra)
+  const float* ln_stats; const float* ln_c; float ln_eps;
+  void* y2; float* stats_out;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,29 +129,193 @@ struct Smem {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kStagingOffset = kStages * kStageBytes;                  // 8 epilogue warps x 4 KB transpose staging
+  static constexpr int kRowStatOffset = kStagingOffset + kNumEpilogueWarps * 4096;  // 8 warps x 32 rows x (rstd, mean*rstd)
+  static constexpr int kBarOffset = kRowStatOffset + kNumEpilogueWarps * 256;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
-// kStages: depth of the TMA->MMA ring.  Rings are kept shallow enough (64x4: 96 KB, 128x3: 96 KB) for two CTAs to
-// share an SM, so one CTA's epilogue overlaps the other's main loop (scripts/gemm_sweep.py: deeper rings with one
-// CTA per SM measured slower for every shape of this model).
-template <int BLOCK_N, bool kMasked, int kStages>
-__global__ void __launch_bounds__(kMasked ? 384 : 256, 1)
+// ---- epilogue ------------------------------------------------------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (32 columns of a chunk); touching global memory in that mapping
+// means 32 different 128-byte lines per warp instruction.  The chunk is therefore transposed through a 4 KB
+// XOR-swizzled staging tile per warp, and all element-wise work (bias, ReLU, dropout, residual, folded LayerNorm,
+// straight-through mask gradients) runs in the COALESCED mapping: 8 lanes x 16 bytes cover one row's 128 bytes, a
+// warp instruction covers 4 full rows.
+//
+// Forward element-wise stage in the ROW mapping (thread = accumulator row, f = its 32 columns of the chunk, residual
+// already added through the staging transpose): [folded LayerNorm] + bias, ReLU, dropout, + residual; kFull adds the
+// dropout / LayerNorm / row-statistics code.
+template <bool kFull>
+__device__ __forceinline__ void epilogue_row(const GemmArgs& args, float (&f)[32], const float (&res)[32], int row, int col0,
+                                             float ln_rstd, float ln_mr) {
+  const bool vec = (args.N & 3) == 0 && col0 + 32 <= args.N;
+  if (vec) {
+    if (kFull && args.ln_stats) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = __ldg((const float4*)(args.ln_c + col0) + j);
+        f[4 * j] = ln_rstd * f[4 * j] - ln_mr * c.x; f[4 * j + 1] = ln_rstd * f[4 * j + 1] - ln_mr * c.y;
+        f[4 * j + 2] = ln_rstd * f[4 * j + 2] - ln_mr * c.z; f[4 * j + 3] = ln_rstd * f[4 * j + 3] - ln_mr * c.w;
+      }
+    }
+    if (args.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg((const float4*)(args.bias + col0) + j);
+        f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col0 + j < args.N) {
+        if (kFull && args.ln_stats) f[j] = ln_rstd * f[j] - ln_mr * __ldg(args.ln_c + col0 + j);
+        if (args.bias) f[j] += __ldg(args.bias + col0 + j);
+      }
+    }
+  }
+  if (args.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (kFull && args.dropout_p > 0.f) {
+    // inverted dropout, keep mask = Philox(drop_seed, drop_stream, element); one draw serves 4 consecutive elements
+    const sc::Philox dph(args.drop_seed);
+    const float keep = 1.f / (1.f - args.dropout_p);
+    const size_t e0 = (size_t)row * args.N + col0;
+    if ((e0 & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 rr = dph((e0 >> 2) + j, args.drop_stream);
+        f[4 * j] *= sc::u24(rr.x) >= args.dropout_p ? keep : 0.f; f[4 * j + 1] *= sc::u24(rr.y) >= args.dropout_p ? keep : 0.f;
+        f[4 * j + 2] *= sc::u24(rr.z) >= args.dropout_p ? keep : 0.f; f[4 * j + 3] *= sc::u24(rr.w) >= args.dropout_p ? keep : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] *= sc::keep_scale(dph, e0 + j, args.drop_stream, args.dropout_p);
+    }
+  }
+  if (args.residual) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += res[j];
+  }
+  if (kFull && args.stats_out) {
+    // (sum, M2 about the chunk mean) of this row's 32-column chunk; the LayerNorm consumer merges the N/32 chunks
+    float sm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sm += f[j];
+    const float mu = sm * (1.f / 32.f);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float dlt = f[j] - mu; m2 += dlt * dlt; }
+    if (row < args.M) *(float2*)(args.stats_out + ((size_t)row * (args.N >> 5) + (col0 >> 5)) * 2) = make_float2(sm, m2);
+  }
+}
+
+// Store stage in the COALESCED mapping: 4 consecutive columns of one row (fp32 and/or bf16 copy).
+template <bool kFull>
+__device__ __forceinline__ void epilogue_store4(const GemmArgs& args, const float4& f, int row, int col) {
+  const size_t e = (size_t)row * args.N + col;
+  if ((args.N & 3) == 0) {
+    if (args.y_bf16 || (kFull && args.y2)) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
+      uint2 o;
+      o.x = *(const uint32_t*)&lo; o.y = *(const uint32_t*)&hi;
+      *(uint2*)((__nv_bfloat16*)(args.y_bf16 ? args.y : args.y2) + e) = o;
+    }
+    if (!args.y_bf16) *(float4*)((float*)args.y + e) = f;
+    return;
+  }
+  const float x[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col + i >= args.N) break;
+    if (args.y_bf16) ((__nv_bfloat16*)args.y)[e + i] = __float2bfloat16_rn(x[i]);
+    else ((float*)args.y)[e + i] = x[i];
+  }
+}
+
+// One float4 of the weight-gradient tile (K2): dW = dWm (.) m ; dS = dWm (.) W (.) sigmoid'(S) (+ sparsity term); the
+// mask is regenerated from (seed, stream, element).  Split-K partial sums go out as vector reductions into
+// pre-zeroed buffers; the sparsity term is added by split 0 only.
+__device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, int row, int col, bool atomic, bool first_split) {
+  const sc::Philox wph(args.seed);
+  const float sp = first_split ? args.sp_coeff : 0.f;
+  const size_t e = (size_t)row * args.N + col;
+  const float g[4] = {f.x, f.y, f.z, f.w};
+  if ((args.N & 3) == 0) {
+    const float4 w4 = __ldg((const float4*)(args.wg_w + e));
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = s4;
+    if (args.wg_s) s4 = __ldg((const float4*)(args.wg_s + e));
+    if (args.wg_u) u4 = __ldg((const float4*)(args.wg_u + e));
+    const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+    float m[4];
+    if (args.mask_mode == SC_MASK_BERNOULLI) {
+      sc::bernoulli4(wph, e >> 2, args.stream_id, sv, m);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = sc::mask_value(args.mask_mode, sv[i], uv[i], wph, e + i, args.stream_id);
+    }
+    float gw[4], gs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc::mask_grad_elem(args.mask_mode, g[i], wv[i], sv[i], m[i], args.bypass, sp, gw[i], gs[i]);
+    if (atomic) {
+      if (args.dw)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(args.dw + e), "f"(gw[0]), "f"(gw[1]), "f"(gw[2]), "f"(gw[3]) : "memory");
+      if (args.ds)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(args.ds + e), "f"(gs[0]), "f"(gs[1]), "f"(gs[2]), "f"(gs[3]) : "memory");
+    } else {
+      if (args.dw) {
+        float4 o = make_float4(gw[0], gw[1], gw[2], gw[3]);
+        if (args.accumulate) { const float4 p = *(const float4*)(args.dw + e); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        *(float4*)(args.dw + e) = o;
+      }
+      if (args.ds) {
+        float4 o = make_float4(gs[0], gs[1], gs[2], gs[3]);
+        if (args.accumulate) { const float4 p = *(const float4*)(args.ds + e); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+        *(float4*)(args.ds + e) = o;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col + i >= args.N) break;
+    const float sv = args.wg_s ? __ldg(args.wg_s + e + i) : 0.f;
+    const float m = sc::mask_value(args.mask_mode, sv, args.wg_u ? __ldg(args.wg_u + e + i) : 0.f, wph, e + i, args.stream_id);
+    float gw, gs;
+    sc::mask_grad_elem(args.mask_mode, g[i], __ldg(args.wg_w + e + i), sv, m, args.bypass, sp, gw, gs);
+    if (atomic) {
+      if (args.dw) atomicAdd(args.dw + e + i, gw);
+      if (args.ds) atomicAdd(args.ds + e + i, gs);
+    } else {
+      if (args.dw) args.dw[e + i] = (args.accumulate ? args.dw[e + i] : 0.f) + gw;
+      if (args.ds) args.ds[e + i] = (args.accumulate ? args.ds[e + i] : 0.f) + gs;
+    }
+  }
+}
+
+// Persistent kernel: CTA c processes work units c, c + gridDim.x, ...  (unit = output tile x K split; N-tiles of one
+// M block are adjacent units so that concurrently running CTAs share the A tile through L2).  The accumulator is
+// double-buffered in TMEM (2 x BLOCK_N columns): the epilogue of unit i overlaps the TMA/MMA main loop of unit i+1.
+// kStages: depth of the TMA->MMA smem ring.
+// kEpi: 0 = plain forward epilogue, 1 = full forward epilogue (dropout, folded LayerNorm, statistics), 2 = weight gradient
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi>
+__global__ void __launch_bounds__(kMasked ? 512 : 384, 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
   using L = Smem<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N;
-  const int m0 = blockIdx.y * BLOCK_M;
-  const int num_kb = (args.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb_total = (args.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_units = args.num_tiles * args.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
@@ -154,12 +326,15 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(&full_bar[s], kMasked ? 1 + kNumTransformWarps : 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], kNumEpilogueWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)BLOCK_N));
+                 "r"((uint32_t)(2 * BLOCK_N)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tcgen05_fence_before();
@@ -170,195 +345,244 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        mbar_expect_tx(&full_bar[s], kMasked ? L::kABytes : L::kStageBytes);
-        tma_load_2d(&tma_a, &full_bar[s], sa, kb * BLOCK_K, m0);
-        if (!kMasked) tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes, kb * BLOCK_K, n0);
+      sc::pdl_wait();  // A (and B) may be written by the previous kernel in the stream
+      int it = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int tile = u / args.splits, split = u - tile * args.splits;
+        const int m0 = (tile / args.tiles_n) * BLOCK_M, n0 = (tile % args.tiles_n) * BLOCK_N;
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = min(kb0 + args.kb_per_split, num_kb_total);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          mbar_expect_tx(&full_bar[s], kMasked ? L::kABytes : L::kStageBytes);
+          tma_load_2d(&tma_a, &full_bar[s], sa, kb * BLOCK_K, m0);
+          if (!kMasked) tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes, kb * BLOCK_K, n0);
+        }
       }
+      sc::pdl_launch();  // all loads of this CTA are in flight: let the next kernel's prologue start
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++lt) {
+        const int split = u % args.splits;
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = min(kb0 + args.kb_per_split, num_kb_total);
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
-        const uint64_t da = make_smem_desc(sa);
-        const uint64_t db = make_smem_desc(sa + L::kABytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + L::kABytes);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 32 B (16 bf16) along K inside the 128B swizzle row: +2 in 16-byte units
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) along K inside the 128B swizzle row: +2 in 16-byte units
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        tcgen05_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        tcgen05_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      tcgen05_commit(tmem_full_bar);  // accumulator complete
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < args.M;
-    const bool vec_ok = (args.N % 8) == 0;
-#pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= args.N) continue;
-      float f[32];
+  } else if (warp >= 4 && warp < 4 + kNumEpilogueWarps) {
+    // ===== epilogue: TMEM -> registers -> swizzled staging (transpose) -> coalesced global access =====
+    sc::pdl_wait();  // residual / statistics come from, and y may still be read by, the previous kernel
+    const int ew = warp - 4;
+    const int q = ew & 3;      // TMEM lane quarter this warp may read
+    const int half = ew >> 2;  // which of the tile's 32-column chunks (even / odd) this warp takes
+    uint8_t* stg = smem + L::kStagingOffset + ew * 4096;
+    const int jsw = lane & 7;  // swizzle key of this thread's own row (row-mapping: row = lane)
+    int lt = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++lt) {
+      const int tile = u / args.splits, split = u - tile * args.splits;
+      const int m0 = (tile / args.tiles_n) * BLOCK_M, n0 = (tile % args.tiles_n) * BLOCK_N;
+      const int buf = lt & 1;
+      const int rbase = m0 + q * 32;
+      float ln_rstd = 1.f, ln_mr = 0.f;
+      if (kEpi == 1 && args.ln_stats && rbase + lane < args.M) {
+        // merge the K/32 chunk statistics of row (rbase + lane) (Chan et al.): unbiased std, a*(x-mean)/(std+eps)+b
+        const int parts = args.K >> 5;
+        const float2* sp = (const float2*)(args.ln_stats + (size_t)(rbase + lane) * parts * 2);
+        float tot = 0.f, m2 = 0.f, mean;
+        if (parts == 16) {
+          // d_model = 512: the 16 (sum, M2) pairs of the row are 128 contiguous bytes -> 8 independent 16-byte loads
+          float4 sv[8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      if (args.wgrad) {
-        // K2: dW = dWm (.) m ; dS = dWm (.) W (.) sigmoid'(S) (+ sparsity term), mask regenerated from (seed, stream, element)
-        const sc::Philox wph(args.seed);
+          for (int p = 0; p < 8; ++p) sv[p] = ((const float4*)sp)[p];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col >= args.N) continue;
-          const size_t e = (size_t)row * args.N + col;
-          const float sv = args.wg_s ? __ldg(args.wg_s + e) : 0.f;
-          const float m = sc::mask_value(args.mask_mode, sv, args.wg_u ? __ldg(args.wg_u + e) : 0.f, wph, e, args.stream_id);
-          float gw, gs;
-          sc::mask_grad_elem(args.mask_mode, f[j], __ldg(args.wg_w + e), sv, m, args.bypass, args.sp_coeff, gw, gs);
-          if (args.dw) args.dw[e] = (args.accumulate ? args.dw[e] : 0.f) + gw;
-          if (args.ds) args.ds[e] = (args.accumulate ? args.ds[e] : 0.f) + gs;
-        }
-        continue;
-      }
-      if (args.dropout_p > 0.f) {
-        // training forward epilogue with dropout: scalar path (bias, act, dropout, residual)
-        const sc::Philox dph(args.drop_seed);
+          for (int p = 0; p < 8; ++p) tot += sv[p].x + sv[p].z;
+          mean = tot / (float)args.K;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col >= args.N) continue;
-          const size_t e = (size_t)row * args.N + col;
-          float x = f[j];
-          if (args.bias) x += __ldg(args.bias + col);
-          if (args.relu) x = fmaxf(x, 0.f);
-          x *= sc::keep_scale(dph, e, args.drop_stream, args.dropout_p);
-          if (args.residual) x += __ldg(args.residual + e);
-          if (args.y_bf16) ((__nv_bfloat16*)args.y)[e] = __float2bfloat16_rn(x);
-          else ((float*)args.y)[e] = x;
-        }
-        continue;
-      }
-      if (vec_ok && col0 + 32 <= args.N) {
-        if (args.bias) {
-          const float4* bp = (const float4*)(args.bias + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b = __ldg(bp + j);
-            f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-          }
-        }
-        if (args.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (args.residual) {
-          const float4* rp = (const float4*)(args.residual + (size_t)row * args.N + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 r = __ldg(rp + j);
-            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
-          }
-        }
-        if (args.y_bf16) {
-          uint4* yp = (uint4*)((__nv_bfloat16*)args.y + (size_t)row * args.N + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            uint4 o;
-            o.x = *(uint32_t*)&p0; o.y = *(uint32_t*)&p1; o.z = *(uint32_t*)&p2; o.w = *(uint32_t*)&p3;
-            yp[j] = o;
+          for (int p = 0; p < 8; ++p) {
+            const float d0 = sv[p].x * (1.f / 32.f) - mean, d1 = sv[p].z * (1.f / 32.f) - mean;
+            m2 += sv[p].y + sv[p].w + 32.f * (d0 * d0 + d1 * d1);
           }
         } else {
-          float4* yp = (float4*)((float*)args.y + (size_t)row * args.N + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) yp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int p = 0; p < parts; ++p) tot += sp[p].x;
+          mean = tot / (float)args.K;
+          for (int p = 0; p < parts; ++p) {
+            const float2 pv = sp[p];
+            const float dlt = pv.x * (1.f / 32.f) - mean;
+            m2 += pv.y + 32.f * dlt * dlt;
+          }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col >= args.N) continue;
-          float x = f[j];
-          if (args.bias) x += __ldg(args.bias + col);
-          if (args.relu) x = fmaxf(x, 0.f);
-          if (args.residual) x += __ldg(args.residual + (size_t)row * args.N + col);
-          if (args.y_bf16) ((__nv_bfloat16*)args.y)[(size_t)row * args.N + col] = __float2bfloat16_rn(x);
-          else ((float*)args.y)[(size_t)row * args.N + col] = x;
-        }
+        ln_rstd = 1.f / (sqrtf(m2 / (float)(args.K - 1)) + args.ln_eps);
+        ln_mr = ln_rstd * mean;
       }
+      mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= args.N || rbase >= args.M) continue;  // warp-uniform
+        // coalesced mapping: lane handles 16-byte piece (lane & 7) of rows (lane >> 3) + 4 i, i = 0..7
+        const int pj = lane & 7;
+        const int col = col0 + pj * 4;
+        // the residual chunk is requested (coalesced, 8 rows in flight per lane) before the accumulator is awaited
+        float4 rres[8];
+        const bool has_res = kEpi != 2 && args.residual != nullptr;
+        if (has_res) {
+          const bool vec = (args.N & 3) == 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row = rbase + i * 4 + (lane >> 3);
+            if (row < args.M && col < args.N) {
+              const float* rp = args.residual + (size_t)row * args.N + col;  // plain loads: written by the predecessor
+              if (vec) rres[i] = *(const float4*)rp;
+              else {
+                rres[i].x = rp[0];
+                if (col + 1 < args.N) rres[i].y = rp[1];
+                if (col + 2 < args.N) rres[i].z = rp[2];
+                if (col + 3 < args.N) rres[i].w = rp[3];
+              }
+            }
+          }
+        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+        if (kEpi != 2) {
+          float f[32], res[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); res[j] = 0.f; }
+          if (has_res) {
+            // residual: coalesced mapping -> staging -> row mapping (16-byte piece p of row r sits at piece p ^ (r & 7))
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + (lane >> 3);
+              *(float4*)(stg + rl * 128 + ((pj ^ (rl & 7)) << 4)) = rres[i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = *(const float4*)(stg + lane * 128 + ((j ^ jsw) << 4));
+              res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w;
+            }
+            __syncwarp();
+          }
+          epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *(float4*)(stg + lane * 128 + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + (lane >> 3);
+            const float4 o = *(const float4*)(stg + rl * 128 + ((pj ^ (rl & 7)) << 4));
+            if (rbase + rl < args.M && col < args.N) epilogue_store4<kEpi == 1>(args, o, rbase + rl, col);
+          }
+        } else {
+          // weight gradient: transpose the raw accumulator, element-wise work in the coalesced mapping
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *(uint4*)(stg + lane * 128 + ((j ^ jsw) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + (lane >> 3);
+            const float4 g4 = *(const float4*)(stg + rl * 128 + ((pj ^ (rl & 7)) << 4));
+            if (rbase + rl < args.M && col < args.N) epilogue_wgrad4(args, g4, rbase + rl, col, args.splits > 1, split == 0);
+          }
+        }
+        __syncwarp();  // staging is rewritten by the next chunk
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-  } else if (kMasked && warp >= 8) {
+  } else if (kMasked && warp >= kFirstTransformWarp) {
     // ===== B transform: fp32 W (+ mask logits) -> masked bf16 operand tile (swizzled K-major) =====
-    const int t = threadIdx.x - 256;  // 0..127
+    sc::pdl_wait();
+    const int t = threadIdx.x - 32 * kFirstTransformWarp;  // 0..127
     const int chunk = t & 15;         // float4 index inside the 64-wide k block
     const int rbase = t >> 4;         // 0..7
     const sc::Philox philox(args.seed);
     constexpr int kPasses = BLOCK_N / 8;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % kStages;
-      const uint32_t ph = (kb / kStages) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* sb = smem + s * L::kStageBytes + L::kABytes;
-      const int k = kb * BLOCK_K + chunk * 4;
+    int it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int tile = u / args.splits, split = u - tile * args.splits;
+      const int n0 = (tile % args.tiles_n) * BLOCK_N;
+      const int kb0 = split * args.kb_per_split;
+      const int kb1 = min(kb0 + args.kb_per_split, num_kb_total);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sb = smem + s * L::kStageBytes + L::kABytes;
+        const int k = kb * BLOCK_K + chunk * 4;
 #pragma unroll 4
-      for (int p = 0; p < kPasses; ++p) {
-        const int r = rbase + p * 8;
-        const int n = n0 + r;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < args.N && k < args.K) {
-          const size_t e = (size_t)n * args.K + k;
-          w = __ldg((const float4*)(args.w32 + e));
-          if (args.mask_mode != SC_MASK_NONE) {
-            const float4 sv = __ldg((const float4*)(args.mask + e));
-            float m[4];
-            const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
-            if (args.mask_mode == SC_MASK_ROUND) {
+        for (int p = 0; p < kPasses; ++p) {
+          const int r = rbase + p * 8;
+          const int n = n0 + r;
+          float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < args.N && k < args.K) {
+            const size_t e = (size_t)n * args.K + k;
+            w = __ldg((const float4*)(args.w32 + e));
+            if (args.mask_mode != SC_MASK_NONE) {
+              const float4 sv = __ldg((const float4*)(args.mask + e));
+              float m[4];
+              const float sa[4] = {sv.x, sv.y, sv.z, sv.w};
+              if (args.mask_mode == SC_MASK_ROUND) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) m[i] = sc::mask_round(sa[i]);
-            } else if (args.mask_mode == SC_MASK_BERNOULLI) {
-              sc::bernoulli4(philox, e >> 2, args.stream_id, sa, m);
-            } else if (args.mask_mode == SC_MASK_UNIFORM) {
-              const float4 u = __ldg((const float4*)(args.uniforms + e));
-              m[0] = u.x < sc::sigmoidf_(sa[0]) ? 1.f : 0.f;
-              m[1] = u.y < sc::sigmoidf_(sa[1]) ? 1.f : 0.f;
-              m[2] = u.z < sc::sigmoidf_(sa[2]) ? 1.f : 0.f;
-              m[3] = u.w < sc::sigmoidf_(sa[3]) ? 1.f : 0.f;
-            } else {
+                for (int i = 0; i < 4; ++i) m[i] = sc::mask_round(sa[i]);
+              } else if (args.mask_mode == SC_MASK_BERNOULLI) {
+                sc::bernoulli4(philox, e >> 2, args.stream_id, sa, m);
+              } else if (args.mask_mode == SC_MASK_UNIFORM) {
+                const float4 uu = __ldg((const float4*)(args.uniforms + e));
+                m[0] = uu.x < sc::sigmoidf_(sa[0]) ? 1.f : 0.f;
+                m[1] = uu.y < sc::sigmoidf_(sa[1]) ? 1.f : 0.f;
+                m[2] = uu.z < sc::sigmoidf_(sa[2]) ? 1.f : 0.f;
+                m[3] = uu.w < sc::sigmoidf_(sa[3]) ? 1.f : 0.f;
+              } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) m[i] = sa[i];
+                for (int i = 0; i < 4; ++i) m[i] = sa[i];
+              }
+              w.x *= m[0]; w.y *= m[1]; w.z *= m[2]; w.w *= m[3];
             }
-            w.x *= m[0]; w.y *= m[1]; w.z *= m[2]; w.w *= m[3];
           }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(w.z, w.w);
+          uint2 o;
+          o.x = *(uint32_t*)&lo; o.y = *(uint32_t*)&hi;
+          // element (r, kk = chunk*4): 16-byte chunk index kk/8 = chunk>>1, XOR-swizzled with r%8
+          const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)chunk >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)chunk & 1u) << 3);
+          *(uint2*)(sb + off) = o;
         }
-        __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(w.z, w.w);
-        uint2 o;
-        o.x = *(uint32_t*)&lo; o.y = *(uint32_t*)&hi;
-        // element (r, kk = chunk*4): 16-byte chunk index kk/8 = chunk>>1, XOR-swizzled with r%8
-        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)chunk >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)chunk & 1u) << 3);
-        *(uint2*)(sb + off) = o;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
     }
   }
 
@@ -366,7 +590,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)));
   }
 }
 
@@ -402,9 +626,19 @@ int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int box_row
   return SC_OK;
 }
 
-template <int BLOCK_N, bool kMasked, int kStages>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages>;
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_splits, cudaStream_t stream) {
+  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi>;
   constexpr int smem = Smem<BLOCK_N, kStages>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
@@ -412,8 +646,33 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cuda
     SC_CHECK(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((a.N + BLOCK_N - 1) / BLOCK_N, (a.M + BLOCK_M - 1) / BLOCK_M);
-  kern<<<grid, kMasked ? 384 : 256, smem, stream>>>(ta, tb, a);
+  a.tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
+  a.num_tiles = a.tiles_n * ((a.M + BLOCK_M - 1) / BLOCK_M);
+  const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
+  // split K (weight gradients only: few output tiles, thousands of tokens to contract) until the SMs are covered
+  int splits = 1;
+  if (a.wgrad) {
+    splits = want_splits > 0 ? want_splits : (a.num_tiles >= sm_count() ? 1 : (sm_count() + a.num_tiles - 1) / a.num_tiles);
+    splits = max(1, min(splits, num_kb / 4 > 0 ? num_kb / 4 : 1));
+  }
+  a.kb_per_split = (num_kb + splits - 1) / splits;
+  a.splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;
+  if (a.wgrad && a.splits > 1 && !a.accumulate) {
+    if (a.dw) cudaMemsetAsync(a.dw, 0, (size_t)a.M * a.N * sizeof(float), stream);
+    if (a.ds) cudaMemsetAsync(a.ds, 0, (size_t)a.M * a.N * sizeof(float), stream);
+  }
+  // persistent grid, never more CTAs than work units
+  static int env_per_sm = -1;
+  if (env_per_sm < 0) { const char* e = getenv("SC_GEMM_PER_SM"); env_per_sm = e ? atoi(e) : 0; }
+  // one persistent CTA per SM: two co-resident CTAs of this kernel measured slower than one CTA looping over two tiles
+  const int per_sm = env_per_sm > 0 ? env_per_sm : 1;
+  const int units = a.num_tiles * a.splits;
+  dim3 grid(min(units, per_sm * sm_count()));
+  cudaError_t e = sc::launch_pdl(kern, grid, dim3(kMasked ? 512 : 384), (size_t)smem, stream, ta, tb, a);
+  if (e != cudaSuccess) {
+    sc_set_error("sc_gemm_bf16_kernel: launch failed: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
   SC_LAUNCH_CHECK("sc_gemm_bf16_kernel");
   return SC_OK;
 }
@@ -432,6 +691,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   SC_CHECK(y_dtype == SC_F32 || y_dtype == SC_BF16, SC_ERR_DTYPE, "sc_linear: bad y dtype %d", y_dtype);
   const bool wgrad = ex && ex->wgrad;
   const bool masked = (w_dtype == SC_F32);
+  SC_CHECK(!(masked && wgrad), SC_ERR_UNSUPPORTED, "sc_linear_wgrad: operands must be in the activation dtype");
   SC_CHECK(masked || mask_mode == SC_MASK_NONE || wgrad, SC_ERR_DTYPE,
            "sc_linear(bf16): mask modes need fp32 master weights (bf16 weights are expected pre-masked)");
   if (masked && mask_mode != SC_MASK_NONE) {
@@ -439,16 +699,29 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     SC_CHECK(mask_mode != SC_MASK_UNIFORM || uniforms != nullptr, SC_ERR_SHAPE, "sc_linear: uniforms missing");
     SC_CHECK(K % 4 == 0, SC_ERR_SHAPE, "K %% 4");
   }
-  const long tiles128 = (long)((N + 127) / 128) * ((M + 127) / 128);
-  int force_stages = 0;
-  if (block_n >= 1000) {  // tuning hook: tile_n = 1000 * stages + block_n
+  if (ex && (ex->ln_stats || ex->stats_out || ex->y2)) {
+    SC_CHECK(!wgrad, SC_ERR_UNSUPPORTED, "sc_linear: LayerNorm folding is a forward feature");
+    SC_CHECK(!ex->ln_stats || (K % 32 == 0 && ex->ln_c != nullptr && ((uintptr_t)ex->ln_c & 15) == 0), SC_ERR_SHAPE,
+             "sc_linear_ln: K=%d must be a multiple of 32 and ln_c 16-byte aligned", K);
+    SC_CHECK(!(ex->stats_out || ex->y2) || N % 32 == 0, SC_ERR_SHAPE, "sc_linear_ln: N=%d must be a multiple of 32 to emit row statistics", N);
+    SC_CHECK(!ex->y2 || (y_dtype == SC_F32 && ((uintptr_t)ex->y2 & 15) == 0), SC_ERR_DTYPE, "sc_linear_ln: the bf16 copy needs an fp32 y");
+  }
+  const int sms = sm_count();
+  const long mt = (M + 127) / 128;
+  int force_stages = 0, force_splits = 0;
+  if (block_n >= 100000) {  // tuning hook: tile_n = 100000 * splits + 1000 * stages + block_n
+    force_splits = block_n / 100000;
+    block_n %= 100000;
+  }
+  if (block_n >= 1000) {
     force_stages = block_n / 1000;
     block_n %= 1000;
   }
   if (block_n == 0) {
-    // fill the 148 SMs: prefer the widest tile that still yields >= ~1 wave
-    // measured with scripts/gemm_sweep.py (in-graph, L2-warm): 128-wide tiles win once they fill the 148 SMs
-    block_n = (tiles128 >= 148) ? 128 : 64;
+    // widest tile that still gives most SMs a tile (scripts/gemm_sweep.py, in-graph, L2-warm, round 1 numbers in DESIGN.md)
+    const long t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+    block_n = (t256 >= sms && !masked) ? 256 : (t128 >= 100 ? 128 : 64);
+    if (wgrad) block_n = (t128 >= sms / 4) ? 128 : 64;
     if (N <= 64) block_n = 64;
   }
   CUtensorMap ta, tb;
@@ -461,25 +734,32 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     tb = ta;
   }
   GemmArgs a;
+  memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K;
   a.w32 = masked ? (const float*)w : nullptr;
   a.mask = mask; a.uniforms = uniforms; a.mask_mode = mask_mode;
   a.seed = seed; a.stream_id = stream_id;
   a.bias = bias; a.residual = residual; a.y = y; a.y_bf16 = (y_dtype == SC_BF16); a.relu = relu;
-  a.dropout_p = 0.f; a.drop_seed = 0; a.drop_stream = 0; a.wgrad = 0; a.bypass = 0; a.sp_coeff = 0.f; a.accumulate = 0;
-  a.wg_w = nullptr; a.wg_s = nullptr; a.wg_u = nullptr; a.dw = nullptr; a.ds = nullptr;
   if (ex) {
     a.dropout_p = ex->dropout_p; a.drop_seed = ex->drop_seed; a.drop_stream = ex->drop_stream;
     a.wgrad = ex->wgrad; a.bypass = ex->bypass; a.sp_coeff = ex->sp_coeff; a.accumulate = ex->accumulate;
     a.wg_w = ex->wg_w; a.wg_s = ex->wg_s; a.wg_u = ex->wg_u; a.dw = ex->dw; a.ds = ex->ds;
+    a.ln_stats = ex->ln_stats; a.ln_c = ex->ln_c; a.ln_eps = ex->ln_eps; a.y2 = ex->y2; a.stats_out = ex->stats_out;
   }
-#define SC_GEMM_CASE(BN, ST) \
-  if (block_n == BN && stages == ST) return masked ? launch<BN, true, ST>(ta, tb, a, stream) : launch<BN, false, ST>(ta, tb, a, stream)
+  const int epi = a.wgrad ? 2 : ((a.dropout_p > 0.f || a.ln_stats || a.y2 || a.stats_out) ? 1 : 0);
+#define SC_GEMM_CASE(BN, ST)                                                                                          \
+  if (block_n == BN && stages == ST) {                                                                                \
+    if (masked) return epi ? launch<BN, true, ST, 1>(ta, tb, a, force_splits, stream)                                 \
+                           : launch<BN, true, ST, 0>(ta, tb, a, force_splits, stream);                                \
+    return epi == 2 ? launch<BN, false, ST, 2>(ta, tb, a, force_splits, stream)                                       \
+         : epi == 1 ? launch<BN, false, ST, 1>(ta, tb, a, force_splits, stream)                                       \
+                    : launch<BN, false, ST, 0>(ta, tb, a, force_splits, stream);                                      \
+  }
   int stages = force_stages;
-  if (stages == 0) stages = block_n == 64 ? 4 : block_n == 256 ? 4 : 3;
-  SC_GEMM_CASE(64, 4); SC_GEMM_CASE(64, 8);
-  SC_GEMM_CASE(128, 3); SC_GEMM_CASE(128, 4); SC_GEMM_CASE(128, 6);
-  SC_GEMM_CASE(256, 4);
+  if (stages == 0) stages = block_n == 64 ? 4 : block_n == 256 ? 3 : 4;
+  SC_GEMM_CASE(64, 4); SC_GEMM_CASE(64, 6);
+  SC_GEMM_CASE(128, 3); SC_GEMM_CASE(128, 4); SC_GEMM_CASE(128, 5);
+  SC_GEMM_CASE(256, 3);
 #undef SC_GEMM_CASE
   SC_CHECK(false, SC_ERR_UNSUPPORTED, "sc_linear(bf16): tile %d x %d stages not instantiated", block_n, stages);
   return SC_OK;

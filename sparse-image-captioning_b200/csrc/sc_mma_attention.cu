@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(128) enc_attn_mma_kernel(const EncAttnArgs a) 
   extern __shared__ __align__(16) unsigned char smem_x[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * a.warps + warp;
+  sc::pdl_launch();
+  sc::pdl_wait();
   if (w >= a.B * a.h) return;
   const int b = w / a.h, hh = w - b * a.h;
   constexpr int kRows = 16 * NT;
@@ -198,6 +200,8 @@ __global__ void __launch_bounds__(256) cross_attn_mma_kernel(const CrossAttnArgs
   extern __shared__ __align__(16) unsigned char smem_x[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * a.warps + warp;
+  sc::pdl_launch();
+  sc::pdl_wait();
   if (w >= a.B * a.h) return;
   const int b = w / a.h, hh = w - b * a.h;
   constexpr int kRows = 16 * NT;
@@ -335,7 +339,7 @@ int sc_bias_attention_fwd(const void* q, const void* k, const void* v, int ldq, 
       cudaFuncSetAttribute(enc_attn_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
       attr = true;                                                                                                 \
     }                                                                                                              \
-    enc_attn_mma_kernel<NTV><<<blocks, 32 * warps, smem, stream>>>(a);                                             \
+    sc::launch_pdl(enc_attn_mma_kernel<NTV>, dim3(blocks), dim3(32 * warps), smem, stream, a);                     \
   } break
   switch (NT) {
     ENC_CASE(1); ENC_CASE(2); ENC_CASE(3); ENC_CASE(4); ENC_CASE(5); ENC_CASE(6); ENC_CASE(7); ENC_CASE(8);
@@ -372,7 +376,7 @@ int sc_cross_attn_mma_launch(const void* q, int ldq, const void* mem_k, const vo
       cudaFuncSetAttribute(cross_attn_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   \
       attr = true;                                                                                                 \
     }                                                                                                              \
-    cross_attn_mma_kernel<NTV><<<blocks, 32 * warps, smem, stream>>>(a);                                           \
+    sc::launch_pdl(cross_attn_mma_kernel<NTV>, dim3(blocks), dim3(32 * warps), smem, stream, a);                   \
   } break
   switch (NT) {
     X_CASE(1); X_CASE(2); X_CASE(3); X_CASE(4); X_CASE(5); X_CASE(6); X_CASE(7); X_CASE(8);

@@ -62,9 +62,13 @@ def _att_parts(share_att):
 
 
 class _Lin:
-    """One packed linear: dense weight in the activation dtype and/or CSR, fp32 bias."""
+    """One packed linear: dense weight in the activation dtype and/or CSR, fp32 bias.
 
-    def __init__(self, w, b, adt, backend, csr_threshold):
+    ``norm=(a_2, b_2)``: the LayerNorm in front of this linear (SublayerConnection, transformer.py:345-358) is folded
+    into it for the bf16 tensor path: ``wf = (W (.) a_2)`` in bf16, ``ln_c = rowsum(wf)``, ``bias_f = W b_2 + bias``;
+    ``ln()`` then consumes the un-normalised bf16 residual stream + its row statistics (sc_linear_ln)."""
+
+    def __init__(self, w, b, adt, backend, csr_threshold, norm=None):
         w = w.detach().float().contiguous()
         self.N, self.K = w.shape
         self.bias = None if b is None else b.detach().float().contiguous()
@@ -74,6 +78,20 @@ class _Lin:
         self.w = None
         if not use_csr:
             self.w = K.cast_bf16(w) if adt == torch.bfloat16 else w
+        self.wf = None
+        if norm is not None and not use_csr and adt == torch.bfloat16 and self.K % 32 == 0:
+            a2, b2 = norm
+            self.wf = (w * a2.float()[None, :]).to(torch.bfloat16).contiguous()
+            self.ln_c = self.wf.float().sum(1).contiguous()
+            self.bias_f = (w @ b2.float() + (self.bias if self.bias is not None else 0.0)).contiguous()
+
+    def ln(self, xb, stats, out, relu=False):
+        """out = act(LayerNorm(x) W^T + b) from the bf16 copy of x and its chunk statistics."""
+        return K.linear_ln(xb, self.wf, self.bias_f, out=out, relu=relu, ln_stats=stats, ln_c=self.ln_c)
+
+    def produce(self, x, out, out_bf16, stats, residual=None, relu=False):
+        """out (fp32 residual stream) = act(x W^T + b) + residual, plus its bf16 copy and chunk statistics."""
+        return K.linear_ln(x, self.w, self.bias, residual=residual, relu=relu, out=out, out_bf16=out_bf16, stats_out=stats)
 
     def __call__(self, x, out, residual=None, relu=False):
         if self.csr is not None:
@@ -144,7 +162,7 @@ class OrtEngine:
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, precision="bf16", sparse_backend="dense",
-                 csr_threshold=0.97, device="cuda", use_graphs=True, no_history=False):
+                 csr_threshold=0.97, device="cuda", use_graphs=True, no_history=False, ln_fold=False):
         if not torch.cuda.is_available():
             raise RuntimeError("OrtEngine needs a CUDA device: the B200 path has no CPU fallback")
         lib.load()
@@ -160,10 +178,14 @@ class OrtEngine:
         sd.update({k: v.to(self.dev).to_dense() for k, v in state_dict.items() if torch.is_tensor(v) and v.is_sparse})
         d, adt = cfg.d_model, self.adt
 
-        def lin(prefixes, backend="dense"):
+        # LayerNorm folding (bf16 tensor path only): every pre-norm is absorbed by the GEMM that consumes it
+        self.ln_fold = bool(ln_fold) and adt == torch.bfloat16 and d % 32 == 0
+
+        def lin(prefixes, backend="dense", norm=None):
             ws = torch.cat([sd[p + ".weight"].float() for p in prefixes], 0)
             bs = torch.cat([sd[p + ".bias"].float() for p in prefixes], 0)
-            return _Lin(ws, bs, adt, backend, csr_threshold)
+            nrm = (sd[norm + ".a_2"], sd[norm + ".b_2"]) if (norm and self.ln_fold) else None
+            return _Lin(ws, bs, adt, backend, csr_threshold, norm=nrm)
 
         self.att_embed = lin(["att_embed.0"])
         # ---- encoder (unique modules only; shared layers re-use the pack) ----
@@ -176,13 +198,13 @@ class OrtEngine:
             p = f"model.encoder.layers.{pos}"
             parts = sorted(set((qi, ki, vi)))
             e = {
-                "qkv": lin([f"{p}.self_attn.linears.{j}" for j in parts]),
+                "qkv": lin([f"{p}.self_attn.linears.{j}" for j in parts], norm=f"{p}.sublayer.0.norm"),
                 "offs": tuple(parts.index(j) * d for j in (qi, ki, vi)),
                 "ld": len(parts) * d,
                 "o": lin([f"{p}.self_attn.linears.{oi}"]),
                 "wg_w": torch.cat([sd[f"{p}.self_attn.WGs.{j}.weight"].float() for j in range(cfg.num_heads)], 0).contiguous(),
                 "wg_b": torch.cat([sd[f"{p}.self_attn.WGs.{j}.bias"].float() for j in range(cfg.num_heads)], 0).contiguous(),
-                "ff1": lin([f"{p}.feed_forward.w_1"]),
+                "ff1": lin([f"{p}.feed_forward.w_1"], norm=f"{p}.sublayer.1.norm"),
                 "ff2": lin([f"{p}.feed_forward.w_2"]),
                 "n0": _Norm(sd, f"{p}.sublayer.0.norm"),
                 "n1": _Norm(sd, f"{p}.sublayer.1.norm"),
@@ -210,16 +232,16 @@ class OrtEngine:
                 # cross-attention: key = linears.0(memory), value = linears.1(memory)
                 kv_parts = [0, 1]
             e = {
-                "qkv": lin([f"{p}.self_attn.linears.{j}" for j in parts], be),
+                "qkv": lin([f"{p}.self_attn.linears.{j}" for j in parts], be, norm=f"{p}.sublayer.0.norm"),
                 "offs": tuple(parts.index(j) * d for j in (qi, ki, vi)),
                 "ld": len(parts) * d,
                 "o": lin([f"{p}.self_attn.linears.{oi}"], be),
-                "cq": lin([f"{p}.src_attn.linears.{qi}"], be),
-                "ckv": lin([f"{p}.src_attn.linears.{j}" for j in kv_parts]),
+                "cq": lin([f"{p}.src_attn.linears.{qi}"], be, norm=f"{p}.sublayer.1.norm"),
+                "ckv": lin([f"{p}.src_attn.linears.{j}" for j in kv_parts], norm="model.encoder.norm"),
                 "ckv_offs": tuple(kv_parts.index(j) * d for j in (ki, vi)),
                 "ckv_ld": len(kv_parts) * d,
                 "co": lin([f"{p}.src_attn.linears.{oi}"], be),
-                "ff1": lin([f"{p}.feed_forward.w_1"], be),
+                "ff1": lin([f"{p}.feed_forward.w_1"], be, norm=f"{p}.sublayer.2.norm"),
                 "ff2": lin([f"{p}.feed_forward.w_2"], be),
                 "n0": _Norm(sd, f"{p}.sublayer.0.norm"),
                 "n1": _Norm(sd, f"{p}.sublayer.1.norm"),
@@ -232,7 +254,10 @@ class OrtEngine:
         L = cfg.max_seq_length
         pe = sd.get("model.tgt_embed.1.pe")
         self.pe = (pe[0, : L + 2] if pe is not None else _positional_encoding(d, L + 2, self.dev)).float().contiguous()
-        self.generator = lin(["model.generator.proj"], be)
+        self.generator = lin(["model.generator.proj"], be, norm="model.decoder.norm")
+        # the folded decode path needs every decoder linear on the dense tensor path
+        self.fold_dec = self.ln_fold and all(
+            e[k].csr is None for e in self.dec.values() for k in ("qkv", "o", "cq", "co", "ff1", "ff2")) and self.generator.csr is None
         self._enc_ws = {}
         self._dec_ws = {}
         self._streams = {}
@@ -267,6 +292,10 @@ class OrtEngine:
         ws.hid = torch.zeros(M, ff, device=dev, dtype=adt)
         ws.mem = torch.zeros(M, d, device=dev, dtype=adt)
         ws.memkv = {u: torch.zeros(M, e["ckv_ld"], device=dev, dtype=adt) for u, e in self.dec.items()}
+        ws.fold = self.ln_fold and not masked
+        if ws.fold:
+            ws.xb = torch.zeros(M, d, device=dev, dtype=adt)
+            ws.stats = torch.zeros(M, d // 32, 2, device=dev)
         ws.box_bias = (torch.zeros(len(self.enc), B, c.num_heads, N, N, device=dev)
                        if self.split_box_attn and N <= 128 else None)
         ws.graph = None
@@ -279,7 +308,11 @@ class OrtEngine:
         dk = d // h
         if ws.att_a is not ws.att_in:
             K.cast_bf16(ws.att_in, out=ws.att_a)
-        self.att_embed(ws.att_a, ws.x, relu=True)
+        fold = ws.fold
+        if fold:
+            self.att_embed.produce(ws.att_a, ws.x, ws.xb, ws.stats, relu=True)
+        else:
+            self.att_embed(ws.att_a, ws.x, relu=True)
         if ws.att_mask is not None:
             K.mask_rows(ws.x, ws.att_mask.view(-1))
         trig = not c.no_box_trigonometric_embedding
@@ -287,10 +320,13 @@ class OrtEngine:
             K.box_bias_all(ws.boxes, self.wg_w_all, self.wg_b_all, ws.box_bias, B=B, N=N, layers=len(self.enc), h=h, trig=trig)
         for u in self.enc_uids:
             e = self.enc[u]
-            e["n0"](ws.x, ws.xn)
             ld = e["ld"]
             qkv = ws.qkv.view(-1)[: B * N * ld].view(B * N, ld)
-            e["qkv"](ws.xn, qkv)
+            if fold:
+                e["qkv"].ln(ws.xb, ws.stats, qkv)
+            else:
+                e["n0"](ws.x, ws.xn)
+                e["qkv"](ws.xn, qkv)
             qo, ko, vo = e["offs"]
             if ws.box_bias is not None:
                 K.bias_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.box_bias[self.enc_slot[u]], ws.att_mask, ws.att,
@@ -298,13 +334,22 @@ class OrtEngine:
             else:
                 K.box_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.boxes, e["wg_w"], e["wg_b"], ws.att_mask, ws.att,
                                 B=B, N=N, h=h, dk=dk, ldq=ld, ldk=ld, ldv=ld, ldo=d, trig=trig)
-            e["o"](ws.att, ws.x, residual=ws.x)
-            e["n1"](ws.x, ws.xn)
-            e["ff1"](ws.xn, ws.hid, relu=True)
-            e["ff2"](ws.hid, ws.x, residual=ws.x)
-        self.enc_norm(ws.x, ws.mem)
-        for u, e in self.dec.items():
-            e["ckv"](ws.mem, ws.memkv[u])
+            if fold:
+                e["o"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x)
+                e["ff1"].ln(ws.xb, ws.stats, ws.hid, relu=True)
+                e["ff2"].produce(ws.hid, ws.x, ws.xb, ws.stats, residual=ws.x)
+            else:
+                e["o"](ws.att, ws.x, residual=ws.x)
+                e["n1"](ws.x, ws.xn)
+                e["ff1"](ws.xn, ws.hid, relu=True)
+                e["ff2"](ws.hid, ws.x, residual=ws.x)
+        if fold:
+            for u, e in self.dec.items():
+                e["ckv"].ln(ws.xb, ws.stats, ws.memkv[u])
+        else:
+            self.enc_norm(ws.x, ws.mem)
+            for u, e in self.dec.items():
+                e["ckv"](ws.mem, ws.memkv[u])
 
     def encode(self, att_feats, boxes, att_masks=None, slot=0):
         """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V.
@@ -358,6 +403,9 @@ class OrtEngine:
         ws.qc = torch.zeros(R, d, device=dev, dtype=adt)
         ws.hid = torch.zeros(R, ff, device=dev, dtype=adt)
         ws.logits = torch.zeros(R, V, device=dev)
+        if self.fold_dec:
+            ws.xb = torch.zeros(R, d, device=dev, dtype=adt)
+            ws.stats = torch.zeros(R, d // 32, 2, device=dev)
         ws.cache = {u: (torch.zeros(L * e["apps"], R, d, device=dev, dtype=adt),
                         torch.zeros(L * e["apps"], R, d, device=dev, dtype=adt)) for u, e in self.dec.items()}
         ws.state = GreedyState(R, L, dev) if greedy else BeamState(B, beam, L, dev)
@@ -369,14 +417,21 @@ class OrtEngine:
     def _decode_step(self, ws, enc, t, anc):
         c = self.cfg
         R, d, h, N = ws.R, c.d_model, c.num_heads, ws.N
-        K.embed_pe(ws.state.tokens, self.table, self.pe, T=1, pos0=t, out=ws.x)
+        fold = self.fold_dec
+        if fold:
+            K.embed_pe_stats(ws.state.tokens, self.table, self.pe, ws.x, ws.xb, ws.stats, T=1, pos0=t)
+        else:
+            K.embed_pe(ws.state.tokens, self.table, self.pe, T=1, pos0=t, out=ws.x)
         used = {u: 0 for u in self.dec}
         for u in self.dec_uids:
             e = self.dec[u]
-            e["n0"](ws.x, ws.xn)
             ld = e["ld"]
             qkv = ws.qkv.view(-1)[: R * ld].view(R, ld)
-            e["qkv"](ws.xn, qkv)
+            if fold:
+                e["qkv"].ln(ws.xb, ws.stats, qkv)
+            else:
+                e["n0"](ws.x, ws.xn)
+                e["qkv"](ws.xn, qkv)
             qo, ko, vo = e["offs"]
             apps = e["apps"]
             slot = t * apps + used[u]
@@ -385,19 +440,31 @@ class OrtEngine:
             K.self_attn_step(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ck, cv, anc, ws.att, R=R, D=d, h=h,
                              n_prev=0 if self.no_history else slot, write_slot=-1 if self.no_history else slot,
                              ldq=ld, ldk=ld, ldv=ld, ldo=d, anc_ld=anc.shape[1], slot_div=apps)
-            e["o"](ws.att, ws.x, residual=ws.x)
-            e["n1"](ws.x, ws.xn)
-            e["cq"](ws.xn, ws.qc)
+            if fold:
+                e["o"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x)
+                e["cq"].ln(ws.xb, ws.stats, ws.qc)
+            else:
+                e["o"](ws.att, ws.x, residual=ws.x)
+                e["n1"](ws.x, ws.xn)
+                e["cq"](ws.xn, ws.qc)
             mkv = enc.memkv[u]
             ko2, vo2 = e["ckv_offs"]
             K.cross_attn_step(ws.qc, mkv[:, ko2:], mkv[:, vo2:], enc.att_mask, ws.att, B=ws.B, beam=ws.beam, N=N, D=d, h=h,
                               ldq=d, ldm=e["ckv_ld"], ldo=d)
-            e["co"](ws.att, ws.x, residual=ws.x)
-            e["n2"](ws.x, ws.xn)
-            e["ff1"](ws.xn, ws.hid, relu=True)
-            e["ff2"](ws.hid, ws.x, residual=ws.x)
-        self.dec_norm(ws.x, ws.xn)
-        self.generator(ws.xn, ws.logits)
+            if fold:
+                e["co"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x)
+                e["ff1"].ln(ws.xb, ws.stats, ws.hid, relu=True)
+                e["ff2"].produce(ws.hid, ws.x, ws.xb, ws.stats, residual=ws.x)
+            else:
+                e["co"](ws.att, ws.x, residual=ws.x)
+                e["n2"](ws.x, ws.xn)
+                e["ff1"](ws.xn, ws.hid, relu=True)
+                e["ff2"](ws.hid, ws.x, residual=ws.x)
+        if fold:
+            self.generator.ln(ws.xb, ws.stats, ws.logits)
+        else:
+            self.dec_norm(ws.x, ws.xn)
+            self.generator(ws.xn, ws.logits)
 
     def _beam_body(self, ws, enc, opt):
         c = self.cfg

@@ -39,6 +39,27 @@ def linear(x, w, bias=None, *, mask=None, mask_mode=MASK_NONE, uniforms=None, se
     return out
 
 
+def linear_ln(x, w, bias=None, *, residual=None, relu=False, out=None, tile_n=0, ln_stats=None, ln_c=None, eps=1e-6,
+              out_bf16=None, stats_out=None):
+    """sc_linear_ln: bf16 tensor-core GEMM with a folded LayerNorm on its input (``ln_stats``/``ln_c``) and/or the
+    residual-stream producer epilogue (``out_bf16`` copy + ``stats_out`` row statistics).  x, w bf16."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
+    for t, n in ((x, "x"), (w, "w"), (bias, "bias"), (residual, "residual"), (out, "out"), (ln_stats, "ln_stats"), (ln_c, "ln_c"),
+                 (out_bf16, "out_bf16"), (stats_out, "stats_out")):
+        _chk(t, n)
+    lib.call("sc_linear_ln", lib.ptr(x), lib.ptr(w), lib.ptr(bias), lib.ptr(residual), lib.ptr(out), lib.dtype_code(out.dtype),
+             M, N, K, int(relu), tile_n, lib.ptr(ln_stats), lib.ptr(ln_c), float(eps), lib.ptr(out_bf16), lib.ptr(stats_out),
+             lib.stream(), meta=("gemm_bf16", M, N, K, 2, 2, out.element_size(), False))
+    return out
+
+
+def set_pdl(enabled):
+    """Programmatic dependent launch between consecutive kernels of a stream (on by default)."""
+    lib.load().sc_set_pdl(int(bool(enabled)))
+
+
 class CsrWeight:
     """CSR form of a pruned [N,K] weight: row_ptr int32 [N+1], col uint16 [nnz] (stored in an int16 tensor),
     values in the activation dtype.  Built from a dense (already masked) tensor; also accepts the reference's
@@ -101,6 +122,16 @@ def embed_pe(tokens, table, pe, *, T=1, pos0=0, mask=None, mask_mode=MASK_NONE, 
     lib.call("sc_embed_pe", lib.ptr(tokens), lib.ptr(table), lib.ptr(mask), mask_mode, lib.ptr(uniforms), seed, stream_id,
              lib.ptr(pe), lib.ptr(out), lib.dtype_code(out.dtype), rows, D, V, T, pos0, math.sqrt(D), lib.stream())
     return out
+
+
+def embed_pe_stats(tokens, table, pe, x32, xb, stats, *, T=1, pos0=0):
+    """sc_embed_pe_stats: embedding + positional encoding -> fp32 stream, bf16 copy, chunk statistics."""
+    rows = tokens.numel()
+    V, D = table.shape
+    assert tokens.dtype == torch.int32 and xb.dtype == torch.bfloat16 and x32.dtype == torch.float32
+    lib.call("sc_embed_pe_stats", lib.ptr(tokens), lib.ptr(table), lib.ptr(pe), lib.ptr(x32), lib.ptr(xb), lib.ptr(stats), rows, D, V,
+             T, pos0, math.sqrt(D), lib.stream())
+    return x32
 
 
 def apply_mask(w, mask, mask_mode, *, uniforms=None, seed=0, stream_id=0, out_dtype=torch.float32, out=None):

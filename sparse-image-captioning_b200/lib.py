@@ -18,9 +18,12 @@ _p, _i, _f, _u64, _sz, _l = C.c_void_p, C.c_int, C.c_float, C.c_ulonglong, C.c_s
 # name -> argtypes (mirrors include/sc_b200.h; tests/test_abi.py checks header and table agree)
 SIGNATURES = {
     "sc_linear": [_p, _i, _p, _i, _p, _i, _p, _u64, _u64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "sc_linear_ln": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p],
+    "sc_set_pdl": [_i],
     "sc_csr_spmm": [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "sc_layernorm": [_p, _p, _p, _p, _i, _i, _i, _f, _p],
     "sc_embed_pe": [_p, _p, _p, _i, _p, _u64, _u64, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p],
+    "sc_embed_pe_stats": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "sc_apply_mask": [_p, _p, _i, _p, _u64, _u64, _p, _i, _sz, _p],
     "sc_mask_count": [_p, _sz, _p, _p],
     "sc_cast_f32_bf16": [_p, _p, _sz, _p],

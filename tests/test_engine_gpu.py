@@ -67,6 +67,39 @@ def test_bf16_engine_close_to_oracle(backend):
     torch.testing.assert_close(lp.cpu()[:, 0, 0][first], rlp[:, 0, 0][first], rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_bf16_layernorm_folding(masked):
+    """LayerNorm folded into the consuming GEMMs (sc_linear_ln) vs the separate LayerNorm kernel vs the fp32 oracle, with
+    non-trivial a_2 / b_2 and a residual stream whose mean is not zero."""
+    cfg, ocfg, sd = _medium(seed=9, d_model=256, dim_feedforward=512, num_heads=4)
+    g = torch.Generator().manual_seed(0)
+    for k in list(sd):
+        if k.endswith(".a_2"):
+            sd[k] = 0.5 + torch.rand(sd[k].shape, generator=g)
+        elif k.endswith(".b_2"):
+            sd[k] = 0.3 * torch.randn(sd[k].shape, generator=g)
+    data = O.synthetic_inputs(12, 36, cfg["att_feat_size"], seed=6)
+    am = None
+    if masked:
+        am = torch.ones(12, 36)
+        am[3, 20:] = 0
+        am[7, 30:] = 0
+    opt = {"beam_size": 3}
+    rseq, rlp = O.sample(sd, ocfg, data["att_feats"], data["boxes"], am, opt)
+    outs = {}
+    for fold in (True, False):
+        eng = _engine(sd, cfg, precision="bf16", ln_fold=fold)
+        assert eng.fold_dec == fold
+        seq, lp = eng.sample(data["att_feats"], data["boxes"], am, opt)
+        outs[fold] = (seq.cpu(), lp.cpu())
+        first = seq.cpu()[:, 0, 0] == rseq[:, 0, 0]
+        assert float(first.float().mean()) >= 0.75
+        torch.testing.assert_close(lp.cpu()[:, 0, 0][first], rlp[:, 0, 0][first], rtol=2e-2, atol=2e-2)
+    both = outs[True][0][:, 0, 0] == outs[False][0][:, 0, 0]
+    assert float(both.float().mean()) >= 0.75
+    torch.testing.assert_close(outs[True][1][:, 0, 0][both], outs[False][1][:, 0, 0][both], rtol=2e-2, atol=2e-2)
+
+
 def test_fp32_engine_medium_matches_oracle():
     cfg, ocfg, sd = _medium(seed=5, max_seq_length=12)
     data = O.synthetic_inputs(8, 36, cfg["att_feat_size"], seed=4)

@@ -77,6 +77,62 @@ def test_linear_bf16_dense(K, shape, tile_n):
     assert rel_err(yb.float(), ref) < 1e-2
 
 
+@pytest.mark.parametrize("shape,tile_n", [((19000, 1024, 256), 0), ((19000, 1024, 256), 5128), ((40000, 512, 128), 64),
+                                          ((5000, 2304, 192), 0)])
+def test_linear_bf16_persistent(K, shape, tile_n):
+    """More output tiles than resident CTAs: every CTA loops over several tiles with the double-buffered TMEM
+    accumulator (epilogue of tile i overlapping the main loop of tile i+1)."""
+    M, N, Kd = shape
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=5)
+    xb, wb = x.bfloat16(), w.bfloat16()
+    dev = "cuda"
+    for rep in range(2):
+        y = K.linear(xb.to(dev), wb.to(dev), b.to(dev), residual=r.to(dev), relu=False, tile_n=tile_n)
+    ref = torch.nn.functional.linear(xb.float(), wb.float(), b) + r
+    assert rel_err(y, ref) < 2e-5, shape
+
+
+@pytest.mark.parametrize("shape", [(1536, 512, 512), (300, 1536, 512), (130, 96, 64)])
+def test_linear_ln_fold(K, shape):
+    """LayerNorm folded around the GEMM: a producer GEMM emits the fp32 residual stream, its bf16 copy and the chunk
+    statistics; the consumer GEMM applies a*(x-mean)/(std+eps)+b through pre-scaled weights (transformer.py:329-358)."""
+    M, N, D = shape
+    g = torch.Generator().manual_seed(11)
+    h = torch.randn(M, 256, generator=g)
+    wp = torch.randn(D, 256, generator=g) / 16
+    bp = torch.randn(D, generator=g)
+    res = torch.randn(M, D, generator=g) * 2 + 0.5
+    a2, b2 = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g) * 0.1
+    w = torch.randn(N, D, generator=g) / math.sqrt(D)
+    bias = torch.randn(N, generator=g)
+    dev = "cuda"
+    x32 = torch.empty(M, D, device=dev)
+    xb = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    stats = torch.zeros(M, D // 32, 2, device=dev)
+    K.linear_ln(h.bfloat16().to(dev), wp.bfloat16().to(dev), bp.to(dev), residual=res.to(dev), out=x32, out_bf16=xb, stats_out=stats)
+    x_ref = torch.nn.functional.linear(h.bfloat16().double(), wp.bfloat16().double(), bp.double()) + res.double()
+    assert rel_err(x32, x_ref) < 2e-5
+    assert torch.equal(xb.cpu(), x32.cpu().bfloat16())
+    mean_ref = x_ref.mean(1)
+    st = stats.double().cpu()
+    assert rel_err(st[:, :, 0].sum(1) / D, mean_ref) < 1e-5
+    # consumer
+    wf = (w * a2).bfloat16()
+    ln_c = wf.float().sum(1)
+    bias_f = w @ b2 + bias
+    y = torch.empty(M, N, device=dev)
+    K.linear_ln(xb, wf.to(dev), bias_f.to(dev), out=y, ln_stats=stats, ln_c=ln_c.to(dev), relu=False)
+    xn = a2.double() * (x_ref - mean_ref[:, None]) / (x_ref.std(1, keepdim=True) + 1e-6) + b2.double()
+    y_ref = xn @ w.double().t() + bias.double()
+    # operands are bf16 (x copy and scaled weights): bf16-level agreement with the fp64 LayerNorm + linear
+    assert rel_err(y, y_ref) < 2e-2
+    # exactness of the algebra: same quantised operands, float64 arithmetic
+    xq = xb.cpu().double()
+    rstd = 1.0 / (x_ref.std(1) + 1e-6)
+    y_alg = rstd[:, None] * (xq @ wf.double().t()) - (rstd * mean_ref)[:, None] * ln_c.double() + bias_f.double()
+    assert rel_err(y, y_alg) < 5e-5
+
+
 @pytest.mark.parametrize("mode", [0, 1, 3, 4])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (300, 200, 512), (1536, 512, 2048), (100, 771, 512)])
 def test_linear_bf16_masked_prologue(K, shape, mode):

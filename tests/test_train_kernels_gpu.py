@@ -38,7 +38,7 @@ def _masked_weight_autograd(W, S, U, mode, bypass):
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode,bypass", [(0, False), (4, False), (4, True), (3, False), (1, False)])
-@pytest.mark.parametrize("shape", [(70, 40, 96), (300, 512, 520)])
+@pytest.mark.parametrize("shape", [(70, 40, 96), (300, 512, 520), (3000, 136, 128)])  # last one: split-K wgrad
 def test_masked_linear_backward(K, dt, mode, bypass, shape):
     """dX via (W.m)^T operand, dW/dS via the fused wgrad epilogue, db via colsum."""
     M, N, Kd = shape
