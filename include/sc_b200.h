@@ -174,11 +174,14 @@ int sc_linear_dropout(const void* x, int x_dtype, const void* w, int w_dtype, co
 
 /* K2 — autograd of MaskedLinear (pruning/sampler.py:15-17,32-34): dWm[N,K] = dyT[N,M] * xT[K,M]^T with the fused
  * straight-through epilogue  dW (+)= dWm.m ;  dS (+)= dWm.W.sigmoid'(S) [.1 if bypass or raw] + sparsity_coeff*sigmoid'(S).
- * dyT/xT are transposed activations (M = padded token count, multiple of 8 for bf16). */
+ * dyT/xT are transposed activations (M = padded token count, multiple of 8 for bf16).
+ * workspace (optional, device, 16-byte aligned, >= N*K*4 bytes; more bytes allow more K splits): when given, the GEMM
+ * stores split-K partial products there and a second kernel reduces them and applies the epilogue once per element
+ * (measured faster than the fused epilogue for every shape of this model); NULL = single fused kernel. */
 int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, const float* mask, int mask_mode,
                     const float* uniforms, unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad,
                     float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K, int M, int tile_n,
-                    sc_stream_t stream);
+                    void* workspace, size_t workspace_bytes, sc_stream_t stream);
 
 /* out = g*keep*scale (cast), outT = its transpose (leading dim ldT, caller zero-pads); keep = (h != 0) when the saved
  * post-ReLU/dropout activation h is given, else the regenerated Philox dropout mask when dropout_p > 0. */

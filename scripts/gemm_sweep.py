@@ -7,7 +7,7 @@ import sparse_caption_b200.kernels as K
 shapes = [(1536,512,512),(1536,1536,512),(1536,2048,512),(1536,512,2048),(1536,10000,512),
           (18432,512,2048),(18432,1536,512),(18432,2048,512),(18432,512,512),(18432,1024,512),
           (6144,512,512),(6144,1536,512),(6144,2048,512),(6144,512,2048),(4250,512,512),(4250,2048,512),(4250,512,2048),(4250,10000,512),(1800,1536,512),(1800,2048,512)]
-cfgs = [(0,0),(64,4),(64,6),(128,3),(128,5),(256,3)]
+cfgs = [(0,0),(64,3),(64,4),(64,6),(128,3),(128,5),(256,3)]
 dev = "cuda"
 if os.environ.get("SC_PDL") == "0": K.set_pdl(False)
 if len(sys.argv) > 1: shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]

@@ -20,6 +20,12 @@ int sc_gemm_f32_launch(const float* x, const float* w, const float* mask, int ma
                        unsigned long long seed, unsigned long long stream_id, const float* bias, const float* residual,
                        void* y, int y_dtype, int M, int N, int K, int relu, const ScGemmExtra* ex, cudaStream_t stream);
 
+int sc_gemm_wgrad_splits(int N, int K, int M, int max_splits);
+extern "C" int sc_mask_grad_reduce_launch(const float* part, int splits, size_t stride, const float* w, const float* mask,
+                                          int mask_mode, const float* uniforms, unsigned long long seed,
+                                          unsigned long long stream_id, int bypass, float sp_coeff, float* dw, float* ds,
+                                          int accumulate, size_t n, cudaStream_t stream);
+
 static int linear_dispatch(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
                            const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,
                            const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, int tile_n,
@@ -78,12 +84,28 @@ int sc_linear_dropout(const void* x, int x_dtype, const void* w, int w_dtype, co
 //   dW (+)= dWm (.) m ;  dS (+)= dWm (.) W (.) sigmoid'(S) [(.) 1 when bypass / raw] + sparsity_coeff * sigmoid'(S)
 // dyT, xT: transposed activations in `dtype`; w, mask: the fp32 weight and its logits (mask regenerated from
 // (mask_mode, seed, stream_id, element) exactly as the forward drew it); dw / ds may be NULL.
+// workspace != NULL (bf16 operands): two kernels - the GEMM stores split-K partial products dWm_s (fp32, plain coalesced
+// stores) into the workspace, sc_mask_grad_reduce sums them and applies the straight-through epilogue once per element at
+// full-GPU parallelism.  workspace == NULL: one kernel with the epilogue fused into the GEMM (split-K through atomics).
 int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, const float* mask, int mask_mode,
                     const float* uniforms, unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad,
                     float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K, int M, int tile_n,
-                    cudaStream_t stream) {
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   SC_CHECK(w != nullptr && (dw != nullptr || ds != nullptr), SC_ERR_SHAPE, "sc_linear_wgrad: w and one of dw/ds are required");
   SC_CHECK(mask_mode == SC_MASK_NONE || mask != nullptr, SC_ERR_SHAPE, "sc_linear_wgrad: mask missing");
+  const size_t nk = (size_t)N * K;
+  if (workspace != nullptr && dtype == SC_BF16 && nk % 4 == 0 && workspace_bytes >= nk * sizeof(float)) {
+    SC_CHECK(((uintptr_t)workspace & 15) == 0, SC_ERR_ALIGN, "sc_linear_wgrad: workspace must be 16-byte aligned");
+    const int max_splits = (int)(workspace_bytes / (nk * sizeof(float)) > 64 ? 64 : workspace_bytes / (nk * sizeof(float)));
+    const int splits = sc_gemm_wgrad_splits(N, K, M, max_splits);
+    ScGemmExtra ex = {};
+    ex.partial_splits = splits; ex.split_stride = nk;
+    int rc = linear_dispatch(dyT, dtype, xT, dtype, nullptr, SC_MASK_NONE, nullptr, 0, 0, nullptr, nullptr, workspace, SC_F32, N, K,
+                             M, 0, tile_n, &ex, stream);
+    if (rc) return rc;
+    return sc_mask_grad_reduce_launch((const float*)workspace, splits, nk, w, mask, mask_mode, uniforms, seed, stream_id,
+                                      bypass_sigmoid_grad, sparsity_coeff, dw, ds, accumulate, nk, stream);
+  }
   ScGemmExtra ex = {};
   ex.wgrad = 1; ex.bypass = bypass_sigmoid_grad; ex.sp_coeff = sparsity_coeff; ex.accumulate = accumulate;
   ex.wg_w = w; ex.wg_s = mask; ex.wg_u = uniforms; ex.dw = dw; ex.ds = ds;

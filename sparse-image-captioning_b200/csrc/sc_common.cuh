@@ -50,6 +50,8 @@ struct ScGemmExtra {
   const float* ln_stats; const float* ln_c; float ln_eps;
   // producer of the residual stream: also emit a bf16 copy of y (the next GEMM's TMA operand) and the row statistics
   void* y2; float* stats_out;
+  // split-K partial products (two-kernel weight gradient): split s stores its fp32 tile at y + s * split_stride
+  int partial_splits; size_t split_stride;
 };
 
 // Programmatic dependent launch (griddepcontrol): kernels launched through sc::launch_pdl may start while their

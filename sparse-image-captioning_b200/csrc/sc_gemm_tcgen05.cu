@@ -24,12 +24,15 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumTransformWarps = 4;
-constexpr int kNumEpilogueWarps = 8;   // two per TMEM lane quarter, splitting the tile's 32-column chunks
-constexpr int kFirstTransformWarp = 4 + kNumEpilogueWarps;
+// Epilogue warps: 8 (two per TMEM lane quarter, splitting the tile's 32-column chunks) for the wide / deep-ring
+// configurations that own an SM, 4 for the small-problem configurations, whose footprint (<= 113 KB smem, <= 128
+// registers x 256 threads) lets two CTAs - e.g. of different streams - share an SM.
+__host__ __device__ constexpr int num_epilogue_warps(int block_n, int stages) { return (block_n == 256 || stages >= 5) ? 8 : 4; }
 
 struct GemmArgs {
   int M, N, K;
   int tiles_n, num_tiles, splits, kb_per_split;  // persistent schedule: unit u -> (tile = u / splits, split = u % splits)
+  size_t split_stride;   // split-K partial products: split s stores its fp32 tile at y + s * split_stride (0: single output)
   const float* w32;      // kMasked: fp32 weights [N,K]
   const float* mask;     // kMasked: fp32 logits / raw mask / nullptr
   const float* uniforms; // SC_MASK_UNIFORM
@@ -126,13 +129,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 template <int BLOCK_N, int kStages>
 struct Smem {
+  static constexpr int kNumEpilogueWarps = num_epilogue_warps(BLOCK_N, kStages);
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingOffset = kStages * kStageBytes;                  // 8 epilogue warps x 4 KB transpose staging
-  static constexpr int kRowStatOffset = kStagingOffset + kNumEpilogueWarps * 4096;  // 8 warps x 32 rows x (rstd, mean*rstd)
-  static constexpr int kBarOffset = kRowStatOffset + kNumEpilogueWarps * 256;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + tmem ptr + alignment slack
+  static constexpr int kStagingOffset = kStages * kStageBytes;  // epilogue warps x 4 KB transpose staging
+  // direct (4-warp) configurations with 64-wide tiles prefetch the fp32 residual tile (128 rows x 64 columns) with
+  // cp.async while the main loop runs; the area is shared with the weight-gradient staging (never used together)
+  static constexpr int kResPrefetchBytes = (kNumEpilogueWarps == 4 && BLOCK_N == 64) ? BLOCK_M * BLOCK_N * 4 : 0;
+  static constexpr int kEpiBytes = kNumEpilogueWarps * 4096 > kResPrefetchBytes ? kNumEpilogueWarps * 4096 : kResPrefetchBytes;
+  static constexpr int kUsed = kStagingOffset + kEpiBytes;
+  // 1 KB of slack: up to 768 B of alignment padding in front, the barriers + TMEM pointer in its last 256 B
+  static constexpr int kTotal = kUsed + 1024;
 };
 
 // ---- epilogue ------------------------------------------------------------------------------------------------
@@ -212,10 +220,41 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& args, float (&f)[32
   }
 }
 
+// Store stage in the ROW mapping (latency-oriented small-problem configurations): the thread writes its 32 columns.
+template <bool kFull>
+__device__ __forceinline__ void epilogue_store_row(const GemmArgs& args, const float (&f)[32], int row, int col0, size_t yoff) {
+  const size_t e0 = (size_t)row * args.N + col0 + yoff;
+  if ((args.N & 7) == 0 && col0 + 32 <= args.N) {
+    if (args.y_bf16 || (kFull && args.y2)) {
+      uint4* yp = (uint4*)((__nv_bfloat16*)(args.y_bf16 ? args.y : args.y2) + e0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), p1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+        const __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), p3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+        uint4 o;
+        o.x = *(const uint32_t*)&p0; o.y = *(const uint32_t*)&p1; o.z = *(const uint32_t*)&p2; o.w = *(const uint32_t*)&p3;
+        yp[j] = o;
+      }
+    }
+    if (!args.y_bf16) {
+      float4* yp = (float4*)((float*)args.y + e0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) yp[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (col0 + j >= args.N) continue;
+    if (args.y_bf16) ((__nv_bfloat16*)args.y)[e0 + j] = __float2bfloat16_rn(f[j]);
+    else ((float*)args.y)[e0 + j] = f[j];
+  }
+}
+
 // Store stage in the COALESCED mapping: 4 consecutive columns of one row (fp32 and/or bf16 copy).
 template <bool kFull>
-__device__ __forceinline__ void epilogue_store4(const GemmArgs& args, const float4& f, int row, int col) {
-  const size_t e = (size_t)row * args.N + col;
+__device__ __forceinline__ void epilogue_store4(const GemmArgs& args, const float4& f, int row, int col, size_t yoff) {
+  const size_t e = (size_t)row * args.N + col + yoff;
   if ((args.N & 3) == 0) {
     if (args.y_bf16 || (kFull && args.y2)) {
       const __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y), hi = __floats2bfloat162_rn(f.z, f.w);
@@ -238,16 +277,13 @@ __device__ __forceinline__ void epilogue_store4(const GemmArgs& args, const floa
 // One float4 of the weight-gradient tile (K2): dW = dWm (.) m ; dS = dWm (.) W (.) sigmoid'(S) (+ sparsity term); the
 // mask is regenerated from (seed, stream, element).  Split-K partial sums go out as vector reductions into
 // pre-zeroed buffers; the sparsity term is added by split 0 only.
-__device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, int row, int col, bool atomic, bool first_split) {
+__device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, int row, int col, bool atomic, bool first_split,
+                                                const float4& w4, const float4& s4, const float4& u4) {
   const sc::Philox wph(args.seed);
   const float sp = first_split ? args.sp_coeff : 0.f;
   const size_t e = (size_t)row * args.N + col;
   const float g[4] = {f.x, f.y, f.z, f.w};
   if ((args.N & 3) == 0) {
-    const float4 w4 = __ldg((const float4*)(args.wg_w + e));
-    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = s4;
-    if (args.wg_s) s4 = __ldg((const float4*)(args.wg_s + e));
-    if (args.wg_u) u4 = __ldg((const float4*)(args.wg_u + e));
     const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
     float m[4];
     if (args.mask_mode == SC_MASK_BERNOULLI) {
@@ -301,12 +337,16 @@ __device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, 
 // kStages: depth of the TMA->MMA smem ring.
 // kEpi: 0 = plain forward epilogue, 1 = full forward epilogue (dropout, folded LayerNorm, statistics), 2 = weight gradient
 template <int BLOCK_N, bool kMasked, int kStages, int kEpi>
-__global__ void __launch_bounds__(kMasked ? 512 : 384, 1)
+__global__ void __launch_bounds__(32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0)),
+                                  (!kMasked && kEpi != 2 && num_epilogue_warps(BLOCK_N, kStages) == 4) ? 2 : 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
   using L = Smem<BLOCK_N, kStages>;
+  constexpr int kNumEpilogueWarps = L::kNumEpilogueWarps;
+  constexpr int kFirstTransformWarp = 4 + kNumEpilogueWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + L::kBarOffset);
+  if (smem - smem_raw > 768) __trap();  // the barrier block below would overlap the tiles (never with a 1 KB-aligned base)
+  uint64_t* full_bar = (uint64_t*)(smem_raw + L::kTotal - 256);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
@@ -400,8 +440,15 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     sc::pdl_wait();  // residual / statistics come from, and y may still be read by, the previous kernel
     const int ew = warp - 4;
     const int q = ew & 3;      // TMEM lane quarter this warp may read
-    const int half = ew >> 2;  // which of the tile's 32-column chunks (even / odd) this warp takes
+    const int half = ew >> 2;  // 8 warps: which of the tile's 32-column chunks (even / odd) this warp takes
+    constexpr int kChunkStep = kNumEpilogueWarps / 4;
+    // kDirect: single-wave, latency-bound problems.  The thread keeps its accumulator row, loads / prefetches the
+    // residual in the same mapping and stores straight from registers (no transposes on the critical path).
+    constexpr bool kDirect = (kNumEpilogueWarps == 4) && (kEpi != 2);
+    constexpr bool kPrefetchRes = kDirect && L::kResPrefetchBytes > 0;
     uint8_t* stg = smem + L::kStagingOffset + ew * 4096;
+    float4* pre = (float4*)(smem + L::kStagingOffset);  // residual prefetch: piece j of epilogue thread t at [j * 128 + t]
+    const int et = threadIdx.x - 128;                    // 0..127 (4-warp configurations)
     const int jsw = lane & 7;  // swizzle key of this thread's own row (row-mapping: row = lane)
     int lt = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++lt) {
@@ -440,12 +487,61 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         ln_rstd = 1.f / (sqrtf(m2 / (float)(args.K - 1)) + args.ln_eps);
         ln_mr = ln_rstd * mean;
       }
+      bool pre_ok = false;
+      if (kPrefetchRes) {
+        // fp32 residual row of this thread -> shared memory while the main loop runs (16-byte cp.async, no registers)
+        pre_ok = args.residual != nullptr && (args.N & 3) == 0 && rbase + lane < args.M;
+        if (pre_ok) {
+          const float* rp = args.residual + (size_t)(rbase + lane) * args.N + n0;
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 4; ++j) {
+            if (n0 + 4 * j < args.N)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(pre + j * 128 + et)), "l"(rp + 4 * j) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
+      if (kPrefetchRes) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += 2) {
+      for (int c = half; c < BLOCK_N / 32; c += kChunkStep) {
         const int col0 = n0 + c * 32;
         if (col0 >= args.N || rbase >= args.M) continue;  // warp-uniform
+        if (kDirect || (kEpi != 2 && args.residual == nullptr)) {
+          // (the throughput configurations only take the transposed path below for fp32 residual streams: without a
+          // residual to read, storing the row straight from registers measured faster)
+          const int row = rbase + lane;
+          float res[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) res[j] = 0.f;
+          if (args.residual != nullptr && row < args.M) {
+            if (kPrefetchRes && pre_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (col0 + 4 * j < args.N) {
+                  const float4 r4 = pre[(c * 8 + j) * 128 + et];
+                  res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w;
+                }
+              }
+            } else if ((args.N & 3) == 0 && col0 + 32 <= args.N) {
+              const float4* rp = (const float4*)(args.residual + (size_t)row * args.N + col0);  // plain loads (PDL)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 r4 = rp[j]; res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < args.N) res[j] = args.residual[(size_t)row * args.N + col0 + j];
+            }
+          }
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          epilogue_row<kEpi == 1>(args, f, res, row, col0, ln_rstd, ln_mr);
+          if (row < args.M) epilogue_store_row<kEpi == 1>(args, f, row, col0, (size_t)split * args.split_stride);
+          continue;
+        }
         // coalesced mapping: lane handles 16-byte piece (lane & 7) of rows (lane >> 3) + 4 i, i = 0..7
         const int pj = lane & 7;
         const int col = col0 + pj * 4;
@@ -467,6 +563,21 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 if (col + 2 < args.N) rres[i].z = rp[2];
                 if (col + 3 < args.N) rres[i].w = rp[3];
               }
+            }
+          }
+        }
+        // weight gradient: W, logits (and injected uniforms) of the 8 rows this lane serves, all in flight together
+        float4 wg_w4[kEpi == 2 ? 8 : 1], wg_s4[kEpi == 2 ? 8 : 1], wg_u4[kEpi == 2 ? 8 : 1];
+        if (kEpi == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            wg_w4[i] = wg_s4[i] = wg_u4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row = rbase + i * 4 + (lane >> 3);
+            if ((args.N & 3) == 0 && row < args.M && col < args.N) {
+              const size_t e = (size_t)row * args.N + col;
+              wg_w4[i] = __ldg((const float4*)(args.wg_w + e));
+              if (args.wg_s) wg_s4[i] = __ldg((const float4*)(args.wg_s + e));
+              if (args.wg_u) wg_u4[i] = __ldg((const float4*)(args.wg_u + e));
             }
           }
         }
@@ -500,7 +611,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int i = 0; i < 8; ++i) {
             const int rl = i * 4 + (lane >> 3);
             const float4 o = *(const float4*)(stg + rl * 128 + ((pj ^ (rl & 7)) << 4));
-            if (rbase + rl < args.M && col < args.N) epilogue_store4<kEpi == 1>(args, o, rbase + rl, col);
+            if (rbase + rl < args.M && col < args.N) epilogue_store4<kEpi == 1>(args, o, rbase + rl, col, (size_t)split * args.split_stride);
           }
         } else {
           // weight gradient: transpose the raw accumulator, element-wise work in the coalesced mapping
@@ -512,7 +623,8 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           for (int i = 0; i < 8; ++i) {
             const int rl = i * 4 + (lane >> 3);
             const float4 g4 = *(const float4*)(stg + rl * 128 + ((pj ^ (rl & 7)) << 4));
-            if (rbase + rl < args.M && col < args.N) epilogue_wgrad4(args, g4, rbase + rl, col, args.splits > 1, split == 0);
+            if (rbase + rl < args.M && col < args.N)
+              epilogue_wgrad4(args, g4, rbase + rl, col, args.splits > 1, split == 0, wg_w4[i], wg_s4[i], wg_u4[i]);
           }
         }
         __syncwarp();  // staging is rewritten by the next chunk
@@ -649,9 +761,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   a.tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
   a.num_tiles = a.tiles_n * ((a.M + BLOCK_M - 1) / BLOCK_M);
   const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
-  // split K (weight gradients only: few output tiles, thousands of tokens to contract) until the SMs are covered
+  // split K (weight gradients only: few output tiles, thousands of tokens to contract) until the SMs are covered.
+  // want_splits > 0: the caller (sc_linear_wgrad with a workspace) stores one fp32 partial product per split and
+  // reduces them in sc_mask_grad_reduce; otherwise the fused epilogue adds its partials with vector reductions.
   int splits = 1;
-  if (a.wgrad) {
+  if (a.wgrad || want_splits > 0) {
     splits = want_splits > 0 ? want_splits : (a.num_tiles >= sm_count() ? 1 : (sm_count() + a.num_tiles - 1) / a.num_tiles);
     splits = max(1, min(splits, num_kb / 4 > 0 ? num_kb / 4 : 1));
   }
@@ -664,11 +778,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   // persistent grid, never more CTAs than work units
   static int env_per_sm = -1;
   if (env_per_sm < 0) { const char* e = getenv("SC_GEMM_PER_SM"); env_per_sm = e ? atoi(e) : 0; }
-  // one persistent CTA per SM: two co-resident CTAs of this kernel measured slower than one CTA looping over two tiles
+  // one persistent CTA of a launch per SM: two co-resident CTAs of the SAME GEMM measured slower than one CTA looping
+  // over two tiles (the small configurations still leave room for CTAs of other streams)
   const int per_sm = env_per_sm > 0 ? env_per_sm : 1;
   const int units = a.num_tiles * a.splits;
   dim3 grid(min(units, per_sm * sm_count()));
-  cudaError_t e = sc::launch_pdl(kern, grid, dim3(kMasked ? 512 : 384), (size_t)smem, stream, ta, tb, a);
+  constexpr int threads = 32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0));
+  cudaError_t e = sc::launch_pdl(kern, grid, dim3(threads), (size_t)smem, stream, ta, tb, a);
   if (e != cudaSuccess) {
     sc_set_error("sc_gemm_bf16_kernel: launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -678,6 +794,22 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
 }
 
 }  // namespace
+
+// Split count the weight-gradient GEMM [N,K] = dyT [N,M] * xT[K,M]^T would use with `max_splits` partial buffers.
+int sc_gemm_wgrad_splits(int N, int K, int M, int max_splits) {
+  const long t128 = (long)((N + 127) / 128) * ((K + 127) / 128);
+  const int bn = (t128 >= sm_count() / 4) ? 128 : 64;
+  const long tiles = (long)((N + 127) / 128) * ((K + bn - 1) / bn);
+  const int num_kb = (M + BLOCK_K - 1) / BLOCK_K;
+  // as many splits as keep all work units in ONE wave, at most 4 (the reduction re-reads every partial product):
+  // measured with scripts/wgrad_sweep.py, e.g. 64 tiles: 2 splits 16.4 us, 3 splits 20.4 us
+  int splits = (int)(sm_count() / tiles);
+  splits = max(1, min(splits, 4));
+  splits = max(1, min(splits, num_kb / 4 > 0 ? num_kb / 4 : 1));
+  splits = min(splits, max(1, max_splits));
+  const int per = (num_kb + splits - 1) / splits;
+  return (num_kb + per - 1) / per;
+}
 
 // Internal entry used by sc_linear (sc_api.cu).
 int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* mask, int mask_mode, const float* uniforms,
@@ -721,7 +853,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     // widest tile that still gives most SMs a tile (scripts/gemm_sweep.py, in-graph, L2-warm, round 1 numbers in DESIGN.md)
     const long t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
     block_n = (t256 >= sms && !masked) ? 256 : (t128 >= 100 ? 128 : 64);
-    if (wgrad) block_n = (t128 >= sms / 4) ? 128 : 64;
+    if (wgrad || (ex && ex->partial_splits > 0)) block_n = (t128 >= sms / 4) ? 128 : 64;
     if (N <= 64) block_n = 64;
   }
   CUtensorMap ta, tb;
@@ -745,6 +877,11 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     a.wgrad = ex->wgrad; a.bypass = ex->bypass; a.sp_coeff = ex->sp_coeff; a.accumulate = ex->accumulate;
     a.wg_w = ex->wg_w; a.wg_s = ex->wg_s; a.wg_u = ex->wg_u; a.dw = ex->dw; a.ds = ex->ds;
     a.ln_stats = ex->ln_stats; a.ln_c = ex->ln_c; a.ln_eps = ex->ln_eps; a.y2 = ex->y2; a.stats_out = ex->stats_out;
+    if (ex->partial_splits > 0) {
+      SC_CHECK(!wgrad && y_dtype == SC_F32 && !bias && !residual && !relu, SC_ERR_UNSUPPORTED, "split-K partial products are plain fp32 tiles");
+      force_splits = ex->partial_splits;
+      a.split_stride = ex->split_stride;
+    }
   }
   const int epi = a.wgrad ? 2 : ((a.dropout_p > 0.f || a.ln_stats || a.y2 || a.stats_out) ? 1 : 0);
 #define SC_GEMM_CASE(BN, ST)                                                                                          \
@@ -756,9 +893,9 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
                     : launch<BN, false, ST, 0>(ta, tb, a, force_splits, stream);                                      \
   }
   int stages = force_stages;
-  if (stages == 0) stages = block_n == 64 ? 4 : block_n == 256 ? 3 : 4;
-  SC_GEMM_CASE(64, 4); SC_GEMM_CASE(64, 6);
-  SC_GEMM_CASE(128, 3); SC_GEMM_CASE(128, 4); SC_GEMM_CASE(128, 5);
+  if (stages == 0) stages = (block_n == 128 && (long)mt * ((N + 127) / 128) > 2L * sms) ? 5 : 3;  // 128x5: multi-wave throughput config
+  SC_GEMM_CASE(64, 3); SC_GEMM_CASE(64, 4); SC_GEMM_CASE(64, 6);
+  SC_GEMM_CASE(128, 3); SC_GEMM_CASE(128, 5);
   SC_GEMM_CASE(256, 3);
 #undef SC_GEMM_CASE
   SC_CHECK(false, SC_ERR_UNSUPPORTED, "sc_linear(bf16): tile %d x %d stages not instantiated", block_n, stages);

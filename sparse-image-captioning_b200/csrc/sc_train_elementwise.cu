@@ -115,6 +115,73 @@ __global__ void __launch_bounds__(256) mask_grad_kernel(const float* __restrict_
   }
 }
 
+// Split-K reduction fused with the straight-through mask gradient: dWm = sum_s part[s]; dW = dWm (.) m;
+// dS = dWm (.) W (.) sigmoid'(S) + sp_coeff sigmoid'(S).  One float4 per thread, every operand streamed once, coalesced.
+__global__ void __launch_bounds__(256) mask_grad_reduce_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                               const float* __restrict__ w, const float* __restrict__ s, int mode,
+                                                               const float* __restrict__ uni, unsigned long long seed,
+                                                               unsigned long long stream, int bypass, float sp_coeff,
+                                                               float* __restrict__ dw, float* __restrict__ ds, int accumulate,
+                                                               size_t n4) {
+  const sc::Philox ph(seed);
+  sc::pdl_wait();
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = g * 4;
+    float4 acc = *(const float4*)(part + e);
+    for (int k = 1; k < splits; ++k) {
+      const float4 p = *(const float4*)(part + (size_t)k * stride + e);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    const float4 w4 = __ldg((const float4*)(w + e));
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), u4 = s4;
+    if (s) s4 = __ldg((const float4*)(s + e));
+    if (uni) u4 = __ldg((const float4*)(uni + e));
+    const float gv[4] = {acc.x, acc.y, acc.z, acc.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+    float m[4];
+    if (mode == SC_MASK_BERNOULLI) {
+      sc::bernoulli4(ph, g, stream, sv, m);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = sc::mask_value(mode, sv[i], uv[i], ph, e + i, stream);
+    }
+    float gw[4], gs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc::mask_grad_elem(mode, gv[i], wv[i], sv[i], m[i], bypass, sp_coeff, gw[i], gs[i]);
+    if (dw) {
+      float4 o = make_float4(gw[0], gw[1], gw[2], gw[3]);
+      if (accumulate) { const float4 p = *(const float4*)(dw + e); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+      *(float4*)(dw + e) = o;
+    }
+    if (ds) {
+      float4 o = make_float4(gs[0], gs[1], gs[2], gs[3]);
+      if (accumulate) { const float4 p = *(const float4*)(ds + e); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+      *(float4*)(ds + e) = o;
+    }
+  }
+}
+
+// column sums of a [rows, cols] matrix: one CTA per 32 columns x row slice, partial sums added atomically
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_split_kernel(const T* __restrict__ x, float* __restrict__ out, int rows, int cols,
+                                                           int rows_per_cta) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float s = 0.f;
+  if (c < cols)
+    for (int r = r0 + ty; r < r1; r += 8) s += sc::to_f32<T>(x[(size_t)r * cols + c]);
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
 // column sums of a [rows, cols] matrix: one CTA per 32 columns
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int rows, int cols,
@@ -345,8 +412,35 @@ int sc_mask_grad(const float* dwm, const float* w, const float* mask, int mask_m
   return SC_OK;
 }
 
+// second kernel of the two-kernel weight gradient (sc_linear_wgrad with a workspace)
+int sc_mask_grad_reduce_launch(const float* part, int splits, size_t stride, const float* w, const float* mask, int mask_mode,
+                               const float* uniforms, unsigned long long seed, unsigned long long stream_id, int bypass,
+                               float sp_coeff, float* dw, float* ds, int accumulate, size_t n, cudaStream_t stream) {
+  SC_CHECK(n > 0 && n % 4 == 0, SC_ERR_SHAPE, "sc_mask_grad_reduce: n=%zu must be a positive multiple of 4", n);
+  const size_t n4 = n / 4;
+  cudaError_t e = sc::launch_pdl(mask_grad_reduce_kernel, dim3(grid_for(n4, 256)), dim3(256), 0, stream, part, splits, stride, w, mask,
+                                 mask_mode, uniforms, seed, stream_id, bypass, sp_coeff, dw, ds, accumulate, n4);
+  SC_CHECK(e == cudaSuccess, (int)e, "sc_mask_grad_reduce: %s", cudaGetErrorString(e));
+  SC_LAUNCH_CHECK("sc_mask_grad_reduce");
+  return SC_OK;
+}
+
 int sc_colsum(const void* x, int dtype, float* out, int rows, int cols, int accumulate, cudaStream_t stream) {
   SC_CHECK(rows > 0 && cols > 0, SC_ERR_SHAPE, "sc_colsum: rows=%d cols=%d", rows, cols);
+  if (rows >= 512) {
+    // tall matrices (bias gradients over thousands of tokens): split the rows over ~2 CTAs per SM
+    const int gx = (cols + 31) / 32;
+    int gy = (2 * 148 + gx - 1) / gx;
+    int rpc = (rows + gy - 1) / gy;
+    rpc = (rpc + 7) / 8 * 8;
+    gy = (rows + rpc - 1) / rpc;
+    if (!accumulate) cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), stream);
+    if (dtype == SC_F32) colsum_split_kernel<float><<<dim3(gx, gy), 256, 0, stream>>>((const float*)x, out, rows, cols, rpc);
+    else if (dtype == SC_BF16) colsum_split_kernel<__nv_bfloat16><<<dim3(gx, gy), 256, 0, stream>>>((const __nv_bfloat16*)x, out, rows, cols, rpc);
+    else SC_CHECK(false, SC_ERR_DTYPE, "sc_colsum: bad dtype");
+    SC_LAUNCH_CHECK("sc_colsum");
+    return SC_OK;
+  }
   const int grid = (cols + 31) / 32;
   if (dtype == SC_F32) colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)x, out, rows, cols, accumulate);
   else if (dtype == SC_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, out, rows, cols, accumulate);

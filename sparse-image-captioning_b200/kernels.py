@@ -260,7 +260,7 @@ def linear_dropout(x, w, bias=None, *, mask=None, mask_mode=MASK_NONE, uniforms=
 
 
 def linear_wgrad(dyT, xT, w, mask, mask_mode, dw, ds, *, M, uniforms=None, seed=0, stream_id=0, bypass=False, sp_coeff=0.0,
-                 accumulate=False, tile_n=0):
+                 accumulate=False, tile_n=0, workspace=None):
     """dWm = dyT[N,Mp] @ xT[K,Mp]^T with the fused straight-through epilogue into dw / ds (either may be None).
     ``M`` = padded token count (columns of dyT / xT, multiple of 8 in bf16)."""
     N, K = w.shape
@@ -269,7 +269,7 @@ def linear_wgrad(dyT, xT, w, mask, mask_mode, dw, ds, *, M, uniforms=None, seed=
         mask_mode = MASK_NONE
     lib.call("sc_linear_wgrad", lib.ptr(dyT), lib.ptr(xT), lib.dtype_code(dyT.dtype), lib.ptr(w), lib.ptr(mask), mask_mode,
              lib.ptr(uniforms), seed, stream_id, int(bypass), float(sp_coeff), lib.ptr(dw), lib.ptr(ds), int(accumulate), N, K,
-             M, tile_n, lib.stream(),
+             M, tile_n, lib.ptr(workspace), 0 if workspace is None else workspace.numel() * workspace.element_size(), lib.stream(),
              meta=("gemm_bf16" if dyT.dtype == torch.bfloat16 else "gemm_f32", N, K, M, dyT.element_size(), xT.element_size(), 4, False))
 
 

@@ -240,6 +240,9 @@ class OrtTrainer:
         ws.dbias = torch.zeros(B, h, N, N, **f32)
         ws.dwg = torch.zeros(h, ws.wg_eff[0].shape[1], **f32)
         ws.dtable = torch.zeros(V, d, **f32)
+        # split-K partial products of the weight-gradient GEMMs (sc_linear_wgrad workspace): up to 8 fp32 copies of the
+        # largest non-vocabulary weight, at least 2 of the generator
+        ws.wgrad_ws = torch.zeros(max(8 * max(ff * d, F * d, 3 * d * d), 2 * self.Vp * d), **f32)
         self._ws[key] = ws
         return ws
 
@@ -300,7 +303,7 @@ class OrtTrainer:
         K.transpose(x_saved, xT)
         K.linear_wgrad(gT, xT, W, S, mode, self._group(self.g, wname, count),
                        self._group(self.gs, wname, count) if S is not None else None, M=Mp, uniforms=U, seed=seed, stream_id=stream,
-                       bypass=self.bypass)
+                       bypass=self.bypass, workspace=ws.wgrad_ws if self.adt == torch.bfloat16 else None)
 
     def _ln(self, name, x, out):
         return K.layernorm(x, self.p[name + ".a_2"], self.p[name + ".b_2"], out=out)

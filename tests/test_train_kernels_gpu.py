@@ -78,6 +78,17 @@ def test_masked_linear_backward(K, dt, mode, bypass, shape):
     assert rel_err(dw, Wd.grad) < 3e-5
     if mode:
         assert rel_err(ds, ds_ref) < 3e-5
+    if dt == torch.bfloat16:
+        # two-kernel variant: split-K partial products in a workspace + sc_mask_grad_reduce
+        for nsplit in (1, 6):
+            wsp = torch.empty(nsplit * N * Kd, device=DEV)
+            dw2 = torch.full((N, Kd), 7.0, device=DEV)
+            ds2 = torch.full((N, Kd), 7.0, device=DEV)
+            K.linear_wgrad(dyT, xT, Wg, Sg if mode else None, mode, dw2, ds2 if mode else None, M=Mp, uniforms=Ug, bypass=bypass,
+                           sp_coeff=sp if mode in (1, 4) else 0.0, workspace=wsp)
+            assert rel_err(dw2, Wd.grad) < 3e-5
+            if mode:
+                assert rel_err(ds2, ds_ref) < 3e-5
     db = torch.zeros(N, device=DEV)
     K.colsum(dyb, db)
     assert rel_err(db, dyq.sum(0)) < 1e-5
