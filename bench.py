@@ -110,7 +110,8 @@ def train_arm(args, dev, world, rank, dist_mod=None):
     cfg = ModelCfg(dict(CFG, max_seq_length=17))
     from sparse_caption_b200 import distributed as D
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
-    tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888)  # same mask seed on every rank
+    tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888,  # same mask seed on every rank
+                    use_graph=not args.no_train_graph)
     B, S, T = args.train_images, 5, 17
     g = torch.Generator().manual_seed(8888 + rank)
     att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank, pin=True)
@@ -156,6 +157,7 @@ def train_arm(args, dev, world, rank, dist_mod=None):
         return None
     # GEMM share / tensor roofline from one instrumented step
     lib.profile = []
+    tr.use_graph = False  # per-launch event timing needs the eager launch sequence
     tr.train_step(att, boxes, seqs, masks, seq_per_img=S, all_reduce=None, global_tokens=gtok, **opt)  # rank-local
     torch.cuda.synchronize(dev)
     prof, lib.profile = lib.profile, None
@@ -186,6 +188,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the SMP training arm (BASELINE.json configs[1])")
     ap.add_argument("--train-images", type=int, default=50, help="images per GPU per training step (5 captions each)")
     ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--no-train-graph", action="store_true", help="diagnostic: eager launches instead of the captured training graph")
     ap.add_argument("--cpu-images", type=int, default=64)
     ap.add_argument("--ln-fold", action="store_true", help="LayerNorm folded into the consuming GEMMs (sc_linear_ln) instead of separate LayerNorm kernels")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostic: disable programmatic dependent launch")

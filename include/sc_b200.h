@@ -184,13 +184,17 @@ int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, 
                     void* workspace, size_t workspace_bytes, sc_stream_t stream);
 
 /* out = g*keep*scale (cast), outT = its transpose (leading dim ldT, caller zero-pads); keep = (h != 0) when the saved
- * post-ReLU/dropout activation h is given, else the regenerated Philox dropout mask when dropout_p > 0. */
+ * post-ReLU/dropout activation h is given, else the regenerated Philox dropout mask when dropout_p > 0.
+ * colsum_accum (optional, fp32 [cols], pre-zeroed or holding a running sum): += column sums of `out` = the bias gradient. */
 int sc_prep_grad(const float* g, const void* h, int h_dtype, void* out, void* outT, int ldT, int out_dtype, int rows, int cols,
-                 float scale, float dropout_p, unsigned long long seed, unsigned long long stream_id, sc_stream_t stream);
+                 float scale, float dropout_p, unsigned long long seed, unsigned long long stream_id, float* colsum_accum,
+                 sc_stream_t stream);
 int sc_transpose(const void* x, int x_dtype, void* y, int ldT, int y_dtype, int rows, int cols, sc_stream_t stream);
-/* (W . mask)^T -> [K,N]: B operand of the dX GEMM */
+/* (W . mask)^T -> [K,N]: B operand of the dX GEMM; out_plain (optional, same dtype, [N,K]) receives W . mask from the
+ * same pass, i.e. the forward operand and its transpose share one mask sample and one read of W and S */
 int sc_apply_mask_transposed(const float* w, const float* mask, int mask_mode, const float* uniforms, unsigned long long seed,
-                             unsigned long long stream_id, void* outT, int out_dtype, int N, int K, sc_stream_t stream);
+                             unsigned long long stream_id, void* outT, int out_dtype, int N, int K, void* out_plain,
+                             sc_stream_t stream);
 /* elementwise straight-through gradient from a dense dWm (embedding table, WG heads) */
 int sc_mask_grad(const float* dwm, const float* w, const float* mask, int mask_mode, const float* uniforms,
                  unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad, float sparsity_coeff,
@@ -208,12 +212,16 @@ int sc_embedding_bwd(const int* tokens, const float* dy, float* dtable, int rows
 
 /* PruningMixin.compute_sparsity_loss from the binarized count (pruning/prune.py:228-269):
  * out3 = { |target - sparsity|, d(scaled loss)/d(nnz), sparsity } */
-int sc_sparsity_coeff(const unsigned long long* count, double total, float target, float scale, float* out3, sc_stream_t stream);
+int sc_sparsity_coeff(const unsigned long long* count, double total, float target, float scale, const float* scale_dev,
+                      float* out3, sc_stream_t stream);
 /* clip_grad_value_ + Adam on a flat buffer (utils/optim.py:116-126,187-191); sigmoid_grad_coeff (device scalar, optional)
- * adds coeff*sigmoid'(param) to the gradient before clipping (sparsity loss on the mask-logit group) */
+ * adds coeff*sigmoid'(param) to the gradient before clipping (sparsity loss on the mask-logit group).
+ * CUDA-graph replay: values that change every step may live in device memory instead of the (baked) arguments -
+ *   dyn (optional) = {lr, 1 - beta1^step, sqrt(1 - beta2^step)} overrides lr / step;  scale_dev overrides scale;
+ *   every `seed` argument of this ABI with bit 63 set is a device pointer (low 63 bits) to the 64-bit seed. */
 int sc_adam_clip(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float clip_value, float grad_scale, int step, const float* sigmoid_grad_coeff,
-                 sc_stream_t stream);
+                 const float* dyn, sc_stream_t stream);
 
 /* teacher-forcing attention with saved probabilities + backward (decoder self: causal_T = T; cross: groups = images with
  * S*T query rows; encoder box attention: additive bias): transformer.py:230-295, relation_transformer.py:258-293 */

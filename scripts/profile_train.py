@@ -11,7 +11,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 dev = torch.device("cuda")
 cfg = ModelCfg(dict(bench.CFG, max_seq_length=17))
 sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
-tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888)
+GRAPH = os.environ.get("SC_TRAIN_GRAPH", "1") == "1"
+tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888, use_graph=GRAPH)
 S, T = 5, 17
 g = torch.Generator().manual_seed(8888)
 att, boxes = synthetic.synthetic_inputs(B, 36, 2048, seed=8888, pin=True)
@@ -31,6 +32,7 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"host enqueue ms/step {(t1-t0)/5*1e3:.2f}  wall ms/step {(t2-t0)/5*1e3:.2f}")
+tr.use_graph = False  # per-kernel event timing needs the eager launch sequence
 agg = collections.defaultdict(lambda: [0.0, 0])
 for rep in range(3):
     lib.profile = []

@@ -113,7 +113,12 @@ __device__ __forceinline__ float sigmoidf_(float s) { return 1.f / (1.f + __expf
 // Philox4x32-10 (Salmon et al. 2011).  One call yields 4 x 32 random bits.
 struct Philox {
   uint32_t k0, k1;
-  __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  // seed: an immediate value, or - bit 63 set - a DEVICE POINTER (low 63 bits) to the 64-bit seed.  The pointer form
+  // lets a captured CUDA graph draw fresh masks / dropout on every replay: the host rewrites the seed word per step.
+  __device__ __forceinline__ Philox(uint64_t seed) {
+    if (seed >> 63) seed = *(const unsigned long long*)(seed & 0x7fffffffffffffffull);
+    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+  }
   __device__ __forceinline__ uint4 operator()(uint64_t ctr, uint64_t stream) const {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
     uint32_t a = k0, b = k1;

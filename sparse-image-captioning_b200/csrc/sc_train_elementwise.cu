@@ -23,7 +23,8 @@ template <typename T> __device__ __forceinline__ T cvt(float v) { return sc::fro
 template <typename HT, typename OT>
 __global__ void __launch_bounds__(256) prep_grad_kernel(const float* __restrict__ g, const HT* __restrict__ h, OT* __restrict__ out,
                                                         OT* __restrict__ outT, int ldT, int rows, int cols, float scale, float p,
-                                                        unsigned long long seed, unsigned long long stream) {
+                                                        unsigned long long seed, unsigned long long stream,
+                                                        float* __restrict__ colsum) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -42,8 +43,16 @@ __global__ void __launch_bounds__(256) prep_grad_kernel(const float* __restrict_
     }
     tile[ty + i * 8][tx] = v;
   }
-  if (!outT) return;
+  if (!outT && !colsum) return;
   __syncthreads();
+  if (colsum && ty == 0 && c0 + tx < cols) {
+    // bias gradient: column sums of the masked gradient (in the precision the GEMMs consume), one atomic per tile column
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += sc::to_f32<OT>(cvt<OT>(tile[r][tx]));
+    atomicAdd(colsum + c0 + tx, t);
+  }
+  if (!outT) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + i * 8, r = r0 + tx;
@@ -74,7 +83,8 @@ using sc::mask_value;
 template <typename OT>
 __global__ void __launch_bounds__(256) apply_mask_t_kernel(const float* __restrict__ w, const float* __restrict__ mask, int mode,
                                                            const float* __restrict__ uni, unsigned long long seed,
-                                                           unsigned long long stream, OT* __restrict__ outT, int N, int Kd) {
+                                                           unsigned long long stream, OT* __restrict__ outT, int N, int Kd,
+                                                           OT* __restrict__ out) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -86,6 +96,7 @@ __global__ void __launch_bounds__(256) apply_mask_t_kernel(const float* __restri
     if (n < N && k < Kd) {
       const size_t e = (size_t)n * Kd + k;
       v = w[e] * mask_value(mode, mask ? mask[e] : 0.f, uni ? uni[e] : 0.f, ph, e, stream);
+      if (out) out[e] = cvt<OT>(v);  // the forward operand W (.) m from the same pass (and the same mask sample)
     }
     tile[ty + i * 8][tx] = v;
   }
@@ -328,9 +339,10 @@ __global__ void __launch_bounds__(128) embedding_bwd_kernel(const int* __restric
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
                                                         float wd, float clip, float grad_scale, float bc1, float bc2_sqrt,
-                                                        const float* __restrict__ sig_coeff) {
+                                                        const float* __restrict__ sig_coeff, const float* __restrict__ dyn) {
   // sig_coeff (mask-logit group only): gradient of the sparsity loss, coeff * sigmoid'(S), with S = the parameter itself
   const float sc_ = sig_coeff ? *sig_coeff : 0.f;
+  if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2_sqrt = dyn[2]; }  // per-step values of a captured graph
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
     const float pi = p[i];
@@ -347,7 +359,9 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
 
 // PruningMixin.compute_sparsity_loss (pruning/prune.py:228-269) from the binarized-mask count:
 //   out[0] = |target - sparsity| ; out[1] = d(scaled loss)/d(nnz) = sign(target - sparsity) / total * scale ; out[2] = sparsity
-__global__ void sparsity_coeff_kernel(const unsigned long long* count, double total, float target, float scale, float* out) {
+__global__ void sparsity_coeff_kernel(const unsigned long long* count, double total, float target, float scale,
+                                      const float* scale_dev, float* out) {
+  if (scale_dev) scale = *scale_dev;
   const double sparsity = 1.0 - (double)(*count) / total;
   const double diff = (double)target - sparsity;
   out[0] = (float)fabs(diff);
@@ -366,10 +380,11 @@ int grid_for(size_t n, int block) {
 extern "C" {
 
 int sc_prep_grad(const float* g, const void* h, int h_dtype, void* out, void* outT, int ldT, int out_dtype, int rows, int cols,
-                 float scale, float dropout_p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
+                 float scale, float dropout_p, unsigned long long seed, unsigned long long stream_id, float* colsum_accum,
+                 cudaStream_t stream) {
   SC_CHECK(rows > 0 && cols > 0, SC_ERR_SHAPE, "sc_prep_grad: rows=%d cols=%d", rows, cols);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-#define PG(HT, OT) prep_grad_kernel<HT, OT><<<grid, 256, 0, stream>>>(g, (const HT*)h, (OT*)out, (OT*)outT, ldT, rows, cols, scale, dropout_p, seed, stream_id)
+#define PG(HT, OT) prep_grad_kernel<HT, OT><<<grid, 256, 0, stream>>>(g, (const HT*)h, (OT*)out, (OT*)outT, ldT, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum)
   if (out_dtype == SC_BF16) { if (h_dtype == SC_BF16) PG(__nv_bfloat16, __nv_bfloat16); else PG(float, __nv_bfloat16); }
   else if (out_dtype == SC_F32) { if (h_dtype == SC_BF16) PG(__nv_bfloat16, float); else PG(float, float); }
   else SC_CHECK(false, SC_ERR_DTYPE, "sc_prep_grad: bad dtype");
@@ -391,12 +406,13 @@ int sc_transpose(const void* x, int x_dtype, void* y, int ldT, int y_dtype, int 
 }
 
 int sc_apply_mask_transposed(const float* w, const float* mask, int mask_mode, const float* uniforms, unsigned long long seed,
-                             unsigned long long stream_id, void* outT, int out_dtype, int N, int K, cudaStream_t stream) {
+                             unsigned long long stream_id, void* outT, int out_dtype, int N, int K, void* out_plain,
+                             cudaStream_t stream) {
   SC_CHECK(N > 0 && K > 0, SC_ERR_SHAPE, "sc_apply_mask_transposed: N=%d K=%d", N, K);
   SC_CHECK(mask_mode == SC_MASK_NONE || mask != nullptr, SC_ERR_SHAPE, "sc_apply_mask_transposed: mask missing");
   dim3 grid((K + 31) / 32, (N + 31) / 32);
-  if (out_dtype == SC_BF16) apply_mask_t_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, mask, mask_mode, uniforms, seed, stream_id, (__nv_bfloat16*)outT, N, K);
-  else if (out_dtype == SC_F32) apply_mask_t_kernel<float><<<grid, 256, 0, stream>>>(w, mask, mask_mode, uniforms, seed, stream_id, (float*)outT, N, K);
+  if (out_dtype == SC_BF16) apply_mask_t_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(w, mask, mask_mode, uniforms, seed, stream_id, (__nv_bfloat16*)outT, N, K, (__nv_bfloat16*)out_plain);
+  else if (out_dtype == SC_F32) apply_mask_t_kernel<float><<<grid, 256, 0, stream>>>(w, mask, mask_mode, uniforms, seed, stream_id, (float*)outT, N, K, (float*)out_plain);
   else SC_CHECK(false, SC_ERR_DTYPE, "sc_apply_mask_transposed: bad dtype");
   SC_LAUNCH_CHECK("sc_apply_mask_transposed");
   return SC_OK;
@@ -483,21 +499,22 @@ int sc_embedding_bwd(const int* tokens, const float* dy, float* dtable, int rows
   return SC_OK;
 }
 
-int sc_sparsity_coeff(const unsigned long long* count, double total, float target, float scale, float* out3, cudaStream_t stream) {
+int sc_sparsity_coeff(const unsigned long long* count, double total, float target, float scale, const float* scale_dev,
+                      float* out3, cudaStream_t stream) {
   SC_CHECK(count && out3 && total > 0, SC_ERR_SHAPE, "sc_sparsity_coeff: bad args");
-  sparsity_coeff_kernel<<<1, 1, 0, stream>>>(count, total, target, scale, out3);
+  sparsity_coeff_kernel<<<1, 1, 0, stream>>>(count, total, target, scale, scale_dev, out3);
   SC_LAUNCH_CHECK("sc_sparsity_coeff");
   return SC_OK;
 }
 
 int sc_adam_clip(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float clip_value, float grad_scale, int step, const float* sigmoid_grad_coeff,
-                 cudaStream_t stream) {
+                 const float* dyn, cudaStream_t stream) {
   SC_CHECK(n > 0 && step >= 1, SC_ERR_SHAPE, "sc_adam_clip: n=%zu step=%d", n, step);
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
   adam_clip_kernel<<<grid_for(n, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                         clip_value, grad_scale, bc1, bc2, sigmoid_grad_coeff);
+                                                         clip_value, grad_scale, bc1, bc2, sigmoid_grad_coeff, dyn);
   SC_LAUNCH_CHECK("sc_adam_clip");
   return SC_OK;
 }

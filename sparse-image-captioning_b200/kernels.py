@@ -273,14 +273,16 @@ def linear_wgrad(dyT, xT, w, mask, mask_mode, dw, ds, *, M, uniforms=None, seed=
              meta=("gemm_bf16" if dyT.dtype == torch.bfloat16 else "gemm_f32", N, K, M, dyT.element_size(), xT.element_size(), 4, False))
 
 
-def prep_grad(g, *, h=None, out=None, outT=None, scale=1.0, p=0.0, seed=0, stream_id=0):
-    """out = g * keep * scale (cast), outT = its transpose with leading dim outT.shape[1] (zero padded)."""
+def prep_grad(g, *, h=None, out=None, outT=None, scale=1.0, p=0.0, seed=0, stream_id=0, colsum=None):
+    """out = g * keep * scale (cast), outT = its transpose with leading dim outT.shape[1] (zero padded);
+    ``colsum`` (fp32 [cols]) accumulates the column sums of out (bias gradient)."""
     rows, cols = g.shape
     assert g.dtype == torch.float32
     ref = out if out is not None else outT
     ldT = outT.shape[1] if outT is not None else rows
     lib.call("sc_prep_grad", lib.ptr(g), lib.ptr(h), lib.dtype_code(h.dtype) if h is not None else F32, lib.ptr(out),
-             lib.ptr(outT), ldT, lib.dtype_code(ref.dtype), rows, cols, float(scale), float(p), seed, stream_id, lib.stream())
+             lib.ptr(outT), ldT, lib.dtype_code(ref.dtype), rows, cols, float(scale), float(p), seed, stream_id, lib.ptr(colsum),
+             lib.stream())
 
 
 def transpose(x, outT):
@@ -290,13 +292,14 @@ def transpose(x, outT):
     return outT
 
 
-def apply_mask_transposed(w, mask, mask_mode, outT, *, uniforms=None, seed=0, stream_id=0):
+def apply_mask_transposed(w, mask, mask_mode, outT, *, uniforms=None, seed=0, stream_id=0, out=None):
+    """outT [K,N] = (w (.) mask)^T; ``out`` [N,K] (optional, same dtype) = w (.) mask from the same pass."""
     N, K = w.shape
-    assert tuple(outT.shape) == (K, N)
+    assert tuple(outT.shape) == (K, N) and (out is None or (tuple(out.shape) == (N, K) and out.dtype == outT.dtype))
     if mask is None:
         mask_mode = MASK_NONE
     lib.call("sc_apply_mask_transposed", lib.ptr(w), lib.ptr(mask), mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(outT),
-             lib.dtype_code(outT.dtype), N, K, lib.stream())
+             lib.dtype_code(outT.dtype), N, K, lib.ptr(out), lib.stream())
     return outT
 
 
@@ -333,15 +336,17 @@ def embedding_bwd(tokens, dy, dtable, scale):
     lib.call("sc_embedding_bwd", lib.ptr(tokens), lib.ptr(dy), lib.ptr(dtable), rows, D, dtable.shape[0], float(scale), lib.stream())
 
 
-def adam_clip(param, grad, m, v, *, lr, betas, eps, weight_decay, clip, grad_scale, step, sigmoid_grad_coeff=None):
+def adam_clip(param, grad, m, v, *, lr, betas, eps, weight_decay, clip, grad_scale, step, sigmoid_grad_coeff=None, dyn=None):
+    """``dyn``: optional device fp32 [3] = {lr, 1 - b1^step, sqrt(1 - b2^step)} read at run time (CUDA-graph replay)."""
     lib.call("sc_adam_clip", lib.ptr(param), lib.ptr(grad), lib.ptr(m), lib.ptr(v), param.numel(), float(lr), float(betas[0]),
              float(betas[1]), float(eps), float(weight_decay), float(clip), float(grad_scale), int(step),
-             lib.ptr(sigmoid_grad_coeff), lib.stream())
+             lib.ptr(sigmoid_grad_coeff), lib.ptr(dyn), lib.stream())
 
 
-def sparsity_coeff(count, total, target, scale, out3):
+def sparsity_coeff(count, total, target, scale, out3, scale_dev=None):
     """out3 = [|target - sparsity|, d(scaled loss)/d(nnz), sparsity] from the device-side binarized-mask count."""
-    lib.call("sc_sparsity_coeff", lib.ptr(count), float(total), float(target), float(scale), lib.ptr(out3), lib.stream())
+    lib.call("sc_sparsity_coeff", lib.ptr(count), float(total), float(target), float(scale), lib.ptr(scale_dev), lib.ptr(out3),
+             lib.stream())
     return out3
 
 

@@ -40,16 +40,16 @@ SIGNATURES = {
     # training
     "sc_linear_dropout": [_p, _i, _p, _i, _p, _i, _p, _u64, _u64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_linear_wgrad": [_p, _p, _i, _p, _p, _i, _p, _u64, _u64, _i, _f, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p],
-    "sc_prep_grad": [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _u64, _u64, _p],
+    "sc_prep_grad": [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _u64, _u64, _p, _p],
     "sc_transpose": [_p, _i, _p, _i, _i, _i, _i, _p],
-    "sc_apply_mask_transposed": [_p, _p, _i, _p, _u64, _u64, _p, _i, _i, _i, _p],
+    "sc_apply_mask_transposed": [_p, _p, _i, _p, _u64, _u64, _p, _i, _i, _i, _p, _p],
     "sc_mask_grad": [_p, _p, _p, _i, _p, _u64, _u64, _i, _f, _p, _p, _i, _sz, _p],
     "sc_colsum": [_p, _i, _p, _i, _i, _i, _p],
     "sc_layernorm_bwd": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p],
     "sc_logsoftmax_nll": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p],
     "sc_embedding_bwd": [_p, _p, _p, _i, _i, _i, _f, _p],
-    "sc_adam_clip": [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _i, _p, _p],
-    "sc_sparsity_coeff": [_p, C.c_double, _f, _f, _p, _p],
+    "sc_adam_clip": [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p],
+    "sc_sparsity_coeff": [_p, C.c_double, _f, _f, _p, _p, _p],
     "sc_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_attention_bwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_box_bias_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p],

@@ -27,7 +27,7 @@ def _round_up(n, m):
 class OrtTrainer:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, mask_type: Optional[str] = "supermask",
                  precision="bf16", device="cuda", dropout=0.1 / 3, drop_prob_src=0.5, bypass_sigmoid_grad=False, seed=0,
-                 mask_init_value=5.0, uniforms: Optional[Dict[str, torch.Tensor]] = None):
+                 mask_init_value=5.0, uniforms: Optional[Dict[str, torch.Tensor]] = None, use_graph=False):
         assert cfg.share_att_encoder is None and cfg.share_att_decoder is None and not cfg.share_layer_encoder \
             and not cfg.share_layer_decoder, "ACORT weight sharing is an inference-side feature in this round"
         self.cfg = cfg
@@ -39,6 +39,14 @@ class OrtTrainer:
         self.seed = int(seed)
         self.step_id = 0
         self.training = True
+        # CUDA-graph mode: the whole step (forward, backward, optimizer) is captured once per batch shape and replayed;
+        # everything that changes per step (Philox seeds, lr, Adam bias corrections, sparsity-loss scale) is read from
+        # small device buffers that the host rewrites before each replay (sc_b200.h: seed pointers, `dyn`)
+        self.use_graph = bool(use_graph)
+        self._seeds_host = torch.zeros(3, dtype=torch.int64).pin_memory() if self.use_graph else None
+        self._seeds_dev = torch.zeros(3, dtype=torch.int64, device=self.dev)
+        self._dyn_host = torch.zeros(8, dtype=torch.float32).pin_memory() if self.use_graph else None
+        self._dyn_dev = torch.zeros(8, dtype=torch.float32, device=self.dev)
         d, L = cfg.d_model, cfg.num_layers
         sd = state_dict
         # ---- parameter layout: fused groups are contiguous so that [q;k;v] / [k;v] / WG blocks are single views ----
@@ -114,6 +122,7 @@ class OrtTrainer:
             pad[offs_s[k]: offs_s[k] + sd[k].numel()] = False
         self.flat_s[pad] = -1.0
         self._s_pad_mask = pad
+        self._s_pad_idx = pad.nonzero().view(-1)  # index form: index_fill_ is CUDA-graph capturable
         self.stream_of = {k: i + 1 for i, k in enumerate(order)}
         # injected uniforms (parity tests): same layout as flat_s
         self.flat_u = None
@@ -133,7 +142,7 @@ class OrtTrainer:
         self.sp_count = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._ws = {}
         self.premask = True   # False: mask inside the GEMM operand prologue (K1 fused variant)
-        self._wm, self._wm_step = {}, {}
+        self._wm, self._wmT, self._wm_step = {}, {}, {}
 
     # ---------------------------------------------------------------------------------------------------------
     def _group(self, table, first, count):
@@ -166,16 +175,26 @@ class OrtTrainer:
             return K.MASK_UNIFORM if self.flat_u is not None else K.MASK_BERNOULLI
         return K.MASK_RAW
 
+    def _sd(self, i):
+        """Philox seed i (0 masks, 1 dropout, 2 attention dropout): an immediate value, or in graph mode a device pointer
+        (bit 63 set) to the seed word the host rewrites every step."""
+        if self.use_graph:
+            return (1 << 63) | (self._seeds_dev.data_ptr() + 8 * i)
+        return self.seed + i
+
+    def _step_base(self):
+        return 0 if self.use_graph else self.step_id * 4096
+
     def _mask_args(self, wname, count=1):
         """(weight view, logits view, mode, uniforms view, seed, stream) of a (fused) masked weight."""
         W = self._group(self.p, wname, count)
         if not self.mask_type:
             return W, None, K.MASK_NONE, None, 0, 0
-        return (W, self._group(self.s, wname, count), self.mask_mode(), self._u(wname, count), self.seed,
-                self.step_id * 4096 + self.stream_of[wname])
+        return (W, self._group(self.s, wname, count), self.mask_mode(), self._u(wname, count), self._sd(0),
+                self._step_base() + self.stream_of[wname])
 
     def _drop_stream(self, site):
-        return self.step_id * 4096 + 2048 + site
+        return self._step_base() + 2048 + site
 
     # ---------------------------------------------------------------------------------------------------------
     def _get_ws(self, B, N, S, T, masked):
@@ -258,14 +277,19 @@ class OrtTrainer:
             wm = self._wm.get(key)
             if wm is None:
                 wm = self._wm[key] = torch.empty(W.shape, device=self.dev, dtype=torch.bfloat16)
+                self._wmT[key] = torch.empty(W.shape[1], W.shape[0], device=self.dev, dtype=torch.bfloat16)
             if self._wm_step.get(key) != (self.step_id, self.training):
-                K.apply_mask(W, S, mode, uniforms=U, seed=seed, stream_id=stream, out=wm)
+                if self.training:
+                    # one pass over W and S: the forward operand W (.) m and the dX operand (W (.) m)^T, same mask sample
+                    K.apply_mask_transposed(W, S, mode, self._wmT[key], uniforms=U, seed=seed, stream_id=stream, out=wm)
+                else:
+                    K.apply_mask(W, S, mode, uniforms=U, seed=seed, stream_id=stream, out=wm)
                 self._wm_step[key] = (self.step_id, self.training)
-            K.linear_dropout(x, wm, b, residual=residual, relu=relu, out=out, p=p, drop_seed=self.seed + 1,
+            K.linear_dropout(x, wm, b, residual=residual, relu=relu, out=out, p=p, drop_seed=self._sd(1),
                              drop_stream=self._drop_stream(site))
             return out
         K.linear_dropout(x, W, b, mask=S, mask_mode=mode, uniforms=U, seed=seed, stream_id=stream, residual=residual,
-                         relu=relu, out=out, p=p, drop_seed=self.seed + 1, drop_stream=self._drop_stream(site))
+                         relu=relu, out=out, p=p, drop_seed=self._sd(1), drop_stream=self._drop_stream(site))
         return out
 
     def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None):
@@ -279,23 +303,27 @@ class OrtTrainer:
         Mp = K.pad8(M)
         p = p if self.training else 0.0
         gT = ws.gT[: N * Mp].view(N, Mp)
+        bname = wname.replace(".weight", ".bias")
+        gbias = self._group(self.g, bname, count) if bname in self.g else None
         if g_ready is not None:
             gb = g_ready
             if Mp != M:
                 gT[:, M:].zero_()
             K.transpose(gb, gT)
+            if gbias is not None:
+                K.colsum(gb, gbias)
         else:
             gb = ws.gb[: M * N].view(M, N)
             if Mp != M:
                 gT[:, M:].zero_()
+            # the bias gradient (column sums) is accumulated by the same pass (flat_gw is zeroed at the start of the backward)
             K.prep_grad(g, h=h, out=gb, outT=gT, scale=(1.0 / (1.0 - p)) if (h is not None and p > 0) else 1.0,
-                        p=0.0 if h is not None else p, seed=self.seed + 1, stream_id=self._drop_stream(site))
-        bname = wname.replace(".weight", ".bias")
-        if bname in self.g:
-            K.colsum(gb, self._group(self.g, bname, count))
+                        p=0.0 if h is not None else p, seed=self._sd(1), stream_id=self._drop_stream(site), colsum=gbias)
         if dx is not None:
-            wT = ws.wT[: Kd * N].view(Kd, N)
-            K.apply_mask_transposed(W, S, mode, wT, uniforms=U, seed=seed, stream_id=stream)
+            wT = self._wmT.get((wname, count)) if (self.adt == torch.bfloat16 and self.premask and self.training) else None
+            if wT is None:
+                wT = ws.wT[: Kd * N].view(Kd, N)
+                K.apply_mask_transposed(W, S, mode, wT, uniforms=U, seed=seed, stream_id=stream)
             K.linear(gb, wT, None, residual=dx_residual, out=dx)
         xT = ws.xT[: Kd * Mp].view(Kd, Mp)
         if Mp != M:
@@ -352,12 +380,12 @@ class OrtTrainer:
             if Sg is None:
                 ws.wg_eff[l].copy_(Wg)
             else:
-                ws.wg_eff[l].copy_(K.apply_mask(Wg, Sg, mode, uniforms=U, seed=seed, stream_id=stream))
+                K.apply_mask(Wg, Sg, mode, uniforms=U, seed=seed, stream_id=stream, out=ws.wg_eff[l])
             K.box_bias_fwd(ws.boxes, ws.wg_eff[l], self._group(self.p, f"{p}.self_attn.WGs.0.bias", h), ws.e_bias[l], B=B, N=N, h=h,
                            trig=trig)
             q = ws.e_qkv[l]
             K.attention_fwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_att[l], ws.e_probs[l], G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d,
-                            ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.att_mask, bias=ws.e_bias[l], p=pd, seed=self.seed + 2,
+                            ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.att_mask, bias=ws.e_bias[l], p=pd, seed=self._sd(2),
                             stream_id=self._drop_stream(10 + l))
             self._lin(f"{p}.self_attn.linears.3.weight", ws.e_att[l], x1, residual=x0, p=pd, site=20 + l)
             self._ln(f"{p}.sublayer.1.norm", x1, ws.e_xn2[l])
@@ -370,7 +398,7 @@ class OrtTrainer:
         W, S_, mode, U, seed, stream = self._mask_args("model.tgt_embed.0.lut.weight")
         K.embed_pe(ws.tokens, W, self.pe, T=T, pos0=0, mask=S_, mask_mode=mode, uniforms=U, seed=seed, stream_id=stream, out=ws.y[0])
         if pd > 0:
-            K.prep_grad(ws.y[0], out=ws.y[0], p=pd, seed=self.seed + 1, stream_id=self._drop_stream(2))
+            K.prep_grad(ws.y[0], out=ws.y[0], p=pd, seed=self._sd(1), stream_id=self._drop_stream(2))
         for l in range(L):
             p = f"model.decoder.layers.{l}"
             y0, y1, y2, y3 = ws.y[3 * l], ws.y[3 * l + 1], ws.y[3 * l + 2], ws.y[3 * l + 3]
@@ -378,14 +406,14 @@ class OrtTrainer:
             self._lin(f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], ws.d_qkv[l], count=3)
             q = ws.d_qkv[l]
             K.attention_fwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_att[l], ws.d_probs[l], G=R, Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d,
-                            ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.key_valid, causal_T=T, p=pd, seed=self.seed + 2,
+                            ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.key_valid, causal_T=T, p=pd, seed=self._sd(2),
                             stream_id=self._drop_stream(50 + l))
             self._lin(f"{p}.self_attn.linears.3.weight", ws.d_att[l], y1, residual=y0, p=pd, site=60 + l)
             self._ln(f"{p}.sublayer.1.norm", y1, ws.d_yn2[l])
             self._lin(f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], ws.d_qc[l])
             kv = ws.memkv[l]
             K.attention_fwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.d_catt[l], ws.c_probs[l], G=B, Tq=S * T, Tk=N, h=h, dk=dk, ldq=d,
-                            ldk=2 * d, ldv=2 * d, ldo=d, key_valid=ws.att_mask, p=pd, seed=self.seed + 2,
+                            ldk=2 * d, ldv=2 * d, ldo=d, key_valid=ws.att_mask, p=pd, seed=self._sd(2),
                             stream_id=self._drop_stream(70 + l))
             self._lin(f"{p}.src_attn.linears.3.weight", ws.d_catt[l], y2, residual=y1, p=pd, site=80 + l)
             self._ln(f"{p}.sublayer.2.norm", y2, ws.d_yn3[l])
@@ -403,10 +431,8 @@ class OrtTrainer:
         dk = d // h
         pd = self.p_drop if self.training else 0.0
         trig = not c.no_box_trigonometric_embedding
-        # norm gradients accumulate through atomics: zero them (everything else is overwritten)
-        for k in self.names:
-            if k.endswith("a_2") or k.endswith("b_2"):
-                self.g[k].zero_()
+        # norm and bias gradients accumulate through atomics: one memset of the flat buffer (weights are overwritten)
+        self.flat_gw.zero_()
         ws.loss_sum.zero_()
         K.logsoftmax_nll(ws.logits, ws.targets, ws.tok_w, ws.inv_norm, ws.loss_sum, ws.dlogits)
         ga_d = ws.ga.view(-1)[: MD * d].view(MD, d)
@@ -431,7 +457,7 @@ class OrtTrainer:
             dqc = ws.gq.view(-1)[: MD * d].view(MD, d)
             K.attention_bwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.c_probs[l], ga_c, dqc, ws.dmemkv[:, 0:], ws.dmemkv[:, d:],
                             dtype=self.adt, G=B, Tq=S * T, Tk=N, h=h, dk=dk, ldq=d, ldk=2 * d, ldv=2 * d, ldd=d, ldgq=d, ldgk=2 * d,
-                            ldgv=2 * d, p=pd, seed=self.seed + 2, stream_id=self._drop_stream(70 + l))
+                            ldgv=2 * d, p=pd, seed=self._sd(2), stream_id=self._drop_stream(70 + l))
             ga_c2 = ws.ga.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], dqc, dx=ga_c2)
             self._ln_bwd(f"{p}.sublayer.1.norm", y1, ga_c2, nxt, dres=cur)
@@ -444,7 +470,7 @@ class OrtTrainer:
             gq = ws.gq[:MD]
             K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_probs[l], ga_s, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
                             G=R, Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
-                            p=pd, seed=self.seed + 2, stream_id=self._drop_stream(50 + l))
+                            p=pd, seed=self._sd(2), stream_id=self._drop_stream(50 + l))
             ga_s2 = ws.ga.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], gq, count=3, dx=ga_s2)
             self._ln_bwd(f"{p}.sublayer.0.norm", y0, ga_s2, nxt, dres=cur)
@@ -478,7 +504,7 @@ class OrtTrainer:
             gq = ws.gq[:ME]
             K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
                             G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
-                            dbias=ws.dbias, p=pd, seed=self.seed + 2, stream_id=self._drop_stream(10 + l))
+                            dbias=ws.dbias, p=pd, seed=self._sd(2), stream_id=self._drop_stream(10 + l))
             ws.dwg.zero_()
             gb_wg = self._group(self.g, f"{p}.self_attn.WGs.0.bias", h)
             gb_wg.zero_()
@@ -498,23 +524,68 @@ class OrtTrainer:
 
     # ---------------------------------------------------------------------------------------------------------
     def optimizer_step(self, *, lr, mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0,
-                       grad_scale=1.0, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1):
+                       grad_scale=1.0, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1, _dyn=False):
         """clip_gradient(0.1) + Adam for the two parameter groups of train_n_prune_transformer.py:67-82, with the
-        sparsity-loss gradient (prune.py:228-269) folded into the mask-logit update."""
-        self.opt_step += 1
+        sparsity-loss gradient (prune.py:228-269) folded into the mask-logit update.  ``_dyn``: graph mode - lr, the Adam
+        bias corrections and the sparsity scale come from ``self._dyn_dev`` (``_upload_step``), no host bookkeeping."""
+        if not _dyn:
+            self.opt_step += 1
+        dyn = self._dyn_dev if _dyn else None
         K.adam_clip(self.flat_w, self.flat_gw, self.m_w, self.v_w, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip=clip,
-                    grad_scale=grad_scale, step=self.opt_step)
+                    grad_scale=grad_scale, step=max(1, self.opt_step), dyn=dyn[0:3] if _dyn else None)
         if self.masked and self.mask_type == "supermask":
             coeff = None
             if sparsity_target is not None and sparsity_weight:
                 anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
                 self.sp_count.zero_()
                 K.lib.call("sc_mask_count", K.lib.ptr(self.flat_s), self.flat_s.numel(), K.lib.ptr(self.sp_count), K.lib.stream())
-                K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out)
+                K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out,
+                                 scale_dev=dyn[6:7] if _dyn else None)
                 coeff = self.sp_out[1:2]
             K.adam_clip(self.flat_s, self.flat_gs, self.m_s, self.v_s, lr=mask_lr, betas=betas, eps=mask_eps, weight_decay=0.0,
-                        clip=clip, grad_scale=grad_scale, step=self.opt_step, sigmoid_grad_coeff=coeff)
-            self.flat_s[self._s_pad_mask] = -1.0
+                        clip=clip, grad_scale=grad_scale, step=max(1, self.opt_step), sigmoid_grad_coeff=coeff,
+                        dyn=dyn[3:6] if _dyn else None)
+            if self._s_pad_idx.numel():
+                self.flat_s.index_fill_(0, self._s_pad_idx, -1.0)
+
+    def _upload_step(self, *, lr, mask_lr=100.0, betas=(0.9, 0.98), sparsity_weight=0.0, current_step=0, max_step=1, **_):
+        """Per-step scalars of the captured graph -> pinned host words -> device (two tiny async copies)."""
+        self.opt_step += 1
+        golden = 0x9E3779B97F4A7C15
+        for i in range(3):
+            v = (self.seed + i + self.step_id * golden) & 0xFFFFFFFFFFFFFFFF
+            self._seeds_host[i] = v - (1 << 64) if v >= (1 << 63) else v
+        bc1 = 1.0 - betas[0] ** self.opt_step
+        bc2 = math.sqrt(1.0 - betas[1] ** self.opt_step)
+        anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
+        h = self._dyn_host
+        h[0], h[1], h[2], h[3], h[4], h[5], h[6] = lr, bc1, bc2, mask_lr, bc1, bc2, sparsity_weight * (1.0 - anneal)
+        self._seeds_dev.copy_(self._seeds_host, non_blocking=True)
+        self._dyn_dev.copy_(self._dyn_host, non_blocking=True)
+
+    def _graph_body(self, ws, part, opt):
+        self._wm_step = {}  # every body (eager warm-up, capture) re-applies the masks
+        if part in ("all", "fwdbwd"):
+            self.forward(ws)
+            self.loss_and_backward(ws)
+        if part in ("all", "opt"):
+            self.optimizer_step(_dyn=True, **opt)
+
+    def _run_graphed(self, ws, part, opt):
+        key = (part, tuple(sorted((k, float(v)) for k, v in opt.items() if k in ("clip", "eps", "mask_eps", "weight_decay",
+                                                                                "grad_scale", "sparsity_target"))))
+        graphs = ws.__dict__.setdefault("graphs", {})
+        if key not in graphs:
+            # the first step of a shape runs eagerly (it is a real step and also warms every kernel up), then the same
+            # launch sequence is captured for all later steps
+            self._graph_body(ws, part, opt)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_body(ws, part, opt)
+            graphs[key] = g
+            return
+        graphs[key].replay()
 
     def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None, **opt):
         """One full SMP step.  ``all_reduce``: callable applied to the flat gradient buffers (NCCL sum) when data-parallel."""
@@ -523,6 +594,18 @@ class OrtTrainer:
         ws = self._get_ws(B, N, seq_per_img, T, att_masks is not None)
         self.step_id += 1
         self.load_batch(ws, att_feats, boxes, seqs, masks, att_masks, global_tokens)
+        if self.use_graph and self.training:
+            self._upload_step(lr=lr, **opt)
+            opt = dict(opt, lr=lr)
+            if all_reduce is None:
+                self._run_graphed(ws, "all", opt)
+            else:
+                self._run_graphed(ws, "fwdbwd", opt)
+                all_reduce(self.flat_gw)
+                if self.masked:
+                    all_reduce(self.flat_gs)
+                self._run_graphed(ws, "opt", opt)
+            return ws.loss_sum * ws.inv_norm
         self.forward(ws)
         self.loss_and_backward(ws)
         if all_reduce is not None:

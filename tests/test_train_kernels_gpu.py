@@ -62,12 +62,16 @@ def test_masked_linear_backward(K, dt, mode, bypass, shape):
     Mp = K.pad8(M)
     dyT = torch.zeros(N, Mp, dtype=dt, device=DEV)
     dyb = torch.zeros(M, N, dtype=dt, device=DEV)
-    K.prep_grad(dy.to(DEV), out=dyb, outT=dyT)
+    db_fused = torch.zeros(N, device=DEV)
+    K.prep_grad(dy.to(DEV), out=dyb, outT=dyT, colsum=db_fused)
+    assert rel_err(db_fused, dyq.sum(0)) < 1e-5  # bias gradient from the same pass
     xT = torch.zeros(Kd, Mp, dtype=dt, device=DEV)
     K.transpose(x.to(dt).to(DEV), xT)
     WmT = torch.zeros(Kd, N, dtype=dt, device=DEV)
     Wg, Sg, Ug = W.to(DEV), S.to(DEV), U.to(DEV)
-    K.apply_mask_transposed(Wg, Sg if mode else None, mode, WmT, uniforms=Ug)
+    Wm_plain = torch.zeros(N, Kd, dtype=dt, device=DEV)
+    K.apply_mask_transposed(Wg, Sg if mode else None, mode, WmT, uniforms=Ug, out=Wm_plain)
+    assert torch.equal(Wm_plain.t().contiguous(), WmT)  # forward operand and dX operand share the mask sample
     dx = K.linear(dyb, WmT)
     tol = 2e-5 if dt == torch.float32 else 2e-5  # references use the same quantised operands
     assert rel_err(dx, dx_ref) < tol

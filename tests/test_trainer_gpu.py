@@ -149,3 +149,42 @@ def test_dropout_training_runs_and_is_reproducible():
         outs.append((float(loss), tr.flat_w.clone(), tr.flat_s.clone()))
     assert abs(outs[0][0] - outs[1][0]) < 1e-4 * abs(outs[0][0]) and torch.isfinite(outs[0][1]).all()
     assert rel_err(outs[0][1], outs[1][1]) < 1e-3  # atomics in LN/embedding reductions may reorder sums (Adam's first step is sign-like)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_mode_matches_eager(precision):
+    """The captured-graph step (device-side seeds / lr / Adam corrections) takes the same steps as the eager launch
+    sequence: injected uniforms and no dropout make both deterministic up to atomic summation order."""
+    z = golden_io.load("ort_prune_tiny")
+    res = {}
+    for graph in (False, True):
+        tr = _trainer(z, mask_type="supermask", precision=precision, uniforms=z["u"], use_graph=graph)
+        losses = []
+        for step in range(4):  # graph mode: step 0 eager + capture, steps 1..3 replays
+            loss = tr.train_step(z["att_feats"].to(DEV), z["boxes"].to(DEV), z["seqs"], z["masks"], seq_per_img=2,
+                                 lr=1e-3 * (step + 1), sparsity_target=0.9, sparsity_weight=5.0, current_step=step, max_step=10)
+            losses.append(float(loss))
+        res[graph] = (losses, tr.flat_w.clone(), tr.flat_s.clone(), tr.opt_step)
+    assert res[True][3] == res[False][3] == 4
+    for a, b in zip(res[True][0], res[False][0]):
+        assert abs(a - b) < 2e-3 * abs(b), (res[True][0], res[False][0])
+    assert res[False][0][-1] < res[False][0][0]  # the loss moves
+    # a handful of sign-flips of Adam's first steps on near-zero gradients are the only differences
+    assert float((res[True][1] - res[False][1]).abs().mean() / res[False][1].abs().mean()) < 2e-3
+
+
+def test_graph_mode_draws_fresh_masks_every_replay():
+    """Bernoulli masks + dropout inside a replayed graph: the Philox seed is read from device memory, so consecutive
+    replays on the SAME batch (lr = 0: parameters frozen) see different masks and therefore different losses."""
+    z = golden_io.load("ort_prune_tiny")
+    from sparse_caption_b200.engine import ModelCfg
+    from sparse_caption_b200.trainer import OrtTrainer
+    sd = dict(z["w"])
+    for k in list(sd):
+        if k.endswith("_pruning_mask"):
+            sd[k] = torch.zeros_like(sd[k])  # keep probability 0.5: the sample matters
+    tr = OrtTrainer(sd, ModelCfg(z["cfg_dict"]), mask_type="supermask", precision="bf16", seed=11, use_graph=True)
+    losses = [float(tr.train_step(z["att_feats"].to(DEV), z["boxes"].to(DEV), z["seqs"], z["masks"], seq_per_img=2, lr=0.0,
+                                  mask_lr=0.0)) for _ in range(5)]
+    assert len({round(v, 5) for v in losses[1:]}) >= 3, losses
+    assert all(l == l and abs(l) < 1e4 for l in losses)
