@@ -138,7 +138,12 @@ struct Smem {
   // cp.async while the main loop runs; the area is shared with the weight-gradient staging (never used together)
   static constexpr int kResPrefetchBytes = (kNumEpilogueWarps == 4 && BLOCK_N == 64) ? BLOCK_M * BLOCK_N * 4 : 0;
   static constexpr int kEpiBytes = kNumEpilogueWarps * 4096 > kResPrefetchBytes ? kNumEpilogueWarps * 4096 : kResPrefetchBytes;
-  static constexpr int kUsed = kStagingOffset + kEpiBytes;
+  // per-epilogue-warp bias / ln_c slices (BLOCK_N floats each): inside the (otherwise unused) transpose staging for the
+  // direct configurations without residual prefetch, a dedicated area elsewhere
+  static constexpr bool kSliceInStaging = (kNumEpilogueWarps == 4) && kResPrefetchBytes == 0;
+  static constexpr int kSliceOffset = kStagingOffset + kEpiBytes;
+  static constexpr int kSliceBytes = kSliceInStaging ? 0 : kNumEpilogueWarps * BLOCK_N * 8;
+  static constexpr int kUsed = kStagingOffset + kEpiBytes + kSliceBytes;
   // 1 KB of slack: up to 768 B of alignment padding in front, the barriers + TMEM pointer in its last 256 B
   static constexpr int kTotal = kUsed + 1024;
 };
@@ -155,31 +160,22 @@ struct Smem {
 // dropout / LayerNorm / row-statistics code.
 template <bool kFull>
 __device__ __forceinline__ void epilogue_row(const GemmArgs& args, float (&f)[32], const float (&res)[32], int row, int col0,
-                                             float ln_rstd, float ln_mr) {
-  const bool vec = (args.N & 3) == 0 && col0 + 32 <= args.N;
-  if (vec) {
-    if (kFull && args.ln_stats) {
+                                             float ln_rstd, float ln_mr, const float* sb, const float* sc) {
+  // sb / sc: this chunk's 32 bias / ln_c values in shared memory (zero-filled beyond N; staged once per tile so that no
+  // global latency sits between the accumulator load and the stores)
+  if (kFull && args.ln_stats) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 c = __ldg((const float4*)(args.ln_c + col0) + j);
-        f[4 * j] = ln_rstd * f[4 * j] - ln_mr * c.x; f[4 * j + 1] = ln_rstd * f[4 * j + 1] - ln_mr * c.y;
-        f[4 * j + 2] = ln_rstd * f[4 * j + 2] - ln_mr * c.z; f[4 * j + 3] = ln_rstd * f[4 * j + 3] - ln_mr * c.w;
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float4 c = *(const float4*)(sc + 4 * j);
+      f[4 * j] = ln_rstd * f[4 * j] - ln_mr * c.x; f[4 * j + 1] = ln_rstd * f[4 * j + 1] - ln_mr * c.y;
+      f[4 * j + 2] = ln_rstd * f[4 * j + 2] - ln_mr * c.z; f[4 * j + 3] = ln_rstd * f[4 * j + 3] - ln_mr * c.w;
     }
-    if (args.bias) {
+  }
+  if (args.bias) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg((const float4*)(args.bias + col0) + j);
-        f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (col0 + j < args.N) {
-        if (kFull && args.ln_stats) f[j] = ln_rstd * f[j] - ln_mr * __ldg(args.ln_c + col0 + j);
-        if (args.bias) f[j] += __ldg(args.bias + col0 + j);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = *(const float4*)(sb + 4 * j);
+      f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
     }
   }
   if (args.relu) {
@@ -487,6 +483,18 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         ln_rstd = 1.f / (sqrtf(m2 / (float)(args.K - 1)) + args.ln_eps);
         ln_mr = ln_rstd * mean;
       }
+      // this tile's bias / ln_c values -> the warp's shared-memory slice
+      float* sbias = (float*)(L::kSliceInStaging ? (smem + L::kStagingOffset + ew * 4096) : (smem + L::kSliceOffset + ew * BLOCK_N * 8));
+      float* slnc = sbias + BLOCK_N;
+      if (kEpi != 2) {
+        __syncwarp();
+        for (int i = lane; i < BLOCK_N; i += 32) {
+          const int cc = n0 + i;
+          sbias[i] = (args.bias && cc < args.N) ? __ldg(args.bias + cc) : 0.f;
+          if (kEpi == 1) slnc[i] = (args.ln_stats && cc < args.N) ? __ldg(args.ln_c + cc) : 0.f;
+        }
+        __syncwarp();
+      }
       bool pre_ok = false;
       if (kPrefetchRes) {
         // fp32 residual row of this thread -> shared memory while the main loop runs (16-byte cp.async, no registers)
@@ -538,7 +546,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          epilogue_row<kEpi == 1>(args, f, res, row, col0, ln_rstd, ln_mr);
+          epilogue_row<kEpi == 1>(args, f, res, row, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
           if (row < args.M) epilogue_store_row<kEpi == 1>(args, f, row, col0, (size_t)split * args.split_stride);
           continue;
         }
@@ -602,7 +610,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
             __syncwarp();
           }
-          epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr);
+          epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *(float4*)(stg + lane * 128 + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
