@@ -183,6 +183,13 @@ int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, 
                     float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K, int M, int tile_n,
                     void* workspace, size_t workspace_bytes, sc_stream_t stream);
 
+/* K2 without transposed operands (bf16): dy [M, N] and x [M, K] row-major, read as MN-major UMMA tiles through TMA boxes
+ * of 64 tokens x 64 features; M needs no padding.  Two-kernel form, workspace as for sc_linear_wgrad (required). */
+int sc_linear_wgrad_rowmajor(const void* dy, const void* x, const float* w, const float* mask, int mask_mode,
+                             const float* uniforms, unsigned long long seed, unsigned long long stream_id,
+                             int bypass_sigmoid_grad, float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K,
+                             int M, void* workspace, size_t workspace_bytes, sc_stream_t stream);
+
 /* out = g*keep*scale (cast), outT = its transpose (leading dim ldT, caller zero-pads); keep = (h != 0) when the saved
  * post-ReLU/dropout activation h is given, else the regenerated Philox dropout mask when dropout_p > 0.
  * colsum_accum (optional, fp32 [cols], pre-zeroed or holding a running sum): += column sums of `out` = the bias gradient. */

@@ -115,4 +115,27 @@ int sc_linear_wgrad(const void* dyT, const void* xT, int dtype, const float* w, 
                          K, M, 0, tile_n, &ex, stream);
 }
 
+// K2 without transposed copies: dy [M, N] and x [M, K] are the row-major bf16 activations as the forward / the
+// gradient preparation left them; the GEMM reads them as MN-major UMMA tiles (TMA boxes of 64 tokens x 64 features),
+// token counts need no padding (out-of-range rows are zero-filled by TMA).  Always the two-kernel form (workspace).
+int sc_linear_wgrad_rowmajor(const void* dy, const void* x, const float* w, const float* mask, int mask_mode,
+                             const float* uniforms, unsigned long long seed, unsigned long long stream_id,
+                             int bypass_sigmoid_grad, float sparsity_coeff, float* dw, float* ds, int accumulate, int N, int K,
+                             int M, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  SC_CHECK(w != nullptr && (dw != nullptr || ds != nullptr), SC_ERR_SHAPE, "sc_linear_wgrad_rowmajor: w and one of dw/ds are required");
+  SC_CHECK(mask_mode == SC_MASK_NONE || mask != nullptr, SC_ERR_SHAPE, "sc_linear_wgrad_rowmajor: mask missing");
+  const size_t nk = (size_t)N * K;
+  SC_CHECK(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= nk * sizeof(float) && nk % 4 == 0,
+           SC_ERR_WORKSPACE, "sc_linear_wgrad_rowmajor: 16-byte aligned workspace of >= %zu bytes needed", nk * sizeof(float));
+  const int max_splits = (int)(workspace_bytes / (nk * sizeof(float)) > 64 ? 64 : workspace_bytes / (nk * sizeof(float)));
+  const int splits = sc_gemm_wgrad_splits(N, K, M, max_splits);
+  ScGemmExtra ex = {};
+  ex.partial_splits = splits; ex.split_stride = nk; ex.mn_major = 1;
+  int rc = sc_gemm_bf16_launch(dy, x, SC_BF16, nullptr, SC_MASK_NONE, nullptr, 0, 0, nullptr, nullptr, workspace, SC_F32, N, K, M, 0,
+                               0, &ex, stream);
+  if (rc) return rc;
+  return sc_mask_grad_reduce_launch((const float*)workspace, splits, nk, w, mask, mask_mode, uniforms, seed, stream_id,
+                                    bypass_sigmoid_grad, sparsity_coeff, dw, ds, accumulate, nk, stream);
+}
+
 }  // extern "C"

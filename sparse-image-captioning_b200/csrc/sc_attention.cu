@@ -31,6 +31,53 @@ struct AttnArgs {
 
 using sc::keep_scale;
 
+// Stage `rows` rows of `dk` elements (global row stride ld, 16-byte aligned) into fp32 shared memory with row stride kst.
+// 16-byte loads, four in flight per thread: the scalar version of this loop was latency-bound (ncu: >40 % of the
+// forward kernel's stall samples were long-scoreboard waits on 2-byte loads).
+template <typename T>
+__device__ __forceinline__ void stage_f32(float* dst, int kst, const T* src, size_t ld, int rows, int dk, int tid, int nthr) {
+  constexpr int kVec = 16 / (int)sizeof(T);
+  const int vpr = dk / kVec;
+  const int total = rows * vpr;
+  if ((dk % kVec) != 0 || (ld % kVec) != 0 || (((uintptr_t)src) & 15) != 0) {
+    for (int e = tid; e < rows * dk; e += nthr) {
+      const int j = e / dk, d = e - j * dk;
+      dst[j * kst + d] = sc::to_f32<T>(src[(size_t)j * ld + d]);
+    }
+    return;
+  }
+  for (int e0 = 0; e0 < total; e0 += 4 * nthr) {
+    uint4 buf[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * nthr + tid;
+      if (e < total) {
+        const int j = e / vpr, c = e - j * vpr;
+        buf[u] = *(const uint4*)(src + (size_t)j * ld + c * kVec);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * nthr + tid;
+      if (e < total) {
+        const int j = e / vpr, c = e - j * vpr;
+        float* o = dst + j * kst + c * kVec;
+        if (sizeof(T) == 2) {
+          const uint32_t w[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o[2 * i] = __uint_as_float(w[i] << 16);
+            o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+          }
+        } else {
+          o[0] = __uint_as_float(buf[u].x); o[1] = __uint_as_float(buf[u].y);
+          o[2] = __uint_as_float(buf[u].z); o[3] = __uint_as_float(buf[u].w);
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
   extern __shared__ float sm[];
@@ -38,22 +85,27 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
   const int Tq = a.Tq, Tk = a.Tk, dk = a.dk, kst = dk + 1;
   float* sK = sm;
   float* sV = sK + Tk * kst;
-  float* sQ = sV + Tk * kst;  // [4][dk]
+  float* sQ = sV + Tk * kst;       // [Tq][dk]: every query row of the group, staged once
+  float* sB = sQ + Tq * dk;        // [Tq][Tk] additive bias (encoder) or unused
+  float* sM = sB + (a.bias ? Tq * Tk : 0);  // [Tk] key validity
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* qp = (const T*)a.q; const T* kp = (const T*)a.k; const T* vp = (const T*)a.v;
-  for (int e = tid; e < Tk * dk; e += 128) {
-    const int j = e / dk, d = e - j * dk;
-    const size_t row = (size_t)g * Tk + j;
-    sK[j * kst + d] = sc::to_f32<T>(kp[row * a.ldk + hh * dk + d]);
-    sV[j * kst + d] = sc::to_f32<T>(vp[row * a.ldv + hh * dk + d]);
+  // all global reads of the CTA are issued up front with 16-byte loads; the row loop below only touches shared memory
+  // (ncu on the per-row version: the q / bias loads of every row were exposed long-scoreboard stalls)
+  stage_f32<T>(sK, kst, kp + (size_t)g * Tk * a.ldk + hh * dk, a.ldk, Tk, dk, tid, 128);
+  stage_f32<T>(sV, kst, vp + (size_t)g * Tk * a.ldv + hh * dk, a.ldv, Tk, dk, tid, 128);
+  stage_f32<T>(sQ, dk, qp + (size_t)g * Tq * a.ldq + hh * dk, a.ldq, Tq, dk, tid, 128);
+  if (a.bias) {
+    const float* bp = a.bias + ((size_t)g * a.h + hh) * Tq * Tk;
+    for (int e = tid; e < Tq * Tk; e += 128) sB[e] = bp[e];
   }
+  for (int j = tid; j < Tk; j += 128) sM[j] = a.key_valid ? a.key_valid[(size_t)g * Tk + j] : 1.f;
   __syncthreads();
   const float sqrt_dk = sqrtf((float)dk);
   const sc::Philox ph(a.seed);
   for (int i = warp; i < Tq; i += 4) {
     const size_t qrow = (size_t)g * Tq + i;
-    for (int d = lane; d < dk; d += 32) sQ[warp * dk + d] = sc::to_f32<T>(qp[qrow * a.ldq + hh * dk + d]);
-    __syncwarp();
+    const float* sq = sQ + i * dk;
     const size_t pbase = (((size_t)g * a.h + hh) * Tq + i) * Tk;
     const int climit = a.causal_T > 0 ? (i % a.causal_T) : Tk;
     float s_[kMaxPass];
@@ -64,11 +116,11 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
       float s = -INFINITY;
       if (j < Tk) {
         float dot = 0.f;
-        for (int d = 0; d < dk; ++d) dot = fmaf(sQ[warp * dk + d], sK[j * kst + d], dot);
+        for (int d = 0; d < dk; ++d) dot = fmaf(sq[d], sK[j * kst + d], dot);
         s = dot / sqrt_dk;
-        const bool masked = (a.key_valid && a.key_valid[(size_t)g * Tk + j] == 0.f) || (a.causal_T > 0 && j > climit);
+        const bool masked = (sM[j] == 0.f) || (a.causal_T > 0 && j > climit);
         if (masked) s = -1e9f;
-        if (a.bias) s += a.bias[pbase + j];
+        if (a.bias) s += sB[i * Tk + j];
       }
       s_[ps] = s;
       mx = fmaxf(mx, s);
@@ -106,7 +158,6 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnArgs a) {
     T* op = (T*)a.out;
     if (lane < dk) op[qrow * a.ldo + hh * dk + lane] = sc::from_f32<T>(o0);
     if (lane + 32 < dk) op[qrow * a.ldo + hh * dk + lane + 32] = sc::from_f32<T>(o1);
-    __syncwarp();
   }
 }
 
@@ -123,17 +174,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
   float* sdS = sPd + Tq * pst;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const T* qp = (const T*)a.q; const T* kp = (const T*)a.k; const T* vp = (const T*)a.v;
-  for (int e = tid; e < Tk * dk; e += 256) {
-    const int j = e / dk, d = e - j * dk;
-    const size_t row = (size_t)g * Tk + j;
-    sK[j * kst + d] = sc::to_f32<T>(kp[row * a.ldk + hh * dk + d]);
-    sV[j * kst + d] = sc::to_f32<T>(vp[row * a.ldv + hh * dk + d]);
-  }
-  for (int e = tid; e < Tq * dk; e += 256) {
-    const int i = e / dk, d = e - i * dk;
-    const size_t row = (size_t)g * Tq + i;
-    sQ[i * kst + d] = sc::to_f32<T>(qp[row * a.ldq + hh * dk + d]);
-    sdO[i * kst + d] = a.d_out[row * a.ldd + hh * dk + d];
+  stage_f32<T>(sK, kst, kp + (size_t)g * Tk * a.ldk + hh * dk, a.ldk, Tk, dk, tid, 256);
+  stage_f32<T>(sV, kst, vp + (size_t)g * Tk * a.ldv + hh * dk, a.ldv, Tk, dk, tid, 256);
+  stage_f32<T>(sQ, kst, qp + (size_t)g * Tq * a.ldq + hh * dk, a.ldq, Tq, dk, tid, 256);
+  stage_f32<float>(sdO, kst, a.d_out + (size_t)g * Tq * a.ldd + hh * dk, a.ldd, Tq, dk, tid, 256);
+  {
+    // saved probabilities of the whole (group, head) -> sPd, coalesced, before the row loop
+    const float* pp = a.probs + ((size_t)g * a.h + hh) * Tq * Tk;
+    for (int e = tid; e < Tq * Tk; e += 256) { const int i = e / Tk, j = e - i * Tk; sPd[i * pst + j] = pp[e]; }
   }
   __syncthreads();
   const float inv_sqrt = 1.f / sqrtf((float)dk);
@@ -150,7 +198,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
       if (j < Tk) {
         float dot = 0.f;
         for (int d = 0; d < dk; ++d) dot = fmaf(sdO[i * kst + d], sV[j * kst + d], dot);
-        const float p = a.probs[pbase + j];
+        const float p = sPd[i * pst + j];
         const float m = keep_scale(ph, pbase + j, a.stream, a.dropout_p);
         sPd[i * pst + j] = p * m;
         P_[ps] = p;
@@ -353,8 +401,8 @@ int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int l
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.key_valid = key_valid; a.bias = bias; a.probs = probs;
   a.out = out; a.ldo = ldo; a.G = G; a.Tq = Tq; a.Tk = Tk; a.h = h; a.dk = dk; a.causal_T = causal_T;
   a.dropout_p = dropout_p; a.seed = seed; a.stream = stream_id;
-  const size_t smem = sizeof(float) * (2 * (size_t)Tk * (dk + 1) + 4 * dk);
-  SC_CHECK(smem <= 200 * 1024, SC_ERR_UNSUPPORTED, "sc_attention_fwd: shared memory %zu", smem);
+  const size_t smem = sizeof(float) * (2 * (size_t)Tk * (dk + 1) + (size_t)Tq * dk + (bias ? (size_t)Tq * Tk : 0) + Tk);
+  SC_CHECK(smem <= 200 * 1024, SC_ERR_UNSUPPORTED, "sc_attention_fwd: Tq=%d Tk=%d need %zu bytes of shared memory", Tq, Tk, smem);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

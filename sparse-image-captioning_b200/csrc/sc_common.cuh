@@ -52,6 +52,8 @@ struct ScGemmExtra {
   void* y2; float* stats_out;
   // split-K partial products (two-kernel weight gradient): split s stores its fp32 tile at y + s * split_stride
   int partial_splits; size_t split_stride;
+  // operands given as x [K, M] and w [K, N] row-major (y = x^T w): MN-major UMMA tiles, no transposed copies
+  int mn_major;
 };
 
 // Programmatic dependent launch (griddepcontrol): kernels launched through sc::launch_pdl may start while their

@@ -100,9 +100,22 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
   return d;
 }
-// kind::f16, A=B=bf16, D=f32, both K-major
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major, SWIZZLE_128B operand tile (weight gradient: A[n, token] / B[k, token] read from row-major [tokens, n|k]
+// activations WITHOUT a transpose): TMA boxes of 64 tokens x 64 MN-elements; one 128-byte row per token, 8 tokens per
+// 1024-byte swizzle atom (stride byte offset), the next 64 MN-elements in the next 8 KB box (leading byte offset).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;   // leading byte offset: next 64 elements along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset: next 8 elements along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, A=B=bf16, D=f32; mn = 0: both operands K-major, 1: both MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn << 15) | ((uint32_t)mn << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -332,7 +345,8 @@ __device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, 
 // double-buffered in TMEM (2 x BLOCK_N columns): the epilogue of unit i overlaps the TMA/MMA main loop of unit i+1.
 // kStages: depth of the TMA->MMA smem ring.
 // kEpi: 0 = plain forward epilogue, 1 = full forward epilogue (dropout, folded LayerNorm, statistics), 2 = weight gradient
-template <int BLOCK_N, bool kMasked, int kStages, int kEpi>
+// kMN: both operands are given transposed ([K, M] and [K, N] row-major, i.e. MN-major tiles): y = x^T w.
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false>
 __global__ void __launch_bounds__(32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0)),
                                   (!kMasked && kEpi != 2 && num_epilogue_warps(BLOCK_N, kStages) == 4) ? 2 : 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
@@ -394,8 +408,17 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::kStageBytes;
           mbar_expect_tx(&full_bar[s], kMasked ? L::kABytes : L::kStageBytes);
-          tma_load_2d(&tma_a, &full_bar[s], sa, kb * BLOCK_K, m0);
-          if (!kMasked) tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes, kb * BLOCK_K, n0);
+          if (kMN) {
+            // boxes of {64 MN-elements, 64 tokens}: coordinate 0 = position along M / N, coordinate 1 = token
+#pragma unroll
+            for (int hb = 0; hb < BLOCK_M / 64; ++hb) tma_load_2d(&tma_a, &full_bar[s], sa + hb * 8192, m0 + hb * 64, kb * BLOCK_K);
+#pragma unroll
+            for (int hb = 0; hb < BLOCK_N / 64; ++hb)
+              tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes + hb * 8192, n0 + hb * 64, kb * BLOCK_K);
+          } else {
+            tma_load_2d(&tma_a, &full_bar[s], sa, kb * BLOCK_K, m0);
+            if (!kMasked) tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes, kb * BLOCK_K, n0);
+          }
         }
       }
       sc::pdl_launch();  // all loads of this CTA are in flight: let the next kernel's prologue start
@@ -403,7 +426,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, kMN ? 1 : 0);
       int it = 0, lt = 0;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++lt) {
         const int split = u % args.splits;
@@ -419,12 +442,14 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
-          const uint64_t da = make_smem_desc(sa);
-          const uint64_t db = make_smem_desc(sa + L::kABytes);
+          const uint64_t da = kMN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+          const uint64_t db = kMN ? make_smem_desc_mn(sa + L::kABytes) : make_smem_desc(sa + L::kABytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 32 B (16 bf16) along K inside the 128B swizzle row: +2 in 16-byte units
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            // K-major: advance 32 B (16 bf16) along K inside the 128B swizzle row: +2 in 16-byte units;
+            // MN-major: 16 tokens = two 1024-byte atoms: +128 units
+            const uint64_t adv = kMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
+            umma_bf16(tmem_d, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
@@ -746,6 +771,21 @@ int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int box_row
   return SC_OK;
 }
 
+// bf16 [rows = K index, cols = M/N index] row-major, box = [64 rows, 64 cols], SWIZZLE_128B (MN-major operands)
+int make_tmap_mn(CUtensorMap* map, const void* ptr, int rows, int cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  SC_CHECK(fn != nullptr, SC_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BLOCK_K};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SC_CHECK(r == CUDA_SUCCESS, SC_ERR_DRIVER, "cuTensorMapEncodeTiled (MN-major) failed with CUresult %d", (int)r);
+  return SC_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -756,9 +796,9 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool kMasked, int kStages, int kEpi>
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_splits, cudaStream_t stream) {
-  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi>;
+  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi, kMN>;
   constexpr int smem = Smem<BLOCK_N, kStages>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
@@ -825,7 +865,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
                         void* y, int y_dtype, int M, int N, int K, int relu, int block_n, const ScGemmExtra* ex,
                         cudaStream_t stream) {
   SC_CHECK(M > 0 && N > 0 && K > 0, SC_ERR_SHAPE, "sc_linear: empty problem M=%d N=%d K=%d", M, N, K);
-  SC_CHECK(K % 8 == 0, SC_ERR_SHAPE, "sc_linear(bf16): K=%d must be a multiple of 8 (16-byte TMA rows)", K);
+  SC_CHECK(K % 8 == 0 || (ex && ex->mn_major), SC_ERR_SHAPE, "sc_linear(bf16): K=%d must be a multiple of 8 (16-byte TMA rows)", K);
   SC_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0, SC_ERR_ALIGN,
            "sc_linear(bf16): x, w, y must be 16-byte aligned");
   SC_CHECK(y_dtype == SC_F32 || y_dtype == SC_BF16, SC_ERR_DTYPE, "sc_linear: bad y dtype %d", y_dtype);
@@ -864,14 +904,26 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     if (wgrad || (ex && ex->partial_splits > 0)) block_n = (t128 >= sms / 4) ? 128 : 64;
     if (N <= 64) block_n = 64;
   }
+  const bool mn = ex && ex->mn_major;
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, x, M, K, BLOCK_M);
-  if (rc) return rc;
-  if (!masked) {
-    rc = make_tmap(&tb, w, N, K, block_n);
+  int rc;
+  if (mn) {
+    SC_CHECK(!masked && !wgrad && M % 8 == 0 && N % 8 == 0, SC_ERR_SHAPE,
+             "MN-major operands: bf16, M=%d and N=%d must be multiples of 8 (16-byte rows)", M, N);
+    if (block_n > 128) block_n = 128;
+    rc = make_tmap_mn(&ta, x, K, M);
+    if (rc) return rc;
+    rc = make_tmap_mn(&tb, w, K, N);
     if (rc) return rc;
   } else {
-    tb = ta;
+    rc = make_tmap(&ta, x, M, K, BLOCK_M);
+    if (rc) return rc;
+    if (!masked) {
+      rc = make_tmap(&tb, w, N, K, block_n);
+      if (rc) return rc;
+    } else {
+      tb = ta;
+    }
   }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
@@ -892,6 +944,11 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     }
   }
   const int epi = a.wgrad ? 2 : ((a.dropout_p > 0.f || a.ln_stats || a.y2 || a.stats_out) ? 1 : 0);
+  if (mn) {
+    SC_CHECK(epi == 0, SC_ERR_UNSUPPORTED, "MN-major operands serve the plain epilogue only");
+    return block_n == 128 ? launch<128, false, 3, 0, true>(ta, tb, a, force_splits, stream)
+                          : launch<64, false, 3, 0, true>(ta, tb, a, force_splits, stream);
+  }
 #define SC_GEMM_CASE(BN, ST)                                                                                          \
   if (block_n == BN && stages == ST) {                                                                                \
     if (masked) return epi ? launch<BN, true, ST, 1>(ta, tb, a, force_splits, stream)                                 \

@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // da / db partial sums of the rows this warp handles stay in registers; shared-memory and global atomics happen once
+  // per warp / per CTA (the per-row version serialised 532 CTAs x 1024 global atomics on the same addresses)
+  float acc_a[kMaxPerLane], acc_b[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) { acc_a[i] = 0.f; acc_b[i] = 0.f; }
   for (int row = blockIdx.x * 8 + warp_in_cta; row < rows; row += gridDim.x * 8) {
     const float* xr = x + (size_t)row * D;
     float c[kMaxPerLane], g[kMaxPerLane];
@@ -252,8 +257,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       float dyv = 0.f;
       if (col < D) {
         dyv = sc::to_f32<GT>(dy[(size_t)row * D + col]);
-        atomicAdd(&s_acc[col], dyv * c[i] * r);
-        atomicAdd(&s_acc[D + col], dyv);
+        acc_a[i] += dyv * c[i] * r;
+        acc_b[i] += dyv;
         g[i] = dyv * a[col];
       } else {
         g[i] = 0.f;
@@ -272,6 +277,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         if (dres) v += dres[(size_t)row * D + col];
         dx[(size_t)row * D + col] = v;
       }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int col = lane + i * 32;
+    if (col < D) {
+      atomicAdd(&s_acc[col], acc_a[i]);
+      atomicAdd(&s_acc[D + col], acc_b[i]);
     }
   }
   __syncthreads();
@@ -469,7 +482,7 @@ int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtyp
                      float* db, int rows, int D, float eps, cudaStream_t stream) {
   SC_CHECK(rows > 0 && D > 1 && D <= 2048, SC_ERR_SHAPE, "sc_layernorm_bwd: rows=%d D=%d", rows, D);
   int blocks = (rows + 7) / 8;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   const size_t smem = 2 * (size_t)D * sizeof(float);
 #define LNB(T, P) layernorm_bwd_kernel<T, P><<<blocks, 256, smem, stream>>>(x, a, (const T*)dy, dres, dx, da, db, rows, D, eps)
   if (dy_dtype == SC_F32) { if (D <= 128) LNB(float, 4); else if (D <= 512) LNB(float, 16); else LNB(float, 64); }

@@ -273,6 +273,20 @@ def linear_wgrad(dyT, xT, w, mask, mask_mode, dw, ds, *, M, uniforms=None, seed=
              meta=("gemm_bf16" if dyT.dtype == torch.bfloat16 else "gemm_f32", N, K, M, dyT.element_size(), xT.element_size(), 4, False))
 
 
+def linear_wgrad_rowmajor(dy, x, w, mask, mask_mode, dw, ds, *, workspace, uniforms=None, seed=0, stream_id=0, bypass=False,
+                          sp_coeff=0.0, accumulate=False):
+    """Weight gradient from the row-major bf16 activations dy [M,N], x [M,K] (no transposed copies): sc_linear_wgrad_rowmajor."""
+    N, K = w.shape
+    M = dy.shape[0]
+    assert dy.shape[1] == N and tuple(x.shape) == (M, K) and dy.dtype == x.dtype == torch.bfloat16
+    _chk(dy, "dy"), _chk(x, "x")
+    if mask is None:
+        mask_mode = MASK_NONE
+    lib.call("sc_linear_wgrad_rowmajor", lib.ptr(dy), lib.ptr(x), lib.ptr(w), lib.ptr(mask), mask_mode, lib.ptr(uniforms), seed,
+             stream_id, int(bypass), float(sp_coeff), lib.ptr(dw), lib.ptr(ds), int(accumulate), N, K, M, lib.ptr(workspace),
+             workspace.numel() * workspace.element_size(), lib.stream(), meta=("gemm_bf16", N, K, M, 2, 2, 4, False))
+
+
 def prep_grad(g, *, h=None, out=None, outT=None, scale=1.0, p=0.0, seed=0, stream_id=0, colsum=None):
     """out = g * keep * scale (cast), outT = its transpose with leading dim outT.shape[1] (zero padded);
     ``colsum`` (fp32 [cols]) accumulates the column sums of out (bias gradient)."""

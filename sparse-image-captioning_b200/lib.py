@@ -40,6 +40,7 @@ SIGNATURES = {
     # training
     "sc_linear_dropout": [_p, _i, _p, _i, _p, _i, _p, _u64, _u64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_linear_wgrad": [_p, _p, _i, _p, _p, _i, _p, _u64, _u64, _i, _f, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p],
+    "sc_linear_wgrad_rowmajor": [_p, _p, _p, _p, _i, _p, _u64, _u64, _i, _f, _p, _p, _i, _i, _i, _i, _p, _sz, _p],
     "sc_prep_grad": [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _u64, _u64, _p, _p],
     "sc_transpose": [_p, _i, _p, _i, _i, _i, _i, _p],
     "sc_apply_mask_transposed": [_p, _p, _i, _p, _u64, _u64, _p, _i, _i, _i, _p, _p],

@@ -302,19 +302,22 @@ class OrtTrainer:
         M = x_saved.shape[0]
         Mp = K.pad8(M)
         p = p if self.training else 0.0
-        gT = ws.gT[: N * Mp].view(N, Mp)
         bname = wname.replace(".weight", ".bias")
         gbias = self._group(self.g, bname, count) if bname in self.g else None
+        # bf16: the weight-gradient GEMM reads dy [M,N] and x [M,K] as MN-major tiles - no transposed copies, no padding
+        rowmajor = self.adt == torch.bfloat16 and N % 8 == 0 and Kd % 8 == 0
+        gT = None if rowmajor else ws.gT[: N * Mp].view(N, Mp)
         if g_ready is not None:
             gb = g_ready
-            if Mp != M:
-                gT[:, M:].zero_()
-            K.transpose(gb, gT)
+            if not rowmajor:
+                if Mp != M:
+                    gT[:, M:].zero_()
+                K.transpose(gb, gT)
             if gbias is not None:
                 K.colsum(gb, gbias)
         else:
             gb = ws.gb[: M * N].view(M, N)
-            if Mp != M:
+            if not rowmajor and Mp != M:
                 gT[:, M:].zero_()
             # the bias gradient (column sums) is accumulated by the same pass (flat_gw is zeroed at the start of the backward)
             K.prep_grad(g, h=h, out=gb, outT=gT, scale=(1.0 / (1.0 - p)) if (h is not None and p > 0) else 1.0,
@@ -325,13 +328,18 @@ class OrtTrainer:
                 wT = ws.wT[: Kd * N].view(Kd, N)
                 K.apply_mask_transposed(W, S, mode, wT, uniforms=U, seed=seed, stream_id=stream)
             K.linear(gb, wT, None, residual=dx_residual, out=dx)
+        gW = self._group(self.g, wname, count)
+        gS = self._group(self.gs, wname, count) if S is not None else None
+        if rowmajor:
+            K.linear_wgrad_rowmajor(gb, x_saved, W, S, mode, gW, gS, workspace=ws.wgrad_ws, uniforms=U, seed=seed, stream_id=stream,
+                                    bypass=self.bypass)
+            return
         xT = ws.xT[: Kd * Mp].view(Kd, Mp)
         if Mp != M:
             xT[:, M:].zero_()
         K.transpose(x_saved, xT)
-        K.linear_wgrad(gT, xT, W, S, mode, self._group(self.g, wname, count),
-                       self._group(self.gs, wname, count) if S is not None else None, M=Mp, uniforms=U, seed=seed, stream_id=stream,
-                       bypass=self.bypass, workspace=ws.wgrad_ws if self.adt == torch.bfloat16 else None)
+        K.linear_wgrad(gT, xT, W, S, mode, gW, gS, M=Mp, uniforms=U, seed=seed, stream_id=stream, bypass=self.bypass,
+                       workspace=ws.wgrad_ws if self.adt == torch.bfloat16 else None)
 
     def _ln(self, name, x, out):
         return K.layernorm(x, self.p[name + ".a_2"], self.p[name + ".b_2"], out=out)

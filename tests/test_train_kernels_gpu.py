@@ -93,6 +93,16 @@ def test_masked_linear_backward(K, dt, mode, bypass, shape):
             assert rel_err(dw2, Wd.grad) < 3e-5
             if mode:
                 assert rel_err(ds2, ds_ref) < 3e-5
+        if N % 8 == 0 and Kd % 8 == 0:
+            # MN-major variant: the row-major activations themselves, no transposed copies, unpadded token count
+            wsp = torch.empty(4 * N * Kd, device=DEV)
+            dw3 = torch.full((N, Kd), 7.0, device=DEV)
+            ds3 = torch.full((N, Kd), 7.0, device=DEV)
+            K.linear_wgrad_rowmajor(dyb, x.to(dt).to(DEV), Wg, Sg if mode else None, mode, dw3, ds3 if mode else None, workspace=wsp,
+                                    uniforms=Ug, bypass=bypass, sp_coeff=sp if mode in (1, 4) else 0.0)
+            assert rel_err(dw3, Wd.grad) < 3e-5
+            if mode:
+                assert rel_err(ds3, ds_ref) < 3e-5
     db = torch.zeros(N, device=DEV)
     K.colsum(dyb, db)
     assert rel_err(db, dyq.sum(0)) < 1e-5
