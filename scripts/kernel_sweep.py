@@ -5,6 +5,7 @@ import torch
 import sparse_caption_b200.kernels as K
 from sparse_caption_b200.engine import BeamState
 dev = "cuda"
+if os.environ.get("SC_PDL") == "0": K.set_pdl(False)
 def timeit(name, fn, reps=40):
     fn(); torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()

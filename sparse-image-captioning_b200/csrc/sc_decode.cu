@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(256) self_attn_step_kernel(const T* __restrict
                                                              int n_prev, int write_slot) {
   const int chunks = D / 8;
   const int lanes = dk / 8;
-  sc::pdl_launch();
   sc::pdl_wait();
   const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = g < (long)R * chunks;
@@ -105,6 +104,9 @@ __global__ void __launch_bounds__(256) self_attn_step_kernel(const T* __restrict
     for (int i = 0; i < 8; ++i) acc[i] = acc[i] * corr + p * vs.v[i];
     m = mn;
   }
+  // the cache has been streamed: only now may the next kernel's CTAs take SM slots (a trigger at the top cost this
+  // HBM-bound kernel ~20 % in back-to-back measurements)
+  sc::pdl_launch();
   const float inv = 1.f / l;
   Vec8<T> o;
 #pragma unroll
@@ -318,11 +320,10 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 // otherwise re-read through L2), log-softmax statistics, then the row's top-NB candidates by FINAL score
 // (sum + log-prob, ties to the smaller flat index == stable descending sort) -> workspace.
 template <int NB, bool kRegs>
-__global__ void __launch_bounds__(kBeamThreads) beam_row_kernel(const BeamArgs a, float* __restrict__ ws_stats,
+__global__ void __launch_bounds__(kBeamThreads, 4) beam_row_kernel(const BeamArgs a, float* __restrict__ ws_stats,
                                                                 Cand* __restrict__ ws_cand) {
   const int r = blockIdx.x;            // row = b*NB + k
   const int k = r % NB;
-  sc::pdl_launch();
   sc::pdl_wait();
   if (a.t == 0 && k != 0) return;      // first step: every beam holds BOS, only beam 0 is expanded
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -332,64 +333,85 @@ __global__ void __launch_bounds__(kBeamThreads) beam_row_kernel(const BeamArgs a
   // init_logprobs (t == 0) are never temperature-scaled (caption_model.py:135, 218)
   const float T = (a.t == 0) ? 1.0f : a.temperature;
   const float* x = a.logits + (size_t)r * V;
-  float xr[kRegs ? kBeamRegs : 1];
-  float mx = -INFINITY;
-  if (kRegs) {
-#pragma unroll
-    for (int i = 0; i < kBeamRegs; ++i) {
-      const int c = tid + i * kBeamThreads;
-      xr[i] = c < V ? __ldg(x + c) : -INFINITY;
-    }
-#pragma unroll
-    for (int i = 0; i < kBeamRegs; ++i) mx = fmaxf(mx, xr[i]);
-  } else {
-    for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
-  }
-  mx = block_max(mx, s_red);
-  float se = 0.f;
-  if (kRegs) {
-#pragma unroll
-    for (int i = 0; i < kBeamRegs; ++i) se += expf(xr[i] - mx);  // exp(-inf) = 0 for the padding lanes
-  } else {
-    for (int i = tid; i < V; i += kBeamThreads) se += expf(x[i] - mx);
-  }
-  se = block_sum(se, s_red);
-  // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
-  const float ls = logf(se);
-  float mx2 = 0.f, ls2 = 0.f;
-  if (T != 1.0f) {
-    // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
-    mx2 = (0.f - ls) / T;
-    float se2 = 0.f;
-    if (kRegs) {
-#pragma unroll
-      for (int i = 0; i < kBeamRegs; ++i) se2 += expf(((xr[i] - mx) - ls) / T - mx2);
-    } else {
-      for (int i = tid; i < V; i += kBeamThreads) se2 += expf(((x[i] - mx) - ls) / T - mx2);
-    }
-    ls2 = logf(block_sum(se2, s_red));
-  }
-  if (tid == 0) {
-    ws_stats[r * 4 + 0] = mx; ws_stats[r * 4 + 1] = ls; ws_stats[r * 4 + 2] = mx2; ws_stats[r * 4 + 3] = ls2;
-  }
   Cand top[NB];
 #pragma unroll
   for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
   const float base = a.sum[r];
   const int prev = (a.constraint && a.t > 0) ? a.seq_in[(size_t)r * a.L + a.t - 1] : -1;
+  float mx = -INFINITY, ls, mx2 = 0.f, ls2 = 0.f;
   if (kRegs) {
+    // Register path (V <= 10240, V % 4 == 0): the row is read once with 16-byte loads.  The kernel used to be
+    // issue-bound (~75 instructions per logit: accurate expf + a full score per element); now per logit: one max, one
+    // compare against the thread's NB-th best RAW logit, one ex2.approx.  Within a row the final score
+    // s = sum + log_softmax(x) is a monotone function of x, so the thread's top-NB by (x, smaller index) are its
+    // top-NB by (s, smaller index) unless >= NB+1 candidates collapse to one fp32 score at the cut; exact scores are
+    // then computed for the NB survivors only and every merge below ranks by (s, idx) as before.
+    float4 xr[kBeamRegs / 4];
+    const float4* x4 = (const float4*)x;
+    const int V4 = V >> 2;
 #pragma unroll
-    for (int i = 0; i < kBeamRegs; ++i) {
-      const int c = tid + i * kBeamThreads;
-      if (c < V) {
-        float lp = (xr[i] - mx) - ls;
+    for (int i = 0; i < kBeamRegs / 4; ++i) {
+      const int c4 = tid + i * kBeamThreads;
+      xr[i] = c4 < V4 ? __ldg(x4 + c4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    Cand rawtop[NB];  // .s = raw logit
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { rawtop[i].s = -INFINITY; rawtop[i].idx = 0x7fffffff; }
+#pragma unroll
+    for (int i = 0; i < kBeamRegs / 4; ++i) {
+      const int c0 = (tid + i * kBeamThreads) * 4;
+      float v[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
+      mx = fmaxf(mx, fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
+      if (prev >= c0 && prev < c0 + 4) v[prev - c0] = -INFINITY;  // decoding_constraint: never a candidate
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (v[e] > rawtop[NB - 1].s) {  // ascending index order: strict '>' keeps the smaller index on ties
+          Cand cd; cd.s = v[e]; cd.idx = c0 + e;
+          topk_insert<NB>(rawtop, cd);
+        }
+      }
+    }
+    mx = block_max(mx, s_red);
+    sc::pdl_launch();  // the row is in registers: the merge kernel's CTAs may be scheduled
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBeamRegs / 4; ++i)
+      se += __expf(xr[i].x - mx) + __expf(xr[i].y - mx) + __expf(xr[i].z - mx) + __expf(xr[i].w - mx);  // exp(-inf) = 0
+    se = block_sum(se, s_red);
+    ls = logf(se);  // torch.log_softmax: lp = (x - max) - log(sum exp(x - max))
+    if (T != 1.0f) {
+      // reference re-normalises log_softmax(lp / T) for t > 0 (caption_model.py:218); max(lp) = -ls
+      mx2 = (0.f - ls) / T;
+      float se2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kBeamRegs / 4; ++i) {
+        se2 += __expf(((xr[i].x - mx) - ls) / T - mx2) + __expf(((xr[i].y - mx) - ls) / T - mx2) +
+               __expf(((xr[i].z - mx) - ls) / T - mx2) + __expf(((xr[i].w - mx) - ls) / T - mx2);
+      }
+      ls2 = logf(block_sum(se2, s_red));
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      if (rawtop[i].idx != 0x7fffffff && rawtop[i].s > -INFINITY) {
+        float lp = (rawtop[i].s - mx) - ls;
         if (T != 1.0f) lp = (lp / T - mx2) - ls2;
-        if (c == prev) lp = -INFINITY;
-        Cand cd; cd.s = base + lp; cd.idx = k * V + c;
+        Cand cd; cd.s = base + lp; cd.idx = k * V + rawtop[i].idx;
         topk_insert<NB>(top, cd);
       }
     }
   } else {
+    for (int i = tid; i < V; i += kBeamThreads) mx = fmaxf(mx, x[i]);
+    mx = block_max(mx, s_red);
+    float se = 0.f;
+    for (int i = tid; i < V; i += kBeamThreads) se += __expf(x[i] - mx);
+    se = block_sum(se, s_red);
+    ls = logf(se);
+    if (T != 1.0f) {
+      mx2 = (0.f - ls) / T;
+      float se2 = 0.f;
+      for (int i = tid; i < V; i += kBeamThreads) se2 += __expf(((x[i] - mx) - ls) / T - mx2);
+      ls2 = logf(block_sum(se2, s_red));
+    }
     for (int i = tid; i < V; i += kBeamThreads) {
       float lp = (x[i] - mx) - ls;
       if (T != 1.0f) lp = (lp / T - mx2) - ls2;
@@ -397,6 +419,9 @@ __global__ void __launch_bounds__(kBeamThreads) beam_row_kernel(const BeamArgs a
       Cand cd; cd.s = base + lp; cd.idx = k * V + i;
       topk_insert<NB>(top, cd);
     }
+  }
+  if (tid == 0) {
+    ws_stats[r * 4 + 0] = mx; ws_stats[r * 4 + 1] = ls; ws_stats[r * 4 + 2] = mx2; ws_stats[r * 4 + 3] = ls2;
   }
   // warp merge: every lane offers its sorted list; NB rounds of arg-best over the heads
   {
@@ -706,7 +731,7 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
   float* ws_stats = (float*)workspace;
   Cand* ws_cand = (Cand*)(ws_stats + (size_t)B * beam * 4);
-  const bool regs = V <= kBeamThreads * kBeamRegs;
+  const bool regs = V <= kBeamThreads * kBeamRegs && (V & 3) == 0 && ((uintptr_t)logits & 15) == 0;
 #define BEAM_LAUNCH(NBV)                                                                                     \
   do {                                                                                                        \
     if (regs) sc::launch_pdl(beam_row_kernel<NBV, true>, dim3(B * NBV), dim3(kBeamThreads), 0, stream, a, ws_stats, ws_cand);  \

@@ -15,7 +15,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  sc::pdl_launch();
   sc::pdl_wait();
   if (warp >= rows) return;
   const float* xr = x + (size_t)warp * D;
@@ -27,6 +26,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     v[i] = c < D ? xr[c] : 0.f;
     s += v[i];
   }
+  sc::pdl_launch();  // after the row is loaded
   const float mean = sc::warp_sum(s) / (float)D;
   float q = 0.f;
 #pragma unroll
