@@ -25,6 +25,14 @@ opt = dict(lr=3e-4, sparsity_target=0.95, sparsity_weight=30.0, current_step=100
 for _ in range(3):
     tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt)
 torch.cuda.synchronize()
+if os.environ.get("SC_NCU_RANGE") == "1":
+    # ncu --profile-from-start off: exactly one eager step inside the profiler range
+    tr.use_graph = False
+    tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt); torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt); torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 t0 = time.perf_counter()
 for _ in range(5):
     tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt)

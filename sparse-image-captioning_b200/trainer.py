@@ -589,11 +589,15 @@ class OrtTrainer:
             self._graph_body(ws, part, opt)
             torch.cuda.synchronize(self.dev)
             g = torch.cuda.CUDAGraph()
+            before = K.lib.launch_count
             with torch.cuda.graph(g):
                 self._graph_body(ws, part, opt)
             graphs[key] = g
+            # kernels of ours inside the captured graph: every replay launches this many (bench.py gpu_launches)
+            ws.__dict__.setdefault("graph_launches", {})[key] = K.lib.launch_count - before
             return
         graphs[key].replay()
+        K.lib.launch_count += ws.graph_launches[key]
 
     def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None, **opt):
         """One full SMP step.  ``all_reduce``: callable applied to the flat gradient buffers (NCCL sum) when data-parallel."""
