@@ -202,6 +202,13 @@ int sc_transpose(const void* x, int x_dtype, void* y, int ldT, int y_dtype, int 
 int sc_apply_mask_transposed(const float* w, const float* mask, int mask_mode, const float* uniforms, unsigned long long seed,
                              unsigned long long stream_id, void* outT, int out_dtype, int N, int K, void* out_plain,
                              sc_stream_t stream);
+/* every masked weight of a training step in one launch.  descs: device array of n_desc descriptors of ten 64-bit words
+ * {w, s, uniforms, out [N,K], outT [K,N] (either may be 0), N, K (multiple of 4), stream_id, tile_start, tiles_k}; tensor i
+ * owns the 64x64 tiles [tile_start_i, tile_start_{i+1}), tiles_k = ceil(K/64); element e of tensor i uses the Philox
+ * stream stream_base + stream_id_i, i.e. the same sample sc_apply_mask_transposed / the wgrad epilogues regenerate
+ * (replaces the per-layer sigmoid -> bernoulli -> mul chain of sparse_caption/pruning/masked_layer.py:84-110) */
+int sc_apply_mask_batched(const void* descs, int n_desc, long total_tiles, int mask_mode, unsigned long long seed,
+                          unsigned long long stream_base, int out_dtype, sc_stream_t stream);
 /* elementwise straight-through gradient from a dense dWm (embedding table, WG heads) */
 int sc_mask_grad(const float* dwm, const float* w, const float* mask, int mask_mode, const float* uniforms,
                  unsigned long long seed, unsigned long long stream_id, int bypass_sigmoid_grad, float sparsity_coeff,

@@ -312,10 +312,12 @@ __global__ void __launch_bounds__(256) box_bias_fwd_kernel(const float* __restri
 }
 
 // dWG[h,f] += sum_pairs dpre * emb_f ; db[h] += sum_pairs dpre, with dpre = dbias * exp(-bias) where the clamp/ReLU
-// were inactive (bias > log 1e-6).  CTA per image; 32 pairs of embedding at a time in shared memory.
+// were inactive (bias > log 1e-6).  CTA per (image, slice of pairs_per_cta pairs): one CTA per image left two thirds
+// of the SMs idle at 50 images; 32 pairs of embedding at a time in shared memory.
 __global__ void __launch_bounds__(256) box_bias_bwd_kernel(const float* __restrict__ boxes, const float* __restrict__ bias,
                                                            const float* __restrict__ dbias, float* __restrict__ dwg_w,
-                                                           float* __restrict__ dwg_b, int B, int N, int h, int trig, DimMat dm) {
+                                                           float* __restrict__ dwg_b, int B, int N, int h, int trig, DimMat dm,
+                                                           int pairs_per_cta) {
   __shared__ float s_emb[32][65];
   __shared__ float s_dpre[kMaxHeads][33];
   const int b = blockIdx.x;
@@ -324,7 +326,8 @@ __global__ void __launch_bounds__(256) box_bias_bwd_kernel(const float* __restri
   const int hh = tid >> 5, f0 = tid & 31;  // thread owns (head hh, features f0 and f0+32)
   float a0 = 0.f, a1 = 0.f, ab = 0.f;
   const int pairs = N * N;
-  for (int p0 = 0; p0 < pairs; p0 += 32) {
+  const int p_end = min(pairs, ((int)blockIdx.y + 1) * pairs_per_cta);
+  for (int p0 = (int)blockIdx.y * pairs_per_cta; p0 < p_end; p0 += 32) {
     __syncthreads();
     {  // 256 threads fill 32 pairs x 8 (c,f-octet) slots: thread -> (pair = tid/8, c = (tid%8)/2, half = tid%2)
       const int pl = tid >> 3, sub = tid & 7;
@@ -390,6 +393,16 @@ int check_common(const char* name, int G, int Tq, int Tk, int h, int dk) {
 
 }  // namespace
 
+// tensor-path kernels (sc_mma_attention_train.cu): SC_ERR_UNSUPPORTED = shape not served, nothing launched
+int sc_attn_train_fwd_mma_launch(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* key_valid,
+                                 const float* bias, float* probs, void* out, int ldo, int G, int Tq, int Tk, int h, int dk,
+                                 int causal_T, float dropout_p, unsigned long long seed, unsigned long long stream_id,
+                                 cudaStream_t stream);
+int sc_attn_train_bwd_mma_launch(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
+                                 const float* d_out, int ldd, float* dq, float* dk_, float* dv, int ldgq, int ldgk, int ldgv,
+                                 float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p, unsigned long long seed,
+                                 unsigned long long stream_id, cudaStream_t stream);
+
 extern "C" {
 
 int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* key_valid,
@@ -397,6 +410,11 @@ int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int l
                      float dropout_p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
   int rc = check_common("sc_attention_fwd", G, Tq, Tk, h, dk);
   if (rc) return rc;
+  if (dtype == SC_BF16 && probs != nullptr) {
+    rc = sc_attn_train_fwd_mma_launch(q, k, v, ldq, ldk, ldv, key_valid, bias, probs, out, ldo, G, Tq, Tk, h, dk, causal_T,
+                                      dropout_p, seed, stream_id, stream);
+    if (rc != SC_ERR_UNSUPPORTED) return rc;
+  }
   AttnArgs a = {};
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.key_valid = key_valid; a.bias = bias; a.probs = probs;
   a.out = out; a.ldo = ldo; a.G = G; a.Tq = Tq; a.Tk = Tk; a.h = h; a.dk = dk; a.causal_T = causal_T;
@@ -424,6 +442,11 @@ int sc_attention_bwd(const void* q, const void* k, const void* v, int ldq, int l
   int rc = check_common("sc_attention_bwd", G, Tq, Tk, h, dk);
   if (rc) return rc;
   SC_CHECK(probs != nullptr, SC_ERR_SHAPE, "sc_attention_bwd: saved probabilities missing");
+  if (dtype == SC_BF16) {
+    rc = sc_attn_train_bwd_mma_launch(q, k, v, ldq, ldk, ldv, probs, d_out, ldd, dq, dk_, dv, ldgq, ldgk, ldgv, dbias, G, Tq, Tk,
+                                      h, dk, dropout_p, seed, stream_id, stream);
+    if (rc != SC_ERR_UNSUPPORTED) return rc;
+  }
   AttnArgs a = {};
   a.q = q; a.k = k; a.v = v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.probs = const_cast<float*>(probs);
   a.G = G; a.Tq = Tq; a.Tk = Tk; a.h = h; a.dk = dk; a.dropout_p = dropout_p; a.seed = seed; a.stream = stream_id;
@@ -458,7 +481,12 @@ int sc_box_bias_fwd(const float* boxes, const float* wg_w, const float* wg_b, fl
 int sc_box_bias_bwd(const float* boxes, const float* bias, const float* dbias, float* dwg_w, float* dwg_b, int B, int N, int h,
                     int trig, float wave_len, cudaStream_t stream) {
   SC_CHECK(B > 0 && N > 0 && h >= 1 && h <= kMaxHeads, SC_ERR_UNSUPPORTED, "sc_box_bias_bwd: B=%d N=%d h=%d", B, N, h);
-  box_bias_bwd_kernel<<<B, 256, 0, stream>>>(boxes, bias, dbias, dwg_w, dwg_b, B, N, h, trig, make_dim_mat(wave_len));
+  // ~3 CTAs per SM; slices are multiples of the 32-pair staging step
+  const int pairs = N * N;
+  int slices = (3 * 148 + B - 1) / B;
+  int ppc = ((pairs + slices - 1) / slices + 31) / 32 * 32;
+  slices = (pairs + ppc - 1) / ppc;
+  box_bias_bwd_kernel<<<dim3(B, slices), 256, 0, stream>>>(boxes, bias, dbias, dwg_w, dwg_b, B, N, h, trig, make_dim_mat(wave_len), ppc);
   SC_LAUNCH_CHECK("sc_box_bias_bwd");
   return SC_OK;
 }

@@ -60,6 +60,79 @@ __global__ void __launch_bounds__(256) prep_grad_kernel(const float* __restrict_
   }
 }
 
+
+// Row-major-only variant (the bf16 trainer feeds dy to the weight-gradient GEMM as MN-major tiles, so no transposed copy
+// is needed): 16-byte loads / 8-byte bf16 stores, CTA = 64 rows x 128 columns, one Philox draw per 4 elements, bias
+// gradient accumulated in registers over the thread's 8 rows -> shared memory -> one vector reduction per 4 columns.
+template <typename HT>
+__global__ void __launch_bounds__(256) prep_grad_vec_kernel(const float* __restrict__ g, const HT* __restrict__ h,
+                                                            __nv_bfloat16* __restrict__ out, int rows, int cols, float scale, float p,
+                                                            unsigned long long seed, unsigned long long stream,
+                                                            float* __restrict__ colsum) {
+  __shared__ float4 s_cs[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + tx * 4;
+  const int r0 = blockIdx.y * 64 + ty;
+  const sc::Philox ph(seed);
+  const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  float4 gv[8];
+  float hk[8][4];
+  bool ok[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + 8 * i;
+    ok[i] = r < rows && c < cols;
+    gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    hk[i][0] = hk[i][1] = hk[i][2] = hk[i][3] = 1.f;
+    if (ok[i]) {
+      const size_t e = (size_t)r * cols + c;
+      gv[i] = *(const float4*)(g + e);
+      if (h) {
+        if (sizeof(HT) == 2) {
+          const uint2 hv = *(const uint2*)((const __nv_bfloat16*)h + e);
+          hk[i][0] = __uint_as_float(hv.x << 16); hk[i][1] = __uint_as_float(hv.x & 0xffff0000u);
+          hk[i][2] = __uint_as_float(hv.y << 16); hk[i][3] = __uint_as_float(hv.y & 0xffff0000u);
+        } else {
+          const float4 hv = *(const float4*)((const float*)h + e);
+          hk[i][0] = hv.x; hk[i][1] = hv.y; hk[i][2] = hv.z; hk[i][3] = hv.w;
+        }
+      }
+    }
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (!ok[i]) continue;
+    const size_t e = (size_t)(r0 + 8 * i) * cols + c;
+    float v[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+    if (h) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = hk[i][j] != 0.f ? v[j] * scale : 0.f;
+    } else if (p > 0.f) {
+      const uint4 rr = ph(e >> 2, stream);
+      v[0] *= sc::u24(rr.x) >= p ? keep : 0.f; v[1] *= sc::u24(rr.y) >= p ? keep : 0.f;
+      v[2] *= sc::u24(rr.z) >= p ? keep : 0.f; v[3] *= sc::u24(rr.w) >= p ? keep : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= scale;
+    }
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 o; o.x = *(const uint32_t*)&lo; o.y = *(const uint32_t*)&hi;
+    *(uint2*)(out + e) = o;
+    // the bias gradient sums the values the GEMMs consume (bf16-rounded)
+    cs[0] += __low2float(lo); cs[1] += __high2float(lo); cs[2] += __low2float(hi); cs[3] += __high2float(hi);
+  }
+  if (!colsum) return;
+  s_cs[ty][tx] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float4 t = s_cs[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { const float4 q = s_cs[w][tx]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + c), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+  }
+}
+
 template <typename IT, typename OT>
 __global__ void __launch_bounds__(256) transpose_kernel(const IT* __restrict__ x, OT* __restrict__ y, int ldT, int rows, int cols) {
   __shared__ float tile[32][33];
@@ -105,6 +178,97 @@ __global__ void __launch_bounds__(256) apply_mask_t_kernel(const float* __restri
   for (int i = 0; i < 4; ++i) {
     const int k = k0 + ty + i * 8, n = n0 + tx;
     if (n < N && k < Kd) outT[(size_t)k * N + n] = cvt<OT>(tile[tx][ty + i * 8]);
+  }
+}
+
+
+// All masked weights of a training step in ONE launch (the per-tensor version was 68 launches of 6-10 us for 512x512
+// tensors).  desc i = {w, s, u, out, outT, N, K, stream, tile_start, tiles_k} (10 x 64-bit words, device memory);
+// CTA = one 64 x 64 tile of one tensor, found by binary search over tile_start.  One Philox draw per 4 elements
+// (bernoulli4: the same sample mask_value() regenerates element-wise in the weight-gradient epilogue).
+struct MaskDesc {
+  const float* w; const float* s; const float* u; void* out; void* outT;
+  long long N, K; unsigned long long stream; long long tile_start, tiles_k;
+};
+
+template <typename OT>
+__global__ void __launch_bounds__(256) apply_mask_batched_kernel(const MaskDesc* __restrict__ descs, int n_desc, int mode,
+                                                                 unsigned long long seed, unsigned long long stream_base) {
+  __shared__ float tile[64][65];
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile_start <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const MaskDesc d = descs[lo];
+  const int local = (int)((long long)blockIdx.x - d.tile_start);
+  const int N = (int)d.N, Kd = (int)d.K;
+  const int k0 = (local % (int)d.tiles_k) * 64, n0 = (local / (int)d.tiles_k) * 64;
+  const unsigned long long stream = stream_base + d.stream;
+  const sc::Philox ph(seed);
+  const int tid = threadIdx.x;
+  const int c4 = (tid & 15) * 4;
+  OT* out = (OT*)d.out;
+  // issue all loads of the thread first (4 rows x {w, s, u})
+  float4 wv[4], sv[4], uv[4];
+  bool ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + (tid >> 4) + 16 * i, k = k0 + c4;
+    ok[i] = n < N && k < Kd;
+    wv[i] = sv[i] = uv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok[i]) {
+      const size_t e = (size_t)n * Kd + k;
+      wv[i] = __ldg((const float4*)(d.w + e));
+      if (mode != SC_MASK_NONE) sv[i] = __ldg((const float4*)(d.s + e));
+      if (mode == SC_MASK_UNIFORM) uv[i] = __ldg((const float4*)(d.u + e));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (tid >> 4) + 16 * i;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok[i]) {
+      const size_t e = (size_t)(n0 + r) * Kd + k0 + c4;
+      const float sa[4] = {sv[i].x, sv[i].y, sv[i].z, sv[i].w}, ua[4] = {uv[i].x, uv[i].y, uv[i].z, uv[i].w};
+      float m[4];
+      if (mode == SC_MASK_BERNOULLI) {
+        sc::bernoulli4(ph, e >> 2, stream, sa, m);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = sc::mask_value(mode, sa[j], ua[j], ph, e + j, stream);
+      }
+      v[0] = wv[i].x * m[0]; v[1] = wv[i].y * m[1]; v[2] = wv[i].z * m[2]; v[3] = wv[i].w * m[3];
+      if (out) {
+        if (sizeof(OT) == 2) {
+          const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v[0], v[1]), hi2 = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 o; o.x = *(const uint32_t*)&lo2; o.y = *(const uint32_t*)&hi2;
+          *(uint2*)((__nv_bfloat16*)d.out + e) = o;
+        } else {
+          *(float4*)((float*)d.out + e) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    tile[r][c4] = v[0]; tile[r][c4 + 1] = v[1]; tile[r][c4 + 2] = v[2]; tile[r][c4 + 3] = v[3];
+  }
+  if (!d.outT) return;
+  __syncthreads();
+  // transposed store: a warp writes 64 consecutive n of one k row (two per lane)
+  const int lane = tid & 31, wq = tid >> 5;
+  OT* outT = (OT*)d.outT;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int kk = wq + 8 * i, k = k0 + kk, n = n0 + 2 * lane;
+    if (k >= Kd || n >= N) continue;
+    const float a = tile[2 * lane][kk], b = tile[2 * lane + 1][kk];
+    OT* o = outT + (size_t)k * N + n;
+    if ((N & 1) == 0) {
+      if (sizeof(OT) == 2) { const __nv_bfloat162 pr = __floats2bfloat162_rn(a, b); *(uint32_t*)o = *(const uint32_t*)&pr; }
+      else *(float2*)o = make_float2(a, b);
+    } else {
+      o[0] = cvt<OT>(a);
+      if (n + 1 < N) o[1] = cvt<OT>(b);
+    }
   }
 }
 
@@ -294,6 +458,93 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
+
+// D = 512 (d_model): one row per warp, 16-byte accesses, every load of the row (x, dy, residual gradient) issued before
+// the first reduction; parameter gradients go warp -> shared memory -> one vector reduction per 4 columns and CTA.
+template <typename GT>
+__global__ void __launch_bounds__(256) layernorm_bwd512_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                               const GT* __restrict__ dy, const float* __restrict__ dres,
+                                                               float* __restrict__ dx, float* __restrict__ da,
+                                                               float* __restrict__ db, int rows, float eps) {
+  constexpr int D = 512;
+  __shared__ float4 s_part[2][8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  float4 pa[4], pb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pa[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < rows) {
+    const size_t base = (size_t)row * D;
+    float c[4][4], g[4][4], dyv[4][4], rs[4][4];
+    float4 av[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 4 * (lane + 32 * i);
+      const float4 xv = *(const float4*)(x + base + col);
+      c[i][0] = xv.x; c[i][1] = xv.y; c[i][2] = xv.z; c[i][3] = xv.w;
+      if (sizeof(GT) == 2) {
+        const uint2 dv = *(const uint2*)((const __nv_bfloat16*)dy + base + col);
+        dyv[i][0] = __uint_as_float(dv.x << 16); dyv[i][1] = __uint_as_float(dv.x & 0xffff0000u);
+        dyv[i][2] = __uint_as_float(dv.y << 16); dyv[i][3] = __uint_as_float(dv.y & 0xffff0000u);
+      } else {
+        const float4 dv = *(const float4*)((const float*)dy + base + col);
+        dyv[i][0] = dv.x; dyv[i][1] = dv.y; dyv[i][2] = dv.z; dyv[i][3] = dv.w;
+      }
+      rs[i][0] = rs[i][1] = rs[i][2] = rs[i][3] = 0.f;
+      if (dres) { const float4 rv = *(const float4*)(dres + base + col); rs[i][0] = rv.x; rs[i][1] = rv.y; rs[i][2] = rv.z; rs[i][3] = rv.w; }
+      av[i] = __ldg((const float4*)(a + col));
+    }
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm += c[i][j];
+    const float mu = sc::warp_sum(sm) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { c[i][j] -= mu; q += c[i][j] * c[i][j]; }
+    const float sigma = sqrtf(sc::warp_sum(q) / (float)(D - 1));
+    const float r = 1.f / (sigma + eps);
+    float sg = 0.f, sgc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float aa[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        g[i][j] = dyv[i][j] * aa[j];
+        sg += g[i][j];
+        sgc += g[i][j] * c[i][j];
+      }
+      pa[i] = make_float4(dyv[i][0] * c[i][0] * r, dyv[i][1] * c[i][1] * r, dyv[i][2] * c[i][2] * r, dyv[i][3] * c[i][3] * r);
+      pb[i] = make_float4(dyv[i][0], dyv[i][1], dyv[i][2], dyv[i][3]);
+    }
+    sg = sc::warp_sum(sg) / (float)D;
+    sgc = sc::warp_sum(sgc);
+    const float k2 = (sigma > 0.f) ? r * r * sgc / ((float)(D - 1) * sigma) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 4 * (lane + 32 * i);
+      float4 o;
+      o.x = r * (g[i][0] - sg) - k2 * c[i][0] + rs[i][0];
+      o.y = r * (g[i][1] - sg) - k2 * c[i][1] + rs[i][1];
+      o.z = r * (g[i][2] - sg) - k2 * c[i][2] + rs[i][2];
+      o.w = r * (g[i][3] - sg) - k2 * c[i][3] + rs[i][3];
+      *(float4*)(dx + base + col) = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { s_part[0][warp][lane + 32 * i] = pa[i]; s_part[1][warp][lane + 32 * i] = pb[i]; }
+  __syncthreads();
+  const int which = threadIdx.x >> 7, c4 = threadIdx.x & 127;
+  float4 t = s_part[which][0][c4];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) { const float4 q4 = s_part[which][w][c4]; t.x += q4.x; t.y += q4.y; t.z += q4.z; t.w += q4.w; }
+  float* dst = (which ? db : da) + 4 * c4;
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+}
+
 // log-softmax + masked NLL, forward and backward in one pass over the logits (one CTA per row).
 //   loss_sum += -w_r * logp[target_r]   ;   dlogits = (softmax - onehot) * w_r * inv_norm   (written in GT)
 template <typename GT>
@@ -396,6 +647,16 @@ int sc_prep_grad(const float* g, const void* h, int h_dtype, void* out, void* ou
                  float scale, float dropout_p, unsigned long long seed, unsigned long long stream_id, float* colsum_accum,
                  cudaStream_t stream) {
   SC_CHECK(rows > 0 && cols > 0, SC_ERR_SHAPE, "sc_prep_grad: rows=%d cols=%d", rows, cols);
+  if (out_dtype == SC_BF16 && outT == nullptr && out != nullptr && cols % 4 == 0 && (((uintptr_t)g | (uintptr_t)h) & 15) == 0 &&
+      ((uintptr_t)out & 7) == 0 && (colsum_accum == nullptr || ((uintptr_t)colsum_accum & 15) == 0)) {
+    dim3 vgrid((cols + 127) / 128, (rows + 63) / 64);
+    if (h_dtype == SC_BF16 && h != nullptr)
+      prep_grad_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, stream>>>(g, (const __nv_bfloat16*)h, (__nv_bfloat16*)out, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum);
+    else
+      prep_grad_vec_kernel<float><<<vgrid, 256, 0, stream>>>(g, (const float*)h, (__nv_bfloat16*)out, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum);
+    SC_LAUNCH_CHECK("sc_prep_grad");
+    return SC_OK;
+  }
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
 #define PG(HT, OT) prep_grad_kernel<HT, OT><<<grid, 256, 0, stream>>>(g, (const HT*)h, (OT*)out, (OT*)outT, ldT, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum)
   if (out_dtype == SC_BF16) { if (h_dtype == SC_BF16) PG(__nv_bfloat16, __nv_bfloat16); else PG(float, __nv_bfloat16); }
@@ -428,6 +689,20 @@ int sc_apply_mask_transposed(const float* w, const float* mask, int mask_mode, c
   else if (out_dtype == SC_F32) apply_mask_t_kernel<float><<<grid, 256, 0, stream>>>(w, mask, mask_mode, uniforms, seed, stream_id, (float*)outT, N, K, (float*)out_plain);
   else SC_CHECK(false, SC_ERR_DTYPE, "sc_apply_mask_transposed: bad dtype");
   SC_LAUNCH_CHECK("sc_apply_mask_transposed");
+  return SC_OK;
+}
+
+int sc_apply_mask_batched(const void* descs, int n_desc, long total_tiles, int mask_mode, unsigned long long seed,
+                          unsigned long long stream_base, int out_dtype, cudaStream_t stream) {
+  SC_CHECK(descs != nullptr && n_desc > 0 && total_tiles > 0 && total_tiles < (1L << 31), SC_ERR_SHAPE,
+           "sc_apply_mask_batched: n_desc=%d total_tiles=%ld", n_desc, total_tiles);
+  static_assert(sizeof(MaskDesc) == 80, "descriptor = 10 x 64-bit words");
+  if (out_dtype == SC_BF16)
+    apply_mask_batched_kernel<__nv_bfloat16><<<(unsigned)total_tiles, 256, 0, stream>>>((const MaskDesc*)descs, n_desc, mask_mode, seed, stream_base);
+  else if (out_dtype == SC_F32)
+    apply_mask_batched_kernel<float><<<(unsigned)total_tiles, 256, 0, stream>>>((const MaskDesc*)descs, n_desc, mask_mode, seed, stream_base);
+  else SC_CHECK(false, SC_ERR_DTYPE, "sc_apply_mask_batched: bad dtype");
+  SC_LAUNCH_CHECK("sc_apply_mask_batched");
   return SC_OK;
 }
 
@@ -481,6 +756,14 @@ int sc_colsum(const void* x, int dtype, float* out, int rows, int cols, int accu
 int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
                      float* db, int rows, int D, float eps, cudaStream_t stream) {
   SC_CHECK(rows > 0 && D > 1 && D <= 2048, SC_ERR_SHAPE, "sc_layernorm_bwd: rows=%d D=%d", rows, D);
+  if (D == 512 && ((((uintptr_t)x | (uintptr_t)a | (uintptr_t)dy | (uintptr_t)dres | (uintptr_t)dx | (uintptr_t)da | (uintptr_t)db) & 15) == 0) &&
+      (dy_dtype == SC_F32 || dy_dtype == SC_BF16)) {
+    const int nb = (rows + 7) / 8;
+    if (dy_dtype == SC_F32) layernorm_bwd512_kernel<float><<<nb, 256, 0, stream>>>(x, a, (const float*)dy, dres, dx, da, db, rows, eps);
+    else layernorm_bwd512_kernel<__nv_bfloat16><<<nb, 256, 0, stream>>>(x, a, (const __nv_bfloat16*)dy, dres, dx, da, db, rows, eps);
+    SC_LAUNCH_CHECK("sc_layernorm_bwd");
+    return SC_OK;
+  }
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;
   const size_t smem = 2 * (size_t)D * sizeof(float);

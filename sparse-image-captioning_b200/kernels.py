@@ -317,6 +317,25 @@ def apply_mask_transposed(w, mask, mask_mode, outT, *, uniforms=None, seed=0, st
     return outT
 
 
+def mask_descriptors(items, device):
+    """Descriptor table of sc_apply_mask_batched.  items: (w [N,K] fp32, s | None, u | None, out | None, outT | None, stream_id).
+    Returns (int64 device tensor [n, 10], total 64x64 tiles)."""
+    rows, start = [], 0
+    for w, s, u, out, outT, sid in items:
+        N, K = w.shape
+        assert K % 4 == 0 and w.is_contiguous() and (out is None or out.is_contiguous()) and (outT is None or outT.is_contiguous())
+        tk = (K + 63) // 64
+        rows.append([w.data_ptr(), 0 if s is None else s.data_ptr(), 0 if u is None else u.data_ptr(),
+                     0 if out is None else out.data_ptr(), 0 if outT is None else outT.data_ptr(), N, K, int(sid), start, tk])
+        start += tk * ((N + 63) // 64)
+    return torch.tensor(rows, dtype=torch.int64).to(device), start
+
+
+def apply_mask_batched(desc, total_tiles, mask_mode, *, seed=0, stream_base=0, out_dtype=torch.bfloat16):
+    lib.call("sc_apply_mask_batched", lib.ptr(desc), desc.shape[0], total_tiles, mask_mode, seed, stream_base,
+             lib.dtype_code(out_dtype), lib.stream())
+
+
 def mask_grad(dwm, w, mask, mask_mode, dw, ds, *, uniforms=None, seed=0, stream_id=0, bypass=False, sp_coeff=0.0,
               accumulate=False):
     if mask is None:

@@ -44,6 +44,7 @@ SIGNATURES = {
     "sc_prep_grad": [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _f, _u64, _u64, _p, _p],
     "sc_transpose": [_p, _i, _p, _i, _i, _i, _i, _p],
     "sc_apply_mask_transposed": [_p, _p, _i, _p, _u64, _u64, _p, _i, _i, _i, _p, _p],
+    "sc_apply_mask_batched": [_p, _i, _l, _i, _u64, _u64, _i, _p],
     "sc_mask_grad": [_p, _p, _p, _i, _p, _u64, _u64, _i, _f, _p, _p, _i, _sz, _p],
     "sc_colsum": [_p, _i, _p, _i, _i, _i, _p],
     "sc_layernorm_bwd": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p],

@@ -143,6 +143,7 @@ class OrtTrainer:
         self._ws = {}
         self.premask = True   # False: mask inside the GEMM operand prologue (K1 fused variant)
         self._wm, self._wmT, self._wm_step = {}, {}, {}
+        self._premask_desc = None
 
     # ---------------------------------------------------------------------------------------------------------
     def _group(self, table, first, count):
@@ -192,6 +193,40 @@ class OrtTrainer:
             return W, None, K.MASK_NONE, None, 0, 0
         return (W, self._group(self.s, wname, count), self.mask_mode(), self._u(wname, count), self._sd(0),
                 self._step_base() + self.stream_of[wname])
+
+    def _premask_keys(self):
+        """(first weight name, fused count) of every linear the teacher-forcing forward runs, in launch order."""
+        L = self.cfg.num_layers
+        keys = [("att_embed.0.weight", 1)]
+        for l in range(L):
+            p = f"model.encoder.layers.{l}"
+            keys += [(f"{p}.self_attn.linears.0.weight", 3), (f"{p}.self_attn.linears.3.weight", 1),
+                     (f"{p}.feed_forward.w_1.weight", 1), (f"{p}.feed_forward.w_2.weight", 1)]
+        keys += [(f"model.decoder.layers.{l}.src_attn.linears.1.weight", 2) for l in range(L)]
+        for l in range(L):
+            p = f"model.decoder.layers.{l}"
+            keys += [(f"{p}.self_attn.linears.0.weight", 3), (f"{p}.self_attn.linears.3.weight", 1),
+                     (f"{p}.src_attn.linears.0.weight", 1), (f"{p}.src_attn.linears.3.weight", 1),
+                     (f"{p}.feed_forward.w_1.weight", 1), (f"{p}.feed_forward.w_2.weight", 1)]
+        keys.append(("model.generator.proj.weight", 1))
+        return keys
+
+    def _premask_all(self):
+        """W (.) m (bf16) and its transpose for EVERY linear of the step in one launch (sc_apply_mask_batched): the forward
+        operand, the dX operand and the weight-gradient epilogue all see the same Philox sample."""
+        if self._premask_desc is None:
+            items = []
+            for key in self._premask_keys():
+                wname, count = key
+                W, S, mode, U, seed, stream = self._mask_args(wname, count)
+                wm = self._wm[key] = torch.empty(W.shape, device=self.dev, dtype=torch.bfloat16)
+                wT = self._wmT[key] = torch.empty(W.shape[1], W.shape[0], device=self.dev, dtype=torch.bfloat16)
+                items.append((W, S, U, wm, wT, self.stream_of[wname]))
+            self._premask_desc = K.mask_descriptors(items, self.dev) + ([k for k in self._premask_keys()],)
+        desc, tiles, keys = self._premask_desc
+        K.apply_mask_batched(desc, tiles, self.mask_mode(), seed=self._sd(0), stream_base=self._step_base())
+        for key in keys:
+            self._wm_step[key] = (self.step_id, self.training)
 
     def _drop_stream(self, site):
         return self._step_base() + 2048 + site
@@ -375,6 +410,8 @@ class OrtTrainer:
         trig = not c.no_box_trigonometric_embedding
         if ws.att_a is not ws.att_in:
             K.cast_bf16(ws.att_in, out=ws.att_a)
+        if self.adt == torch.bfloat16 and self.premask and self.training:
+            self._premask_all()
         self._lin("att_embed.0.weight", ws.att_a, ws.xe[0], relu=True, p=self.p_src, site=1)
         if ws.att_mask is not None:
             K.mask_rows(ws.xe[0], ws.att_mask.view(-1))

@@ -321,3 +321,108 @@ def test_box_bias_fwd_bwd(K):
     K.box_bias_bwd(boxes.to(DEV), bias, dbias.to(DEV), dw, db, B=B, N=N, h=h)
     assert rel_err(dw, ww.grad) < 2e-3
     assert rel_err(db, wb.grad) < 2e-3
+
+
+@pytest.mark.parametrize("case", ["self", "cross", "box", "wide"])
+def test_attention_fwd_bwd_tensor_path(K, case):
+    """bf16, d_k = 64: sc_attention_fwd / _bwd run the mma.sync kernels (sc_mma_attention_train.cu).  Operands are
+    bf16-exact; P, dS and dO are rounded to bf16 inside the kernel, hence the 2e-2 bound north_star states for bf16."""
+    g = torch.Generator().manual_seed(11)
+    h, dk = 2, 64
+    D = h * dk
+    if case == "self":
+        G, Tq, Tk, causal = 5, 17, 17, 17
+        kv = (torch.rand(G, Tk, generator=g) > 0.2).float()
+        kv[:, 0] = 1
+        bias = None
+    elif case == "cross":
+        G, Tq, Tk, causal = 3, 5 * 17, 36, 0
+        kv = torch.ones(G, Tk)
+        kv[1, 30:] = 0
+        bias = None
+    elif case == "box":
+        G, Tq, Tk, causal = 3, 36, 36, 0
+        kv = torch.ones(G, Tk)
+        kv[2, 33:] = 0
+        bias = torch.randn(G, h, Tq, Tk, generator=g)
+    else:
+        G, Tq, Tk, causal = 2, 150, 50, 0   # more m-tiles than warps, 4 key tiles
+        kv = None
+        bias = torch.randn(G, h, Tq, Tk, generator=g)
+    dt = torch.bfloat16
+    q = torch.randn(G * Tq, D, generator=g).to(dt)
+    k = torch.randn(G * Tk, D, generator=g).to(dt)
+    v = torch.randn(G * Tk, D, generator=g).to(dt)
+    dO = torch.randn(G * Tq, D, generator=g)
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    bd = bias.double().requires_grad_(True) if bias is not None else None
+    out_ref, p_ref = _attn_ref(qd, kd, vd, h, G, Tq, Tk, kv, bd, causal)
+    out_ref.backward(dO.double())
+    out = torch.zeros(G * Tq, D, dtype=dt, device=DEV)
+    probs = torch.zeros(G, h, Tq, Tk, device=DEV)
+    qg, kg, vg = q.to(DEV), k.to(DEV), v.to(DEV)
+    K.attention_fwd(qg, kg, vg, out, probs, G=G, Tq=Tq, Tk=Tk, h=h, dk=dk, ldq=D, ldk=D, ldv=D, ldo=D,
+                    key_valid=None if kv is None else kv.to(DEV), bias=None if bias is None else bias.to(DEV), causal_T=causal)
+    assert rel_err(out.float(), out_ref.detach()) < 2e-2
+    assert rel_err(probs, p_ref.detach()) < 1e-4  # scores accumulate in fp32 from bf16-exact operands
+    dq = torch.full((G * Tq, D), float("nan"), device=DEV)
+    dkk = torch.full((G * Tk, D), float("nan"), device=DEV)
+    dv = torch.full((G * Tk, D), float("nan"), device=DEV)
+    dbias = torch.zeros(G, h, Tq, Tk, device=DEV) if bias is not None else None
+    K.attention_bwd(qg, kg, vg, probs, dO.to(DEV), dq, dkk, dv, dtype=dt, G=G, Tq=Tq, Tk=Tk, h=h, dk=dk, ldq=D, ldk=D, ldv=D, ldd=D,
+                    ldgq=D, ldgk=D, ldgv=D, dbias=dbias)
+    assert rel_err(dq, qd.grad) < 2e-2
+    assert rel_err(dkk, kd.grad) < 2e-2
+    assert rel_err(dv, vd.grad) < 2e-2
+    if bias is not None:
+        assert rel_err(dbias, bd.grad) < 2e-2
+
+
+def test_attention_dropout_consistency_tensor_path(K):
+    """bf16 / d_k = 64: the backward regenerates the forward's dropout mask (<out, dO> == <V, dV>)."""
+    g = torch.Generator().manual_seed(12)
+    G, Tq, Tk, h, dk = 4, 40, 36, 2, 64
+    D = h * dk
+    q = torch.randn(G * Tq, D, generator=g).to(DEV).bfloat16()
+    k, v = (torch.randn(G * Tk, D, generator=g).to(DEV).bfloat16() for _ in range(2))
+    out = torch.zeros(G * Tq, D, device=DEV, dtype=torch.bfloat16)
+    probs = torch.zeros(G, h, Tq, Tk, device=DEV)
+    K.attention_fwd(q, k, v, out, probs, G=G, Tq=Tq, Tk=Tk, h=h, dk=dk, ldq=D, ldk=D, ldv=D, ldo=D, p=0.4, seed=3, stream_id=9)
+    assert abs(float(probs.sum()) - G * h * Tq) < 1e-2  # saved probabilities are pre-dropout
+    dO = torch.randn(G * Tq, D, generator=g).to(DEV)
+    dq, dkk, dv = torch.zeros(G * Tq, D, device=DEV), torch.zeros(G * Tk, D, device=DEV), torch.zeros(G * Tk, D, device=DEV)
+    K.attention_bwd(q, k, v, probs, dO, dq, dkk, dv, dtype=torch.bfloat16, G=G, Tq=Tq, Tk=Tk, h=h, dk=dk, ldq=D, ldk=D, ldv=D, ldd=D,
+                    ldgq=D, ldgk=D, ldgv=D, p=0.4, seed=3, stream_id=9)
+    lhs = float((out.float() * dO).sum())
+    rhs = float((v.float() * dv).sum())
+    assert abs(lhs - rhs) < 2e-2 * max(1.0, abs(lhs))
+    # the same mask, element for element: out equals (probs (.) keep) V with keep recovered from the fp32 kernel's rule
+    out32 = torch.zeros(G * Tq, D, device=DEV)
+    probs32 = torch.zeros(G, h, Tq, Tk, device=DEV)
+    K.attention_fwd(q.float(), k.float(), v.float(), out32, probs32, G=G, Tq=Tq, Tk=Tk, h=h, dk=dk, ldq=D, ldk=D, ldv=D, ldo=D,
+                    p=0.4, seed=3, stream_id=9)
+    assert rel_err(out.float(), out32) < 2e-2
+
+
+def test_apply_mask_batched_matches_per_tensor(K):
+    """One launch for all masked weights == the per-tensor kernel, bit for bit (same Philox sample), in every mode."""
+    g = torch.Generator().manual_seed(13)
+    shapes = [(512, 512), (200, 72), (1000, 512), (64, 2048), (8, 64)]
+    for mode in (K.MASK_BERNOULLI, K.MASK_ROUND, K.MASK_UNIFORM, K.MASK_RAW, K.MASK_NONE):
+        items, refs = [], []
+        for i, (N, Kd) in enumerate(shapes):
+            W = torch.randn(N, Kd, generator=g).to(DEV)
+            S = (torch.randn(N, Kd, generator=g) * 2).to(DEV)
+            U = torch.rand(N, Kd, generator=g).to(DEV)
+            out = torch.full((N, Kd), 7.0, device=DEV, dtype=torch.bfloat16)
+            outT = torch.full((Kd, N), 7.0, device=DEV, dtype=torch.bfloat16)
+            items.append((W, None if mode == K.MASK_NONE else S, U if mode == K.MASK_UNIFORM else None, out, outT, 5 + i))
+            r, rT = torch.empty_like(out), torch.empty_like(outT)
+            K.apply_mask_transposed(W, None if mode == K.MASK_NONE else S, mode, rT, uniforms=U if mode == K.MASK_UNIFORM else None,
+                                    seed=99, stream_id=4096 + 5 + i, out=r)
+            refs.append((r, rT))
+        desc, tiles = K.mask_descriptors(items, DEV)
+        K.apply_mask_batched(desc, tiles, mode, seed=99, stream_base=4096)
+        for (W, S, U, out, outT, sid), (r, rT) in zip(items, refs):
+            assert torch.equal(out, r), (mode, tuple(W.shape))
+            assert torch.equal(outT, rT), (mode, tuple(W.shape))
