@@ -230,7 +230,8 @@ def main():
     from sparse_caption_b200.engine import ModelCfg, OrtEngine
     lib.load()
     if args.no_pdl:
-        lib.load().sc_set_pdl(0)
+        from sparse_caption_b200 import kernels as _K
+        _K.set_pdl(False)
     cfg = ModelCfg(CFG)
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=SPARSITY, device=dev)
     eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold)

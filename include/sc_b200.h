@@ -68,7 +68,8 @@ int sc_linear_ln(const void* x, const void* w, const float* bias, const float* r
                  int K, int relu, int tile_n, const float* ln_stats, const float* ln_c, float ln_eps, void* y_bf16_copy,
                  float* stats_out, sc_stream_t stream);
 
-/* Programmatic dependent launch (griddepcontrol) between consecutive kernels of a stream: 1 = on (default), 0 = off. */
+/* Programmatic dependent launch (griddepcontrol) between consecutive kernels of a stream: 1 = on everywhere (default),
+ * 0 = off; otherwise a mask: bit 0 = GEMM + inference kernels, bit 1 = training row / attention kernels. */
 int sc_set_pdl(int enabled);
 
 /* K3b — the same product from CSR weights (rows = output features, 16-bit column indices, values in x's dtype).

@@ -13,6 +13,8 @@ cfg = ModelCfg(dict(bench.CFG, max_seq_length=17))
 sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
 GRAPH = os.environ.get("SC_TRAIN_GRAPH", "1") == "1"
 tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888, use_graph=GRAPH)
+if "SC_PDL_MASK" in os.environ:
+    tr.pdl_mask = int(os.environ["SC_PDL_MASK"])
 S, T = 5, 17
 g = torch.Generator().manual_seed(8888)
 att, boxes = synthetic.synthetic_inputs(B, 36, 2048, seed=8888, pin=True)
@@ -40,6 +42,13 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"host enqueue ms/step {(t1-t0)/5*1e3:.2f}  wall ms/step {(t2-t0)/5*1e3:.2f}")
+if os.environ.get("SC_WALL_ONLY") == "1":
+    t0 = time.perf_counter()
+    for _ in range(40):
+        tr.train_step(att, boxes, seqs, masks, seq_per_img=S, **opt)
+    torch.cuda.synchronize()
+    print(f"wall ms/step over 40 steps {(time.perf_counter()-t0)/40*1e3:.3f}")
+    sys.exit(0)
 tr.use_graph = False  # per-kernel event timing needs the eager launch sequence
 agg = collections.defaultdict(lambda: [0.0, 0])
 for rep in range(3):

@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(256) box_bias_fwd_kernel(const float* __restri
                                                            const float* __restrict__ wg_b, float* __restrict__ bias, int B, int N,
                                                            int h, int trig, DimMat dm) {
   __shared__ float s_wg[kMaxHeads * 64 + kMaxHeads];
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int dim_g = trig ? 64 : 4;
   for (int i = threadIdx.x; i < h * dim_g; i += 256) s_wg[i] = wg_w[i];
   for (int i = threadIdx.x; i < h; i += 256) s_wg[h * dim_g + i] = wg_b[i];
@@ -320,6 +322,8 @@ __global__ void __launch_bounds__(256) box_bias_bwd_kernel(const float* __restri
                                                            int pairs_per_cta) {
   __shared__ float s_emb[32][65];
   __shared__ float s_dpre[kMaxHeads][33];
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int dim_g = trig ? 64 : 4;
@@ -473,7 +477,7 @@ int sc_box_bias_fwd(const float* boxes, const float* wg_w, const float* wg_b, fl
   SC_CHECK(((uintptr_t)boxes & 15) == 0, SC_ERR_ALIGN, "sc_box_bias_fwd: boxes must be 16-byte aligned");
   long blocks = ((long)B * N * N + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  box_bias_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(boxes, wg_w, wg_b, bias, B, N, h, trig, make_dim_mat(wave_len));
+  sc::launch_pdl_aux(box_bias_fwd_kernel, dim3((int)blocks), dim3(256), 0, stream, boxes, wg_w, wg_b, bias, B, N, h, trig, make_dim_mat(wave_len));
   SC_LAUNCH_CHECK("sc_box_bias_fwd");
   return SC_OK;
 }
@@ -486,7 +490,7 @@ int sc_box_bias_bwd(const float* boxes, const float* bias, const float* dbias, f
   int slices = (3 * 148 + B - 1) / B;
   int ppc = ((pairs + slices - 1) / slices + 31) / 32 * 32;
   slices = (pairs + ppc - 1) / ppc;
-  box_bias_bwd_kernel<<<dim3(B, slices), 256, 0, stream>>>(boxes, bias, dbias, dwg_w, dwg_b, B, N, h, trig, make_dim_mat(wave_len), ppc);
+  sc::launch_pdl_aux(box_bias_bwd_kernel, dim3(B, slices), dim3(256), 0, stream, boxes, bias, dbias, dwg_w, dwg_b, B, N, h, trig, make_dim_mat(wave_len), ppc);
   SC_LAUNCH_CHECK("sc_box_bias_bwd");
   return SC_OK;
 }

@@ -129,6 +129,8 @@ __device__ __forceinline__ void mma_pb(float (&o)[kDk / 8][4], const float (&p)[
 template <int NT>
 __global__ void __launch_bounds__(256) attn_train_fwd_mma_kernel(const TrainAttnArgs a) {
   extern __shared__ __align__(16) unsigned char smem_x[];
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int gi = blockIdx.x, hh = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x, nwarps = nthr >> 5;
   const int Tq = a.Tq, Tk = a.Tk;
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(256) attn_train_fwd_mma_kernel(const TrainAttn
 template <int NT>
 __global__ void __launch_bounds__(256) attn_train_bwd_mma_kernel(const TrainAttnArgs a) {
   extern __shared__ __align__(16) unsigned char smem_x[];
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int gi = blockIdx.x, hh = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x, nwarps = nthr >> 5;
   const int Tq = a.Tq, Tk = a.Tk;
@@ -393,7 +397,7 @@ int sc_attn_train_fwd_mma_launch(const void* q, const void* k, const void* v, in
       cudaFuncSetAttribute(attn_train_fwd_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
       attr = true;                                                                                                      \
     }                                                                                                                   \
-    attn_train_fwd_mma_kernel<NTV><<<grid, 32 * warps, smem, stream>>>(a);                                              \
+    sc::launch_pdl_aux(attn_train_fwd_mma_kernel<NTV>, grid, dim3(32 * warps), smem, stream, a);                                              \
   } break
   switch (NT) {
     F_CASE(1); F_CASE(2); F_CASE(3); F_CASE(4); F_CASE(5); F_CASE(6); F_CASE(7); F_CASE(8);
@@ -428,7 +432,7 @@ int sc_attn_train_bwd_mma_launch(const void* q, const void* k, const void* v, in
       cudaFuncSetAttribute(attn_train_bwd_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
       attr = true;                                                                                                      \
     }                                                                                                                   \
-    attn_train_bwd_mma_kernel<NTV><<<grid, 32 * warps, smem, stream>>>(a);                                              \
+    sc::launch_pdl_aux(attn_train_bwd_mma_kernel<NTV>, grid, dim3(32 * warps), smem, stream, a);                                              \
   } break
   switch (NT) {
     B_CASE(1); B_CASE(2); B_CASE(3); B_CASE(4); B_CASE(5); B_CASE(6); B_CASE(7); B_CASE(8);

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(256) prep_grad_vec_kernel(const float* __restr
                                                             unsigned long long seed, unsigned long long stream,
                                                             float* __restrict__ colsum) {
   __shared__ float4 s_cs[8][32];
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + tx * 4;
   const int r0 = blockIdx.y * 64 + ty;
@@ -468,6 +470,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd512_kernel(const float* __re
                                                                float* __restrict__ db, int rows, float eps) {
   constexpr int D = 512;
   __shared__ float4 s_part[2][8][128];
+  sc::pdl_launch();
+  sc::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   float4 pa[4], pb[4];
@@ -651,9 +655,9 @@ int sc_prep_grad(const float* g, const void* h, int h_dtype, void* out, void* ou
       ((uintptr_t)out & 7) == 0 && (colsum_accum == nullptr || ((uintptr_t)colsum_accum & 15) == 0)) {
     dim3 vgrid((cols + 127) / 128, (rows + 63) / 64);
     if (h_dtype == SC_BF16 && h != nullptr)
-      prep_grad_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, stream>>>(g, (const __nv_bfloat16*)h, (__nv_bfloat16*)out, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum);
+      sc::launch_pdl_aux(prep_grad_vec_kernel<__nv_bfloat16>, vgrid, dim3(256), 0, stream, g, (const __nv_bfloat16*)h, (__nv_bfloat16*)out, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum);
     else
-      prep_grad_vec_kernel<float><<<vgrid, 256, 0, stream>>>(g, (const float*)h, (__nv_bfloat16*)out, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum);
+      sc::launch_pdl_aux(prep_grad_vec_kernel<float>, vgrid, dim3(256), 0, stream, g, (const float*)h, (__nv_bfloat16*)out, rows, cols, scale, dropout_p, seed, stream_id, colsum_accum);
     SC_LAUNCH_CHECK("sc_prep_grad");
     return SC_OK;
   }
@@ -759,8 +763,8 @@ int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtyp
   if (D == 512 && ((((uintptr_t)x | (uintptr_t)a | (uintptr_t)dy | (uintptr_t)dres | (uintptr_t)dx | (uintptr_t)da | (uintptr_t)db) & 15) == 0) &&
       (dy_dtype == SC_F32 || dy_dtype == SC_BF16)) {
     const int nb = (rows + 7) / 8;
-    if (dy_dtype == SC_F32) layernorm_bwd512_kernel<float><<<nb, 256, 0, stream>>>(x, a, (const float*)dy, dres, dx, da, db, rows, eps);
-    else layernorm_bwd512_kernel<__nv_bfloat16><<<nb, 256, 0, stream>>>(x, a, (const __nv_bfloat16*)dy, dres, dx, da, db, rows, eps);
+    if (dy_dtype == SC_F32) sc::launch_pdl_aux(layernorm_bwd512_kernel<float>, dim3(nb), dim3(256), 0, stream, x, a, (const float*)dy, dres, dx, da, db, rows, eps);
+    else sc::launch_pdl_aux(layernorm_bwd512_kernel<__nv_bfloat16>, dim3(nb), dim3(256), 0, stream, x, a, (const __nv_bfloat16*)dy, dres, dx, da, db, rows, eps);
     SC_LAUNCH_CHECK("sc_layernorm_bwd");
     return SC_OK;
   }
