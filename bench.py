@@ -127,7 +127,7 @@ def train_arm(args, dev, world, rank, dist_mod=None):
         masks[r, :n + 2] = 1
     seqs, masks = seqs.pin_memory(), masks.pin_memory()
     opt = dict(lr=3e-4, sparsity_target=0.95, sparsity_weight=30.0, current_step=100, max_step=1000)
-    all_reduce = D.make_all_reduce()  # NCCL SUM over the flat weight + mask-logit gradient buffers when world > 1
+    all_reduce = D.make_all_reduce(async_op=True)  # NCCL SUM of the gradient buckets each backward phase finishes (world > 1)
     gtok = D.global_token_count(masks.to(dev), T)
 
     def step():
@@ -167,7 +167,7 @@ def train_arm(args, dev, world, rank, dist_mod=None):
     peaks = load_peaks()
     tf = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms else 0.0
     return {"metric": "smp_train_images_per_sec", "value": world * B / (ms / 1e3), "unit": "images/s", "n_gpus": world, "ms_per_step": ms,
-            "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce(sum) of flat fp32 weight+logit gradients after the backward, 2 calls/step",
+            "collective": "none (1 GPU)" if world == 1 else "NCCL all-reduce(sum) of fp32 weight+logit gradient buckets, started after each of the 4 backward phases (overlaps the next phase)",
             "images_per_gpu_per_step": B, "captions_per_image": S, "positions": T, "dtype": "bf16 GEMM / fp32 master+logits",
             "loss": float(loss), "gpu_launches_per_step": launches, "h2d_bytes_per_step": att.numel() * 4 + boxes.numel() * 4 + seqs.numel() * 8 + masks.numel() * 4,
             "includes": "H2D of the batch, Bernoulli masks, dropout, sparsity loss, clip + Adam (2 groups)",
@@ -176,14 +176,25 @@ def train_arm(args, dev, world, rank, dist_mod=None):
                          "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sus"], "share_of_step": gemm_ms / tot_ms if tot_ms else None}}
 
 
+def _claim_stdout():
+    """Route everything that libraries print on fd 1 (e.g. NCCL's version banner) to stderr; the returned file object
+    is the real stdout, used for the ONE JSON line of the driver contract."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=512, help="images per GPU per step")
-    ap.add_argument("--backend", default="dense", choices=["dense", "csr", "auto"])
+    ap.add_argument("--backend", default="dense", choices=["dense", "csr", "sell", "auto"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the SMP training arm (BASELINE.json configs[1])")
     ap.add_argument("--train-images", type=int, default=50, help="images per GPU per training step (5 captions each)")
@@ -215,7 +226,7 @@ def main():
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                            "sample": f"{steps} x {args.cpu_images} images, same model/beam/length, torch fp32 on host cores"},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out, flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
@@ -354,7 +365,7 @@ def main():
             _, M, N, Kd, xs, wsz, ys, _m = meta
             d["flops"] += 2.0 * M * N * Kd
             d["bytes"] += M * Kd * xs + N * Kd * wsz + M * N * ys
-        elif meta and meta[0] == "csr_spmm":
+        elif meta and meta[0] in ("csr_spmm", "sell_spmm"):
             _, M, N, Kd, xs, nnz, ys = meta
             d["flops"] += 2.0 * M * nnz
             d["bytes"] += M * Kd * xs + nnz * (xs + 2) + M * N * ys
@@ -382,7 +393,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "train": train}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

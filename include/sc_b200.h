@@ -78,6 +78,12 @@ int sc_csr_spmm(const void* x, int dtype, const int* row_ptr, const unsigned sho
                 const float* bias, const float* residual, void* y, int y_dtype, int M, int N, int K, int relu,
                 sc_stream_t stream);
 
+/* K3b' — the same product from SLICED-ELL weights (slab = 32 output features, entry i of feature 32 s + l at
+ * slab_ptr[s] + 32 i + l; slab widths are multiples of 4, padding entries are (column 0, value 0)).
+ * x bf16: entries uint32 = (column << 16) | bf16 bits; x fp32: entries {uint32 column, fp32 value}.  K <= 6400. */
+int sc_sell_spmm(const void* x, int dtype, const int* slab_ptr, const void* entries, const float* bias,
+                 const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, sc_stream_t stream);
+
 /* K9 — LayerNorm a*(x-mean)/(std_unbiased+eps)+b (models/transformer.py:329-341).  x fp32 [rows,D]. */
 int sc_layernorm(const float* x, const float* a, const float* b, void* y, int y_dtype, int rows, int D, float eps,
                  sc_stream_t stream);

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 900 python -m pytest tests/test_train_kernels_gpu.py tests/test_trainer_gpu.py tests/test_dropin_gpu.py -q -m gpu > gpurun_out/t_train.log 2>&1; echo "tests exit=$? $(tail -n 1 gpurun_out/t_train.log)"
+grep -E "^E  |Error|FAILED" gpurun_out/t_train.log | head -30
+for m in 0 1; do echo "pdl mask=$m: $(SC_WALL_ONLY=1 SC_PDL_MASK=$m python scripts/profile_train.py 2>&1 | tail -1)"; done
+echo "ring=1 (no side stream): $(SC_WALL_ONLY=1 SC_WGRAD_RING=1 python scripts/profile_train.py 2>&1 | tail -1)"
+echo "ring=2: $(SC_WALL_ONLY=1 SC_WGRAD_RING=2 python scripts/profile_train.py 2>&1 | tail -1)"

@@ -13,6 +13,8 @@ cfg = ModelCfg(dict(bench.CFG, max_seq_length=17))
 sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
 GRAPH = os.environ.get("SC_TRAIN_GRAPH", "1") == "1"
 tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888, use_graph=GRAPH)
+if "SC_WGRAD_RING" in os.environ:
+    tr.wgrad_ring = int(os.environ["SC_WGRAD_RING"])
 if "SC_PDL_MASK" in os.environ:
     tr.pdl_mask = int(os.environ["SC_PDL_MASK"])
 S, T = 5, 17

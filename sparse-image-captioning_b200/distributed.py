@@ -26,12 +26,16 @@ def global_token_count(masks: torch.Tensor, T: int, group=None) -> torch.Tensor:
     return cnt
 
 
-def make_all_reduce(group=None):
-    """Callable for OrtTrainer.train_step(all_reduce=...): in-place SUM over ranks of one flat gradient buffer."""
+def make_all_reduce(group=None, async_op=False):
+    """Callable for OrtTrainer.train_step(all_reduce=...): in-place SUM over ranks of one (slice of a) flat gradient
+    buffer.  ``async_op``: return the work handle instead of waiting, so that the trainer can overlap the exchange of
+    the buckets one backward phase finished with the next phase (OrtTrainer.grad_buckets); ``handle.wait()`` orders
+    the current CUDA stream after the collective (NCCL) or blocks the host (gloo)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
 
     def _ar(flat):
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return work if async_op else None
 
     return _ar

@@ -73,8 +73,14 @@ class _Lin:
         self.N, self.K = w.shape
         self.bias = None if b is None else b.detach().float().contiguous()
         self.sparsity = float((w == 0).sum()) / w.numel()
-        use_csr = backend == "csr" or (backend == "auto" and self.sparsity >= csr_threshold)
+        use_csr = backend == "csr"
+        # sliced-ELL (K3b'): the measured winner over the dense tensor-core GEMM at decode sizes from `csr_threshold` up
+        # ("K3a vs K3b"); its X tile [K][8] fp32 must fit in shared memory
+        use_sell = (backend == "sell" or (backend == "auto" and self.sparsity >= csr_threshold)) and self.K * 32 <= 200 * 1024 \
+            and self.K % 8 == 0
         self.csr = K.CsrWeight(w, adt) if use_csr else None
+        self.sell = K.SellWeight(w, adt) if use_sell else None
+        use_csr = use_csr or use_sell  # "not on the dense path"
         self.w = None
         if not use_csr:
             self.w = K.cast_bf16(w) if adt == torch.bfloat16 else w
@@ -94,6 +100,8 @@ class _Lin:
         return K.linear_ln(x, self.w, self.bias, residual=residual, relu=relu, out=out, out_bf16=out_bf16, stats_out=stats)
 
     def __call__(self, x, out, residual=None, relu=False):
+        if self.sell is not None:
+            return K.sell_spmm(x, self.sell, self.bias, residual=residual, relu=relu, out=out)
         if self.csr is not None:
             return K.csr_spmm(x, self.csr, self.bias, residual=residual, relu=relu, out=out)
         return K.linear(x, self.w, self.bias, residual=residual, relu=relu, out=out)
@@ -157,12 +165,13 @@ class OrtEngine:
 
     ``state_dict``: dense-class parameter names (``relation_transformer``); masked weights must already be folded
     (``prune.fold_masks`` does that on device).  ``precision``: "bf16" (tcgen05 tensor-core GEMMs, bf16 activations)
-    or "fp32" (fp32 verification kernels).  ``sparse_backend``: "dense" | "csr" | "auto" for the decoder linears
-    (K3a vs K3b); the encoder always runs the dense tensor path (M = B*N rows is large).
+    or "fp32" (fp32 verification kernels).  ``sparse_backend``: "dense" | "csr" | "sell" | "auto" for the decoder linears
+    (K3a vs K3b / K3b'; "auto" = sliced-ELL for tensors at or above ``csr_threshold`` sparsity); the encoder always runs
+    the dense tensor path (M = B*N rows is large).
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, precision="bf16", sparse_backend="dense",
-                 csr_threshold=0.97, device="cuda", use_graphs=True, no_history=False, ln_fold=False):
+                 csr_threshold=0.995, device="cuda", use_graphs=True, no_history=False, ln_fold=False):
         if not torch.cuda.is_available():
             raise RuntimeError("OrtEngine needs a CUDA device: the B200 path has no CPU fallback")
         lib.load()
@@ -257,7 +266,7 @@ class OrtEngine:
         self.generator = lin(["model.generator.proj"], be, norm="model.decoder.norm")
         # the folded decode path needs every decoder linear on the dense tensor path
         self.fold_dec = self.ln_fold and all(
-            e[k].csr is None for e in self.dec.values() for k in ("qkv", "o", "cq", "co", "ff1", "ff2")) and self.generator.csr is None
+            e[k].w is not None for e in self.dec.values() for k in ("qkv", "o", "cq", "co", "ff1", "ff2")) and self.generator.w is not None
         self._enc_ws = {}
         self._dec_ws = {}
         self._streams = {}

@@ -107,6 +107,67 @@ def csr_spmm(x, csr, bias=None, *, residual=None, relu=False, out=None, out_dtyp
     return out
 
 
+class SellWeight:
+    """Sliced-ELL form (slab = 32 output features) of a pruned [N,K] weight for sc_sell_spmm: ``slab_ptr`` int32
+    [slabs+1] in entries, ``entries`` int32 [total] = (column << 16) | bf16 bits, or int32 [total, 2] = {column, fp32 bits}
+    in fp32 mode.  Built once from the dense (already masked) tensor or the reference's COO ``to_sparse()`` tensors."""
+
+    def __init__(self, w, dtype):
+        if w.is_sparse:
+            w = w.to_dense()
+        w = w.detach().float()
+        N, K = w.shape
+        assert K <= 65536
+        dev = w.device
+        slabs = (N + 31) // 32
+        Np = slabs * 32
+        wp = torch.zeros(Np, K, device=dev)
+        wp[:N] = w
+        nz = wp != 0
+        counts = nz.sum(1)                                              # [Np]
+        width = counts.view(slabs, 32).max(1).values                    # widest row of each slab
+        width = ((width + 3) // 4 * 4).clamp_min(4)
+        slab_ptr = torch.zeros(slabs + 1, dtype=torch.int64, device=dev)
+        slab_ptr[1:] = torch.cumsum(width * 32, 0)
+        total = int(slab_ptr[-1])
+        # rank of every non-zero inside its row (columns ascending)
+        rows, cols = nz.nonzero(as_tuple=True)
+        row_start = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(rows.numel(), device=dev) - row_start[rows]
+        pos = slab_ptr[rows // 32] + rank * 32 + (rows % 32)
+        vals = wp[rows, cols]
+        if dtype == torch.bfloat16:
+            bits = vals.to(torch.bfloat16).view(torch.int16).to(torch.int64) & 0xFFFF
+            packed = (cols << 16) | bits
+            packed = torch.where(packed >= (1 << 31), packed - (1 << 32), packed)
+            ent = torch.zeros(total, dtype=torch.int64, device=dev)
+            ent[pos] = packed
+            self.entries = ent.to(torch.int32).contiguous()
+        else:
+            ent = torch.zeros(total, 2, dtype=torch.int32, device=dev)
+            ent[pos, 0] = cols.to(torch.int32)
+            ent[pos, 1] = vals.contiguous().view(torch.int32)
+            self.entries = ent.contiguous()
+        self.slab_ptr = slab_ptr.to(torch.int32).contiguous()
+        self.shape = (N, K)
+        self.dtype = dtype
+        self.nnz = int(rows.numel())
+        self.padded = total
+
+
+def sell_spmm(x, sw, bias=None, *, residual=None, relu=False, out=None, out_dtype=None):
+    M, K = x.shape
+    N = sw.shape[0]
+    assert sw.shape[1] == K and sw.dtype == x.dtype
+    _chk(x, "x")
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype or torch.float32)
+    lib.call("sc_sell_spmm", lib.ptr(x), lib.dtype_code(x.dtype), lib.ptr(sw.slab_ptr), lib.ptr(sw.entries), lib.ptr(bias),
+             lib.ptr(residual), lib.ptr(out), lib.dtype_code(out.dtype), M, N, K, int(relu), lib.stream(),
+             meta=("sell_spmm", M, N, K, x.element_size(), sw.nnz, out.element_size()))
+    return out
+
+
 def layernorm(x, a, b, *, eps=1e-6, out=None, out_dtype=None):
     rows, D = x.shape
     _chk(x, "x")

@@ -144,7 +144,9 @@ class OrtTrainer:
         self.premask = True   # False: mask inside the GEMM operand prologue (K1 fused variant)
         self._wm, self._wmT, self._wm_step = {}, {}, {}
         self._premask_desc = None
-        self.pdl_mask = 0
+        self.pdl_mask = 2            # sc_set_pdl mask while the step is launched / captured (see train_step)
+        self.wgrad_ring = 4          # 1: weight gradients stay on the main stream
+        self._side = None
 
     # ---------------------------------------------------------------------------------------------------------
     def _group(self, table, first, count):
@@ -284,6 +286,11 @@ class OrtTrainer:
         # backward scratch
         nmax = max(self.Vp, ff, 3 * d, F)
         ws.gb = torch.zeros(max(ME, MD) * max(ff, 3 * d), **a)         # grad operand [M, N]
+        # bf16: the weight-gradient GEMMs (+ their split-K reductions) run on a side stream next to the dX chain; the
+        # gradient operand they read lives in a ring so that the next layers can already overwrite "their" buffer
+        ws.gb_ring = [ws.gb] + [torch.zeros_like(ws.gb) for _ in range(self.wgrad_ring - 1)] if self._side_wgrad() else [ws.gb]
+        ws.gb_free = [None] * len(ws.gb_ring)   # event: the side-stream consumer of ring slot i has finished
+        ws.gb_next = 0
         ws.gT = torch.zeros(nmax * Mp, **a)                            # grad operand transposed [N, Mp]
         ws.xT = torch.zeros(max(ff, F, d) * Mp, **a)                   # activation transposed [K, Mp]
         ws.wT = torch.zeros(max(self.Vp * d, ff * d, F * d, 3 * d * d), **a)  # (W.m)^T [K, N]
@@ -300,6 +307,14 @@ class OrtTrainer:
         ws.wgrad_ws = torch.zeros(max(8 * max(ff * d, F * d, 3 * d * d), 2 * self.Vp * d), **f32)
         self._ws[key] = ws
         return ws
+
+    def _side_wgrad(self):
+        return self.adt == torch.bfloat16 and self.wgrad_ring > 1
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.dev)
+        return self._side
 
     # ---- linear forward / backward helpers ------------------------------------------------------------------
     def _lin(self, wname, x, out, *, count=1, relu=False, residual=None, p=0.0, site=0, bias=True):
@@ -343,6 +358,8 @@ class OrtTrainer:
         # bf16: the weight-gradient GEMM reads dy [M,N] and x [M,K] as MN-major tiles - no transposed copies, no padding
         rowmajor = self.adt == torch.bfloat16 and N % 8 == 0 and Kd % 8 == 0
         gT = None if rowmajor else ws.gT[: N * Mp].view(N, Mp)
+        side = rowmajor and len(ws.gb_ring) > 1
+        slot = None
         if g_ready is not None:
             gb = g_ready
             if not rowmajor:
@@ -352,7 +369,14 @@ class OrtTrainer:
             if gbias is not None:
                 K.colsum(gb, gbias)
         else:
-            gb = ws.gb[: M * N].view(M, N)
+            if side:
+                slot = ws.gb_next
+                ws.gb_next = (slot + 1) % len(ws.gb_ring)
+                if ws.gb_free[slot] is not None:
+                    torch.cuda.current_stream(self.dev).wait_event(ws.gb_free[slot])
+                gb = ws.gb_ring[slot][: M * N].view(M, N)
+            else:
+                gb = ws.gb[: M * N].view(M, N)
             if not rowmajor and Mp != M:
                 gT[:, M:].zero_()
             # the bias gradient (column sums) is accumulated by the same pass (flat_gw is zeroed at the start of the backward)
@@ -366,6 +390,20 @@ class OrtTrainer:
             K.linear(gb, wT, None, residual=dx_residual, out=dx)
         gW = self._group(self.g, wname, count)
         gS = self._group(self.gs, wname, count) if S is not None else None
+        if side:
+            # fork after the gradient operand exists (the dX GEMM above only reads it), join before the optimizer
+            main, st = torch.cuda.current_stream(self.dev), self._side_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                K.linear_wgrad_rowmajor(gb, x_saved, W, S, mode, gW, gS, workspace=ws.wgrad_ws, uniforms=U, seed=seed,
+                                        stream_id=stream, bypass=self.bypass)
+                if slot is not None:
+                    ws.gb_free[slot] = torch.cuda.Event()
+                    ws.gb_free[slot].record(st)
+            ws.side_used = True
+            return
         if rowmajor:
             K.linear_wgrad_rowmajor(gb, x_saved, W, S, mode, gW, gS, workspace=ws.wgrad_ws, uniforms=U, seed=seed, stream_id=stream,
                                     bypass=self.bypass)
@@ -471,22 +509,73 @@ class OrtTrainer:
 
     def loss_and_backward(self, ws):
         """LanguageModelCriterion + full backward; gradients land in flat_gw / flat_gs (overwritten, not accumulated)."""
+        for phase in range(self.N_PHASES):
+            self.backward_phase(ws, phase)
+        return ws.loss_sum
+
+    # The backward in three phases whose gradients are final when the phase ends, so that a data-parallel run can start
+    # the all-reduce of a finished bucket while the next phase computes (grad_buckets):
+    #   0: loss, generator, decoder norm, decoder layers L-1 .. L/2     1: decoder layers L/2-1 .. 0, embedding
+    #   2: encoder norm, encoder layers L-1 .. L/2                      3: encoder layers L/2-1 .. 0, att_embed
+    N_PHASES = 4
+
+    def grad_buckets(self, phase):
+        """[(flat gradient buffer, start, end)] of the parameter ranges whose gradients are final after `phase`."""
+        L = self.cfg.num_layers
+        half = L // 2
+        def rng(offs, keys, first, last):
+            # [offset of `first`, offset of `last`) in a layout; names that are not in the layout (norms / biases in the
+            # logit layout) move forward to the next name that is
+            def at(name):
+                if name is None:
+                    return None
+                i = self.names.index(name)
+                while i < len(self.names) and self.names[i] not in offs:
+                    i += 1
+                return offs[self.names[i]] if i < len(self.names) else None
+            return at(first), at(last)
+        dec0, dech = "model.decoder.layers.0.self_attn.linears.0.weight", f"model.decoder.layers.{half}.self_attn.linears.0.weight"
+        lut, gen = "model.tgt_embed.0.lut.weight", "model.generator.proj.weight"
+        ench = f"model.encoder.layers.{half}.self_attn.linears.0.weight"
+        spans = {0: [(dech, lut), (gen, None)], 1: [(dec0, dech), (lut, gen)], 2: [(ench, dec0)], 3: [(self.names[0], ench)]}[phase]
+        out = []
+        for flat, offs in ((self.flat_gw, self._offs_w), (self.flat_gs, self._offs_s) if self.masked else (None, None)):
+            if flat is None:
+                continue
+            for first, last in spans:
+                a, b = rng(offs, None, first, last)
+                a = 0 if a is None else a
+                b = flat.numel() if b is None else b
+                if b > a:
+                    out.append((flat, a, b))
+        return out
+
+    def backward_phase(self, ws, phase):
         c = self.cfg
         B, N, S, T, ME, MD, R = ws.B, ws.N, ws.S, ws.T, ws.ME, ws.MD, ws.R
         d, h, L, ff = c.d_model, c.num_heads, c.num_layers, c.dim_feedforward
         dk = d // h
         pd = self.p_drop if self.training else 0.0
         trig = not c.no_box_trigonometric_embedding
-        # norm and bias gradients accumulate through atomics: one memset of the flat buffer (weights are overwritten)
-        self.flat_gw.zero_()
-        ws.loss_sum.zero_()
-        K.logsoftmax_nll(ws.logits, ws.targets, ws.tok_w, ws.inv_norm, ws.loss_sum, ws.dlogits)
-        ga_d = ws.ga.view(-1)[: MD * d].view(MD, d)
-        self._lin_bwd(ws, "model.generator.proj.weight", ws.yf, None, g_ready=ws.dlogits, dx=ga_d)
-        cur, nxt = ws.dres[0][:MD], ws.dres[1][:MD]
-        self._ln_bwd("model.decoder.norm", ws.y[3 * L], ga_d, cur)
-        ws.dmem.zero_()
-        for l in reversed(range(L)):
+        ws.gb_free = [None] * len(ws.gb_ring)
+        ws.gb_next = 0
+        ws.side_used = False
+        half = L // 2
+        if phase == 0:
+            # norm and bias gradients accumulate through atomics: one memset of the flat buffer (weights are overwritten)
+            self.flat_gw.zero_()
+            ws.loss_sum.zero_()
+            K.logsoftmax_nll(ws.logits, ws.targets, ws.tok_w, ws.inv_norm, ws.loss_sum, ws.dlogits)
+            ga_d = ws.ga.view(-1)[: MD * d].view(MD, d)
+            self._lin_bwd(ws, "model.generator.proj.weight", ws.yf, None, g_ready=ws.dlogits, dx=ga_d)
+            ws.cur = 0
+            self._ln_bwd("model.decoder.norm", ws.y[3 * L], ga_d, ws.dres[0][:MD])
+            ws.dmem.zero_()
+        if phase >= 2:
+            self._backward_encoder(ws, phase - 2)
+            return
+        cur, nxt = ws.dres[ws.cur][:MD], ws.dres[1 - ws.cur][:MD]
+        for l in (reversed(range(half, L)) if phase == 0 else reversed(range(half))):
             p = f"model.decoder.layers.{l}"
             y0, y1, y2 = ws.y[3 * l], ws.y[3 * l + 1], ws.y[3 * l + 2]
             ga_ff = ws.ga.view(-1)[: MD * ff].view(MD, ff)
@@ -521,6 +610,10 @@ class OrtTrainer:
             self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], gq, count=3, dx=ga_s2)
             self._ln_bwd(f"{p}.sublayer.0.norm", y0, ga_s2, nxt, dres=cur)
             cur, nxt = nxt, cur
+        ws.cur = 0 if cur.data_ptr() == ws.dres[0].data_ptr() else 1
+        if phase == 0:
+            self._join_side(ws)
+            return
         # embedding: dropout mask is recoverable from the saved output (dropped entries are exact zeros)
         W, S_, mode, U, seed, stream = self._mask_args("model.tgt_embed.0.lut.weight")
         emb_g = ws.ga.view(-1)[: MD * d].view(MD, d)
@@ -532,10 +625,27 @@ class OrtTrainer:
         K.embedding_bwd(ws.tokens, emb_g, ws.dtable, math.sqrt(d))
         K.mask_grad(ws.dtable, W, S_, mode, self.g["model.tgt_embed.0.lut.weight"],
                     self.gs.get("model.tgt_embed.0.lut.weight"), uniforms=U, seed=seed, stream_id=stream, bypass=self.bypass)
-        # ---- encoder ----
-        cur, nxt = ws.dres[0][:ME], ws.dres[1][:ME]
-        self._ln_bwd("model.encoder.norm", ws.xe[2 * L], ws.dmem, cur)
-        for l in reversed(range(L)):
+        self._join_side(ws)
+
+    def _join_side(self, ws):
+        if ws.side_used:
+            torch.cuda.current_stream(self.dev).wait_stream(self._side_stream())
+            ws.side_used = False
+
+    def _backward_encoder(self, ws, part):
+        """part 0: encoder norm + layers L-1 .. L/2 ; part 1: layers L/2-1 .. 0 + att_embed."""
+        c = self.cfg
+        B, N, S, T, ME, MD, R = ws.B, ws.N, ws.S, ws.T, ws.ME, ws.MD, ws.R
+        d, h, L, ff = c.d_model, c.num_heads, c.num_layers, c.dim_feedforward
+        dk = d // h
+        pd = self.p_drop if self.training else 0.0
+        trig = not c.no_box_trigonometric_embedding
+        half = L // 2
+        if part == 0:
+            ws.cur = 0
+            self._ln_bwd("model.encoder.norm", ws.xe[2 * L], ws.dmem, ws.dres[0][:ME])
+        cur, nxt = ws.dres[ws.cur][:ME], ws.dres[1 - ws.cur][:ME]
+        for l in (reversed(range(half, L)) if part == 0 else reversed(range(half))):
             p = f"model.encoder.layers.{l}"
             x0, x1 = ws.xe[2 * l], ws.xe[2 * l + 1]
             ga_ff = ws.ga.view(-1)[: ME * ff].view(ME, ff)
@@ -563,10 +673,14 @@ class OrtTrainer:
             self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], gq, count=3, dx=ga_a2)
             self._ln_bwd(f"{p}.sublayer.0.norm", x0, ga_a2, nxt, dres=cur)
             cur, nxt = nxt, cur
+        ws.cur = 0 if cur.data_ptr() == ws.dres[0].data_ptr() else 1
+        if part == 0:
+            self._join_side(ws)
+            return
         if ws.att_mask is not None:
             K.mask_rows(cur, ws.att_mask.view(-1))
         self._lin_bwd(ws, "att_embed.0.weight", ws.att_a, cur, h=ws.xe[0], p=self.p_src if self.training else 0.0)
-        return ws.loss_sum
+        self._join_side(ws)
 
     # ---------------------------------------------------------------------------------------------------------
     def optimizer_step(self, *, lr, mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0,
@@ -614,8 +728,20 @@ class OrtTrainer:
         if part in ("all", "fwdbwd"):
             self.forward(ws)
             self.loss_and_backward(ws)
+        if part == "fwd_p0":
+            self.forward(ws)
+            self.backward_phase(ws, 0)
+        if part in ("p1", "p2", "p3"):
+            self.backward_phase(ws, int(part[1]))
         if part in ("all", "opt"):
             self.optimizer_step(_dyn=True, **opt)
+
+    def _exchange(self, all_reduce, phase, handles):
+        """Start the all-reduce of every gradient bucket that `phase` finished (async: the next phase overlaps it)."""
+        for flat, a, b in self.grad_buckets(phase):
+            h = all_reduce(flat[a:b])
+            if h is not None:
+                handles.append(h)
 
     def _run_graphed(self, ws, part, opt):
         key = (part, tuple(sorted((k, float(v)) for k, v in opt.items() if k in ("clip", "eps", "mask_eps", "weight_decay",
@@ -639,8 +765,8 @@ class OrtTrainer:
 
     def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None, **opt):
         """One full SMP step.  ``all_reduce``: callable applied to the flat gradient buffers (NCCL sum) when data-parallel."""
-        # programmatic dependent launch measured SLOWER on the training chain (6.82 vs 6.38 ms/step with it on the GEMMs,
-        # neutral on the row / attention kernels; scripts/gpu_pdl_ab.sh): the step is launched / captured without it
+        # programmatic dependent launch on the GEMMs measured SLOWER on the training chain, on the row / attention kernels
+        # slightly faster (ms/step, side-stream weight gradients on: mask 0 6.22, 1 6.09, 2 5.91, 3 6.08; scripts/gpu_sell.sh)
         prev_pdl = K.set_pdl(self.pdl_mask)
         try:
             return self._train_step(att_feats, boxes, seqs, masks, att_masks, seq_per_img=seq_per_img, lr=lr, all_reduce=all_reduce,
@@ -660,18 +786,25 @@ class OrtTrainer:
             if all_reduce is None:
                 self._run_graphed(ws, "all", opt)
             else:
-                self._run_graphed(ws, "fwdbwd", opt)
-                all_reduce(self.flat_gw)
-                if self.masked:
-                    all_reduce(self.flat_gs)
+                # one graph per backward phase; the buckets a phase finished are exchanged while the next one computes
+                handles = []
+                for phase, part in enumerate(("fwd_p0", "p1", "p2", "p3")):
+                    self._run_graphed(ws, part, opt)
+                    self._exchange(all_reduce, phase, handles)
+                for h in handles:
+                    h.wait()
                 self._run_graphed(ws, "opt", opt)
             return ws.loss_sum * ws.inv_norm
         self.forward(ws)
-        self.loss_and_backward(ws)
-        if all_reduce is not None:
-            all_reduce(self.flat_gw)
-            if self.masked:
-                all_reduce(self.flat_gs)
+        if all_reduce is None:
+            self.loss_and_backward(ws)
+        else:
+            handles = []
+            for phase in range(self.N_PHASES):
+                self.backward_phase(ws, phase)
+                self._exchange(all_reduce, phase, handles)
+            for h in handles:
+                h.wait()
         self.optimizer_step(lr=lr, **opt)
         return ws.loss_sum * ws.inv_norm
 

@@ -49,9 +49,14 @@ def _worker(rank, world, port, out):
     T = z["seqs"].shape[1] - 1
     denom = D.global_token_count(z["masks"][lo * 2: hi * 2], T)
     gw, gs = _grads(z, lo, hi, denom)
+    # weights: bucketed + asynchronous (what OrtTrainer does per backward phase); logits: one blocking call
+    ar_async = D.make_all_reduce(async_op=True)
+    cut = gw.numel() // 3
+    handles = [ar_async(gw[:cut]), ar_async(gw[cut:])]
+    for h in handles:
+        h.wait()
     ar = D.make_all_reduce()
-    ar(gw)
-    ar(gs)
+    assert ar(gs) is None
     if rank == 0:
         torch.save({"gw": gw, "gs": gs, "denom": denom}, out)
     dist.barrier()

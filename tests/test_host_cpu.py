@@ -149,3 +149,27 @@ def test_masked_layer_attributes_and_cpu_refusal():
         lin(torch.zeros(2, 16))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         emb(torch.zeros(2, dtype=torch.long))
+
+
+def test_gradient_buckets_partition_the_flat_buffers():
+    """Data-parallel exchange: the buckets of the three backward phases are disjoint and cover every weight and
+    mask-logit gradient exactly once (OrtTrainer.grad_buckets; layout logic only, no kernel runs on the CPU)."""
+    import torch
+    from oracle import ort_oracle as O
+    from sparse_caption_b200.engine import ModelCfg
+    from sparse_caption_b200.trainer import OrtTrainer
+    for L in (1, 2, 3, 6):
+        cfg = dict(d_model=32, dim_feedforward=64, num_layers=L, num_heads=4, max_seq_length=8, att_feat_size=48, vocab_size=37)
+        sd = O.random_state_dict(O.Cfg(**cfg), seed=3, sparsity=0.0)
+        tr = OrtTrainer(sd, ModelCfg(cfg), mask_type="supermask", precision="fp32", device="cpu")
+        for flat in (tr.flat_gw, tr.flat_gs):
+            cover = torch.zeros(flat.numel(), dtype=torch.int32)
+            for phase in range(tr.N_PHASES):
+                for f, a, b in tr.grad_buckets(phase):
+                    if f is flat:
+                        assert 0 <= a < b <= flat.numel()
+                        cover[a:b] += 1
+            assert int(cover.min()) == 1 and int(cover.max()) == 1, (L, cover.unique())
+        # phase 0 must contain the generator, the last phase the first (att_embed) weight
+        assert any(f is tr.flat_gw and b == tr.flat_gw.numel() for f, a, b in tr.grad_buckets(0))
+        assert any(f is tr.flat_gw and a == 0 for f, a, b in tr.grad_buckets(tr.N_PHASES - 1))

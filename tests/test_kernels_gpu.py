@@ -366,6 +366,27 @@ def test_csr_spmm(K, dt, shape):
     assert rel_err(y, ref) < 2e-5
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(1536, 512, 512, 0.95), (100, 771, 512, 0.99), (300, 512, 2048, 0.9), (20, 64, 96, 0.5),
+                                   (1, 10000, 512, 0.95)])
+def test_sell_spmm(K, dt, shape):
+    """Sliced-ELL product (K3b'): ragged rows, an empty feature row, N not a multiple of the 32-feature slab, M not a
+    multiple of the 8-row tile; fp32 accumulation of exactly representable operands -> 2e-5."""
+    M, N, Kd, sp = shape
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=4)
+    w = w * (torch.rand(N, Kd) >= sp)
+    w[min(3, N - 1)] = 0  # an empty row
+    dev = "cuda"
+    sw = K.SellWeight(w.to(dt).float().to(dev), dt)
+    assert sw.nnz == int((w.to(dt) != 0).sum())
+    for out_dt in (torch.float32, torch.bfloat16):
+        y = K.sell_spmm(x.to(dt).to(dev), sw, b.to(dev), residual=r.to(dev), relu=True, out_dtype=out_dt)
+        ref = torch.relu(torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double(), b.double())) + r.double()
+        assert rel_err(y.float(), ref) < (2e-5 if out_dt == torch.float32 else 1e-2)
+    y2 = K.sell_spmm(x.to(dt).to(dev), sw, None)
+    assert rel_err(y2, torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double())) < 2e-5
+
+
 def _beam_ref(logits, B, beam, V, L, eos, opt):
     """Drive oracle.beam_select + the bookkeeping of oracle.beam_search on a fixed logits sequence."""
     pen = O.length_penalty(opt.get("length_penalty", ""))
