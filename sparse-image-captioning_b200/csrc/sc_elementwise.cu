@@ -134,7 +134,19 @@ __global__ void __launch_bounds__(256) apply_mask_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) mask_count_kernel(const float* __restrict__ s, size_t n, unsigned long long* out) {
   unsigned int c = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  // 16-byte loads, four in flight per thread (the scalar loop ran at a third of the HBM rate); s is 16-byte aligned
+  const size_t n4 = ((uintptr_t)s & 15) == 0 ? n / 4 : 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = g + u * stride < n4 ? __ldg((const float4*)s + g + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      c += (v[u].x > SC_BINARIZE_THRESHOLD) + (v[u].y > SC_BINARIZE_THRESHOLD) + (v[u].z > SC_BINARIZE_THRESHOLD) +
+           (v[u].w > SC_BINARIZE_THRESHOLD);
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     c += s[i] > SC_BINARIZE_THRESHOLD ? 1u : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);

@@ -50,12 +50,15 @@ class OrtTrainer:
         d, L = cfg.d_model, cfg.num_layers
         sd = state_dict
         # ---- parameter layout: fused groups are contiguous so that [q;k;v] / [k;v] / WG blocks are single views ----
-        order = ["att_embed.0.weight", "att_embed.0.bias"]
+        # the one-element WG biases of ALL encoder layers come first, contiguous: the geometry bias of every layer is then
+        # one kernel (sc_box_bias_all) over a single [L*h] bias vector
+        order = [f"model.encoder.layers.{i}.self_attn.WGs.{j}.bias" for i in range(L) for j in range(cfg.num_heads)]
+        order += ["att_embed.0.weight", "att_embed.0.bias"]
         for i in range(L):
             p = f"model.encoder.layers.{i}"
             order += [f"{p}.self_attn.linears.{j}.weight" for j in range(3)] + [f"{p}.self_attn.linears.{j}.bias" for j in range(3)]
             order += [f"{p}.self_attn.linears.3.weight", f"{p}.self_attn.linears.3.bias"]
-            order += [f"{p}.self_attn.WGs.{j}.weight" for j in range(cfg.num_heads)] + [f"{p}.self_attn.WGs.{j}.bias" for j in range(cfg.num_heads)]
+            order += [f"{p}.self_attn.WGs.{j}.weight" for j in range(cfg.num_heads)]
             order += [f"{p}.feed_forward.w_1.weight", f"{p}.feed_forward.w_1.bias", f"{p}.feed_forward.w_2.weight", f"{p}.feed_forward.w_2.bias"]
             order += [f"{p}.sublayer.{j}.norm.{ab}" for j in range(2) for ab in ("a_2", "b_2")]
         order += ["model.encoder.norm.a_2", "model.encoder.norm.b_2"]
@@ -261,12 +264,19 @@ class OrtTrainer:
         ws.xe = [torch.zeros(ME, d, **f32) for _ in range(2 * L + 1)]
         ws.e_xn1 = [torch.zeros(ME, d, **a) for _ in range(L)]
         ws.e_qkv = [torch.zeros(ME, 3 * d, **a) for _ in range(L)]
-        ws.e_bias = [torch.zeros(B, h, N, N, **f32) for _ in range(L)]
+        ws.e_bias_all = torch.zeros(L, B, h, N, N, **f32)
+        ws.e_bias = [ws.e_bias_all[l] for l in range(L)]
         ws.e_probs = [torch.zeros(B, h, N, N, **f32) for _ in range(L)]
         ws.e_att = [torch.zeros(ME, d, **a) for _ in range(L)]
         ws.e_xn2 = [torch.zeros(ME, d, **a) for _ in range(L)]
         ws.e_hid = [torch.zeros(ME, ff, **a) for _ in range(L)]
-        ws.wg_eff = [torch.zeros(h, 64 if not c.no_box_trigonometric_embedding else 4, **f32) for _ in range(L)]
+        dim_g = 64 if not c.no_box_trigonometric_embedding else 4
+        ws.wg_eff_all = torch.zeros(L * h, dim_g, **f32)
+        ws.wg_eff = [ws.wg_eff_all[l * h: (l + 1) * h] for l in range(L)]
+        # all WG biases as one [L*h] view when the layout packed them without padding (h % 4 == 0)
+        b0 = self._offs_w["model.encoder.layers.0.self_attn.WGs.0.bias"]
+        packed = all(self._offs_w[f"model.encoder.layers.{l}.self_attn.WGs.{j}.bias"] == b0 + l * h + j for l in range(L) for j in range(h))
+        ws.wg_b_all = self.flat_w[b0: b0 + L * h] if packed else None
         ws.mem = torch.zeros(ME, d, **a)
         ws.memkv = [torch.zeros(ME, 2 * d, **a) for _ in range(L)]
         ws.y = [torch.zeros(MD, d, **f32) for _ in range(3 * L + 1)]
@@ -454,19 +464,24 @@ class OrtTrainer:
         self._lin("att_embed.0.weight", ws.att_a, ws.xe[0], relu=True, p=self.p_src, site=1)
         if ws.att_mask is not None:
             K.mask_rows(ws.xe[0], ws.att_mask.view(-1))
+        # effective (masked) WG weights of every layer, then the log-geometry bias of all layers and heads in ONE pass over
+        # the box pairs (the sin/cos embedding only depends on the boxes; the reference rebuilds it in each layer)
+        for l in range(L):
+            Wg, Sg, mode, U, seed, stream = self._mask_args(f"model.encoder.layers.{l}.self_attn.WGs.0.weight", h)
+            if Sg is None:
+                ws.wg_eff[l].copy_(Wg)
+            else:
+                K.apply_mask(Wg, Sg, mode, uniforms=U, seed=seed, stream_id=stream, out=ws.wg_eff[l])
+        if ws.wg_b_all is not None:
+            K.box_bias_all(ws.boxes, ws.wg_eff_all, ws.wg_b_all, ws.e_bias_all, B=B, N=N, layers=L, h=h, trig=trig)
         for l in range(L):
             p = f"model.encoder.layers.{l}"
             x0, x1, x2 = ws.xe[2 * l], ws.xe[2 * l + 1], ws.xe[2 * l + 2]
             self._ln(f"{p}.sublayer.0.norm", x0, ws.e_xn1[l])
             self._lin(f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], ws.e_qkv[l], count=3)
-            # effective (masked) WG weights, then the log-geometry bias for all heads
-            Wg, Sg, mode, U, seed, stream = self._mask_args(f"{p}.self_attn.WGs.0.weight", h)
-            if Sg is None:
-                ws.wg_eff[l].copy_(Wg)
-            else:
-                K.apply_mask(Wg, Sg, mode, uniforms=U, seed=seed, stream_id=stream, out=ws.wg_eff[l])
-            K.box_bias_fwd(ws.boxes, ws.wg_eff[l], self._group(self.p, f"{p}.self_attn.WGs.0.bias", h), ws.e_bias[l], B=B, N=N, h=h,
-                           trig=trig)
+            if ws.wg_b_all is None:
+                K.box_bias_fwd(ws.boxes, ws.wg_eff[l], self._group(self.p, f"{p}.self_attn.WGs.0.bias", h), ws.e_bias[l], B=B, N=N,
+                               h=h, trig=trig)
             q = ws.e_qkv[l]
             K.attention_fwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_att[l], ws.e_probs[l], G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d,
                             ldk=3 * d, ldv=3 * d, ldo=d, key_valid=ws.att_mask, bias=ws.e_bias[l], p=pd, seed=self._sd(2),
