@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--no-train-graph", action="store_true", help="diagnostic: eager launches instead of the captured training graph")
     ap.add_argument("--cpu-images", type=int, default=64)
     ap.add_argument("--ln-fold", action="store_true", help="LayerNorm folded into the consuming GEMMs (sc_linear_ln) instead of separate LayerNorm kernels")
+    ap.add_argument("--no-fuse-topk", action="store_true", help="diagnostic: materialise the logits (sc_linear + sc_beam_step) instead of the fused generator + beam row pass")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostic: disable programmatic dependent launch")
     ap.add_argument("--slots", type=int, default=4, help="batches in flight (pipeline slots: stream + workspaces + graphs each)")
     args = ap.parse_args()
@@ -249,7 +250,8 @@ def main():
         _K.set_pdl(False)
     cfg = ModelCfg(CFG)
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=SPARSITY, device=dev)
-    eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold)
+    eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold,
+                    fuse_topk=not args.no_fuse_topk)
     B = args.images
     # two distinct pinned host batches, alternated
     host = [synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
@@ -350,7 +352,7 @@ def main():
     # ---------------- roofline leg: one instrumented step without graphs ----------------
     peaks = load_peaks()
     eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False,
-                     ln_fold=args.ln_fold)
+                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk)
     enc2 = eng2.encode(host[0][0], host[0][1])
     eng2.decode(enc2, opt)
     torch.cuda.synchronize(dev)
@@ -391,8 +393,12 @@ def main():
         w = torch.randn(N, Kd, device=dev).bfloat16()
         bias = torch.randn(N, device=dev)
         res = torch.randn(M, N, device=dev) if has_res else None
-        outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(4)]
-        run = lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs[i % 4])
+        if ys == 0:  # generator fused with the beam row pass: no output tile, 12-float records per (row, tile half)
+            part = torch.empty(M, KK.linear_topk_parts(N), 12, device=dev)
+            run = lambda i: KK.linear_topk(x, w, bias, part)
+        else:
+            outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(4)]
+            run = lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs[i % 4])
         run(0)
         torch.cuda.synchronize(dev)
         gr = torch.cuda.CUDAGraph()

@@ -69,6 +69,19 @@ int sc_linear_ln(const void* x, const void* w, const float* bias, const float* r
                              tile_n, &ex, stream);
 }
 
+// Generator fused with the row pass of the beam step (models/transformer.py:405-413 OutputEmbedding +
+// models/caption_model.py:56-111 beam_step): the [M, N] logits are never written.  For every row and every (256-column
+// tile, epilogue-warp half) the GEMM epilogue leaves one record of 12 floats {max, sum exp(x - max), 5 largest logits,
+// their column indices (int bits)} in partials [M][sc_linear_topk_parts(N)][12]; sc_beam_step_partials reduces them.
+int sc_linear_topk_parts(int N) { return 2 * ((N + 255) / 256); }
+int sc_linear_topk(const void* x, const void* w, const float* bias, int M, int N, int K, float* partials, cudaStream_t stream) {
+  SC_CHECK(partials != nullptr && ((uintptr_t)partials & 3) == 0, SC_ERR_ALIGN, "sc_linear_topk: partials missing");
+  ScGemmExtra ex = {};
+  ex.topk_part = partials;
+  return sc_gemm_bf16_launch(x, w, SC_BF16, nullptr, SC_MASK_NONE, nullptr, 0, 0, bias, nullptr, nullptr, SC_F32, M, N, K, 0, 0, &ex,
+                             stream);
+}
+
 // training forward: y = dropout(act(x (W.m)^T + b), p) + residual, dropout mask = Philox(drop_seed, drop_stream, element)
 int sc_linear_dropout(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
                       const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,

@@ -54,6 +54,8 @@ struct ScGemmExtra {
   int partial_splits; size_t split_stride;
   // operands given as x [K, M] and w [K, N] row-major (y = x^T w): MN-major UMMA tiles, no transposed copies
   int mn_major;
+  // generator fused with the beam step's row pass (kEpi == 3): [M][2 * ceil(N / 256)][12] records, no output tile
+  float* topk_part;
 };
 
 // Programmatic dependent launch (griddepcontrol): kernels launched through sc::launch_pdl may start while their

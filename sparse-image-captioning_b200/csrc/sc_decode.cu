@@ -293,6 +293,8 @@ struct BeamArgs {
   int* tokens_out;                        // [B*beam] token fed at step t+1
   // finished beams: running top-`beam` per image
   int* done_seq; float* done_lp; double* done_p; int* done_count;  // [B,beam,L] [B,beam,L] [B,beam] [B]
+  // fused generator (sc_beam_step_partials): logits == nullptr; the raw logit of candidate j of row r is ws_raw[r*beam + j]
+  const float* ws_raw;
 };
 
 __device__ __forceinline__ float block_max(float v, float* s_red) {
@@ -465,6 +467,75 @@ __global__ void __launch_bounds__(kBeamThreads, 4) beam_row_kernel(const BeamArg
   }
 }
 
+// Phase A for the fused generator (sc_linear_topk): one WARP per row reduces the row's P records
+// {max, sum exp(x - max), kPartTopK largest logits, their columns} to the log-softmax statistics and the row's top-NB
+// candidates (same outputs as beam_row_kernel, plus the raw logit of each candidate for the merge kernel).
+constexpr int kPartTopK = 5;
+constexpr int kPartRec = 2 + 2 * kPartTopK;
+template <int NB>
+__global__ void __launch_bounds__(256) beam_row_partials_kernel(const BeamArgs a, const float* __restrict__ part, int P,
+                                                                float* __restrict__ ws_stats, Cand* __restrict__ ws_cand,
+                                                                float* __restrict__ ws_raw) {
+  sc::pdl_launch();
+  sc::pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.B * NB) return;
+  const int k = r % NB;
+  if (a.t == 0 && k != 0) return;  // first step: only beam 0 is expanded
+  const float* pr = part + (size_t)r * P * kPartRec;
+  // lane-local: running (max, sum) and top-NB by (raw logit, smaller column)
+  float m = -INFINITY, sum = 0.f;
+  Cand top[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
+  for (int p = lane; p < P; p += 32) {
+    const float* rec = pr + (size_t)p * kPartRec;
+    const float pm = rec[0], ps = rec[1];
+    if (pm > -INFINITY) {
+      if (pm > m) { sum = sum * __expf(m - pm) + ps; m = pm; }
+      else sum += ps * __expf(pm - m);
+    }
+#pragma unroll
+    for (int i = 0; i < kPartTopK; ++i) {
+      if (i >= NB) break;  // a record's i-th entry can only matter for i < NB
+      Cand cd; cd.s = rec[2 + i]; cd.idx = __float_as_int(rec[2 + kPartTopK + i]);
+      if (cd.idx != 0x7fffffff) topk_insert<NB>(top, cd);
+    }
+  }
+  // warp: global max, rescaled sum
+  const float M = sc::warp_max(m);
+  float sc_ = (m > -INFINITY) ? sum * __expf(m - M) : 0.f;
+  sc_ = sc::warp_sum(sc_);
+  const float ls = logf(sc_);
+  const float base = a.sum[r];
+  // warp merge of the lanes' sorted lists (NB rounds of arg-best over the heads), ranking by (raw logit, column) - within
+  // a row the final score base + (x - M) - ls is monotone in x
+  int head = 0;
+#pragma unroll
+  for (int rnd = 0; rnd < NB; ++rnd) {
+    Cand c; c.s = -INFINITY; c.idx = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) if (i == head) c = top[i];
+    Cand best = c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Cand other;
+      other.s = __shfl_xor_sync(0xffffffffu, best.s, o);
+      other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+      if (better(other, best)) best = other;
+    }
+    if (head < NB && c.idx == best.idx && c.s == best.s) head++;
+    if (lane == 0) {
+      Cand out; out.s = -INFINITY; out.idx = 0x7fffffff;
+      if (best.idx != 0x7fffffff) { out.s = base + ((best.s - M) - ls); out.idx = k * a.V + best.idx; }
+      ws_cand[(size_t)r * NB + rnd] = out;
+      ws_raw[(size_t)r * NB + rnd] = best.s;
+    }
+  }
+  if (lane == 0) { ws_stats[r * 4 + 0] = M; ws_stats[r * 4 + 1] = ls; ws_stats[r * 4 + 2] = 0.f; ws_stats[r * 4 + 3] = 0.f; }
+}
+
 // Phase B — one small CTA per image: NB-way merge of the rows' sorted candidate lists, then the beam bookkeeping
 // (caption_model.py:84-110, 195-210).
 constexpr int kMergeThreads = 64;
@@ -478,6 +549,7 @@ __global__ void __launch_bounds__(kMergeThreads) beam_merge_kernel(const BeamArg
   sc::pdl_wait();
   const int rows = (a.t == 0) ? 1 : NB;
   __shared__ Cand s_final[NB];
+  __shared__ int s_src[NB];  // winner j came from candidate slot s_src[j] = row k * NB + position
   __shared__ int s_pos, s_last;
   const float T = (a.t == 0) ? 1.0f : a.temperature;
   if (tid == 0) {
@@ -494,7 +566,7 @@ __global__ void __launch_bounds__(kMergeThreads) beam_merge_kernel(const BeamArg
         if (better(c, best)) { best = c; bk = k; }
       }
 #pragma unroll
-      for (int k = 0; k < NB; ++k) if (k == bk) heads[k]++;
+      for (int k = 0; k < NB; ++k) if (k == bk) { s_src[rnd] = k * NB + heads[k]; heads[k]++; }
       s_final[rnd] = best;
     }
   }
@@ -512,7 +584,7 @@ __global__ void __launch_bounds__(kMergeThreads) beam_merge_kernel(const BeamArg
     } else if (s == t) {
       const int word = s_final[j].idx - parent * V;
       a.seq_out[dst] = word;
-      const float x = a.logits[((size_t)b * NB + parent) * V + word];
+      const float x = a.logits ? a.logits[((size_t)b * NB + parent) * V + word] : a.ws_raw[(size_t)b * NB * NB + s_src[j]];
       const float* st = ws_stats + ((size_t)b * NB + parent) * 4;
       float lp = (x - st[0]) - st[1];
       if (T != 1.0f) lp = (lp / T - st[2]) - st[3];
@@ -709,7 +781,8 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
 }
 
 size_t sc_beam_step_workspace_bytes_impl(int B, int beam) {
-  return (size_t)B * beam * (4 * sizeof(float) + (size_t)beam * sizeof(Cand));
+  // row statistics [R][4] | candidates [R][beam] | raw logits of the candidates [R][beam] (fused generator path)
+  return (size_t)B * beam * (4 * sizeof(float) + (size_t)beam * sizeof(Cand) + (size_t)beam * sizeof(float));
 }
 
 int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
@@ -728,7 +801,7 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   a.temperature = temperature; a.constraint = decoding_constraint; a.penalty_kind = penalty_kind;
   a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
   a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
-  a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
+  a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count; a.ws_raw = nullptr;
   float* ws_stats = (float*)workspace;
   Cand* ws_cand = (Cand*)(ws_stats + (size_t)B * beam * 4);
   const bool regs = V <= kBeamThreads * kBeamRegs && (V & 3) == 0 && ((uintptr_t)logits & 15) == 0;
@@ -750,6 +823,47 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   }
 #undef BEAM_LAUNCH
   SC_LAUNCH_CHECK("sc_beam_step");
+  return SC_OK;
+}
+
+// Beam step from the records of sc_linear_topk instead of materialised logits (temperature 1, no decoding constraint,
+// beam <= 5 = the record's candidate count; other options: run sc_linear + sc_beam_step).
+int sc_beam_step_partials(const float* partials, int parts_per_row, int B, int beam, int V, int L, int t, int eos, int pad,
+                          int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out, const float* lp_in,
+                          float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out, int* done_seq,
+                          float* done_lp, double* done_p, int* done_count, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
+  SC_CHECK(B > 0 && beam >= 1 && beam <= kPartTopK, SC_ERR_UNSUPPORTED, "sc_beam_step_partials: beam=%d not in [1,%d]", beam, kPartTopK);
+  SC_CHECK(V >= beam && L > 0 && t >= 0 && t < L && parts_per_row > 0 && partials != nullptr, SC_ERR_SHAPE,
+           "sc_beam_step_partials: V=%d L=%d t=%d parts=%d", V, L, t, parts_per_row);
+  SC_CHECK(workspace != nullptr && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= sc_beam_step_workspace_bytes_impl(B, beam),
+           SC_ERR_WORKSPACE, "sc_beam_step_partials: workspace of %zu bytes (16-byte aligned) needed, got %zu",
+           sc_beam_step_workspace_bytes_impl(B, beam), workspace_bytes);
+  BeamArgs a;
+  a.logits = nullptr; a.B = B; a.beam = beam; a.V = V; a.L = L; a.t = t; a.eos = eos; a.pad = pad;
+  a.temperature = 1.0f; a.constraint = 0; a.penalty_kind = penalty_kind;
+  a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
+  a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
+  a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
+  float* ws_stats = (float*)workspace;
+  Cand* ws_cand = (Cand*)(ws_stats + (size_t)B * beam * 4);
+  float* ws_raw = (float*)(ws_cand + (size_t)B * beam * beam);
+  a.ws_raw = ws_raw;
+  const int R = B * beam;
+#define BEAMP_LAUNCH(NBV)                                                                                                   \
+  do {                                                                                                                       \
+    sc::launch_pdl(beam_row_partials_kernel<NBV>, dim3((R + 7) / 8), dim3(256), 0, stream, a, partials, parts_per_row, ws_stats, ws_cand, ws_raw); \
+    sc::launch_pdl(beam_merge_kernel<NBV>, dim3(B), dim3(kMergeThreads), 0, stream, a, (const float*)ws_stats, (const Cand*)ws_cand); \
+  } while (0)
+  switch (beam) {
+    case 1: BEAMP_LAUNCH(1); break;
+    case 2: BEAMP_LAUNCH(2); break;
+    case 3: BEAMP_LAUNCH(3); break;
+    case 4: BEAMP_LAUNCH(4); break;
+    default: BEAMP_LAUNCH(5); break;
+  }
+#undef BEAMP_LAUNCH
+  SC_LAUNCH_CHECK("sc_beam_step_partials");
   return SC_OK;
 }
 

@@ -51,7 +51,13 @@ struct GemmArgs {
   // folded LayerNorm (consumer) / residual-stream producer (ScGemmExtra)
   const float* ln_stats; const float* ln_c; float ln_eps;
   void* y2; float* stats_out;
+  // kEpi == 3 (generator fused with the beam step's row pass): no output tile; per (row, N tile, epilogue-warp half) one
+  // record {max, sum exp(x - max), kTopK largest values, their columns} -> topk_part[row][tiles_n * 2][kTopKRec]
+  float* topk_part;
 };
+
+constexpr int kTopK = 5;                 // candidates kept per record (beam sizes up to 5 use the fused path)
+constexpr int kTopKRec = 2 + 2 * kTopK;  // floats per record
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -537,6 +543,14 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
       if (kPrefetchRes) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // kEpi == 3: running log-sum-exp statistics and top-kTopK of this thread's row over the warp's chunks of the tile
+      float tk_m = -INFINITY, tk_s = 0.f;
+      float tk_v[kEpi == 3 ? kTopK : 1];
+      int tk_i[kEpi == 3 ? kTopK : 1];
+      if constexpr (kEpi == 3) {
+#pragma unroll
+        for (int i = 0; i < kTopK; ++i) { tk_v[i] = -INFINITY; tk_i[i] = 0x7fffffff; }
+      }
 #pragma unroll 1
       for (int c = half; c < BLOCK_N / 32; c += kChunkStep) {
         const int col0 = n0 + c * 32;
@@ -572,6 +586,31 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           epilogue_row<kEpi == 1>(args, f, res, row, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
+          if constexpr (kEpi == 3) {
+            // columns are visited in ascending order: strict '>' keeps the smaller column on ties
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j >= args.N) f[j] = -INFINITY;
+              cm = fmaxf(cm, f[j]);
+            }
+            if (cm > tk_m) { tk_s *= __expf(tk_m - cm); tk_m = cm; }  // first chunk: 0 * exp(-inf) = 0
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              tk_s += __expf(f[j] - tk_m);
+              if (f[j] > tk_v[kTopK - 1]) {
+                tk_v[kTopK - 1] = f[j]; tk_i[kTopK - 1] = col0 + j;
+#pragma unroll
+                for (int i = kTopK - 1; i > 0; --i) {
+                  if (tk_v[i] > tk_v[i - 1]) {
+                    const float tv = tk_v[i]; tk_v[i] = tk_v[i - 1]; tk_v[i - 1] = tv;
+                    const int ti = tk_i[i]; tk_i[i] = tk_i[i - 1]; tk_i[i - 1] = ti;
+                  }
+                }
+              }
+            }
+            continue;
+          }
           if (row < args.M) epilogue_store_row<kEpi == 1>(args, f, row, col0, (size_t)split * args.split_stride);
           continue;
         }
@@ -661,6 +700,12 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
         __syncwarp();  // staging is rewritten by the next chunk
+      }
+      if constexpr (kEpi == 3) if (rbase + lane < args.M) {
+        float* rec = args.topk_part + ((size_t)(rbase + lane) * (args.tiles_n * kChunkStep) + (size_t)(tile % args.tiles_n) * kChunkStep + half) * kTopKRec;
+        rec[0] = tk_m; rec[1] = tk_s;
+#pragma unroll
+        for (int i = 0; i < kTopK; ++i) { rec[2 + i] = tk_v[i]; rec[2 + kTopK + i] = __int_as_float(tk_i[i]); }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -904,6 +949,12 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     if (wgrad || (ex && ex->partial_splits > 0)) block_n = (t128 >= sms / 4) ? 128 : 64;
     if (N <= 64) block_n = 64;
   }
+  const bool topk = ex && ex->topk_part != nullptr;
+  if (topk) {
+    SC_CHECK(!masked && !wgrad && !residual && !relu && !(ex->mn_major) && !ex->ln_stats && !ex->y2 && !ex->stats_out && ex->dropout_p == 0.f,
+             SC_ERR_UNSUPPORTED, "sc_linear_topk: plain bf16 x / bf16 w / bias only");
+    block_n = 256;
+  }
   const bool mn = ex && ex->mn_major;
   CUtensorMap ta, tb;
   int rc;
@@ -937,6 +988,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     a.wgrad = ex->wgrad; a.bypass = ex->bypass; a.sp_coeff = ex->sp_coeff; a.accumulate = ex->accumulate;
     a.wg_w = ex->wg_w; a.wg_s = ex->wg_s; a.wg_u = ex->wg_u; a.dw = ex->dw; a.ds = ex->ds;
     a.ln_stats = ex->ln_stats; a.ln_c = ex->ln_c; a.ln_eps = ex->ln_eps; a.y2 = ex->y2; a.stats_out = ex->stats_out;
+    a.topk_part = ex->topk_part;
     if (ex->partial_splits > 0) {
       SC_CHECK(!wgrad && y_dtype == SC_F32 && !bias && !residual && !relu, SC_ERR_UNSUPPORTED, "split-K partial products are plain fp32 tiles");
       force_splits = ex->partial_splits;
@@ -944,6 +996,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     }
   }
   const int epi = a.wgrad ? 2 : ((a.dropout_p > 0.f || a.ln_stats || a.y2 || a.stats_out) ? 1 : 0);
+  if (topk) return launch<256, false, 3, 3>(ta, tb, a, force_splits, stream);
   if (mn) {
     SC_CHECK(epi == 0, SC_ERR_UNSUPPORTED, "MN-major operands serve the plain epilogue only");
     return block_n == 128 ? launch<128, false, 3, 0, true>(ta, tb, a, force_splits, stream)

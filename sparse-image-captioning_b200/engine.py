@@ -171,7 +171,7 @@ class OrtEngine:
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, precision="bf16", sparse_backend="dense",
-                 csr_threshold=0.995, device="cuda", use_graphs=True, no_history=False, ln_fold=False):
+                 csr_threshold=0.995, device="cuda", use_graphs=True, no_history=False, ln_fold=False, fuse_topk=True):
         if not torch.cuda.is_available():
             raise RuntimeError("OrtEngine needs a CUDA device: the B200 path has no CPU fallback")
         lib.load()
@@ -181,6 +181,9 @@ class OrtEngine:
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.precision = precision
         self.use_graphs = use_graphs
+        # generator GEMM fused with the beam step's row pass (sc_linear_topk + sc_beam_step_partials): the [R, V] fp32
+        # logits (61 MB per step at 512 images x beam 3) are never written or re-read
+        self.fuse_topk = bool(fuse_topk)
         self.no_history = no_history  # reference quirk Q1 (relation_transformer_prune never enables its KV cache)
         self.sparse_backend = sparse_backend
         sd = {k: v.to(self.dev) for k, v in state_dict.items() if torch.is_tensor(v) and not v.is_sparse}
@@ -412,6 +415,7 @@ class OrtEngine:
         ws.qc = torch.zeros(R, d, device=dev, dtype=adt)
         ws.hid = torch.zeros(R, ff, device=dev, dtype=adt)
         ws.logits = torch.zeros(R, V, device=dev)
+        ws.topk_part = torch.zeros(R, K.linear_topk_parts(V), 12, device=dev) if (not greedy and self._topk_ok(beam)) else None
         if self.fold_dec:
             ws.xb = torch.zeros(R, d, device=dev, dtype=adt)
             ws.stats = torch.zeros(R, d // 32, 2, device=dev)
@@ -423,7 +427,13 @@ class OrtEngine:
         self._dec_ws[key] = ws
         return ws
 
-    def _decode_step(self, ws, enc, t, anc):
+    def _topk_ok(self, beam):
+        """The fused generator + beam row pass serves the dense bf16 tensor path, beam <= 5 (options are checked per call)."""
+        g = self.generator
+        return (self.fuse_topk and self.adt == torch.bfloat16 and g.w is not None and g.w.dtype == torch.bfloat16 and beam <= 5
+                and g.K % 8 == 0 and not self.fold_dec)
+
+    def _decode_step(self, ws, enc, t, anc, fused_topk=False):
         c = self.cfg
         R, d, h, N = ws.R, c.d_model, c.num_heads, ws.N
         fold = self.fold_dec
@@ -473,7 +483,10 @@ class OrtEngine:
             self.generator.ln(ws.xb, ws.stats, ws.logits)
         else:
             self.dec_norm(ws.x, ws.xn)
-            self.generator(ws.xn, ws.logits)
+            if fused_topk:
+                K.linear_topk(ws.xn, self.generator.w, self.generator.bias, ws.topk_part)
+            else:
+                self.generator(ws.xn, ws.logits)
 
     def _beam_body(self, ws, enc, opt):
         c = self.cfg
@@ -481,11 +494,16 @@ class OrtEngine:
         st = ws.state
         st.reset(c.bos_token_id, c.pad_token_id)
         kind, alpha = _parse_penalty(opt.get("length_penalty", ""))
+        fused = (ws.topk_part is not None and float(opt.get("temperature", 1.0)) == 1.0 and not opt.get("decoding_constraint", 0))
         for t in range(L):
-            self._decode_step(ws, enc, t, st.anc[t & 1])
-            K.beam_step(ws.logits, st, t, B=ws.B, beam=ws.beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id,
-                        temperature=opt.get("temperature", 1.0), constraint=opt.get("decoding_constraint", 0),
-                        penalty_kind=kind, penalty_alpha=alpha)
+            self._decode_step(ws, enc, t, st.anc[t & 1], fused_topk=fused)
+            if fused:
+                K.beam_step_partials(ws.topk_part, st, t, B=ws.B, beam=ws.beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id,
+                                     penalty_kind=kind, penalty_alpha=alpha)
+            else:
+                K.beam_step(ws.logits, st, t, B=ws.B, beam=ws.beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id,
+                            temperature=opt.get("temperature", 1.0), constraint=opt.get("decoding_constraint", 0),
+                            penalty_kind=kind, penalty_alpha=alpha)
 
     def _greedy_body(self, ws, enc, opt):
         c = self.cfg

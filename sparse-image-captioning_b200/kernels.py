@@ -284,6 +284,34 @@ def beam_step(logits, st, t, *, B, beam, V, L, eos, pad, temperature=1.0, constr
              st.ws.numel(), lib.stream())
 
 
+def linear_topk_parts(N):
+    """Records per row that sc_linear_topk writes for an N-column generator."""
+    return 2 * ((N + 255) // 256)
+
+
+def linear_topk(x, w, bias, partials):
+    """Generator GEMM whose epilogue keeps only the per-row log-sum-exp partials and top-5 candidates (no logits):
+    partials fp32 [M, linear_topk_parts(N), 12]."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.shape[1] == K
+    assert tuple(partials.shape) == (M, linear_topk_parts(N), 12) and partials.dtype == torch.float32 and partials.is_contiguous()
+    for t, n in ((x, "x"), (w, "w"), (bias, "bias"), (partials, "partials")):
+        _chk(t, n)
+    lib.call("sc_linear_topk", lib.ptr(x), lib.ptr(w), lib.ptr(bias), M, N, K, lib.ptr(partials), lib.stream(),
+             meta=("gemm_bf16", M, N, K, 2, 2, 0, False, False, False))
+    return partials
+
+
+def beam_step_partials(partials, st, t, *, B, beam, V, L, eos, pad, penalty_kind=0, penalty_alpha=0.0):
+    """Beam step from sc_linear_topk records (temperature 1, no decoding constraint, beam <= 5)."""
+    i, o = t & 1, (t + 1) & 1
+    lib.call("sc_beam_step_partials", lib.ptr(partials), partials.shape[1], B, beam, V, L, t, eos, pad, int(penalty_kind),
+             float(penalty_alpha), lib.ptr(st.seq[i]), lib.ptr(st.seq[o]), lib.ptr(st.lp[i]), lib.ptr(st.lp[o]), lib.ptr(st.sum),
+             lib.ptr(st.anc[i]), lib.ptr(st.anc[o]), lib.ptr(st.tokens), lib.ptr(st.done_seq), lib.ptr(st.done_lp),
+             lib.ptr(st.done_p), lib.ptr(st.done_count), lib.ptr(st.ws), st.ws.numel(), lib.stream())
+
+
 def beam_step_workspace_bytes(B, beam):
     return int(lib.load().sc_beam_step_workspace_bytes(B, beam))
 

@@ -450,3 +450,63 @@ def test_beam_step(K, beam, V, opt):
                     constraint=opt.get("decoding_constraint", 0), penalty_kind=kind, penalty_alpha=alpha)
     assert torch.equal(st.done_seq.cpu().long(), ref_seq)
     torch.testing.assert_close(st.done_lp.cpu(), ref_lp, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(1536, 10000, 512), (77, 771, 512), (300, 256, 64), (5, 1000, 128)])
+def test_linear_topk_records(K, shape):
+    """Generator GEMM with the fused row pass: merged records == log-sum-exp and top-5 of the materialised logits."""
+    M, N, Kd = shape
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(M, Kd, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, Kd, generator=g) * 0.2).bfloat16().cuda()
+    b = torch.randn(N, generator=g).cuda()
+    logits = K.linear(x, w, b)  # fp32 logits from the same tensor-core kernel
+    P = K.linear_topk_parts(N)
+    part = torch.full((M, P, 12), float("nan"), device="cuda")
+    K.linear_topk(x, w, b, part)
+    torch.cuda.synchronize()
+    assert not torch.isnan(part[:, :, :7]).any()  # (the column slots hold int bits; an empty slot is 0x7fffffff)
+    m, s = part[:, :, 0], part[:, :, 1]
+    Mx = m.max(1).values
+    lse = Mx + torch.log((s * torch.exp(m - Mx[:, None])).sum(1))
+    torch.testing.assert_close(lse, torch.logsumexp(logits, 1), rtol=1e-5, atol=1e-5)
+    vals = part[:, :, 2:7].reshape(M, -1)
+    idx = part[:, :, 7:12].contiguous().view(torch.int32).reshape(M, -1)
+    k = min(5, N)
+    top = vals.topk(k, 1)
+    ref = logits.topk(k, 1)
+    assert torch.equal(top.values, ref.values)  # same accumulator values, only the selection differs
+    got_idx = idx.gather(1, top.indices)
+    # ties between equal logits may be listed in either order by torch.topk: compare through the values they point at
+    assert torch.equal(logits.gather(1, got_idx.long()), ref.values)
+    assert int(got_idx.min()) >= 0 and int(got_idx.max()) < N
+
+
+def test_beam_step_partials_matches_beam_step(K):
+    """sc_linear_topk + sc_beam_step_partials == sc_linear + sc_beam_step over several steps (same tokens, parents,
+    finished beams; log-probs within fp32 summation-order noise)."""
+    from sparse_caption_b200.engine import BeamState
+    g = torch.Generator().manual_seed(22)
+    B, beam, V, L, Kd = 9, 3, 1000, 6, 128
+    R = B * beam
+    w = (torch.randn(V, Kd, generator=g) * 0.3).bfloat16().cuda()
+    b = torch.randn(V, generator=g).cuda()
+    b[3] += 2.0  # EOS shows up among the candidates
+    sa, sb = BeamState(B, beam, L, "cuda"), BeamState(B, beam, L, "cuda")
+    sa.reset(2, 0); sb.reset(2, 0)
+    part = torch.empty(R, K.linear_topk_parts(V), 12, device="cuda")
+    for t in range(L):
+        x = torch.randn(R, Kd, generator=g).bfloat16().cuda()
+        if t == 0:
+            x = x.view(B, beam, Kd)[:, :1].expand(B, beam, Kd).reshape(R, Kd).contiguous()
+        logits = K.linear(x, w, b)
+        K.beam_step(logits, sa, t, B=B, beam=beam, V=V, L=L, eos=3, pad=0, penalty_kind=1, penalty_alpha=0.7)
+        K.linear_topk(x, w, b, part)
+        K.beam_step_partials(part, sb, t, B=B, beam=beam, V=V, L=L, eos=3, pad=0, penalty_kind=1, penalty_alpha=0.7)
+        o = (t + 1) & 1
+        assert torch.equal(sa.tokens, sb.tokens), t
+        assert torch.equal(sa.seq[o], sb.seq[o]) and torch.equal(sa.anc[o], sb.anc[o]), t
+        torch.testing.assert_close(sa.lp[o], sb.lp[o], rtol=1e-5, atol=2e-5)
+        torch.testing.assert_close(sa.sum, sb.sum, rtol=1e-5, atol=1e-4)
+    assert torch.equal(sa.done_seq, sb.done_seq) and torch.equal(sa.done_count, sb.done_count)
+    torch.testing.assert_close(sa.done_lp, sb.done_lp, rtol=1e-5, atol=2e-5)
