@@ -71,6 +71,7 @@ class _Lin:
     def __init__(self, w, b, adt, backend, csr_threshold, norm=None):
         w = w.detach().float().contiguous()
         self.N, self.K = w.shape
+        self.tile_n = 0  # GEMM tile hint (1000 * stages + block_n; 0 = the kernel's own heuristic)
         self.bias = None if b is None else b.detach().float().contiguous()
         self.sparsity = float((w == 0).sum()) / w.numel()
         use_csr = backend == "csr"
@@ -104,7 +105,7 @@ class _Lin:
             return K.sell_spmm(x, self.sell, self.bias, residual=residual, relu=relu, out=out)
         if self.csr is not None:
             return K.csr_spmm(x, self.csr, self.bias, residual=residual, relu=relu, out=out)
-        return K.linear(x, self.w, self.bias, residual=residual, relu=relu, out=out)
+        return K.linear(x, self.w, self.bias, residual=residual, relu=relu, out=out, tile_n=self.tile_n)
 
 
 class _Norm:
@@ -171,7 +172,8 @@ class OrtEngine:
     """
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, precision="bf16", sparse_backend="dense",
-                 csr_threshold=0.995, device="cuda", use_graphs=True, no_history=False, ln_fold=False, fuse_topk=True):
+                 csr_threshold=0.995, device="cuda", use_graphs=True, no_history=False, ln_fold=False, fuse_topk=True,
+                 dec_tiles=None):
         if not torch.cuda.is_available():
             raise RuntimeError("OrtEngine needs a CUDA device: the B200 path has no CPU fallback")
         lib.load()
@@ -270,6 +272,16 @@ class OrtEngine:
         # the folded decode path needs every decoder linear on the dense tensor path
         self.fold_dec = self.ln_fold and all(
             e[k].w is not None for e in self.dec.values() for k in ("qkv", "o", "cq", "co", "ff1", "ff2")) and self.generator.w is not None
+        # decode-GEMM tile hints {"o": 3256, ...} (1000 * stages + block_n).  With >= 8 batches in flight the wide tiles
+        # give a little more aggregate throughput than the latency-oriented 64-wide default (scripts/gemm_concurrency.py)
+        import os
+        hints = dict(dec_tiles or {})
+        for kv in filter(None, os.environ.get("SC_DEC_TILES", "").split(",")):
+            name, val = kv.split("=")
+            hints[name] = int(val)
+        for name, val in hints.items():
+            for e in self.dec.values():
+                e[name].tile_n = int(val)
         self._enc_ws = {}
         self._dec_ws = {}
         self._streams = {}
