@@ -239,6 +239,13 @@ int sc_colsum(const void* x, int dtype, float* out, int rows, int cols, int accu
 int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
                      float* db, int rows, int D, float eps, sc_stream_t stream);
 
+/* the same backward, also preparing the gradient operand of the NEXT linear of the backward chain (o-proj / ff2, whose
+ * output gradient is dx): next_gb bf16 [rows, D] = dx (.) dropout keep mask of that linear's forward (Philox(seed,
+ * stream_id, element), p = next_dropout_p), next_colsum fp32 [D] += its column sums (the bias gradient).  D == 512. */
+int sc_layernorm_bwd_fused(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
+                           float* db, int rows, int D, float eps, void* next_gb, float* next_colsum, float next_dropout_p,
+                           unsigned long long seed, unsigned long long stream_id, sc_stream_t stream);
+
 /* log_softmax (+ LanguageModelCriterion fwd/bwd when target != NULL): transformer.py:413, utils/losses.py:32-43 */
 int sc_logsoftmax_nll(const float* logits, const int* target, const float* weight, const float* inv_norm, float* loss_sum,
                       void* dlogits, int d_dtype, float* logprobs, int rows, int V, sc_stream_t stream);

@@ -504,20 +504,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 // D = 512 (d_model): one row per warp, 16-byte accesses, every load of the row (x, dy, residual gradient) issued before
 // the first reduction; parameter gradients go warp -> shared memory -> one vector reduction per 4 columns and CTA.
+// Optional fused gradient preparation for the NEXT linear of the backward chain (the one whose output gradient is dx, i.e.
+// o-proj / cross o-proj / ff2: y = x + dropout(linear(.))): gb = bf16(dx (.) dropout keep mask) - the mask the forward
+// GEMM epilogue drew, regenerated from (seed, stream, element) - and its column sums (that linear's bias gradient).
+struct LnbNext {
+  __nv_bfloat16* gb; float* colsum; float p; unsigned long long seed, stream;
+};
 template <typename GT>
 __global__ void __launch_bounds__(256) layernorm_bwd512_kernel(const float* __restrict__ x, const float* __restrict__ a,
                                                                const GT* __restrict__ dy, const float* __restrict__ dres,
                                                                float* __restrict__ dx, float* __restrict__ da,
-                                                               float* __restrict__ db, int rows, float eps) {
+                                                               float* __restrict__ db, int rows, float eps, const LnbNext nx) {
   constexpr int D = 512;
-  __shared__ float4 s_part[2][8][128];
+  __shared__ float4 s_part[3][8][128];
   sc::pdl_launch();
   sc::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
-  float4 pa[4], pb[4];
+  float4 pa[4], pb[4], pc[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pa[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 4; ++i) pa[i] = pb[i] = pc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (row < rows) {
     const size_t base = (size_t)row * D;
     float c[4][4], g[4][4], dyv[4][4], rs[4][4];
@@ -577,17 +583,36 @@ __global__ void __launch_bounds__(256) layernorm_bwd512_kernel(const float* __re
       o.z = r * (g[i][2] - sg) - k2 * c[i][2] + rs[i][2];
       o.w = r * (g[i][3] - sg) - k2 * c[i][3] + rs[i][3];
       *(float4*)(dx + base + col) = o;
+      if (nx.gb) {
+        float v[4] = {o.x, o.y, o.z, o.w};
+        if (nx.p > 0.f) {
+          const sc::Philox ph(nx.seed);
+          const float keep = 1.f / (1.f - nx.p);
+          const uint4 rr = ph((base + col) >> 2, nx.stream);
+          v[0] *= sc::u24(rr.x) >= nx.p ? keep : 0.f; v[1] *= sc::u24(rr.y) >= nx.p ? keep : 0.f;
+          v[2] *= sc::u24(rr.z) >= nx.p ? keep : 0.f; v[3] *= sc::u24(rr.w) >= nx.p ? keep : 0.f;
+        }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 ob; ob.x = *(const uint32_t*)&lo; ob.y = *(const uint32_t*)&hi;
+        *(uint2*)(nx.gb + base + col) = ob;
+        pc[i] = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { s_part[0][warp][lane + 32 * i] = pa[i]; s_part[1][warp][lane + 32 * i] = pb[i]; }
+  for (int i = 0; i < 4; ++i) {
+    s_part[0][warp][lane + 32 * i] = pa[i]; s_part[1][warp][lane + 32 * i] = pb[i];
+    if (nx.colsum) s_part[2][warp][lane + 32 * i] = pc[i];
+  }
   __syncthreads();
-  const int which = threadIdx.x >> 7, c4 = threadIdx.x & 127;
-  float4 t = s_part[which][0][c4];
+  for (int job = threadIdx.x; job < (nx.colsum ? 384 : 256); job += 256) {
+    const int which = job >> 7, c4 = job & 127;
+    float4 t = s_part[which][0][c4];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) { const float4 q4 = s_part[which][w][c4]; t.x += q4.x; t.y += q4.y; t.z += q4.z; t.w += q4.w; }
-  float* dst = (which ? db : da) + 4 * c4;
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+    for (int w = 1; w < 8; ++w) { const float4 q4 = s_part[which][w][c4]; t.x += q4.x; t.y += q4.y; t.z += q4.z; t.w += q4.w; }
+    float* dst = (which == 0 ? da : which == 1 ? db : nx.colsum) + 4 * c4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+  }
 }
 
 // log-softmax + masked NLL, forward and backward in one pass over the logits (one CTA per row).
@@ -807,17 +832,35 @@ int sc_colsum(const void* x, int dtype, float* out, int rows, int cols, int accu
   return SC_OK;
 }
 
+int sc_layernorm_bwd_fused(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
+                           float* db, int rows, int D, float eps, void* next_gb, float* next_colsum, float next_dropout_p,
+                           unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+
 int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
                      float* db, int rows, int D, float eps, cudaStream_t stream) {
+  return sc_layernorm_bwd_fused(x, a, dy, dy_dtype, dres, dx, da, db, rows, D, eps, nullptr, nullptr, 0.f, 0, 0, stream);
+}
+
+// LayerNorm backward that also prepares the gradient operand of the next linear in the backward chain:
+// next_gb (bf16 [rows, D]) = dx (.) dropout keep mask (Philox(seed, stream_id, element), p = next_dropout_p) and
+// next_colsum (fp32 [D], accumulated) += its column sums.  Served for D == 512; next_gb == NULL: plain backward.
+int sc_layernorm_bwd_fused(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
+                           float* db, int rows, int D, float eps, void* next_gb, float* next_colsum, float next_dropout_p,
+                           unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
   SC_CHECK(rows > 0 && D > 1 && D <= 2048, SC_ERR_SHAPE, "sc_layernorm_bwd: rows=%d D=%d", rows, D);
+  LnbNext nx;
+  nx.gb = (__nv_bfloat16*)next_gb; nx.colsum = next_colsum; nx.p = next_dropout_p; nx.seed = seed; nx.stream = stream_id;
+  SC_CHECK(next_gb == nullptr || (D == 512 && ((uintptr_t)next_gb & 7) == 0 && ((uintptr_t)next_colsum & 15) == 0), SC_ERR_UNSUPPORTED,
+           "sc_layernorm_bwd_fused: the fused gradient preparation needs D == 512 and aligned outputs");
   if (D == 512 && ((((uintptr_t)x | (uintptr_t)a | (uintptr_t)dy | (uintptr_t)dres | (uintptr_t)dx | (uintptr_t)da | (uintptr_t)db) & 15) == 0) &&
       (dy_dtype == SC_F32 || dy_dtype == SC_BF16)) {
     const int nb = (rows + 7) / 8;
-    if (dy_dtype == SC_F32) sc::launch_pdl_aux(layernorm_bwd512_kernel<float>, dim3(nb), dim3(256), 0, stream, x, a, (const float*)dy, dres, dx, da, db, rows, eps);
-    else sc::launch_pdl_aux(layernorm_bwd512_kernel<__nv_bfloat16>, dim3(nb), dim3(256), 0, stream, x, a, (const __nv_bfloat16*)dy, dres, dx, da, db, rows, eps);
+    if (dy_dtype == SC_F32) sc::launch_pdl_aux(layernorm_bwd512_kernel<float>, dim3(nb), dim3(256), 0, stream, x, a, (const float*)dy, dres, dx, da, db, rows, eps, nx);
+    else sc::launch_pdl_aux(layernorm_bwd512_kernel<__nv_bfloat16>, dim3(nb), dim3(256), 0, stream, x, a, (const __nv_bfloat16*)dy, dres, dx, da, db, rows, eps, nx);
     SC_LAUNCH_CHECK("sc_layernorm_bwd");
     return SC_OK;
   }
+  SC_CHECK(next_gb == nullptr, SC_ERR_UNSUPPORTED, "sc_layernorm_bwd_fused: unaligned operands");
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 2) blocks = 148 * 2;
   const size_t smem = 2 * (size_t)D * sizeof(float);

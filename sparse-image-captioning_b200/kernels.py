@@ -447,10 +447,18 @@ def colsum(x, out, accumulate=False):
     return out
 
 
-def layernorm_bwd(x, a, dy, dx, da, db, *, dres=None, eps=1e-6):
+def layernorm_bwd(x, a, dy, dx, da, db, *, dres=None, eps=1e-6, next_gb=None, next_colsum=None, next_p=0.0, seed=0, stream_id=0):
+    """LayerNorm backward; ``next_gb`` (bf16 [rows, D], D == 512): also emit dx (.) dropout mask as the gradient operand of
+    the next linear in the backward chain and add its column sums to ``next_colsum`` (sc_layernorm_bwd_fused)."""
     rows, D = x.shape
-    lib.call("sc_layernorm_bwd", lib.ptr(x), lib.ptr(a), lib.ptr(dy), lib.dtype_code(dy.dtype), lib.ptr(dres), lib.ptr(dx),
-             lib.ptr(da), lib.ptr(db), rows, D, eps, lib.stream())
+    if next_gb is None:
+        lib.call("sc_layernorm_bwd", lib.ptr(x), lib.ptr(a), lib.ptr(dy), lib.dtype_code(dy.dtype), lib.ptr(dres), lib.ptr(dx),
+                 lib.ptr(da), lib.ptr(db), rows, D, eps, lib.stream())
+    else:
+        assert next_gb.dtype == torch.bfloat16 and tuple(next_gb.shape) == (rows, D) and next_gb.is_contiguous()
+        lib.call("sc_layernorm_bwd_fused", lib.ptr(x), lib.ptr(a), lib.ptr(dy), lib.dtype_code(dy.dtype), lib.ptr(dres), lib.ptr(dx),
+                 lib.ptr(da), lib.ptr(db), rows, D, eps, lib.ptr(next_gb), lib.ptr(next_colsum), float(next_p), seed, stream_id,
+                 lib.stream())
     return dx
 
 

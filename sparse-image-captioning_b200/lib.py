@@ -52,6 +52,7 @@ SIGNATURES = {
     "sc_mask_grad": [_p, _p, _p, _i, _p, _u64, _u64, _i, _f, _p, _p, _i, _sz, _p],
     "sc_colsum": [_p, _i, _p, _i, _i, _i, _p],
     "sc_layernorm_bwd": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p],
+    "sc_layernorm_bwd_fused": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _f, _p, _p, _f, _u64, _u64, _p],
     "sc_logsoftmax_nll": [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _p],
     "sc_embedding_bwd": [_p, _p, _p, _i, _i, _i, _f, _p],
     "sc_adam_clip": [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p],

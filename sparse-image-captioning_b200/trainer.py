@@ -353,7 +353,7 @@ class OrtTrainer:
                          relu=relu, out=out, p=p, drop_seed=self._sd(1), drop_stream=self._drop_stream(site))
         return out
 
-    def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None):
+    def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None, pre=None):
         """Backward of y = drop(act(x W^T + b)).  g: fp32 [M,N] gradient wrt the layer output (after dropout);
         h: saved post-activation output when the layer has ReLU (mask = h != 0, which also covers its dropout);
         p/site: dropout to regenerate when h is None.  g_ready: (gb, None) when the gradient is already in the
@@ -370,7 +370,10 @@ class OrtTrainer:
         gT = None if rowmajor else ws.gT[: N * Mp].view(N, Mp)
         side = rowmajor and len(ws.gb_ring) > 1
         slot = None
-        if g_ready is not None:
+        if pre is not None:
+            # the LayerNorm backward that produced g already wrote the masked bf16 operand and the bias gradient (_ln_bwd)
+            gb, slot = pre
+        elif g_ready is not None:
             gb = g_ready
             if not rowmajor:
                 if Mp != M:
@@ -380,11 +383,7 @@ class OrtTrainer:
                 K.colsum(gb, gbias)
         else:
             if side:
-                slot = ws.gb_next
-                ws.gb_next = (slot + 1) % len(ws.gb_ring)
-                if ws.gb_free[slot] is not None:
-                    torch.cuda.current_stream(self.dev).wait_event(ws.gb_free[slot])
-                gb = ws.gb_ring[slot][: M * N].view(M, N)
+                gb, slot = self._take_gb(ws, M, N)
             else:
                 gb = ws.gb[: M * N].view(M, N)
             if not rowmajor and Mp != M:
@@ -428,8 +427,28 @@ class OrtTrainer:
     def _ln(self, name, x, out):
         return K.layernorm(x, self.p[name + ".a_2"], self.p[name + ".b_2"], out=out)
 
-    def _ln_bwd(self, name, x, dy, dx, dres=None):
-        return K.layernorm_bwd(x, self.p[name + ".a_2"], dy, dx, self.g[name + ".a_2"], self.g[name + ".b_2"], dres=dres)
+    def _take_gb(self, ws, M, N):
+        """Next gradient-operand buffer of the ring (waits for the side-stream consumer that used it last)."""
+        slot = ws.gb_next
+        ws.gb_next = (slot + 1) % len(ws.gb_ring)
+        if ws.gb_free[slot] is not None:
+            torch.cuda.current_stream(self.dev).wait_event(ws.gb_free[slot])
+        return ws.gb_ring[slot][: M * N].view(M, N), slot
+
+    def _ln_bwd(self, name, x, dy, dx, dres=None, nxt=None, ws=None):
+        """Backward of LayerNorm `name`.  ``nxt = (weight name, dropout p, site)``: the linear whose output gradient is dx
+        comes next in the backward chain - its bf16 gradient operand (dropout mask regenerated) and bias gradient are
+        produced by the same kernel; returns ``pre`` for ``_lin_bwd`` (None when not fused)."""
+        d = x.shape[1]
+        if nxt is None or self.adt != torch.bfloat16 or d != 512 or len(ws.gb_ring) < 2:
+            K.layernorm_bwd(x, self.p[name + ".a_2"], dy, dx, self.g[name + ".a_2"], self.g[name + ".b_2"], dres=dres)
+            return None
+        wname, p, site = nxt
+        gb, slot = self._take_gb(ws, x.shape[0], d)
+        gbias = self.g[wname.replace(".weight", ".bias")]
+        K.layernorm_bwd(x, self.p[name + ".a_2"], dy, dx, self.g[name + ".a_2"], self.g[name + ".b_2"], dres=dres, next_gb=gb,
+                        next_colsum=gbias, next_p=p if self.training else 0.0, seed=self._sd(1), stream_id=self._drop_stream(site))
+        return gb, slot
 
     # ---------------------------------------------------------------------------------------------------------
     def load_batch(self, ws, att_feats, boxes, seqs, masks, att_masks=None, global_tokens=None):
@@ -584,25 +603,29 @@ class OrtTrainer:
             ga_d = ws.ga.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, "model.generator.proj.weight", ws.yf, None, g_ready=ws.dlogits, dx=ga_d)
             ws.cur = 0
-            self._ln_bwd("model.decoder.norm", ws.y[3 * L], ga_d, ws.dres[0][:MD])
+            pre = self._ln_bwd("model.decoder.norm", ws.y[3 * L], ga_d, ws.dres[0][:MD], ws=ws,
+                               nxt=(f"model.decoder.layers.{L - 1}.feed_forward.w_2.weight", pd, 100 + L - 1))
             ws.dmem.zero_()
         if phase >= 2:
             self._backward_encoder(ws, phase - 2)
             return
+        if phase != 0:
+            pre = None  # (a phase starts with a plain gradient preparation: the ring was reset)
+        first = half if phase == 0 else 0  # last layer this phase visits
         cur, nxt = ws.dres[ws.cur][:MD], ws.dres[1 - ws.cur][:MD]
         for l in (reversed(range(half, L)) if phase == 0 else reversed(range(half))):
             p = f"model.decoder.layers.{l}"
             y0, y1, y2 = ws.y[3 * l], ws.y[3 * l + 1], ws.y[3 * l + 2]
             ga_ff = ws.ga.view(-1)[: MD * ff].view(MD, ff)
             # feed-forward sublayer
-            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.d_hid[l], cur, p=pd, site=100 + l, dx=ga_ff)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.d_hid[l], cur, p=pd, site=100 + l, dx=ga_ff, pre=pre)
             ga_dd = ws.gq.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.d_yn3[l], ga_ff, h=ws.d_hid[l], p=pd, dx=ga_dd)
-            self._ln_bwd(f"{p}.sublayer.2.norm", y2, ga_dd, nxt, dres=cur)
+            pre = self._ln_bwd(f"{p}.sublayer.2.norm", y2, ga_dd, nxt, dres=cur, ws=ws, nxt=(f"{p}.src_attn.linears.3.weight", pd, 80 + l))
             cur, nxt = nxt, cur
             # cross-attention sublayer
             ga_c = ws.ga.view(-1)[: MD * d].view(MD, d)
-            self._lin_bwd(ws, f"{p}.src_attn.linears.3.weight", ws.d_catt[l], cur, p=pd, site=80 + l, dx=ga_c)
+            self._lin_bwd(ws, f"{p}.src_attn.linears.3.weight", ws.d_catt[l], cur, p=pd, site=80 + l, dx=ga_c, pre=pre)
             kv = ws.memkv[l]
             dqc = ws.gq.view(-1)[: MD * d].view(MD, d)
             K.attention_bwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.c_probs[l], ga_c, dqc, ws.dmemkv[:, 0:], ws.dmemkv[:, d:],
@@ -610,12 +633,12 @@ class OrtTrainer:
                             ldgv=2 * d, p=pd, seed=self._sd(2), stream_id=self._drop_stream(70 + l))
             ga_c2 = ws.ga.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], dqc, dx=ga_c2)
-            self._ln_bwd(f"{p}.sublayer.1.norm", y1, ga_c2, nxt, dres=cur)
+            pre = self._ln_bwd(f"{p}.sublayer.1.norm", y1, ga_c2, nxt, dres=cur, ws=ws, nxt=(f"{p}.self_attn.linears.3.weight", pd, 60 + l))
             cur, nxt = nxt, cur
             self._lin_bwd(ws, f"{p}.src_attn.linears.1.weight", ws.mem, ws.dmemkv, count=2, dx=ws.dmem, dx_residual=ws.dmem)
             # self-attention sublayer
             ga_s = ws.ga.view(-1)[: MD * d].view(MD, d)
-            self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.d_att[l], cur, p=pd, site=60 + l, dx=ga_s)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.d_att[l], cur, p=pd, site=60 + l, dx=ga_s, pre=pre)
             q = ws.d_qkv[l]
             gq = ws.gq[:MD]
             K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_probs[l], ga_s, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
@@ -623,7 +646,8 @@ class OrtTrainer:
                             p=pd, seed=self._sd(2), stream_id=self._drop_stream(50 + l))
             ga_s2 = ws.ga.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], gq, count=3, dx=ga_s2)
-            self._ln_bwd(f"{p}.sublayer.0.norm", y0, ga_s2, nxt, dres=cur)
+            pre = self._ln_bwd(f"{p}.sublayer.0.norm", y0, ga_s2, nxt, dres=cur, ws=ws,
+                               nxt=(f"model.decoder.layers.{l - 1}.feed_forward.w_2.weight", pd, 100 + l - 1) if l > first else None)
             cur, nxt = nxt, cur
         ws.cur = 0 if cur.data_ptr() == ws.dres[0].data_ptr() else 1
         if phase == 0:
@@ -656,21 +680,24 @@ class OrtTrainer:
         pd = self.p_drop if self.training else 0.0
         trig = not c.no_box_trigonometric_embedding
         half = L // 2
+        pre = None
         if part == 0:
             ws.cur = 0
-            self._ln_bwd("model.encoder.norm", ws.xe[2 * L], ws.dmem, ws.dres[0][:ME])
+            pre = self._ln_bwd("model.encoder.norm", ws.xe[2 * L], ws.dmem, ws.dres[0][:ME], ws=ws,
+                               nxt=(f"model.encoder.layers.{L - 1}.feed_forward.w_2.weight", pd, 40 + L - 1))
+        first = half if part == 0 else 0
         cur, nxt = ws.dres[ws.cur][:ME], ws.dres[1 - ws.cur][:ME]
         for l in (reversed(range(half, L)) if part == 0 else reversed(range(half))):
             p = f"model.encoder.layers.{l}"
             x0, x1 = ws.xe[2 * l], ws.xe[2 * l + 1]
             ga_ff = ws.ga.view(-1)[: ME * ff].view(ME, ff)
-            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.e_hid[l], cur, p=pd, site=40 + l, dx=ga_ff)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.e_hid[l], cur, p=pd, site=40 + l, dx=ga_ff, pre=pre)
             ga_dd = ws.gq.view(-1)[: ME * d].view(ME, d)
             self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.e_xn2[l], ga_ff, h=ws.e_hid[l], p=pd, dx=ga_dd)
-            self._ln_bwd(f"{p}.sublayer.1.norm", x1, ga_dd, nxt, dres=cur)
+            pre = self._ln_bwd(f"{p}.sublayer.1.norm", x1, ga_dd, nxt, dres=cur, ws=ws, nxt=(f"{p}.self_attn.linears.3.weight", pd, 20 + l))
             cur, nxt = nxt, cur
             ga_a = ws.ga.view(-1)[: ME * d].view(ME, d)
-            self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.e_att[l], cur, p=pd, site=20 + l, dx=ga_a)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.e_att[l], cur, p=pd, site=20 + l, dx=ga_a, pre=pre)
             q = ws.e_qkv[l]
             gq = ws.gq[:ME]
             K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
@@ -686,7 +713,8 @@ class OrtTrainer:
                         stream_id=stream, bypass=self.bypass)
             ga_a2 = ws.ga.view(-1)[: ME * d].view(ME, d)
             self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], gq, count=3, dx=ga_a2)
-            self._ln_bwd(f"{p}.sublayer.0.norm", x0, ga_a2, nxt, dres=cur)
+            pre = self._ln_bwd(f"{p}.sublayer.0.norm", x0, ga_a2, nxt, dres=cur, ws=ws,
+                               nxt=(f"model.encoder.layers.{l - 1}.feed_forward.w_2.weight", pd, 40 + l - 1) if l > first else None)
             cur, nxt = nxt, cur
         ws.cur = 0 if cur.data_ptr() == ws.dres[0].data_ptr() else 1
         if part == 0:
