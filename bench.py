@@ -208,8 +208,11 @@ def main():
     ap.add_argument("--ln-fold", action="store_true", help="LayerNorm folded into the consuming GEMMs (sc_linear_ln) instead of separate LayerNorm kernels")
     ap.add_argument("--no-fuse-topk", action="store_true", help="diagnostic: materialise the logits (sc_linear + sc_beam_step) instead of the fused generator + beam row pass")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostic: disable programmatic dependent launch")
-    ap.add_argument("--slots", type=int, default=8, help="batches in flight (pipeline slots: stream + workspaces + graphs each)")
+    ap.add_argument("--slots", type=int, default=0, help="batches in flight (pipeline slots: stream + workspaces + graphs each); 0 = 8 when the timed region is long enough "
+                         "to amortise the pipeline's fill and drain (>= 24 steps), else 4")
     args = ap.parse_args()
+    if args.slots <= 0:
+        args.slots = 8 if args.steps >= 24 else 4
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -225,7 +225,7 @@ def test_d512_bf16_fused_paths_match_unfused():
     tr4, l4, gw4, gs4 = grads(4)
     tr1, l1, gw1, gs1 = grads(1)
     assert len(tr4._ws[(B, 36, S, T, False)].gb_ring) == 4 and len(tr1._ws[(B, 36, S, T, False)].gb_ring) == 1
-    assert l4 == l1
+    assert abs(l4 - l1) < 1e-5 * abs(l1)  # (the loss is an atomic sum over rows: order-dependent in the last bits)
     # same bf16 operands on both paths; only the summation order of the bias / LayerNorm atomics differs
     assert rel_err(gw4, gw1) < 1e-4
     assert rel_err(gs4, gs1) < 1e-4
