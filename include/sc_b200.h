@@ -176,6 +176,13 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
 /* greedy branch of _generate_captions (models/transformer.py:507-561) */
 int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, int* seq,
                    float* seq_lp, int* tokens, int* unfinished, int* live_count, sc_stream_t stream);
+/* multinomial step (num_random_sample > 0, models/transformer.py:531-538): token ~ Categorical(exp(log_softmax(x) / T)) by
+ * inverse CDF in index order with u = uniforms[r] (fp32 [R], tests) or Philox(seed, stream t, row r) when uniforms == NULL
+ * (seed: immediate, or bit 63 set = device pointer to the 64-bit seed, so a captured graph can be re-seeded); the stored
+ * log-prob is the un-tempered log_softmax entry; bookkeeping as sc_greedy_step. */
+int sc_sample_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, float temperature,
+                   const float* uniforms, unsigned long long seed, int* seq, float* seq_lp, int* tokens, int* unfinished,
+                   int* live_count, sc_stream_t stream);
 
 /* K8 — state[i][:, state_ix] (models/caption_model.py:106-110): dst[r] = src[idx[r]], rows of row_bytes */
 int sc_cache_reorder(const void* src, void* dst, const int* idx, long rows, long row_bytes, sc_stream_t stream);

@@ -687,6 +687,64 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
   }
 }
 
+// multinomial step (num_random_sample > 0, models/transformer.py:531-538): it ~ Categorical(exp(logprobs / T)), the stored
+// log-prob is the un-tempered log_softmax entry.  One warp per row; inverse CDF in index order: the sampled token is the
+// first i with sum_{j<=i} w_j > u * sum_j w_j, u = uniforms[r] (tests) or Philox(seed, stream t, row).
+__global__ void __launch_bounds__(256) sample_step_kernel(const float* __restrict__ logits, int R, int V, int L, int t, int eos,
+                                                          int constraint, float inv_T, const float* __restrict__ uniforms,
+                                                          unsigned long long seed, int* __restrict__ seq,
+                                                          float* __restrict__ seq_lp, int* __restrict__ tokens,
+                                                          int* __restrict__ unfinished, int* __restrict__ live_count) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  if (t > 0 && live_count[t - 1] == 0) return;
+  const float* x = logits + (size_t)r * V;
+  const int prev = (constraint && t > 0) ? seq[(size_t)r * L + t - 1] : -1;
+  float rmx = -INFINITY;
+  for (int i = lane; i < V; i += 32) rmx = fmaxf(rmx, x[i]);
+  rmx = sc::warp_max(rmx);
+  float se = 0.f;
+  for (int i = lane; i < V; i += 32) se += expf(x[i] - rmx);
+  se = sc::warp_sum(se);
+  const float lse = rmx + logf(se);
+  float tot = 0.f;
+  // weights relative to the row maximum: exp((lp_i - lp_max) / T) - the same distribution as exp(lp_i / T), without the
+  // underflow of small temperatures
+  for (int i = lane; i < V; i += 32) tot += (i == prev) ? 0.f : expf((x[i] - rmx) * inv_T);
+  tot = sc::warp_sum(tot);
+  float u;
+  if (uniforms) u = uniforms[r];
+  else { const sc::Philox ph(seed); u = sc::u24(ph((uint64_t)r, (uint64_t)t).x); }
+  const float thr = u * tot;
+  float cum = 0.f;
+  int pick = -1;
+  for (int base = 0; base < V && pick < 0; base += 32) {
+    const int i = base + lane;
+    float w = (i < V && i != prev) ? expf((x[i] - rmx) * inv_T) : 0.f;
+    float sc_ = w;  // inclusive scan over the 32 lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, sc_, o);
+      if (lane >= o) sc_ += n;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, w > 0.f && cum + sc_ > thr);
+    if (hit) pick = base + __ffs(hit) - 1;
+    cum += __shfl_sync(0xffffffffu, sc_, 31);
+  }
+  // rounding can leave the threshold a hair above the accumulated total: take the last admissible token
+  if (pick < 0) pick = (V - 1 == prev) ? V - 2 : V - 1;
+  if (lane == 0) {
+    const int unf = unfinished[r];
+    seq[(size_t)r * L + t] = unf ? pick : 0;
+    seq_lp[(size_t)r * L + t] = x[pick] - lse;
+    const int still = unf && (pick != eos);
+    unfinished[r] = still;
+    tokens[r] = pick;
+    if (still) atomicAdd(&live_count[t], 1);
+  }
+}
+
 // K8: dst[r] = src[idx[r]] for rows of row_bytes (16-byte vectorised)
 __global__ void __launch_bounds__(256) reorder_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
                                                            const int* __restrict__ idx, long rows, long vec_per_row) {
@@ -875,6 +933,17 @@ int sc_greedy_step(const float* logits, int R, int V, int L, int t, int eos, int
   greedy_step_kernel<<<(R * 32 + 255) / 256, 256, 0, stream>>>(logits, R, V, L, t, eos, decoding_constraint, seq, seq_lp,
                                                               tokens, unfinished, live_count);
   SC_LAUNCH_CHECK("sc_greedy_step");
+  return SC_OK;
+}
+
+int sc_sample_step(const float* logits, int R, int V, int L, int t, int eos, int decoding_constraint, float temperature,
+                   const float* uniforms, unsigned long long seed, int* seq, float* seq_lp, int* tokens, int* unfinished,
+                   int* live_count, cudaStream_t stream) {
+  SC_CHECK(R > 0 && V > 1 && t >= 0 && t < L && temperature > 0.f, SC_ERR_SHAPE, "sc_sample_step: R=%d V=%d t=%d L=%d T=%f", R, V, t, L,
+           temperature);
+  sample_step_kernel<<<(R * 32 + 255) / 256, 256, 0, stream>>>(logits, R, V, L, t, eos, decoding_constraint, 1.0f / temperature,
+                                                              uniforms, seed, seq, seq_lp, tokens, unfinished, live_count);
+  SC_LAUNCH_CHECK("sc_sample_step");
   return SC_OK;
 }
 

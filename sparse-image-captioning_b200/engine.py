@@ -282,6 +282,8 @@ class OrtEngine:
         for name, val in hints.items():
             for e in self.dec.values():
                 e[name].tile_n = int(val)
+        self._sample_seed = torch.zeros(1, dtype=torch.int64, device=self.dev)  # re-seeds captured sampling graphs
+        self._sample_count = 0
         self._enc_ws = {}
         self._dec_ws = {}
         self._streams = {}
@@ -411,8 +413,8 @@ class OrtEngine:
         ws.launches = lib.launch_count - before
 
     # ------------------------------------------------------------------------------------------------
-    def _get_dec_ws(self, B, beam, N, greedy, slot=0):
-        key = (B, beam, N, greedy, slot)
+    def _get_dec_ws(self, B, beam, N, greedy, slot=0, tag=None):
+        key = (B, beam, N, greedy, slot, tag)
         if key in self._dec_ws:
             return self._dec_ws[key]
         c, dev, adt = self.cfg, self.dev, self.adt
@@ -527,13 +529,48 @@ class OrtEngine:
             K.greedy_step(ws.logits, st, t, R=ws.R, V=V, L=L, eos=c.eos_token_id,
                           constraint=opt.get("decoding_constraint", 0))
 
+    def _sample_body(self, ws, enc, opt):
+        c = self.cfg
+        L, V = c.max_seq_length, c.vocab_size
+        st = ws.state
+        st.reset(c.bos_token_id, c.pad_token_id)
+        for t in range(L):
+            self._decode_step(ws, enc, t, st.anc)
+            K.sample_step(ws.logits, st, t, R=ws.R, V=V, L=L, eos=c.eos_token_id, constraint=opt.get("decoding_constraint", 0),
+                          temperature=opt.get("temperature", 1.0), uniforms=ws.uniforms[t] if ws.uniforms is not None else None,
+                          seed=(1 << 63) | self._sample_seed.data_ptr())
+
     def decode(self, enc, opt):
-        """Beam (beam_size > 1) or greedy search over an encoded batch.  Returns (seq int32 [B,b,L], lp [B,b,L])."""
+        """Beam (beam_size > 1), greedy (beam_size == 1) or multinomial (num_random_sample > 0, models/transformer.py:
+        507-561) decoding over an encoded batch.  Returns (seq int32 [B,b,L], lp [B,b,L]); b = num_random_sample when sampling.
+        ``opt["sample_seed"]`` re-seeds the sampler (default: a counter), ``opt["sample_uniforms"]`` (fp32 [L, B*n], tests)
+        replaces the Philox draws."""
         beam = int(opt.get("beam_size", 1))
-        if opt.get("num_random_sample", 0) > 0:
-            raise NotImplementedError("multinomial sampling is not part of the B200 hot path yet")
         if opt.get("group_size", 1) != 1:
             raise NotImplementedError("diverse beam search (group_size > 1) is out of scope (SURVEY.md section 2.1 #6)")
+        n_rand = int(opt.get("num_random_sample", 0))
+        if n_rand > 0:
+            assert beam < 1, f"Beam size must be < 1, saw {beam}"  # transformer.py:509
+            opt = dict(opt)
+            seed = opt.pop("sample_seed", None)
+            uni = opt.pop("sample_uniforms", None)
+            self._sample_count += 1
+            self._sample_seed.fill_(int(seed) if seed is not None else 0x5CB200 + self._sample_count)
+            ws = self._get_dec_ws(enc.B, n_rand, enc.N, True, enc.slot, tag="sample")
+            ws.uniforms = None
+            if uni is not None:
+                ws.uniforms = uni.to(self.dev, torch.float32).contiguous()
+                assert tuple(ws.uniforms.shape) == (self.cfg.max_seq_length, enc.B * n_rand)
+            body = lambda: self._sample_body(ws, enc, opt)
+            opt_key = (id(enc), "sample", uni is not None, tuple(sorted((k, str(v)) for k, v in opt.items())))
+            if not self.use_graphs or uni is not None:
+                body()
+            else:
+                if ws.graph is None or ws.opt_key != opt_key:
+                    self._warm_and_capture(ws, body)
+                    ws.opt_key = opt_key
+                ws.graph.replay()
+            return ws.state.seq.view(enc.B, n_rand, -1), ws.state.lp.view(enc.B, n_rand, -1)
         greedy = beam == 1
         assert beam <= self.cfg.vocab_size
         ws = self._get_dec_ws(enc.B, beam, enc.N, greedy, enc.slot)

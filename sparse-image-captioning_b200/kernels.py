@@ -321,6 +321,12 @@ def greedy_step(logits, st, t, *, R, V, L, eos, constraint=0):
              lib.ptr(st.tokens), lib.ptr(st.unfinished), lib.ptr(st.live), lib.stream())
 
 
+def sample_step(logits, st, t, *, R, V, L, eos, constraint=0, temperature=1.0, uniforms=None, seed=0):
+    """Multinomial step on a GreedyState (one row per sample): sc_sample_step."""
+    lib.call("sc_sample_step", lib.ptr(logits), R, V, L, t, eos, int(constraint), float(temperature), lib.ptr(uniforms), seed,
+             lib.ptr(st.seq), lib.ptr(st.lp), lib.ptr(st.tokens), lib.ptr(st.unfinished), lib.ptr(st.live), lib.stream())
+
+
 def cache_reorder(src, idx, out=None):
     """dst[r] = src[idx[r]] along dim 0 (K8)."""
     rows = idx.numel()

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sc_linear_topk": [_p, _p, _p, _i, _i, _i, _p, _p],
     "sc_beam_step_partials": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "sc_greedy_step": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "sc_sample_step": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _u64, _p, _p, _p, _p, _p, _p],
     "sc_cache_reorder": [_p, _p, _p, _l, _l, _p],
     # training
     "sc_linear_dropout": [_p, _i, _p, _i, _p, _i, _p, _u64, _u64, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],

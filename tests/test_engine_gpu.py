@@ -140,3 +140,23 @@ def test_pipelined_slots_match_sequential():
                 for j in range(i - i % 3, i + 1):
                     assert torch.equal(outs[j][0].long(), want[j][0]), (rep, j)
                     torch.testing.assert_close(outs[j][1], want[j][1], rtol=1e-5, atol=1e-6)
+
+
+def test_multinomial_sampling_plumbing():
+    """num_random_sample > 0 (models/transformer.py:507-561): B x n rows decode with their own KV history and the image's
+    cross K/V; at temperature -> 0 every sample collapses onto the greedy caption; seeds re-seed captured graphs."""
+    cfg, ocfg, sd = _medium(seed=4)
+    data = O.synthetic_inputs(6, 36, cfg["att_feat_size"], seed=5)
+    eng = _engine(sd, cfg, precision="fp32")
+    gseq, glp = eng.sample(data["att_feats"], data["boxes"], None, {"beam_size": 1})
+    seq, lp = eng.sample(data["att_feats"], data["boxes"], None, {"beam_size": 0, "num_random_sample": 3, "temperature": 0.01})
+    assert tuple(seq.shape) == (6, 3, cfg["max_seq_length"])
+    assert torch.equal(seq, gseq.expand(6, 3, -1))
+    torch.testing.assert_close(lp, glp.expand(6, 3, -1), rtol=1e-5, atol=1e-5)
+    a, _ = eng.sample(data["att_feats"], data["boxes"], None, {"beam_size": 0, "num_random_sample": 3, "sample_seed": 5})
+    b, _ = eng.sample(data["att_feats"], data["boxes"], None, {"beam_size": 0, "num_random_sample": 3, "sample_seed": 5})
+    c, lpc = eng.sample(data["att_feats"], data["boxes"], None, {"beam_size": 0, "num_random_sample": 3, "sample_seed": 6})
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert bool((lpc <= 0).all())
+    # samples of one image differ from each other at temperature 1 (vocabulary 300, 10 steps)
+    assert bool((c[:, 0] != c[:, 1]).any())

@@ -510,3 +510,54 @@ def test_beam_step_partials_matches_beam_step(K):
         torch.testing.assert_close(sa.sum, sb.sum, rtol=1e-5, atol=1e-4)
     assert torch.equal(sa.done_seq, sb.done_seq) and torch.equal(sa.done_count, sb.done_count)
     torch.testing.assert_close(sa.done_lp, sb.done_lp, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("temperature,constraint", [(1.0, 0), (0.7, 1)])
+def test_sample_step_inverse_cdf(K, temperature, constraint):
+    """Multinomial step with injected uniforms == inverse CDF of exp(log_softmax(x) / T) in index order (what
+    torch.multinomial samples from, models/transformer.py:531-538); stored log-prob = un-tempered log_softmax entry."""
+    from sparse_caption_b200.engine import GreedyState
+    g = torch.Generator().manual_seed(31)
+    R, V, L, t = 700, 1000, 6, 2
+    logits = (torch.randn(R, V, generator=g) * 2).cuda()
+    u = torch.rand(R, generator=g).cuda()
+    st = GreedyState(R, L, "cuda")
+    st.reset(2, 0)
+    prevtok = torch.randint(0, V, (R,), generator=g).int().cuda()
+    st.seq[:, t - 1] = prevtok
+    st.live[t - 1] = R
+    K.sample_step(logits, st, t, R=R, V=V, L=L, eos=3, constraint=constraint, temperature=temperature, uniforms=u)
+    lp = torch.log_softmax(logits.double(), 1)
+    w = torch.exp(lp / temperature)
+    if constraint:
+        w.scatter_(1, prevtok.long().unsqueeze(1), 0.0)
+    cdf = torch.cumsum(w, 1)
+    ref = torch.searchsorted(cdf, (u.double() * cdf[:, -1]).unsqueeze(1), right=True).squeeze(1).clamp_max(V - 1)
+    got = st.tokens.long()
+    # fp32 vs fp64 prefix sums may disagree when u lands within rounding of a CDF step
+    assert float((got == ref).float().mean()) > 0.995
+    same = got == ref
+    torch.testing.assert_close(st.lp[:, t][same], lp.gather(1, got.unsqueeze(1)).squeeze(1).float()[same], rtol=1e-5, atol=1e-5)
+    if constraint:
+        assert bool((got != prevtok.long()).all())
+    assert torch.equal(st.seq[:, t].long(), got) and int(st.live[t]) == int((got != 3).sum())
+
+
+def test_sample_step_distribution(K):
+    """Philox-driven sampling reproduces the categorical distribution (20 000 rows sharing one logits row) and is
+    deterministic for a given seed."""
+    from sparse_caption_b200.engine import GreedyState
+    g = torch.Generator().manual_seed(32)
+    R, V, L = 20000, 40, 4
+    row = torch.randn(V, generator=g) * 1.5
+    logits = row.unsqueeze(0).expand(R, V).contiguous().cuda()
+    outs = []
+    for seed in (7, 7, 8):
+        st = GreedyState(R, L, "cuda")
+        st.reset(2, 0)
+        K.sample_step(logits, st, 0, R=R, V=V, L=L, eos=3, seed=seed)
+        outs.append(st.tokens.clone())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    freq = torch.bincount(outs[0].long().cpu(), minlength=V).double() / R
+    p = torch.softmax(row.double(), 0)
+    assert float((freq - p).abs().max()) < 4 * float(torch.sqrt(p.max() * (1 - p.max()) / R)) + 2e-3
