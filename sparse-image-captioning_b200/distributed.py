@@ -39,3 +39,73 @@ def make_all_reduce(group=None, async_op=False):
         return work if async_op else None
 
     return _ar
+
+
+class ShardedExchange:
+    """ZeRO-1 style exchange + update, bucket by bucket: reduce-scatter of a finished gradient range, the owner updates its
+    1/world shard of the parameters (and keeps the only live copy of that shard's Adam moments), all-gather of the updated
+    parameters.  Same bytes on the wire as the all-reduce it replaces, but the optimizer's HBM traffic (28 B per
+    parameter) drops by the world size, and the whole chain of a bucket runs on a side stream underneath the next backward
+    phase ("alternative if all-reduce does not hide").
+
+    ``bucket(grad, param, a, b, update)``: grad / param are the flat fp32 buffers, [a, b) the finished range,
+    ``update(lo, hi)`` applies the optimizer in place to param[lo:hi] from the rank-summed grad[lo:hi].  The range is cut
+    into world equal shards plus a tail of < world elements that every rank updates redundantly (identical inputs ->
+    identical results).  NCCL: everything is enqueued on ``self.stream``; gloo (CPU tests): blocking calls."""
+
+    def __init__(self, group=None, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+        self.stream = torch.cuda.Stream(device) if self.nccl else None
+        self._tmp = None
+
+    def _staging(self, n, like):
+        if self._tmp is None or self._tmp.numel() < n or self._tmp.device != like.device:
+            self._tmp = torch.empty(n, dtype=like.dtype, device=like.device)
+        return self._tmp[:n]
+
+    def shard(self, a, b):
+        """(lo, hi, mid): this rank owns [lo, hi); [mid, b) is the redundantly updated tail."""
+        n = (b - a) // self.world
+        return a + self.rank * n, a + (self.rank + 1) * n, a + n * self.world
+
+    def bucket(self, grad, param, a, b, update):
+        lo, hi, mid = self.shard(a, b)
+        n = hi - lo
+        if self.nccl:
+            cur = torch.cuda.current_stream(grad.device)
+            self.stream.wait_stream(cur)  # the bucket's gradients were produced on the caller's stream
+            with torch.cuda.stream(self.stream):
+                self._bucket(grad, param, a, b, lo, hi, mid, n, update)
+        else:
+            self._bucket(grad, param, a, b, lo, hi, mid, n, update)
+
+    def _bucket(self, grad, param, a, b, lo, hi, mid, n, update):
+        if n > 0:
+            if self.nccl:
+                tmp = self._staging(n, grad)
+                dist.reduce_scatter_tensor(tmp, grad[a:mid], op=dist.ReduceOp.SUM, group=self.group)
+                grad[lo:hi].copy_(tmp)
+            else:  # gloo has no reduce-scatter
+                dist.all_reduce(grad[a:mid], op=dist.ReduceOp.SUM, group=self.group)
+        if b > mid:
+            dist.all_reduce(grad[mid:b], op=dist.ReduceOp.SUM, group=self.group)
+        if n > 0:
+            update(lo, hi)
+        if b > mid:
+            update(mid, b)
+        if n > 0:
+            own = param[lo:hi].clone()
+            if self.nccl:
+                dist.all_gather_into_tensor(param[a:mid], own, group=self.group)
+            else:
+                parts = [torch.empty_like(own) for _ in range(self.world)]
+                dist.all_gather(parts, own, group=self.group)
+                param[a:mid].copy_(torch.cat(parts))
+
+    def finish(self):
+        """Order the caller's stream after every bucket's chain."""
+        if self.nccl:
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)

@@ -751,6 +751,52 @@ class OrtTrainer:
             if self._s_pad_idx.numel():
                 self.flat_s.index_fill_(0, self._s_pad_idx, -1.0)
 
+    def _sparsity_coeff(self, *, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1, **_):
+        """Device scalar d(sparsity loss)/d(nnz) from the CURRENT logits (must run before any logit is updated)."""
+        if not (self.masked and self.mask_type == "supermask") or sparsity_target is None or not sparsity_weight:
+            return None
+        anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
+        self.sp_count.zero_()
+        K.lib.call("sc_mask_count", K.lib.ptr(self.flat_s), self.flat_s.numel(), K.lib.ptr(self.sp_count), K.lib.stream())
+        K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out)
+        return self.sp_out[1:2]
+
+    def _sharded_step(self, ws, exchange, opt, lr):
+        """Data-parallel step with the optimizer sharded over the ranks (distributed.ShardedExchange): after each backward
+        phase the finished buckets go through reduce-scatter -> Adam on the owned shard -> all-gather on the exchange's
+        stream while the next phase computes."""
+        o = dict(mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0, grad_scale=1.0)
+        o.update({k: v for k, v in opt.items() if k in o})
+        coeff = self._sparsity_coeff(**opt)
+        self.opt_step += 1
+        step = max(1, self.opt_step)
+
+        def upd_w(lo, hi):
+            K.adam_clip(self.flat_w[lo:hi], self.flat_gw[lo:hi], self.m_w[lo:hi], self.v_w[lo:hi], lr=lr, betas=o["betas"], eps=o["eps"],
+                        weight_decay=o["weight_decay"], clip=o["clip"], grad_scale=o["grad_scale"], step=step)
+
+        def upd_s(lo, hi):
+            K.adam_clip(self.flat_s[lo:hi], self.flat_gs[lo:hi], self.m_s[lo:hi], self.v_s[lo:hi], lr=o["mask_lr"], betas=o["betas"],
+                        eps=o["mask_eps"], weight_decay=0.0, clip=o["clip"], grad_scale=o["grad_scale"], step=step,
+                        sigmoid_grad_coeff=coeff)
+
+        exchange.finish()  # (the coefficient above must be ordered before the first bucket's update: same stream chain)
+        for phase, part in enumerate(("fwd_p0", "p1", "p2", "p3")):
+            if self.use_graph:
+                self._run_graphed(ws, part, opt)
+            else:
+                if phase == 0:
+                    self.forward(ws)
+                self.backward_phase(ws, phase)
+            for flat, a, b in self.grad_buckets(phase):
+                if flat is self.flat_gw:
+                    exchange.bucket(self.flat_gw, self.flat_w, a, b, upd_w)
+                elif self.mask_type == "supermask":
+                    exchange.bucket(self.flat_gs, self.flat_s, a, b, upd_s)
+        exchange.finish()
+        if self.masked and self.mask_type == "supermask" and self._s_pad_idx.numel():
+            self.flat_s.index_fill_(0, self._s_pad_idx, -1.0)
+
     def _upload_step(self, *, lr, mask_lr=100.0, betas=(0.9, 0.98), sparsity_weight=0.0, current_step=0, max_step=1, **_):
         """Per-step scalars of the captured graph -> pinned host words -> device (two tiny async copies)."""
         self.opt_step += 1
@@ -806,23 +852,33 @@ class OrtTrainer:
         graphs[key].replay()
         K.lib.launch_count += ws.graph_launches[key]
 
-    def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None, **opt):
-        """One full SMP step.  ``all_reduce``: callable applied to the flat gradient buffers (NCCL sum) when data-parallel."""
+    def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None,
+                   exchange=None, **opt):
+        """One full SMP step.  Data parallel: either ``all_reduce`` (callable applied to the gradient buckets, NCCL sum, every
+        rank then runs the whole optimizer) or ``exchange`` (distributed.ShardedExchange: reduce-scatter -> Adam on the owned
+        shard -> all-gather per bucket, overlapped with the backward)."""
         # programmatic dependent launch on the GEMMs measured SLOWER on the training chain, on the row / attention kernels
         # slightly faster (ms/step, side-stream weight gradients on: mask 0 6.22, 1 6.09, 2 5.91, 3 6.08; scripts/gpu_sell.sh)
         prev_pdl = K.set_pdl(self.pdl_mask)
         try:
             return self._train_step(att_feats, boxes, seqs, masks, att_masks, seq_per_img=seq_per_img, lr=lr, all_reduce=all_reduce,
-                                    global_tokens=global_tokens, **opt)
+                                    global_tokens=global_tokens, exchange=exchange, **opt)
         finally:
             K.set_pdl(prev_pdl)
 
-    def _train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None, **opt):
+    def _train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None,
+                    exchange=None, **opt):
         B, N = att_feats.shape[:2]
         T = seqs.shape[1] - 1
         ws = self._get_ws(B, N, seq_per_img, T, att_masks is not None)
         self.step_id += 1
         self.load_batch(ws, att_feats, boxes, seqs, masks, att_masks, global_tokens)
+        if exchange is not None and self.training:
+            if self.use_graph:
+                self._upload_step(lr=lr, **opt)
+                self.opt_step -= 1  # (_sharded_step counts the step itself)
+            self._sharded_step(ws, exchange, dict(opt, lr=lr) if self.use_graph else opt, lr)
+            return ws.loss_sum * ws.inv_norm
         if self.use_graph and self.training:
             self._upload_step(lr=lr, **opt)
             opt = dict(opt, lr=lr)

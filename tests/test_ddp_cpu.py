@@ -80,3 +80,47 @@ def test_sharded_gradients_equal_single_process(tmp_path):
     gw, gs = _grads(z, 0, z["att_feats"].shape[0], denom)
     torch.testing.assert_close(got["gw"], gw, rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(got["gs"], gs, rtol=1e-4, atol=1e-7)
+
+
+def _sharded_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparse_caption_b200 import distributed as D
+    g = torch.Generator().manual_seed(100 + rank)
+    n = 1003  # not a multiple of the world size: exercises the redundantly updated tail
+    param = torch.arange(n, dtype=torch.float32) / 7.0          # identical on every rank
+    grad = torch.randn(n, generator=g)                          # rank-local gradient
+    ex = D.ShardedExchange()
+    calls = []
+
+    def update(lo, hi):  # stand-in optimizer: SGD with lr 0.5 on the rank-summed gradient
+        calls.append((lo, hi))
+        param[lo:hi] -= 0.5 * grad[lo:hi]
+
+    for a, b in ((0, 400), (400, 401), (401, n)):  # three buckets, one shorter than the world size
+        ex.bucket(grad, param, a, b, update)
+    ex.finish()
+    torch.save({"param": param, "grad_local_seed": 100 + rank, "calls": calls}, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_exchange_equals_allreduce_update(tmp_path):
+    """reduce-scatter -> owner update -> all-gather (distributed.ShardedExchange) leaves every rank with the parameters an
+    all-reduce + full update would produce; each element is updated by exactly one rank, tails by all."""
+    out = str(tmp_path / "zero1.pt")
+    port = 31500 + os.getpid() % 2000
+    world = 3
+    mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
+    n = 1003
+    total = sum(torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    want = torch.arange(n, dtype=torch.float32) / 7.0 - 0.5 * total
+    got = [torch.load(f"{out}.{r}") for r in range(world)]
+    for r in range(world):
+        torch.testing.assert_close(got[r]["param"], want, rtol=1e-6, atol=1e-6)
+    # ownership: the shards of bucket (0, 400) partition [0, 399) and the tail [399, 400) is updated by everyone
+    owned = sorted(c for r in range(world) for c in got[r]["calls"] if c[1] <= 399)
+    assert owned == [(0, 133), (133, 266), (266, 399)]
+    assert all((399, 400) in got[r]["calls"] and (400, 401) in got[r]["calls"] for r in range(world))
