@@ -221,7 +221,9 @@ def main():
                          "to amortise the pipeline's fill and drain (>= 24 steps), else 4")
     args = ap.parse_args()
     if args.slots <= 0:
-        args.slots = 8 if args.steps >= 24 else 4
+        # the K timed steps go round-robin over the slots; a slot count that divides K keeps every round of the pipeline
+        # full (K = 10 -> 5 slots: two full rounds instead of 4 + 4 + 2), long runs amortise fill / drain anyway
+        args.slots = 8 if args.steps >= 24 else next((sl for sl in (8, 7, 6, 5, 4) if args.steps % sl == 0), 4)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
