@@ -246,6 +246,12 @@ int sc_colsum(const void* x, int dtype, float* out, int rows, int cols, int accu
 int sc_layernorm_bwd(const float* x, const float* a, const void* dy, int dy_dtype, const float* dres, float* dx, float* da,
                      float* db, int rows, int D, float eps, sc_stream_t stream);
 
+/* dX GEMM of a linear whose input was h = dropout(relu(.)) (feed_forward.w_2, models/transformer.py:315-325): y bf16 [M,N] =
+ * (x w^T) * scale where h (bf16 [M,N]) != 0, else 0 = the gradient operand of the previous linear; colsum (fp32 [N],
+ * accumulated, may be NULL) += column sums of y = its bias gradient.  x bf16 [M,K], w bf16 [N,K]. */
+int sc_linear_hmask(const void* x, const void* w, const void* h, float scale, float* colsum, void* y, int M, int N, int K,
+                    sc_stream_t stream);
+
 /* the same backward, also preparing the gradient operand of the NEXT linear of the backward chain (o-proj / ff2, whose
  * output gradient is dx): next_gb bf16 [rows, D] = dx (.) dropout keep mask of that linear's forward (Philox(seed,
  * stream_id, element), p = next_dropout_p), next_colsum fp32 [D] += its column sums (the bias gradient).  D == 512. */
@@ -280,6 +286,13 @@ int sc_attention_bwd(const void* q, const void* k, const void* v, int ldq, int l
                      const float* d_out, int ldd, float* dq, float* dk_, float* dv, int ldgq, int ldgk, int ldgv, float* dbias,
                      int G, int Tq, int Tk, int h, int dk, float dropout_p, unsigned long long seed,
                      unsigned long long stream_id, sc_stream_t stream);
+/* the same backward with the gradient preparation of the q / k / v projections that follow in the backward chain fused in
+ * (bf16 operands, d_k = 64): dq / dk / dv leave as bf16, bq / bk / bv (fp32 [h * d_k], accumulated, all or none) receive
+ * their column sums = the projections' bias gradients. */
+int sc_attention_bwd_bf16out(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
+                             const float* d_out, int ldd, void* dq, void* dk_, void* dv, int ldgq, int ldgk, int ldgv, float* bq,
+                             float* bk, float* bv, float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p,
+                             unsigned long long seed, unsigned long long stream_id, sc_stream_t stream);
 /* log(max(relu(WG_h . emb(i,j) + b_h), 1e-6)) for all heads, and its gradient to WG (relation_transformer.py:179-183,196-256) */
 int sc_box_bias_fwd(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int h, int trig,
                     float wave_len, sc_stream_t stream);

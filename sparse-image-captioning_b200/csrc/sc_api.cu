@@ -82,6 +82,20 @@ int sc_linear_topk(const void* x, const void* w, const float* bias, int M, int N
                              stream);
 }
 
+// Backward chain, dX GEMM of a linear whose INPUT was h = dropout(relu(.)) (feed-forward w_2): y [M,N] bf16 =
+// (x w^T) * scale where h != 0, else 0 - i.e. the gradient with respect to the pre-activation of the previous linear, ready
+// as its weight-gradient / dX operand - and colsum += column sums of y (that linear's bias gradient).  Replaces the fp32
+// store of dX plus the separate sc_prep_grad pass.
+int sc_linear_hmask(const void* x, const void* w, const void* h, float scale, float* colsum, void* y, int M, int N, int K,
+                    cudaStream_t stream) {
+  SC_CHECK(h != nullptr && ((uintptr_t)h & 15) == 0 && (colsum == nullptr || ((uintptr_t)colsum & 3) == 0), SC_ERR_ALIGN,
+           "sc_linear_hmask: h must be 16-byte aligned");
+  ScGemmExtra ex = {};
+  ex.hmask = h; ex.hscale = scale; ex.colsum = colsum;
+  return sc_gemm_bf16_launch(x, w, SC_BF16, nullptr, SC_MASK_NONE, nullptr, 0, 0, nullptr, nullptr, y, SC_BF16, M, N, K, 0, 0, &ex,
+                             stream);
+}
+
 // training forward: y = dropout(act(x (W.m)^T + b), p) + residual, dropout mask = Philox(drop_seed, drop_stream, element)
 int sc_linear_dropout(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
                       const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,

@@ -407,7 +407,28 @@ int sc_attn_train_bwd_mma_launch(const void* q, const void* k, const void* v, in
                                  float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p, unsigned long long seed,
                                  unsigned long long stream_id, cudaStream_t stream);
 
+int sc_attn_train_bwd_mma_launch2(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
+                                  const float* d_out, int ldd, void* dq, void* dk_, void* dv, int out_bf16, int ldgq, int ldgk, int ldgv,
+                                  float* bq, float* bk, float* bv, float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p,
+                                  unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+
 extern "C" {
+
+// sc_attention_bwd with the gradient preparation of the following q / k / v projections fused in (bf16, d_k = 64 tensor path
+// only; SC_ERR_UNSUPPORTED otherwise, nothing launched): dq / dk / dv are written as bf16 and bq / bk / bv (fp32 [h * d_k],
+// accumulated) receive their column sums, i.e. the projections' bias gradients.
+int sc_attention_bwd_bf16out(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
+                             const float* d_out, int ldd, void* dq, void* dk_, void* dv, int ldgq, int ldgk, int ldgv, float* bq,
+                             float* bk, float* bv, float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p,
+                             unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
+  int rc = check_common("sc_attention_bwd_bf16out", G, Tq, Tk, h, dk);
+  if (rc) return rc;
+  SC_CHECK(probs != nullptr, SC_ERR_SHAPE, "sc_attention_bwd_bf16out: saved probabilities missing");
+  rc = sc_attn_train_bwd_mma_launch2(q, k, v, ldq, ldk, ldv, probs, d_out, ldd, dq, dk_, dv, 1, ldgq, ldgk, ldgv, bq, bk, bv, dbias, G,
+                                     Tq, Tk, h, dk, dropout_p, seed, stream_id, stream);
+  SC_CHECK(rc != SC_ERR_UNSUPPORTED, SC_ERR_UNSUPPORTED, "sc_attention_bwd_bf16out: shape / alignment not served by the tensor path");
+  return rc;
+}
 
 int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* key_valid,
                      const float* bias, float* probs, void* out, int ldo, int G, int Tq, int Tk, int h, int dk, int causal_T,

@@ -56,6 +56,9 @@ struct ScGemmExtra {
   int mn_major;
   // generator fused with the beam step's row pass (kEpi == 3): [M][2 * ceil(N / 256)][12] records, no output tile
   float* topk_part;
+  // dX GEMM preparing the next linear's gradient operand: y (bf16) = acc * hscale where hmask (bf16 [M,N]) != 0 else 0,
+  // colsum (fp32 [N], accumulated) += column sums of y
+  const void* hmask; float hscale; float* colsum;
 };
 
 // Programmatic dependent launch (griddepcontrol): kernels launched through sc::launch_pdl may start while their

@@ -54,6 +54,9 @@ struct GemmArgs {
   // kEpi == 3 (generator fused with the beam step's row pass): no output tile; per (row, N tile, epilogue-warp half) one
   // record {max, sum exp(x - max), kTopK largest values, their columns} -> topk_part[row][tiles_n * 2][kTopKRec]
   float* topk_part;
+  // dX GEMM that prepares the NEXT linear's gradient operand (kEpi == 4, bf16 output, no residual): y = acc * hscale where
+  // the saved post-ReLU/dropout activation hmask[row, col] != 0, else 0; colsum[col] += column sums of the bf16 values
+  const __nv_bfloat16* hmask; float hscale; float* colsum;
 };
 
 constexpr int kTopK = 5;                 // candidates kept per record (beam sizes up to 5 use the fused path)
@@ -585,7 +588,54 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          // kEpi == 4 (hmask): the saved activation of this thread's row chunk is requested before the accumulator load
+          uint4 hm[kEpi == 4 ? 4 : 1];
+          if constexpr (kEpi == 4) {
+            if (args.hmask != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hm[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (row < args.M && (args.N & 7) == 0 && col0 + 32 <= args.N) {
+                const uint4* hp = (const uint4*)(args.hmask + (size_t)row * args.N + col0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hm[j] = hp[j];
+              } else if (row < args.M) {
+                unsigned short* hs = (unsigned short*)hm;
+                for (int j = 0; j < 32; ++j)
+                  hs[j] = (col0 + j < args.N) ? __bfloat16_as_ushort(args.hmask[(size_t)row * args.N + col0 + j]) : (unsigned short)0;
+              }
+            }
+          }
           epilogue_row<kEpi == 1>(args, f, res, row, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
+          if constexpr (kEpi == 4) {
+            if (args.hmask != nullptr) {
+              const unsigned short* hs = (const unsigned short*)hm;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                // (0x0000 and 0x8000 are +-0: "activation was zero" = ReLU inactive or dropped)
+                const float v = ((hs[j] & 0x7fffu) != 0 && row < args.M && col0 + j < args.N) ? f[j] * args.hscale : 0.f;
+                f[j] = __bfloat162float(__float2bfloat16_rn(v));  // the value the consuming GEMMs (and the bias gradient) see
+              }
+              if (args.colsum != nullptr) {
+                // column sums over the warp's 32 rows: recursive halving leaves lane j with the sum of column j
+                float cs[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) cs[j] = f[j];
+#pragma unroll
+                for (int half_w = 16; half_w >= 1; half_w >>= 1) {
+                  const bool upper = (lane & half_w) != 0;
+#pragma unroll
+                  for (int j = 0; j < half_w; ++j) {
+                    // keep the half of the columns this lane stays responsible for, send the other half to the partner
+                    const float keep = upper ? cs[j + half_w] : cs[j];
+                    const float send = upper ? cs[j] : cs[j + half_w];
+                    cs[j] = keep + __shfl_xor_sync(0xffffffffu, send, half_w);
+                  }
+                }
+                // lane's column: bit-reversal-free mapping - lane l ends up owning column l (upper halves took the upper columns)
+                if (col0 + lane < args.N) atomicAdd(args.colsum + col0 + lane, cs[0]);
+              }
+            }
+          }
           if constexpr (kEpi == 3) {
             // columns are visited in ascending order: strict '>' keeps the smaller column on ties
             float cm = -INFINITY;
@@ -989,13 +1039,24 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     a.wg_w = ex->wg_w; a.wg_s = ex->wg_s; a.wg_u = ex->wg_u; a.dw = ex->dw; a.ds = ex->ds;
     a.ln_stats = ex->ln_stats; a.ln_c = ex->ln_c; a.ln_eps = ex->ln_eps; a.y2 = ex->y2; a.stats_out = ex->stats_out;
     a.topk_part = ex->topk_part;
+    a.hmask = (const __nv_bfloat16*)ex->hmask; a.hscale = ex->hscale; a.colsum = ex->colsum;
     if (ex->partial_splits > 0) {
       SC_CHECK(!wgrad && y_dtype == SC_F32 && !bias && !residual && !relu, SC_ERR_UNSUPPORTED, "split-K partial products are plain fp32 tiles");
       force_splits = ex->partial_splits;
       a.split_stride = ex->split_stride;
     }
   }
+  if (a.hmask) {
+    SC_CHECK(!masked && !wgrad && !residual && !bias && !relu && y_dtype == SC_BF16 && !(ex->mn_major), SC_ERR_UNSUPPORTED,
+             "sc_linear_hmask: bf16 operands, bf16 output, no bias / residual / ReLU");
+  }
   const int epi = a.wgrad ? 2 : ((a.dropout_p > 0.f || a.ln_stats || a.y2 || a.stats_out) ? 1 : 0);
+  if (a.hmask) {
+    // own epilogue kind (4) so that the dropout / LayerNorm epilogue keeps its register budget; 3-stage ring
+    if (block_n == 256) return launch<256, false, 3, 4>(ta, tb, a, force_splits, stream);
+    if (block_n == 128) return launch<128, false, 3, 4>(ta, tb, a, force_splits, stream);
+    return launch<64, false, 3, 4>(ta, tb, a, force_splits, stream);
+  }
   if (topk) return launch<256, false, 3, 3>(ta, tb, a, force_splits, stream);
   if (mn) {
     SC_CHECK(epi == 0, SC_ERR_UNSUPPORTED, "MN-major operands serve the plain epilogue only");

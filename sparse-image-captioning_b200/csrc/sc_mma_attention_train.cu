@@ -32,7 +32,27 @@ struct TrainAttnArgs {
   const float* d_out; int ldd;
   float* dq; float* dkk; float* dv; int ldgq, ldgk, ldgv;
   float* dbias;
+  // fused gradient preparation for the q / k / v projections that come next in the backward chain: the gradients leave as
+  // bf16 (the GEMM operand dtype) and their column sums (the projections' bias gradients, [h * 64] each) are accumulated
+  __nv_bfloat16* dq16; __nv_bfloat16* dk16; __nv_bfloat16* dv16;
+  float* bq; float* bk; float* bv;
 };
+
+// Column sums of an accumulator-layout tile (rows g / g + 8 of the quad layout, already masked to valid rows and rounded
+// to bf16) added into acc[n][c]; after the three shuffles lanes 0..3 (g == 0) hold the sums of columns n * 8 + 2 t + c.
+__device__ __forceinline__ void colsum_tile(float (&acc)[kDk / 8][2], const float (&v)[kDk / 8][4]) {
+#pragma unroll
+  for (int n = 0; n < kDk / 8; ++n)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float x = v[n][c] + v[n][2 + c];
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      acc[n][c] += x;
+    }
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -235,7 +255,7 @@ __global__ void __launch_bounds__(256) attn_train_fwd_mma_kernel(const TrainAttn
   }
 }
 
-template <int NT>
+template <int NT, bool kOut16>
 __global__ void __launch_bounds__(256) attn_train_bwd_mma_kernel(const TrainAttnArgs a) {
   extern __shared__ __align__(16) unsigned char smem_x[];
   sc::pdl_launch();
@@ -261,6 +281,11 @@ __global__ void __launch_bounds__(256) attn_train_bwd_mma_kernel(const TrainAttn
   const int g = lane >> 2, t = lane & 3;
   const sc::Philox ph(a.seed);
   const size_t pgh = ((size_t)gi * a.h + hh) * Tq;
+  float csq[kOut16 ? kDk / 8 : 1][2];  // bias-gradient partial sums of this warp's query tiles (lanes 0..3)
+  if constexpr (kOut16) {
+#pragma unroll
+    for (int n = 0; n < kDk / 8; ++n) { csq[n][0] = 0.f; csq[n][1] = 0.f; }
+  }
   // ---- phase A: one warp per 16-query tile ----
   for (int mt = warp; mt < MT; mt += nwarps) {
     const int m0 = mt * 16;
@@ -318,11 +343,32 @@ __global__ void __launch_bounds__(256) attn_train_bwd_mma_kernel(const TrainAttn
     }
     float o[kDk / 8][4];
     mma_pb<NT>(o, s, sK, lane);  // dQ = dS K
+    if constexpr (kOut16) {
 #pragma unroll
-    for (int n = 0; n < kDk / 8; ++n) {
-      const int col = hh * kDk + n * 8 + 2 * t;
-      if (ok0) *(float2*)(a.dq + ((size_t)gi * Tq + r0) * a.ldgq + col) = make_float2(o[n][0] * 0.125f, o[n][1] * 0.125f);
-      if (ok1) *(float2*)(a.dq + ((size_t)gi * Tq + r1) * a.ldgq + col) = make_float2(o[n][2] * 0.125f, o[n][3] * 0.125f);
+      for (int n = 0; n < kDk / 8; ++n) {
+        const int col = hh * kDk + n * 8 + 2 * t;
+        o[n][0] = ok0 ? bf16_round(o[n][0] * 0.125f) : 0.f; o[n][1] = ok0 ? bf16_round(o[n][1] * 0.125f) : 0.f;
+        o[n][2] = ok1 ? bf16_round(o[n][2] * 0.125f) : 0.f; o[n][3] = ok1 ? bf16_round(o[n][3] * 0.125f) : 0.f;
+        if (ok0) *(uint32_t*)(a.dq16 + ((size_t)gi * Tq + r0) * a.ldgq + col) = pack_bf16(o[n][0], o[n][1]);
+        if (ok1) *(uint32_t*)(a.dq16 + ((size_t)gi * Tq + r1) * a.ldgq + col) = pack_bf16(o[n][2], o[n][3]);
+      }
+      if (a.bq) colsum_tile(csq, o);
+    } else {
+#pragma unroll
+      for (int n = 0; n < kDk / 8; ++n) {
+        const int col = hh * kDk + n * 8 + 2 * t;
+        if (ok0) *(float2*)(a.dq + ((size_t)gi * Tq + r0) * a.ldgq + col) = make_float2(o[n][0] * 0.125f, o[n][1] * 0.125f);
+        if (ok1) *(float2*)(a.dq + ((size_t)gi * Tq + r1) * a.ldgq + col) = make_float2(o[n][2] * 0.125f, o[n][3] * 0.125f);
+      }
+    }
+  }
+  if constexpr (kOut16) {
+    if (a.bq && lane < 4) {
+#pragma unroll
+      for (int n = 0; n < kDk / 8; ++n)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (csq[n][c] != 0.f) atomicAdd(a.bq + hh * kDk + n * 8 + 2 * lane + c, csq[n][c]);
     }
   }
   __syncthreads();
@@ -354,6 +400,41 @@ __global__ void __launch_bounds__(256) attn_train_bwd_mma_kernel(const TrainAttn
       }
     }
     const int jr0 = j0 + g, jr1 = jr0 + 8;
+    if constexpr (kOut16) {
+      const bool k0 = jr0 < Tk, k1 = jr1 < Tk;
+#pragma unroll
+      for (int n = 0; n < kDk / 8; ++n) {
+        const int col = hh * kDk + n * 8 + 2 * t;
+        accK[n][0] = k0 ? bf16_round(accK[n][0] * 0.125f) : 0.f; accK[n][1] = k0 ? bf16_round(accK[n][1] * 0.125f) : 0.f;
+        accK[n][2] = k1 ? bf16_round(accK[n][2] * 0.125f) : 0.f; accK[n][3] = k1 ? bf16_round(accK[n][3] * 0.125f) : 0.f;
+        accV[n][0] = k0 ? bf16_round(accV[n][0]) : 0.f; accV[n][1] = k0 ? bf16_round(accV[n][1]) : 0.f;
+        accV[n][2] = k1 ? bf16_round(accV[n][2]) : 0.f; accV[n][3] = k1 ? bf16_round(accV[n][3]) : 0.f;
+        if (k0) {
+          *(uint32_t*)(a.dk16 + ((size_t)gi * Tk + jr0) * a.ldgk + col) = pack_bf16(accK[n][0], accK[n][1]);
+          *(uint32_t*)(a.dv16 + ((size_t)gi * Tk + jr0) * a.ldgv + col) = pack_bf16(accV[n][0], accV[n][1]);
+        }
+        if (k1) {
+          *(uint32_t*)(a.dk16 + ((size_t)gi * Tk + jr1) * a.ldgk + col) = pack_bf16(accK[n][2], accK[n][3]);
+          *(uint32_t*)(a.dv16 + ((size_t)gi * Tk + jr1) * a.ldgv + col) = pack_bf16(accV[n][2], accV[n][3]);
+        }
+      }
+      if (a.bk) {
+        float ck[kDk / 8][2], cv[kDk / 8][2];
+#pragma unroll
+        for (int n = 0; n < kDk / 8; ++n) { ck[n][0] = ck[n][1] = cv[n][0] = cv[n][1] = 0.f; }
+        colsum_tile(ck, accK);
+        colsum_tile(cv, accV);
+        if (lane < 4) {
+#pragma unroll
+          for (int n = 0; n < kDk / 8; ++n)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              atomicAdd(a.bk + hh * kDk + n * 8 + 2 * lane + c, ck[n][c]);
+              atomicAdd(a.bv + hh * kDk + n * 8 + 2 * lane + c, cv[n][c]);
+            }
+        }
+      }
+    } else {
 #pragma unroll
     for (int n = 0; n < kDk / 8; ++n) {
       const int col = hh * kDk + n * 8 + 2 * t;
@@ -365,6 +446,7 @@ __global__ void __launch_bounds__(256) attn_train_bwd_mma_kernel(const TrainAttn
         *(float2*)(a.dkk + ((size_t)gi * Tk + jr1) * a.ldgk + col) = make_float2(accK[n][2] * 0.125f, accK[n][3] * 0.125f);
         *(float2*)(a.dv + ((size_t)gi * Tk + jr1) * a.ldgv + col) = make_float2(accV[n][2], accV[n][3]);
       }
+    }
     }
   }
 }
@@ -408,17 +490,36 @@ int sc_attn_train_fwd_mma_launch(const void* q, const void* k, const void* v, in
   return SC_OK;
 }
 
+int sc_attn_train_bwd_mma_launch2(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
+                                  const float* d_out, int ldd, void* dq, void* dk_, void* dv, int out_bf16, int ldgq, int ldgk, int ldgv,
+                                  float* bq, float* bk, float* bv, float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p,
+                                  unsigned long long seed, unsigned long long stream_id, cudaStream_t stream);
+
 int sc_attn_train_bwd_mma_launch(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
                                  const float* d_out, int ldd, float* dq, float* dk_, float* dv, int ldgq, int ldgk, int ldgv,
                                  float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p, unsigned long long seed,
                                  unsigned long long stream_id, cudaStream_t stream) {
+  return sc_attn_train_bwd_mma_launch2(q, k, v, ldq, ldk, ldv, probs, d_out, ldd, dq, dk_, dv, 0, ldgq, ldgk, ldgv, nullptr, nullptr,
+                                       nullptr, dbias, G, Tq, Tk, h, dk, dropout_p, seed, stream_id, stream);
+}
+
+// out_bf16 != 0: dq / dk / dv are bf16 buffers (the operand dtype of the projection GEMMs that follow in the backward chain)
+// and bq / bk / bv (fp32 [h * 64], accumulated, may be NULL) receive their column sums = the projections' bias gradients.
+int sc_attn_train_bwd_mma_launch2(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const float* probs,
+                                  const float* d_out, int ldd, void* dq_, void* dk_, void* dv_, int out_bf16, int ldgq, int ldgk, int ldgv,
+                                  float* bq, float* bk, float* bv, float* dbias, int G, int Tq, int Tk, int h, int dk, float dropout_p,
+                                  unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
+  float* dq = out_bf16 ? nullptr : (float*)dq_;
+  float* dv = out_bf16 ? nullptr : (float*)dv_;
   if (dk != kDk || Tk > 128 || Tq > 1024) return SC_ERR_UNSUPPORTED;
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(d_out) || (ldq | ldk | ldv) % 8 != 0 || ldd % 4 != 0) return SC_ERR_UNSUPPORTED;
-  if (((uintptr_t)dq | (uintptr_t)dk_ | (uintptr_t)dv) % 8 != 0 || (ldgq | ldgk | ldgv) % 2 != 0) return SC_ERR_UNSUPPORTED;
+  if (((uintptr_t)dq_ | (uintptr_t)dk_ | (uintptr_t)dv_) % 8 != 0 || (ldgq | ldgk | ldgv) % 2 != 0) return SC_ERR_UNSUPPORTED;
+  if (out_bf16 && ((bq == nullptr) != (bk == nullptr) || (bk == nullptr) != (bv == nullptr))) return SC_ERR_UNSUPPORTED;
   TrainAttnArgs a = {};
+  if (out_bf16) { a.dq16 = (__nv_bfloat16*)dq_; a.dk16 = (__nv_bfloat16*)dk_; a.dv16 = (__nv_bfloat16*)dv_; a.bq = bq; a.bk = bk; a.bv = bv; }
   a.q = (const __nv_bfloat16*)q; a.k = (const __nv_bfloat16*)k; a.v = (const __nv_bfloat16*)v; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv;
   a.probs = const_cast<float*>(probs); a.G = G; a.Tq = Tq; a.Tk = Tk; a.h = h; a.dropout_p = dropout_p; a.seed = seed; a.stream = stream_id;
-  a.d_out = d_out; a.ldd = ldd; a.dq = dq; a.dkk = dk_; a.dv = dv; a.ldgq = ldgq; a.ldgk = ldgk; a.ldgv = ldgv; a.dbias = dbias;
+  a.d_out = d_out; a.ldd = ldd; a.dq = dq; a.dkk = out_bf16 ? nullptr : (float*)dk_; a.dv = dv; a.ldgq = ldgq; a.ldgk = ldgk; a.ldgv = ldgv; a.dbias = dbias;
   const int MT = (Tq + 15) / 16, NT = (Tk + 15) / 16;
   const size_t smem = (size_t)(2 * MT * 16 + 2 * NT * 16) * kPitch + (size_t)2 * MT * 16 * (32 * NT + 16);
   if (smem > 200 * 1024) return SC_ERR_UNSUPPORTED;
@@ -429,10 +530,12 @@ int sc_attn_train_bwd_mma_launch(const void* q, const void* k, const void* v, in
   case NTV: {                                                                                                           \
     static bool attr = false;                                                                                           \
     if (!attr) {                                                                                                        \
-      cudaFuncSetAttribute(attn_train_bwd_mma_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
+      cudaFuncSetAttribute(attn_train_bwd_mma_kernel<NTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
+      cudaFuncSetAttribute(attn_train_bwd_mma_kernel<NTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
       attr = true;                                                                                                      \
     }                                                                                                                   \
-    sc::launch_pdl_aux(attn_train_bwd_mma_kernel<NTV>, grid, dim3(32 * warps), smem, stream, a);                                              \
+    if (out_bf16) sc::launch_pdl_aux(attn_train_bwd_mma_kernel<NTV, true>, grid, dim3(32 * warps), smem, stream, a);            \
+    else sc::launch_pdl_aux(attn_train_bwd_mma_kernel<NTV, false>, grid, dim3(32 * warps), smem, stream, a);                    \
   } break
   switch (NT) {
     B_CASE(1); B_CASE(2); B_CASE(3); B_CASE(4); B_CASE(5); B_CASE(6); B_CASE(7); B_CASE(8);

@@ -284,6 +284,18 @@ def beam_step(logits, st, t, *, B, beam, V, L, eos, pad, temperature=1.0, constr
              st.ws.numel(), lib.stream())
 
 
+def linear_hmask(x, w, h, out, *, scale=1.0, colsum=None):
+    """out (bf16 [M,N]) = (x @ w^T) * scale where h != 0 else 0; colsum (fp32 [N]) += column sums of out (sc_linear_hmask)."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert x.dtype == w.dtype == h.dtype == out.dtype == torch.bfloat16 and tuple(h.shape) == tuple(out.shape) == (M, N)
+    for t, n in ((x, "x"), (w, "w"), (h, "h"), (out, "out"), (colsum, "colsum")):
+        _chk(t, n)
+    lib.call("sc_linear_hmask", lib.ptr(x), lib.ptr(w), lib.ptr(h), float(scale), lib.ptr(colsum), lib.ptr(out), M, N, K, lib.stream(),
+             meta=("gemm_bf16", M, N, K, 2, 2, 2, False, False, False))
+    return out
+
+
 def linear_topk_parts(N):
     """Records per row that sc_linear_topk writes for an N-column generator."""
     return 2 * ((N + 255) // 256)
@@ -506,6 +518,15 @@ def attention_bwd(q, k, v, probs, d_out, dq, dk_, dv, *, dtype, G, Tq, Tk, h, dk
     lib.call("sc_attention_bwd", lib.ptr(q), lib.ptr(k), lib.ptr(v), ldq, ldk, ldv, lib.dtype_code(dtype), lib.ptr(probs),
              lib.ptr(d_out), ldd, lib.ptr(dq), lib.ptr(dk_), lib.ptr(dv), ldgq, ldgk, ldgv, lib.ptr(dbias), G, Tq, Tk, h, dk,
              float(p), seed, stream_id, lib.stream())
+
+
+def attention_bwd_bf16out(q, k, v, probs, d_out, dq, dk_, dv, *, G, Tq, Tk, h, dk, ldq, ldk, ldv, ldd, ldgq, ldgk, ldgv, bq=None, bk=None,
+                          bv=None, dbias=None, p=0.0, seed=0, stream_id=0):
+    """attention_bwd whose dq / dk / dv are bf16 GEMM operands and whose bias gradients (column sums) go to bq / bk / bv."""
+    assert dq.dtype == dk_.dtype == dv.dtype == torch.bfloat16
+    lib.call("sc_attention_bwd_bf16out", lib.ptr(q), lib.ptr(k), lib.ptr(v), ldq, ldk, ldv, lib.ptr(probs), lib.ptr(d_out), ldd,
+             lib.ptr(dq), lib.ptr(dk_), lib.ptr(dv), ldgq, ldgk, ldgv, lib.ptr(bq), lib.ptr(bk), lib.ptr(bv), lib.ptr(dbias), G, Tq, Tk,
+             h, dk, float(p), seed, stream_id, lib.stream())
 
 
 def box_bias_fwd(boxes, wg_w, wg_b, bias, *, B, N, h, trig=True, wave_len=1000.0):

@@ -36,6 +36,7 @@ SIGNATURES = {
     "sc_decode_cross_attn_step": [_p, _i, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "sc_beam_step": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "sc_beam_step_workspace_bytes": [_i, _i],
+    "sc_linear_hmask": [_p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
     "sc_linear_topk_parts": [_i],
     "sc_linear_topk": [_p, _p, _p, _i, _i, _i, _p, _p],
     "sc_beam_step_partials": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
@@ -60,6 +61,7 @@ SIGNATURES = {
     "sc_sparsity_coeff": [_p, C.c_double, _f, _f, _p, _p, _p],
     "sc_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_attention_bwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
+    "sc_attention_bwd_bf16out": [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_box_bias_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     "sc_box_bias_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
 }

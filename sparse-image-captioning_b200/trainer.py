@@ -149,6 +149,11 @@ class OrtTrainer:
         self._premask_desc = None
         self.pdl_mask = 2            # sc_set_pdl mask while the step is launched / captured (see train_step)
         self.wgrad_ring = 4          # 1: weight gradients stay on the main stream
+        import os
+        self.fuse_hmask = os.environ.get("SC_NO_HMASK") != "1"      # ff2's dX GEMM prepares ff1's gradient operand
+        # attention backward emitting bf16 operands + bias gradients itself (sc_attention_bwd_bf16out): parity-tested, but
+        # measured SLOWER (5.66 vs 5.58 ms/step: ~640k same-address atomics for the bias sums) - off unless SC_ATTN16=1
+        self.fuse_attn_bwd = os.environ.get("SC_ATTN16") == "1"
         self._side = None
 
     # ---------------------------------------------------------------------------------------------------------
@@ -353,7 +358,8 @@ class OrtTrainer:
                          relu=relu, out=out, p=p, drop_seed=self._sd(1), drop_stream=self._drop_stream(site))
         return out
 
-    def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None, pre=None):
+    def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None, pre=None,
+                 dx_next=None):
         """Backward of y = drop(act(x W^T + b)).  g: fp32 [M,N] gradient wrt the layer output (after dropout);
         h: saved post-activation output when the layer has ReLU (mask = h != 0, which also covers its dropout);
         p/site: dropout to regenerate when h is None.  g_ready: (gb, None) when the gradient is already in the
@@ -391,12 +397,22 @@ class OrtTrainer:
             # the bias gradient (column sums) is accumulated by the same pass (flat_gw is zeroed at the start of the backward)
             K.prep_grad(g, h=h, out=gb, outT=gT, scale=(1.0 / (1.0 - p)) if (h is not None and p > 0) else 1.0,
                         p=0.0 if h is not None else p, seed=self._sd(1), stream_id=self._drop_stream(site), colsum=gbias)
+        nxt_pre = None
         if dx is not None:
             wT = self._wmT.get((wname, count)) if (self.adt == torch.bfloat16 and self.premask and self.training) else None
             if wT is None:
                 wT = ws.wT[: Kd * N].view(Kd, N)
                 K.apply_mask_transposed(W, S, mode, wT, uniforms=U, seed=seed, stream_id=stream)
-            K.linear(gb, wT, None, residual=dx_residual, out=dx)
+            if dx_next is not None and self.fuse_hmask and side and dx_residual is None and Kd % 8 == 0:
+                # this linear's input was h = dropout(relu(previous linear)): the dX GEMM's epilogue applies that mask, stores
+                # the bf16 gradient operand of the previous linear straight into a ring buffer and accumulates its bias
+                # gradient (sc_linear_hmask) - no fp32 dX tensor, no separate sc_prep_grad pass
+                hm, scale, next_wname = dx_next
+                gb_next, slot_next = self._take_gb(ws, M, Kd)
+                K.linear_hmask(gb, wT, hm, gb_next, scale=scale, colsum=self.g[next_wname.replace(".weight", ".bias")])
+                nxt_pre = (gb_next, slot_next)
+            else:
+                K.linear(gb, wT, None, residual=dx_residual, out=dx)
         gW = self._group(self.g, wname, count)
         gS = self._group(self.gs, wname, count) if S is not None else None
         if side:
@@ -412,7 +428,7 @@ class OrtTrainer:
                     ws.gb_free[slot] = torch.cuda.Event()
                     ws.gb_free[slot].record(st)
             ws.side_used = True
-            return
+            return nxt_pre
         if rowmajor:
             K.linear_wgrad_rowmajor(gb, x_saved, W, S, mode, gW, gS, workspace=ws.wgrad_ws, uniforms=U, seed=seed, stream_id=stream,
                                     bypass=self.bypass)
@@ -426,6 +442,12 @@ class OrtTrainer:
 
     def _ln(self, name, x, out):
         return K.layernorm(x, self.p[name + ".a_2"], self.p[name + ".b_2"], out=out)
+
+    def _attn_fused(self, ws):
+        """attention backward writes bf16 gradient operands + bias gradients itself (tensor path: bf16, d_k = 64, ring)."""
+        c = self.cfg
+        return (self.fuse_attn_bwd and self.adt == torch.bfloat16 and c.d_model // c.num_heads == 64 and len(ws.gb_ring) > 1
+                and ws.N <= 128 and ws.T <= 128)
 
     def _take_gb(self, ws, M, N):
         """Next gradient-operand buffer of the ring (waits for the side-stream consumer that used it last)."""
@@ -618,9 +640,10 @@ class OrtTrainer:
             y0, y1, y2 = ws.y[3 * l], ws.y[3 * l + 1], ws.y[3 * l + 2]
             ga_ff = ws.ga.view(-1)[: MD * ff].view(MD, ff)
             # feed-forward sublayer
-            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.d_hid[l], cur, p=pd, site=100 + l, dx=ga_ff, pre=pre)
+            pre1 = self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.d_hid[l], cur, p=pd, site=100 + l, dx=ga_ff, pre=pre,
+                                 dx_next=(ws.d_hid[l], 1.0 / (1.0 - pd) if pd > 0 else 1.0, f"{p}.feed_forward.w_1.weight"))
             ga_dd = ws.gq.view(-1)[: MD * d].view(MD, d)
-            self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.d_yn3[l], ga_ff, h=ws.d_hid[l], p=pd, dx=ga_dd)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.d_yn3[l], ga_ff, h=ws.d_hid[l], p=pd, dx=ga_dd, pre=pre1)
             pre = self._ln_bwd(f"{p}.sublayer.2.norm", y2, ga_dd, nxt, dres=cur, ws=ws, nxt=(f"{p}.src_attn.linears.3.weight", pd, 80 + l))
             cur, nxt = nxt, cur
             # cross-attention sublayer
@@ -628,24 +651,45 @@ class OrtTrainer:
             self._lin_bwd(ws, f"{p}.src_attn.linears.3.weight", ws.d_catt[l], cur, p=pd, site=80 + l, dx=ga_c, pre=pre)
             kv = ws.memkv[l]
             dqc = ws.gq.view(-1)[: MD * d].view(MD, d)
-            K.attention_bwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.c_probs[l], ga_c, dqc, ws.dmemkv[:, 0:], ws.dmemkv[:, d:],
-                            dtype=self.adt, G=B, Tq=S * T, Tk=N, h=h, dk=dk, ldq=d, ldk=2 * d, ldv=2 * d, ldd=d, ldgq=d, ldgk=2 * d,
-                            ldgv=2 * d, p=pd, seed=self._sd(2), stream_id=self._drop_stream(70 + l))
+            pre_q = pre_kv = None
+            if self._attn_fused(ws):
+                gbq, sq = self._take_gb(ws, MD, d)
+                gbkv, skv = self._take_gb(ws, ME, 2 * d)
+                bkv = self._group(self.g, f"{p}.src_attn.linears.1.bias", 2)
+                K.attention_bwd_bf16out(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.c_probs[l], ga_c, gbq, gbkv[:, 0:], gbkv[:, d:], G=B,
+                                        Tq=S * T, Tk=N, h=h, dk=dk, ldq=d, ldk=2 * d, ldv=2 * d, ldd=d, ldgq=d, ldgk=2 * d, ldgv=2 * d,
+                                        bq=self.g[f"{p}.src_attn.linears.0.bias"], bk=bkv[:d], bv=bkv[d:], p=pd, seed=self._sd(2),
+                                        stream_id=self._drop_stream(70 + l))
+                pre_q, pre_kv = (gbq, sq), (gbkv, skv)
+            else:
+                K.attention_bwd(ws.d_qc[l], kv[:, 0:], kv[:, d:], ws.c_probs[l], ga_c, dqc, ws.dmemkv[:, 0:], ws.dmemkv[:, d:],
+                                dtype=self.adt, G=B, Tq=S * T, Tk=N, h=h, dk=dk, ldq=d, ldk=2 * d, ldv=2 * d, ldd=d, ldgq=d, ldgk=2 * d,
+                                ldgv=2 * d, p=pd, seed=self._sd(2), stream_id=self._drop_stream(70 + l))
             ga_c2 = ws.ga.view(-1)[: MD * d].view(MD, d)
-            self._lin_bwd(ws, f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], dqc, dx=ga_c2)
+            self._lin_bwd(ws, f"{p}.src_attn.linears.0.weight", ws.d_yn2[l], dqc, dx=ga_c2, pre=pre_q)
             pre = self._ln_bwd(f"{p}.sublayer.1.norm", y1, ga_c2, nxt, dres=cur, ws=ws, nxt=(f"{p}.self_attn.linears.3.weight", pd, 60 + l))
             cur, nxt = nxt, cur
-            self._lin_bwd(ws, f"{p}.src_attn.linears.1.weight", ws.mem, ws.dmemkv, count=2, dx=ws.dmem, dx_residual=ws.dmem)
+            self._lin_bwd(ws, f"{p}.src_attn.linears.1.weight", ws.mem, ws.dmemkv, count=2, dx=ws.dmem, dx_residual=ws.dmem, pre=pre_kv)
             # self-attention sublayer
             ga_s = ws.ga.view(-1)[: MD * d].view(MD, d)
             self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.d_att[l], cur, p=pd, site=60 + l, dx=ga_s, pre=pre)
             q = ws.d_qkv[l]
             gq = ws.gq[:MD]
-            K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_probs[l], ga_s, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
-                            G=R, Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
-                            p=pd, seed=self._sd(2), stream_id=self._drop_stream(50 + l))
+            pre_qkv = None
+            if self._attn_fused(ws):
+                gb3, s3 = self._take_gb(ws, MD, 3 * d)
+                b3 = self._group(self.g, f"{p}.self_attn.linears.0.bias", 3)
+                K.attention_bwd_bf16out(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_probs[l], ga_s, gb3[:, 0:], gb3[:, d:], gb3[:, 2 * d:], G=R,
+                                        Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d,
+                                        ldgv=3 * d, bq=b3[:d], bk=b3[d: 2 * d], bv=b3[2 * d:], p=pd, seed=self._sd(2),
+                                        stream_id=self._drop_stream(50 + l))
+                pre_qkv = (gb3, s3)
+            else:
+                K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.d_probs[l], ga_s, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
+                                G=R, Tq=T, Tk=T, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
+                                p=pd, seed=self._sd(2), stream_id=self._drop_stream(50 + l))
             ga_s2 = ws.ga.view(-1)[: MD * d].view(MD, d)
-            self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], gq, count=3, dx=ga_s2)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.d_yn1[l], gq, count=3, dx=ga_s2, pre=pre_qkv)
             pre = self._ln_bwd(f"{p}.sublayer.0.norm", y0, ga_s2, nxt, dres=cur, ws=ws,
                                nxt=(f"model.decoder.layers.{l - 1}.feed_forward.w_2.weight", pd, 100 + l - 1) if l > first else None)
             cur, nxt = nxt, cur
@@ -691,18 +735,29 @@ class OrtTrainer:
             p = f"model.encoder.layers.{l}"
             x0, x1 = ws.xe[2 * l], ws.xe[2 * l + 1]
             ga_ff = ws.ga.view(-1)[: ME * ff].view(ME, ff)
-            self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.e_hid[l], cur, p=pd, site=40 + l, dx=ga_ff, pre=pre)
+            pre1 = self._lin_bwd(ws, f"{p}.feed_forward.w_2.weight", ws.e_hid[l], cur, p=pd, site=40 + l, dx=ga_ff, pre=pre,
+                                 dx_next=(ws.e_hid[l], 1.0 / (1.0 - pd) if pd > 0 else 1.0, f"{p}.feed_forward.w_1.weight"))
             ga_dd = ws.gq.view(-1)[: ME * d].view(ME, d)
-            self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.e_xn2[l], ga_ff, h=ws.e_hid[l], p=pd, dx=ga_dd)
+            self._lin_bwd(ws, f"{p}.feed_forward.w_1.weight", ws.e_xn2[l], ga_ff, h=ws.e_hid[l], p=pd, dx=ga_dd, pre=pre1)
             pre = self._ln_bwd(f"{p}.sublayer.1.norm", x1, ga_dd, nxt, dres=cur, ws=ws, nxt=(f"{p}.self_attn.linears.3.weight", pd, 20 + l))
             cur, nxt = nxt, cur
             ga_a = ws.ga.view(-1)[: ME * d].view(ME, d)
             self._lin_bwd(ws, f"{p}.self_attn.linears.3.weight", ws.e_att[l], cur, p=pd, site=20 + l, dx=ga_a, pre=pre)
             q = ws.e_qkv[l]
             gq = ws.gq[:ME]
-            K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
-                            G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
-                            dbias=ws.dbias, p=pd, seed=self._sd(2), stream_id=self._drop_stream(10 + l))
+            pre_qkv = None
+            if self._attn_fused(ws):
+                gb3, s3 = self._take_gb(ws, ME, 3 * d)
+                b3 = self._group(self.g, f"{p}.self_attn.linears.0.bias", 3)
+                K.attention_bwd_bf16out(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gb3[:, 0:], gb3[:, d:], gb3[:, 2 * d:], G=B,
+                                        Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d,
+                                        ldgv=3 * d, bq=b3[:d], bk=b3[d: 2 * d], bv=b3[2 * d:], dbias=ws.dbias, p=pd, seed=self._sd(2),
+                                        stream_id=self._drop_stream(10 + l))
+                pre_qkv = (gb3, s3)
+            else:
+                K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
+                                G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
+                                dbias=ws.dbias, p=pd, seed=self._sd(2), stream_id=self._drop_stream(10 + l))
             ws.dwg.zero_()
             gb_wg = self._group(self.g, f"{p}.self_attn.WGs.0.bias", h)
             gb_wg.zero_()
@@ -712,7 +767,7 @@ class OrtTrainer:
                         self._group(self.gs, f"{p}.self_attn.WGs.0.weight", h) if Sg is not None else None, uniforms=U, seed=seed,
                         stream_id=stream, bypass=self.bypass)
             ga_a2 = ws.ga.view(-1)[: ME * d].view(ME, d)
-            self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], gq, count=3, dx=ga_a2)
+            self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], gq, count=3, dx=ga_a2, pre=pre_qkv)
             pre = self._ln_bwd(f"{p}.sublayer.0.norm", x0, ga_a2, nxt, dres=cur, ws=ws,
                                nxt=(f"model.encoder.layers.{l - 1}.feed_forward.w_2.weight", pd, 40 + l - 1) if l > first else None)
             cur, nxt = nxt, cur

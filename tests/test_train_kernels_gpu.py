@@ -426,3 +426,20 @@ def test_apply_mask_batched_matches_per_tensor(K):
         for (W, S, U, out, outT, sid), (r, rT) in zip(items, refs):
             assert torch.equal(out, r), (mode, tuple(W.shape))
             assert torch.equal(outT, rT), (mode, tuple(W.shape))
+
+
+@pytest.mark.parametrize("shape", [(4250, 2048, 512), (300, 520, 136), (70, 96, 40)])
+def test_linear_hmask(K, shape):
+    """dX GEMM whose epilogue applies the saved-activation mask, stores bf16 and accumulates the bias gradient."""
+    M, N, Kd = shape
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(M, Kd, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(N, Kd, generator=g) * 0.1).bfloat16().to(DEV)
+    h = (torch.randn(M, N, generator=g).clamp_min(0) * (torch.rand(M, N, generator=g) > 0.3)).bfloat16().to(DEV)
+    out = torch.full((M, N), 9.0, device=DEV, dtype=torch.bfloat16)
+    colsum = torch.full((N,), 0.5, device=DEV)
+    K.linear_hmask(x, w, h, out, scale=1.25, colsum=colsum)
+    ref = (x.double() @ w.double().t()) * 1.25 * (h.double() != 0)
+    assert rel_err(out.float(), ref) < 1e-2
+    assert bool((out[h == 0] == 0).all())
+    assert rel_err(colsum - 0.5, out.double().sum(0)) < 1e-4   # sums of the bf16 values that were stored

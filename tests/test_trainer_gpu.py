@@ -214,6 +214,7 @@ def test_d512_bf16_fused_paths_match_unfused():
     def grads(ring):
         tr = OrtTrainer(sd, ModelCfg(cfg), mask_type="supermask", precision="bf16", device=DEV, seed=11, dropout=0.1, drop_prob_src=0.3)
         tr.wgrad_ring = ring
+        tr.fuse_attn_bwd = True  # (off by default for speed; its parity is still checked here)
         ws = tr._get_ws(B, 36, S, T, False)
         tr.step_id = 1
         tr.load_batch(ws, data["att_feats"].to(DEV), data["boxes"].to(DEV), seqs, masks)
