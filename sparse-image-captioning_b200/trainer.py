@@ -352,11 +352,22 @@ class OrtTrainer:
                     K.apply_mask(W, S, mode, uniforms=U, seed=seed, stream_id=stream, out=wm)
                 self._wm_step[key] = (self.step_id, self.training)
             K.linear_dropout(x, wm, b, residual=residual, relu=relu, out=out, p=p, drop_seed=self._sd(1),
-                             drop_stream=self._drop_stream(site))
+                             drop_stream=self._drop_stream(site), tile_n=self._fwd_tile(x.shape[0], wm.shape[0], wm.shape[1], residual is not None))
             return out
         K.linear_dropout(x, W, b, mask=S, mask_mode=mode, uniforms=U, seed=seed, stream_id=stream, residual=residual,
                          relu=relu, out=out, p=p, drop_seed=self._sd(1), drop_stream=self._drop_stream(site))
         return out
+
+    @staticmethod
+    def _fwd_tile(M, N, Kd, has_res):
+        """Tile hints (1000 * stages + block_n) where the sweep over the training shapes (scripts/train_gemm_sweep.py,
+        profiles/r01b_train_gemm_sweep.txt) beat the kernel's own heuristic: the fp32-residual + dropout epilogue is the long
+        pole of the d x d GEMMs and likes the 8-epilogue-warp configurations."""
+        if has_res and N <= 512:
+            return 5128 if M >= 3000 else 6064
+        if not has_res and N >= 2048 and M < 3000:
+            return 3256
+        return 0
 
     def _lin_bwd(self, ws, wname, x_saved, g, *, count=1, h=None, p=0.0, site=0, dx=None, dx_residual=None, g_ready=None, pre=None,
                  dx_next=None):
@@ -412,7 +423,7 @@ class OrtTrainer:
                 K.linear_hmask(gb, wT, hm, gb_next, scale=scale, colsum=self.g[next_wname.replace(".weight", ".bias")])
                 nxt_pre = (gb_next, slot_next)
             else:
-                K.linear(gb, wT, None, residual=dx_residual, out=dx)
+                K.linear(gb, wT, None, residual=dx_residual, out=dx, tile_n=5128 if (N >= 8192 and Kd <= 512) else 0)  # generator dX
         gW = self._group(self.g, wname, count)
         gS = self._group(self.gs, wname, count) if S is not None else None
         if side:
