@@ -69,7 +69,8 @@ int sc_linear_ln(const void* x, const void* w, const float* bias, const float* r
                  float* stats_out, sc_stream_t stream);
 
 /* Programmatic dependent launch (griddepcontrol) between consecutive kernels of a stream: 1 = on everywhere (default),
- * 0 = off; otherwise a mask: bit 0 = GEMM + inference kernels, bit 1 = training row / attention kernels. */
+ * 0 = off; otherwise a mask: bit 0 = GEMM + inference kernels, bit 1 = training row / attention kernels, bit 2 = the GEMM
+ * triggers its dependents as soon as its loads are issued (else implicitly at exit). */
 int sc_set_pdl(int enabled);
 
 /* K3b — the same product from CSR weights (rows = output features, 16-bit column indices, values in x's dtype).

@@ -3,8 +3,8 @@
 #include <cstring>
 
 static thread_local char g_err[512] = "";
-int g_sc_pdl = 3;  // programmatic dependent launch between consecutive kernels of a stream (sc_set_pdl): bit 0 GEMM /
-                   // inference kernels, bit 1 training row / attention kernels
+int g_sc_pdl = 7;  // programmatic dependent launch between consecutive kernels of a stream (sc_set_pdl): bit 0 GEMM /
+                   // inference kernels, bit 1 training row / attention kernels, bit 2 early trigger inside the GEMM (after its loads are issued)
 
 void sc_set_error(const char* fmt, ...) {
   va_list ap;
@@ -45,7 +45,7 @@ extern "C" {
 
 const char* sc_last_error(void) { return g_err; }
 int sc_version(void) { return 101; }
-int sc_set_pdl(int enabled) { g_sc_pdl = enabled == 1 ? 3 : (enabled & 3); return SC_OK; }
+int sc_set_pdl(int enabled) { g_sc_pdl = enabled == 1 ? 7 : (enabled & 7); return SC_OK; }
 
 int sc_linear(const void* x, int x_dtype, const void* w, int w_dtype, const float* mask, int mask_mode,
               const float* uniforms, unsigned long long seed, unsigned long long stream_id, const float* bias,

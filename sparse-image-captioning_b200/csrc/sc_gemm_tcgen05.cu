@@ -51,6 +51,7 @@ struct GemmArgs {
   // folded LayerNorm (consumer) / residual-stream producer (ScGemmExtra)
   const float* ln_stats; const float* ln_c; float ln_eps;
   void* y2; float* stats_out;
+  int pdl_early;  // trigger the dependent launch as soon as this CTA's loads are in flight (else: implicit, at exit)
   // kEpi == 3 (generator fused with the beam step's row pass): no output tile; per (row, N tile, epilogue-warp half) one
   // record {max, sum exp(x - max), kTopK largest values, their columns} -> topk_part[row][tiles_n * 2][kTopKRec]
   float* topk_part;
@@ -430,7 +431,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
       }
-      sc::pdl_launch();  // all loads of this CTA are in flight: let the next kernel's prologue start
+      if (args.pdl_early) sc::pdl_launch();  // all loads of this CTA are in flight: let the next kernel's prologue start
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -1029,6 +1030,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K;
+  a.pdl_early = (g_sc_pdl & 4) ? 1 : 0;
   a.w32 = masked ? (const float*)w : nullptr;
   a.mask = mask; a.uniforms = uniforms; a.mask_mode = mask_mode;
   a.seed = seed; a.stream_id = stream_id;

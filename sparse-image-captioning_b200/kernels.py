@@ -57,15 +57,15 @@ def linear_ln(x, w, bias=None, *, residual=None, relu=False, out=None, tile_n=0,
 
 def set_pdl(enabled):
     """Programmatic dependent launch between consecutive kernels of a stream (on by default).  True / False, or a mask:
-    bit 0 = GEMM + inference kernels, bit 1 = training row / attention kernels."""
+    bit 0 = GEMM + inference kernels, bit 1 = training row / attention kernels, bit 2 = early trigger inside the GEMM."""
     global _pdl_mask
     prev = _pdl_mask
-    _pdl_mask = 3 if enabled is True or enabled == 1 else int(enabled) & 3
+    _pdl_mask = 7 if enabled is True or enabled == 1 else int(enabled) & 7
     lib.load().sc_set_pdl(_pdl_mask)
     return prev
 
 
-_pdl_mask = 3
+_pdl_mask = 7
 
 
 class CsrWeight:

@@ -147,7 +147,7 @@ class OrtTrainer:
         self.premask = True   # False: mask inside the GEMM operand prologue (K1 fused variant)
         self._wm, self._wmT, self._wm_step = {}, {}, {}
         self._premask_desc = None
-        self.pdl_mask = 2            # sc_set_pdl mask while the step is launched / captured (see train_step)
+        self.pdl_mask = 3            # sc_set_pdl mask while the step is launched / captured (see train_step)
         self.wgrad_ring = 4          # 1: weight gradients stay on the main stream
         import os
         self.fuse_hmask = os.environ.get("SC_NO_HMASK") != "1"      # ff2's dX GEMM prepares ff1's gradient operand
@@ -923,8 +923,8 @@ class OrtTrainer:
         """One full SMP step.  Data parallel: either ``all_reduce`` (callable applied to the gradient buckets, NCCL sum, every
         rank then runs the whole optimizer) or ``exchange`` (distributed.ShardedExchange: reduce-scatter -> Adam on the owned
         shard -> all-gather per bucket, overlapped with the backward)."""
-        # programmatic dependent launch on the GEMMs measured SLOWER on the training chain, on the row / attention kernels
-        # slightly faster (ms/step, side-stream weight gradients on: mask 0 6.22, 1 6.09, 2 5.91, 3 6.08; scripts/gpu_sell.sh)
+        # programmatic dependent launch, measured on this chain (ms/step): the GEMM's EARLY trigger (bit 2: dependents may start
+        # once its loads are issued) costs time here, PDL with the implicit trigger at exit helps: mask 2 5.42, 3 5.30, 7 5.36
         prev_pdl = K.set_pdl(self.pdl_mask)
         try:
             return self._train_step(att_feats, boxes, seqs, masks, att_masks, seq_per_img=seq_per_img, lr=lr, all_reduce=all_reduce,
