@@ -155,6 +155,10 @@ class OrtTrainer:
         # measured SLOWER (5.66 vs 5.58 ms/step: ~640k same-address atomics for the bias sums) - off unless SC_ATTN16=1
         self.fuse_attn_bwd = os.environ.get("SC_ATTN16") == "1"
         self._side = None
+        self._ost = None
+        # decoder-side Adam on its own stream underneath the encoder backward: measured slower (5.42 vs 5.35 ms/step, the
+        # HBM-bound update slows the backward kernels more than it hides) - off unless SC_OPT_OVERLAP=1
+        self.overlap_opt = os.environ.get("SC_OPT_OVERLAP") == "1"
 
     # ---------------------------------------------------------------------------------------------------------
     def _group(self, table, first, count):
@@ -325,6 +329,11 @@ class OrtTrainer:
 
     def _side_wgrad(self):
         return self.adt == torch.bfloat16 and self.wgrad_ring > 1
+
+    def _opt_stream(self):
+        if self._ost is None:
+            self._ost = torch.cuda.Stream(self.dev)
+        return self._ost
 
     def _side_stream(self):
         if self._side is None:
@@ -793,28 +802,37 @@ class OrtTrainer:
 
     # ---------------------------------------------------------------------------------------------------------
     def optimizer_step(self, *, lr, mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0,
-                       grad_scale=1.0, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1, _dyn=False):
+                       grad_scale=1.0, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1, _dyn=False, part="all"):
         """clip_gradient(0.1) + Adam for the two parameter groups of train_n_prune_transformer.py:67-82, with the
         sparsity-loss gradient (prune.py:228-269) folded into the mask-logit update.  ``_dyn``: graph mode - lr, the Adam
-        bias corrections and the sparsity scale come from ``self._dyn_dev`` (``_upload_step``), no host bookkeeping."""
-        if not _dyn:
+        bias corrections and the sparsity scale come from ``self._dyn_dev`` (``_upload_step``), no host bookkeeping.
+        ``part``: "all", or the two halves of an overlapped update - "hi" = decoder + embedding + generator (their gradients are
+        final after backward phase 1; also computes the sparsity coefficient, which must see the logits before ANY update),
+        "lo" = att_embed + encoder (after the last phase; also re-pins the padding logits)."""
+        if not _dyn and part != "lo":
             self.opt_step += 1
         dyn = self._dyn_dev if _dyn else None
-        K.adam_clip(self.flat_w, self.flat_gw, self.m_w, self.v_w, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip=clip,
-                    grad_scale=grad_scale, step=max(1, self.opt_step), dyn=dyn[0:3] if _dyn else None)
+        cut_w = self._offs_w["model.decoder.layers.0.self_attn.linears.0.weight"]
+        lo_w, hi_w = {"all": (0, self.flat_w.numel()), "hi": (cut_w, self.flat_w.numel()), "lo": (0, cut_w)}[part]
+        K.adam_clip(self.flat_w[lo_w:hi_w], self.flat_gw[lo_w:hi_w], self.m_w[lo_w:hi_w], self.v_w[lo_w:hi_w], lr=lr, betas=betas, eps=eps,
+                    weight_decay=weight_decay, clip=clip, grad_scale=grad_scale, step=max(1, self.opt_step),
+                    dyn=dyn[0:3] if _dyn else None)
         if self.masked and self.mask_type == "supermask":
             coeff = None
             if sparsity_target is not None and sparsity_weight:
-                anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
-                self.sp_count.zero_()
-                K.lib.call("sc_mask_count", K.lib.ptr(self.flat_s), self.flat_s.numel(), K.lib.ptr(self.sp_count), K.lib.stream())
-                K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out,
-                                 scale_dev=dyn[6:7] if _dyn else None)
+                if part != "lo":
+                    anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
+                    self.sp_count.zero_()
+                    K.lib.call("sc_mask_count", K.lib.ptr(self.flat_s), self.flat_s.numel(), K.lib.ptr(self.sp_count), K.lib.stream())
+                    K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out,
+                                     scale_dev=dyn[6:7] if _dyn else None)
                 coeff = self.sp_out[1:2]
-            K.adam_clip(self.flat_s, self.flat_gs, self.m_s, self.v_s, lr=mask_lr, betas=betas, eps=mask_eps, weight_decay=0.0,
-                        clip=clip, grad_scale=grad_scale, step=max(1, self.opt_step), sigmoid_grad_coeff=coeff,
-                        dyn=dyn[3:6] if _dyn else None)
-            if self._s_pad_idx.numel():
+            cut_s = self._offs_s["model.decoder.layers.0.self_attn.linears.0.weight"]
+            lo_s, hi_s = {"all": (0, self.flat_s.numel()), "hi": (cut_s, self.flat_s.numel()), "lo": (0, cut_s)}[part]
+            K.adam_clip(self.flat_s[lo_s:hi_s], self.flat_gs[lo_s:hi_s], self.m_s[lo_s:hi_s], self.v_s[lo_s:hi_s], lr=mask_lr, betas=betas,
+                        eps=mask_eps, weight_decay=0.0, clip=clip, grad_scale=grad_scale, step=max(1, self.opt_step),
+                        sigmoid_grad_coeff=coeff, dyn=dyn[3:6] if _dyn else None)
+            if part != "hi" and self._s_pad_idx.numel():
                 self.flat_s.index_fill_(0, self._s_pad_idx, -1.0)
 
     def _sparsity_coeff(self, *, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1, **_):
@@ -880,6 +898,21 @@ class OrtTrainer:
 
     def _graph_body(self, ws, part, opt):
         self._wm_step = {}  # every body (eager warm-up, capture) re-applies the masks
+        if part == "all" and self.overlap_opt:
+            # the decoder-side half of the optimizer (64 % of the parameters) runs on its own stream underneath the encoder's
+            # backward: its gradients are final after phase 1 and nothing the remaining phases read is touched
+            self.forward(ws)
+            self.backward_phase(ws, 0)
+            self.backward_phase(ws, 1)
+            main, ost = torch.cuda.current_stream(self.dev), self._opt_stream()
+            ost.wait_stream(main)
+            with torch.cuda.stream(ost):
+                self.optimizer_step(_dyn=True, part="hi", **opt)
+            self.backward_phase(ws, 2)
+            self.backward_phase(ws, 3)
+            main.wait_stream(ost)
+            self.optimizer_step(_dyn=True, part="lo", **opt)
+            return
         if part in ("all", "fwdbwd"):
             self.forward(ws)
             self.loss_and_backward(ws)
