@@ -173,3 +173,37 @@ def test_gradient_buckets_partition_the_flat_buffers():
         # phase 0 must contain the generator, the last phase the first (att_embed) weight
         assert any(f is tr.flat_gw and b == tr.flat_gw.numel() for f, a, b in tr.grad_buckets(0))
         assert any(f is tr.flat_gw and a == 0 for f, a, b in tr.grad_buckets(tr.N_PHASES - 1))
+
+
+def test_radix_detokenisation_matches_reference_arithmetic():
+    """Vectorised radix -> word ids (detok.radix_to_word_ids) against a restatement of RadixTokenizer._decode_radix_ids
+    (tokenizer.py:583-602, 684-712) on random captions: with / without <eos>, ragged last groups, bos/pad inside."""
+    import itertools
+    import torch
+    from sparse_caption_b200.detok import radix_to_word_ids
+
+    def ref_decode(ids, base, tpw, eos):
+        ids = list(ids)
+        if eos in ids:
+            ids = ids[: ids.index(eos)]
+        groups = list(itertools.zip_longest(fillvalue=1, *([iter(ids)] * tpw)))
+        return [sum(max(d - 1, 0) * base ** i for i, d in enumerate(reversed(g))) + 4 for g in groups]
+
+    g = torch.Generator().manual_seed(0)
+    for base, tpw, L in ((768, 2, 26), (256, 2, 17), (16, 3, 20), (768, 1, 9)):
+        eos = base + 2
+        seq = torch.randint(0, base + 1, (7, 3, L), generator=g)
+        for b in range(7):
+            for k in range(3):
+                cut = int(torch.randint(0, L + 3, (1,), generator=g))
+                if cut < L:
+                    seq[b, k, cut] = eos
+                    seq[b, k, cut + 1:] = 0
+        seq[0, 0, 0] = base + 1  # a stray <bos> digit is decoded like any other id (as the reference does)
+        words, n = radix_to_word_ids(seq, base, tpw)
+        for b in range(7):
+            for k in range(3):
+                want = ref_decode(seq[b, k].tolist(), base, tpw, eos)
+                assert int(n[b, k]) == len(want)
+                assert words[b, k, : len(want)].tolist() == want
+                assert bool((words[b, k, len(want):] == 0).all())
