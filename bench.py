@@ -412,7 +412,7 @@ def main():
         res = torch.randn(M, N, device=dev) if has_res else None
         if ys == 0:  # generator fused with the beam row pass: no output tile, 12-float records per (row, tile half)
             part = torch.empty(M, KK.linear_topk_parts(N), 12, device=dev)
-            run = lambda i: KK.linear_topk(x, w, bias, part)
+            run = lambda i: KK.linear_topk(x, w, bias, part, candidates=BEAM)
         else:
             outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(4)]
             run = lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs[i % 4])

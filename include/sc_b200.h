@@ -158,11 +158,13 @@ int sc_beam_step_workspace_bytes(int B, int beam);
 /* Generator fused with the row pass of the beam step (OutputEmbedding, models/transformer.py:405-413, + beam_step,
  * models/caption_model.py:56-111): the [M, N] logits are never written.  sc_linear_topk (bf16 x [M,K], bf16 w [N,K], fp32
  * bias) leaves per row sc_linear_topk_parts(N) records of 12 floats {max, sum exp(x - max), 5 largest logits, their
- * columns as int bits} in partials [M][parts][12]; sc_beam_step_partials reduces them to the log-softmax statistics and the
+ * columns as int bits; only the first `candidates` (<= 5, = the beam size) are filled} in partials [M][parts][12];
+ * sc_beam_step_partials reduces them to the log-softmax statistics and the
  * row candidates and then runs the same per-image merge / bookkeeping as sc_beam_step (temperature 1, no decoding
  * constraint, beam <= 5). */
 int sc_linear_topk_parts(int N);
-int sc_linear_topk(const void* x, const void* w, const float* bias, int M, int N, int K, float* partials, sc_stream_t stream);
+int sc_linear_topk(const void* x, const void* w, const float* bias, int M, int N, int K, float* partials, int candidates,
+                   sc_stream_t stream);
 int sc_beam_step_partials(const float* partials, int parts_per_row, int B, int beam, int V, int L, int t, int eos, int pad,
                           int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out, const float* lp_in,
                           float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out, int* done_seq,

@@ -74,10 +74,12 @@ int sc_linear_ln(const void* x, const void* w, const float* bias, const float* r
 // tile, epilogue-warp half) the GEMM epilogue leaves one record of 12 floats {max, sum exp(x - max), 5 largest logits,
 // their column indices (int bits)} in partials [M][sc_linear_topk_parts(N)][12]; sc_beam_step_partials reduces them.
 int sc_linear_topk_parts(int N) { return 2 * ((N + 255) / 256); }
-int sc_linear_topk(const void* x, const void* w, const float* bias, int M, int N, int K, float* partials, cudaStream_t stream) {
+int sc_linear_topk(const void* x, const void* w, const float* bias, int M, int N, int K, float* partials, int candidates,
+                   cudaStream_t stream) {
   SC_CHECK(partials != nullptr && ((uintptr_t)partials & 3) == 0, SC_ERR_ALIGN, "sc_linear_topk: partials missing");
+  SC_CHECK(candidates >= 1 && candidates <= 5, SC_ERR_UNSUPPORTED, "sc_linear_topk: candidates=%d not in [1,5]", candidates);
   ScGemmExtra ex = {};
-  ex.topk_part = partials;
+  ex.topk_part = partials; ex.topk_n = candidates;
   return sc_gemm_bf16_launch(x, w, SC_BF16, nullptr, SC_MASK_NONE, nullptr, 0, 0, bias, nullptr, nullptr, SC_F32, M, N, K, 0, 0, &ex,
                              stream);
 }

@@ -55,7 +55,7 @@ struct ScGemmExtra {
   // operands given as x [K, M] and w [K, N] row-major (y = x^T w): MN-major UMMA tiles, no transposed copies
   int mn_major;
   // generator fused with the beam step's row pass (kEpi == 3): [M][2 * ceil(N / 256)][12] records, no output tile
-  float* topk_part;
+  float* topk_part; int topk_n;  // candidates actually needed per record (<= 3: cheaper epilogue)
   // dX GEMM preparing the next linear's gradient operand: y (bf16) = acc * hscale where hmask (bf16 [M,N]) != 0 else 0,
   // colsum (fp32 [N], accumulated) += column sums of y
   const void* hmask; float hscale; float* colsum;

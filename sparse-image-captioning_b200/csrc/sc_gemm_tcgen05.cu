@@ -547,13 +547,17 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
       if (kPrefetchRes) asm volatile("cp.async.wait_group 0;" ::: "memory");
-      // kEpi == 3: running log-sum-exp statistics and top-kTopK of this thread's row over the warp's chunks of the tile
+      // kEpi == 3 / 5: running log-sum-exp statistics and top-kTK (5 / 3) of this thread's row over the warp's chunks of the
+      // tile.  The insertion is warp-divergent (it runs whenever ANY lane has a new candidate, i.e. for most elements), so
+      // the depth matters: beam <= 3 uses the top-3 variant.
+      constexpr bool kTopkEpi = (kEpi == 3 || kEpi == 5);
+      constexpr int kTK = (kEpi == 5) ? 3 : kTopK;
       float tk_m = -INFINITY, tk_s = 0.f;
-      float tk_v[kEpi == 3 ? kTopK : 1];
-      int tk_i[kEpi == 3 ? kTopK : 1];
-      if constexpr (kEpi == 3) {
+      float tk_v[kTopkEpi ? kTK : 1];
+      int tk_i[kTopkEpi ? kTK : 1];
+      if constexpr (kTopkEpi) {
 #pragma unroll
-        for (int i = 0; i < kTopK; ++i) { tk_v[i] = -INFINITY; tk_i[i] = 0x7fffffff; }
+        for (int i = 0; i < kTK; ++i) { tk_v[i] = -INFINITY; tk_i[i] = 0x7fffffff; }
       }
 #pragma unroll 1
       for (int c = half; c < BLOCK_N / 32; c += kChunkStep) {
@@ -637,7 +641,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               }
             }
           }
-          if constexpr (kEpi == 3) {
+          if constexpr (kTopkEpi) {
             // columns are visited in ascending order: strict '>' keeps the smaller column on ties
             float cm = -INFINITY;
 #pragma unroll
@@ -649,10 +653,10 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               tk_s += __expf(f[j] - tk_m);
-              if (f[j] > tk_v[kTopK - 1]) {
-                tk_v[kTopK - 1] = f[j]; tk_i[kTopK - 1] = col0 + j;
+              if (f[j] > tk_v[kTK - 1]) {
+                tk_v[kTK - 1] = f[j]; tk_i[kTK - 1] = col0 + j;
 #pragma unroll
-                for (int i = kTopK - 1; i > 0; --i) {
+                for (int i = kTK - 1; i > 0; --i) {
                   if (tk_v[i] > tk_v[i - 1]) {
                     const float tv = tk_v[i]; tk_v[i] = tk_v[i - 1]; tk_v[i - 1] = tv;
                     const int ti = tk_i[i]; tk_i[i] = tk_i[i - 1]; tk_i[i - 1] = ti;
@@ -752,11 +756,14 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         __syncwarp();  // staging is rewritten by the next chunk
       }
-      if constexpr (kEpi == 3) if (rbase + lane < args.M) {
+      if constexpr (kTopkEpi) if (rbase + lane < args.M) {
         float* rec = args.topk_part + ((size_t)(rbase + lane) * (args.tiles_n * kChunkStep) + (size_t)(tile % args.tiles_n) * kChunkStep + half) * kTopKRec;
         rec[0] = tk_m; rec[1] = tk_s;
 #pragma unroll
-        for (int i = 0; i < kTopK; ++i) { rec[2 + i] = tk_v[i]; rec[2 + kTopK + i] = __int_as_float(tk_i[i]); }
+        for (int i = 0; i < kTopK; ++i) {
+          rec[2 + i] = i < kTK ? tk_v[i < kTK ? i : 0] : -INFINITY;
+          rec[2 + kTopK + i] = __int_as_float(i < kTK ? tk_i[i < kTK ? i : 0] : 0x7fffffff);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1059,7 +1066,8 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     if (block_n == 128) return launch<128, false, 3, 4>(ta, tb, a, force_splits, stream);
     return launch<64, false, 3, 4>(ta, tb, a, force_splits, stream);
   }
-  if (topk) return launch<256, false, 3, 3>(ta, tb, a, force_splits, stream);
+  if (topk) return ex->topk_n <= 3 ? launch<256, false, 3, 5>(ta, tb, a, force_splits, stream)
+                                   : launch<256, false, 3, 3>(ta, tb, a, force_splits, stream);
   if (mn) {
     SC_CHECK(epi == 0, SC_ERR_UNSUPPORTED, "MN-major operands serve the plain epilogue only");
     return block_n == 128 ? launch<128, false, 3, 0, true>(ta, tb, a, force_splits, stream)

@@ -498,7 +498,7 @@ class OrtEngine:
         else:
             self.dec_norm(ws.x, ws.xn)
             if fused_topk:
-                K.linear_topk(ws.xn, self.generator.w, self.generator.bias, ws.topk_part)
+                K.linear_topk(ws.xn, self.generator.w, self.generator.bias, ws.topk_part, candidates=ws.beam)
             else:
                 self.generator(ws.xn, ws.logits)
 

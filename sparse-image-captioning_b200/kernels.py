@@ -301,7 +301,7 @@ def linear_topk_parts(N):
     return 2 * ((N + 255) // 256)
 
 
-def linear_topk(x, w, bias, partials):
+def linear_topk(x, w, bias, partials, candidates=5):
     """Generator GEMM whose epilogue keeps only the per-row log-sum-exp partials and top-5 candidates (no logits):
     partials fp32 [M, linear_topk_parts(N), 12]."""
     M, K = x.shape
@@ -310,7 +310,7 @@ def linear_topk(x, w, bias, partials):
     assert tuple(partials.shape) == (M, linear_topk_parts(N), 12) and partials.dtype == torch.float32 and partials.is_contiguous()
     for t, n in ((x, "x"), (w, "w"), (bias, "bias"), (partials, "partials")):
         _chk(t, n)
-    lib.call("sc_linear_topk", lib.ptr(x), lib.ptr(w), lib.ptr(bias), M, N, K, lib.ptr(partials), lib.stream(),
+    lib.call("sc_linear_topk", lib.ptr(x), lib.ptr(w), lib.ptr(bias), M, N, K, lib.ptr(partials), int(candidates), lib.stream(),
              meta=("gemm_bf16", M, N, K, 2, 2, 0, False, False, False))
     return partials
 

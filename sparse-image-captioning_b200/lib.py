@@ -38,7 +38,7 @@ SIGNATURES = {
     "sc_beam_step_workspace_bytes": [_i, _i],
     "sc_linear_hmask": [_p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
     "sc_linear_topk_parts": [_i],
-    "sc_linear_topk": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "sc_linear_topk": [_p, _p, _p, _i, _i, _i, _p, _i, _p],
     "sc_beam_step_partials": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "sc_greedy_step": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "sc_sample_step": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _u64, _p, _p, _p, _p, _p, _p],

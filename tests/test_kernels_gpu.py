@@ -452,8 +452,9 @@ def test_beam_step(K, beam, V, opt):
     torch.testing.assert_close(st.done_lp.cpu(), ref_lp, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("cand", [5, 3])
 @pytest.mark.parametrize("shape", [(1536, 10000, 512), (77, 771, 512), (300, 256, 64), (5, 1000, 128)])
-def test_linear_topk_records(K, shape):
+def test_linear_topk_records(K, shape, cand):
     """Generator GEMM with the fused row pass: merged records == log-sum-exp and top-5 of the materialised logits."""
     M, N, Kd = shape
     g = torch.Generator().manual_seed(21)
@@ -463,7 +464,7 @@ def test_linear_topk_records(K, shape):
     logits = K.linear(x, w, b)  # fp32 logits from the same tensor-core kernel
     P = K.linear_topk_parts(N)
     part = torch.full((M, P, 12), float("nan"), device="cuda")
-    K.linear_topk(x, w, b, part)
+    K.linear_topk(x, w, b, part, candidates=cand)
     torch.cuda.synchronize()
     assert not torch.isnan(part[:, :, :7]).any()  # (the column slots hold int bits; an empty slot is 0x7fffffff)
     m, s = part[:, :, 0], part[:, :, 1]
@@ -472,7 +473,7 @@ def test_linear_topk_records(K, shape):
     torch.testing.assert_close(lse, torch.logsumexp(logits, 1), rtol=1e-5, atol=1e-5)
     vals = part[:, :, 2:7].reshape(M, -1)
     idx = part[:, :, 7:12].contiguous().view(torch.int32).reshape(M, -1)
-    k = min(5, N)
+    k = min(cand, N)
     top = vals.topk(k, 1)
     ref = logits.topk(k, 1)
     assert torch.equal(top.values, ref.values)  # same accumulator values, only the selection differs
@@ -501,7 +502,7 @@ def test_beam_step_partials_matches_beam_step(K):
             x = x.view(B, beam, Kd)[:, :1].expand(B, beam, Kd).reshape(R, Kd).contiguous()
         logits = K.linear(x, w, b)
         K.beam_step(logits, sa, t, B=B, beam=beam, V=V, L=L, eos=3, pad=0, penalty_kind=1, penalty_alpha=0.7)
-        K.linear_topk(x, w, b, part)
+        K.linear_topk(x, w, b, part, candidates=beam)
         K.beam_step_partials(part, sb, t, B=B, beam=beam, V=V, L=L, eos=3, pad=0, penalty_kind=1, penalty_alpha=0.7)
         o = (t + 1) & 1
         assert torch.equal(sa.tokens, sb.tokens), t
