@@ -450,7 +450,7 @@ def main():
                 "kernel_time_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (rank 0 at N = 1 only; at N > 1 the driver reads it from the N = 1 line)
         # bounded sample of ~10-20 s of CPU work: rate from one 64-image pass, then one pass sized from it
         v0, _, cores = cpu_arm(1, 1, args.cpu_images)
         n_img = int(min(1024, max(args.cpu_images, 32 * round(v0 * 12 / 32))))
