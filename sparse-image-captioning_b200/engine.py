@@ -299,15 +299,17 @@ class OrtEngine:
             self._streams[slot] = torch.cuda.Stream(self.dev)
         return self._streams[slot]
 
-    def _get_enc_ws(self, B, N, masked, slot=0):
-        key = (B, N, masked, slot)
+    def _get_enc_ws(self, B, N, masked, slot=0, bf16_in=False):
+        key = (B, N, masked, slot, bf16_in)
         if key in self._enc_ws:
             return self._enc_ws[key]
         c, dev, adt = self.cfg, self.dev, self.adt
         d, ff, M = c.d_model, c.dim_feedforward, B * N
         ws = type("EncWs", (), {})()
         ws.B, ws.N, ws.masked, ws.slot = B, N, masked, slot
-        ws.att_in = torch.zeros(M, c.att_feat_size, device=dev)
+        # bf16_in: the caller hands bf16 features (half the H2D bytes); they land directly in the GEMM operand buffer
+        ws.bf16_in = bool(bf16_in) and adt == torch.bfloat16
+        ws.att_in = torch.zeros(M, c.att_feat_size, device=dev) if not ws.bf16_in else None
         ws.att_a = torch.zeros(M, c.att_feat_size, device=dev, dtype=adt) if adt != torch.float32 else ws.att_in
         ws.boxes = torch.zeros(B, N, 4, device=dev)
         ws.att_mask = torch.ones(B, N, device=dev) if masked else None
@@ -332,7 +334,7 @@ class OrtEngine:
         c = self.cfg
         B, N, d, h = ws.B, ws.N, c.d_model, c.num_heads
         dk = d // h
-        if ws.att_a is not ws.att_in:
+        if ws.att_a is not ws.att_in and not ws.bf16_in:
             K.cast_bf16(ws.att_in, out=ws.att_a)
         fold = ws.fold
         if fold:
@@ -381,8 +383,9 @@ class OrtEngine:
         """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V.
         ``slot`` selects an independent set of workspaces/graphs so that several batches can be in flight."""
         B, N, F = att_feats.shape
-        ws = self._get_enc_ws(B, N, att_masks is not None, slot)
-        ws.att_in.copy_(att_feats.reshape(B * N, F), non_blocking=True)
+        bf16_in = att_feats.dtype == torch.bfloat16 and self.adt == torch.bfloat16
+        ws = self._get_enc_ws(B, N, att_masks is not None, slot, bf16_in)
+        (ws.att_a if ws.bf16_in else ws.att_in).copy_(att_feats.reshape(B * N, F), non_blocking=True)
         ws.boxes.copy_(boxes, non_blocking=True)
         if att_masks is not None:
             ws.att_mask.copy_(att_masks.float(), non_blocking=True)
