@@ -431,6 +431,52 @@ def main():
         gemm_fl += 2.0 * M * N * Kd * cnt
         if dom is None or us * cnt > dom[0]:
             dom = (us * cnt, M, N, Kd, us, cnt, xs * M * Kd + wsz * N * Kd + ys * M * N + (4 * M * N if has_res else 0))
+    # the same shapes with `slots` streams running them concurrently - the regime of the timed region (S batches in flight):
+    # microseconds of wall time per GEMM = elapsed / (streams * launches)
+    conc_us, conc_fl = 0.0, 0.0
+    try:
+        streams = [torch.cuda.Stream(dev) for _ in range(S)]
+        cur_s = torch.cuda.current_stream(dev)
+        for (M, N, Kd, xs, wsz, ys, has_res, relu), cnt in shapes.items():
+            graphs = []
+            for st in streams:
+                x = torch.randn(M, Kd, device=dev).bfloat16()
+                w = torch.randn(N, Kd, device=dev).bfloat16()
+                bias = torch.randn(N, device=dev)
+                res = torch.randn(M, N, device=dev) if has_res else None
+                if ys == 0:
+                    part = torch.empty(M, KK.linear_topk_parts(N), 12, device=dev)
+                    run = (lambda x, w, bias, part: (lambda i: KK.linear_topk(x, w, bias, part, candidates=BEAM)))(x, w, bias, part)
+                else:
+                    outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(2)]
+                    run = (lambda x, w, bias, res, outs: (lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs[i % 2])))(x, w, bias, res, outs)
+                run(0)
+                torch.cuda.synchronize(dev)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for i in range(20):
+                        run(i)
+                graphs.append((gr, run))
+
+            def go():
+                for st, (gr, _) in zip(streams, graphs):
+                    st.wait_stream(cur_s)
+                    with torch.cuda.stream(st):
+                        gr.replay()
+                        gr.replay()
+                for st in streams:
+                    cur_s.wait_stream(st)
+            go()
+            torch.cuda.synchronize(dev)
+            e0.record(); go(); e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) * 1e3 / (S * 40)
+            conc_us += us * cnt
+            conc_fl += 2.0 * M * N * Kd * cnt
+            del graphs
+    except Exception as ex:  # diagnostics only
+        print(f"concurrent GEMM timing skipped: {ex}", file=sys.stderr)
+    tf_conc = conc_fl / conc_us / 1e6 if conc_us else None
     tf = gemm_fl / gemm_us / 1e6 if gemm_us else 0.0
     tf_dom = 2.0 * dom[1] * dom[2] * dom[3] / dom[4] / 1e6 if dom else 0.0
     roofline = {"kernel": "sc_gemm_bf16_kernel (tcgen05/TMEM/TMA; every GEMM launch of one step)", "bound": "tensor", "achieved": tf,
@@ -439,6 +485,8 @@ def main():
                 # (profiles/r01b_ncu_full_summary.txt); cold-cache capture, one launch
                 "traffic": NCU_TRAFFIC_DOMINANT_GEMM,
                 "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16_tflops (burst: shapes timed alone, in-graph)",
+                "achieved_in_flight": tf_conc, "frac_in_flight": (tf_conc / peaks["tf_sus"]) if tf_conc else None,
+                "in_flight_note": f"same shapes, {S} streams concurrently (the timed region's regime), wall time per GEMM; vs sustained peak",
                 "launches": g["n"], "avg_launch_us": gemm_us / max(1, g["n"]),
                 "algorithmic_gflop_per_step": gemm_fl / 1e9,
                 "dominant_shape": None if dom is None else {"M": dom[1], "N": dom[2], "K": dom[3], "launches": dom[5], "us_per_launch": dom[4],
