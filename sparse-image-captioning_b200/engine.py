@@ -269,8 +269,9 @@ class OrtEngine:
         pe = sd.get("model.tgt_embed.1.pe")
         self.pe = (pe[0, : L + 2] if pe is not None else _positional_encoding(d, L + 2, self.dev)).float().contiguous()
         self.generator = lin(["model.generator.proj"], be, norm="model.decoder.norm")
+        import os
         # the folded decode path needs every decoder linear on the dense tensor path
-        self.fold_dec = self.ln_fold and all(
+        self.fold_dec = self.ln_fold and os.environ.get("SC_LN_FOLD_ENC_ONLY") != "1" and all(
             e[k].w is not None for e in self.dec.values() for k in ("qkv", "o", "cq", "co", "ff1", "ff2")) and self.generator.w is not None
         # decode-GEMM tile hints {"o": 3256, ...} (1000 * stages + block_n).  With >= 8 batches in flight the wide tiles
         # give a little more aggregate throughput than the latency-oriented 64-wide default (scripts/gemm_concurrency.py)

@@ -51,7 +51,7 @@ def linear_ln(x, w, bias=None, *, residual=None, relu=False, out=None, tile_n=0,
         _chk(t, n)
     lib.call("sc_linear_ln", lib.ptr(x), lib.ptr(w), lib.ptr(bias), lib.ptr(residual), lib.ptr(out), lib.dtype_code(out.dtype),
              M, N, K, int(relu), tile_n, lib.ptr(ln_stats), lib.ptr(ln_c), float(eps), lib.ptr(out_bf16), lib.ptr(stats_out),
-             lib.stream(), meta=("gemm_bf16", M, N, K, 2, 2, out.element_size(), False))
+             lib.stream(), meta=("gemm_bf16", M, N, K, 2, 2, out.element_size(), False, residual is not None, bool(relu)))
     return out
 
 
