@@ -653,15 +653,22 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               tk_s += __expf(f[j] - tk_m);
-              if (f[j] > tk_v[kTK - 1]) {
-                tk_v[kTK - 1] = f[j]; tk_i[kTK - 1] = col0 + j;
+              // branch-free sorted insertion (a divergent `if (new candidate)` ran for almost every element: some lane of the
+              // warp always had one): slot i takes the old slot i-1 when the value beats that one, else the value itself
+              // when it beats slot i; strict '>' keeps the earlier (smaller) column on ties
+              {
+                const float v = f[j];
+                const int cidx = col0 + j;
+                bool pgt[kTK];
 #pragma unroll
-                for (int i = kTK - 1; i > 0; --i) {
-                  if (tk_v[i] > tk_v[i - 1]) {
-                    const float tv = tk_v[i]; tk_v[i] = tk_v[i - 1]; tk_v[i - 1] = tv;
-                    const int ti = tk_i[i]; tk_i[i] = tk_i[i - 1]; tk_i[i - 1] = ti;
-                  }
+                for (int i = 0; i < kTK; ++i) pgt[i] = v > tk_v[i];
+#pragma unroll
+                for (int i = kTK - 1; i >= 1; --i) {
+                  tk_v[i] = pgt[i - 1] ? tk_v[i - 1] : (pgt[i] ? v : tk_v[i]);
+                  tk_i[i] = pgt[i - 1] ? tk_i[i - 1] : (pgt[i] ? cidx : tk_i[i]);
                 }
+                tk_v[0] = pgt[0] ? v : tk_v[0];
+                tk_i[0] = pgt[0] ? cidx : tk_i[0];
               }
             }
             continue;
