@@ -194,7 +194,7 @@ struct MaskDesc {
 };
 
 template <typename OT>
-__global__ void __launch_bounds__(256) apply_mask_batched_kernel(const MaskDesc* __restrict__ descs, int n_desc, int mode,
+__global__ void __launch_bounds__(256, 4) apply_mask_batched_kernel(const MaskDesc* __restrict__ descs, int n_desc, int mode,
                                                                  unsigned long long seed, unsigned long long stream_base) {
   __shared__ float tile[64][65];
   int lo = 0, hi = n_desc - 1;
