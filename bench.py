@@ -314,7 +314,8 @@ def main():
     join()
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # one nvidia-smi poller per job, not per rank
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     fork()
@@ -346,7 +347,8 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
     d2h = out_seq[0].numel() * 4 + out_lp[0].numel() * 4
 
