@@ -1,0 +1,7 @@
+#!/bin/bash
+N=$(nvidia-smi -L | wc -l)
+timeout -s KILL 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 scripts/ddp_check.py 2>&1 | grep -E "^rank.*(CHECK|fraction)"
+run() { env "$@" timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 scripts/ddp_time.py 2>&1 | grep "^N="; }
+run SC_EXCHANGE=none
+run SC_EXCHANGE=allreduce
+run SC_EXCHANGE=allreduce

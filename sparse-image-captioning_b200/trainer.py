@@ -923,13 +923,21 @@ class OrtTrainer:
             self.backward_phase(ws, int(part[1]))
         if part in ("all", "opt"):
             self.optimizer_step(_dyn=True, **opt)
+        if part in ("opt_hi", "opt_lo"):
+            self.optimizer_step(_dyn=True, part=part[4:], **opt)
 
     def _exchange(self, all_reduce, phase, handles):
         """Start the all-reduce of every gradient bucket that `phase` finished (async: the next phase overlaps it)."""
         for flat, a, b in self.grad_buckets(phase):
             h = all_reduce(flat[a:b])
             if h is not None:
-                handles.append(h)
+                handles.append((phase, h))
+
+    @staticmethod
+    def _wait(handles, phases):
+        for ph, h in handles:
+            if ph in phases:
+                h.wait()
 
     def _run_graphed(self, ws, part, opt):
         key = (part, tuple(sorted((k, float(v)) for k, v in opt.items() if k in ("clip", "eps", "mask_eps", "weight_decay",
@@ -985,13 +993,15 @@ class OrtTrainer:
                 self._run_graphed(ws, "all", opt)
             else:
                 # one graph per backward phase; the buckets a phase finished are exchanged while the next one computes
+                # and the decoder-side half of the optimizer (its buckets arrived long ago) runs underneath the last buckets' exchange
                 handles = []
                 for phase, part in enumerate(("fwd_p0", "p1", "p2", "p3")):
                     self._run_graphed(ws, part, opt)
                     self._exchange(all_reduce, phase, handles)
-                for h in handles:
-                    h.wait()
-                self._run_graphed(ws, "opt", opt)
+                self._wait(handles, (0, 1))
+                self._run_graphed(ws, "opt_hi", opt)
+                self._wait(handles, (2, 3))
+                self._run_graphed(ws, "opt_lo", opt)
             return ws.loss_sum * ws.inv_norm
         self.forward(ws)
         if all_reduce is None:
@@ -1001,8 +1011,11 @@ class OrtTrainer:
             for phase in range(self.N_PHASES):
                 self.backward_phase(ws, phase)
                 self._exchange(all_reduce, phase, handles)
-            for h in handles:
-                h.wait()
+            self._wait(handles, (0, 1))
+            self.optimizer_step(lr=lr, part="hi", **opt)
+            self._wait(handles, (2, 3))
+            self.optimizer_step(lr=lr, part="lo", **opt)
+            return ws.loss_sum * ws.inv_norm
         self.optimizer_step(lr=lr, **opt)
         return ws.loss_sum * ws.inv_norm
 
