@@ -380,16 +380,40 @@ class OrtEngine:
             for u, e in self.dec.items():
                 e["ckv"](ws.mem, ws.memkv[u])
 
-    def encode(self, att_feats, boxes, att_masks=None, slot=0):
+    def encode(self, att_feats, boxes, att_masks=None, slot=0, prefetch=False):
         """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V.
-        ``slot`` selects an independent set of workspaces/graphs so that several batches can be in flight."""
+        ``slot`` selects an independent set of workspaces/graphs so that several batches can be in flight.
+        ``prefetch`` (host inputs): the H2D copy goes through a per-slot staging buffer on the slot's own copy stream, so it
+        overlaps the batch that is still decoding on this slot; the slot's compute stream then only does a device-to-device
+        copy.  Measured SLOWER with 5-8 slots in flight (7.08 vs 6.85 ms/step end to end: the other slots already hide the
+        copy, the extra 151 MB device copy and the burst of concurrent H2D requests cost more) - off by default."""
         B, N, F = att_feats.shape
         bf16_in = att_feats.dtype == torch.bfloat16 and self.adt == torch.bfloat16
         ws = self._get_enc_ws(B, N, att_masks is not None, slot, bf16_in)
-        (ws.att_a if ws.bf16_in else ws.att_in).copy_(att_feats.reshape(B * N, F), non_blocking=True)
-        ws.boxes.copy_(boxes, non_blocking=True)
-        if att_masks is not None:
-            ws.att_mask.copy_(att_masks.float(), non_blocking=True)
+        dst = ws.att_a if ws.bf16_in else ws.att_in
+        src = att_feats.reshape(B * N, F)
+        if prefetch and src.device.type == "cpu" and boxes.device.type == "cpu" and att_masks is None:
+            if getattr(ws, "stage", None) is None:
+                ws.stage, ws.stage_boxes = torch.empty_like(dst), torch.empty_like(ws.boxes)
+                ws.copy_stream, ws.stage_free = torch.cuda.Stream(self.dev), None
+            cs, cur = ws.copy_stream, torch.cuda.current_stream(self.dev)
+            if ws.stage_free is not None:
+                cs.wait_event(ws.stage_free)  # the previous batch has been copied out of the staging buffers
+            with torch.cuda.stream(cs):
+                ws.stage.copy_(src, non_blocking=True)
+                ws.stage_boxes.copy_(boxes, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cs)
+            cur.wait_event(ready)
+            dst.copy_(ws.stage, non_blocking=True)
+            ws.boxes.copy_(ws.stage_boxes, non_blocking=True)
+            ws.stage_free = torch.cuda.Event()
+            ws.stage_free.record(cur)
+        else:
+            dst.copy_(src, non_blocking=True)
+            ws.boxes.copy_(boxes, non_blocking=True)
+            if att_masks is not None:
+                ws.att_mask.copy_(att_masks.float(), non_blocking=True)
         self.run_encoder(ws)
         return ws
 
@@ -595,7 +619,7 @@ class OrtEngine:
     # ---- batch pipelining: slot s owns a stream + workspaces + graphs; batches in different slots overlap on the GPU
     # (the decode loop is a chain of ~70 short dependent kernels per step that leaves most SMs idle; a second
     # batch fills them, and its H2D copy hides behind the first batch's compute) ----
-    def submit(self, att_feats, boxes, att_masks=None, opt=None, slot=0, out=None):
+    def submit(self, att_feats, boxes, att_masks=None, opt=None, slot=0, out=None, prefetch=False):
         """Enqueue encode + decode of one batch on slot `slot` without waiting.  ``out``: optional pinned host tensors
         (seq int32 [B,b,L], lp fp32 [B,b,L]) that receive the result asynchronously.  Returns (seq, lp) device views
         that are valid after ``wait(slot)``."""
@@ -605,7 +629,7 @@ class OrtEngine:
         if st is not cur:
             st.wait_stream(cur)
         with torch.cuda.stream(st):
-            enc = self.encode(att_feats, boxes, att_masks, slot=slot)
+            enc = self.encode(att_feats, boxes, att_masks, slot=slot, prefetch=prefetch)
             seq, lp = self.decode(enc, opt)
             if out is not None:
                 out[0].copy_(seq, non_blocking=True)
