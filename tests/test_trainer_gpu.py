@@ -252,3 +252,49 @@ def test_d512_bf16_fused_paths_match_unfused():
     assert all(torch.isfinite(torch.tensor(lg))) and all(torch.isfinite(torch.tensor(le)))
     assert abs(lg[0] - le[0]) < 0.2 * abs(le[0])
     assert torch.isfinite(wg).all() and torch.isfinite(sg).all()
+
+
+def test_full_size_gradient_is_additive_over_image_shards():
+    """BASELINE.json configs[1] at full size (ORT 6x512, V=10000, 50 images x 5 captions, T=17, bf16, supermask): the gradient
+    of the whole batch equals the sum of the gradients of two image shards computed with the GLOBAL token count and the same
+    mask sample - the property the data-parallel exchange relies on (and a check of "encoder once per image", the per-image
+    cross K/V and the loss normalisation at the real size, where the CPU oracle is too slow)."""
+    import bench
+    from sparse_caption_b200 import synthetic
+    from sparse_caption_b200.engine import ModelCfg
+    from sparse_caption_b200.trainer import OrtTrainer
+    cfg = ModelCfg(dict(bench.CFG, max_seq_length=17))
+    sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=DEV)
+    B, S, T = 50, 5, 17
+    g = torch.Generator().manual_seed(4)
+    att, boxes = synthetic.synthetic_inputs(B, 36, 2048, seed=3)
+    R = B * S
+    seqs = torch.zeros(R, T + 1, dtype=torch.long)
+    masks = torch.zeros(R, T + 1)
+    for r in range(R):
+        n = int(torch.randint(6, T - 1, (1,), generator=g))
+        seqs[r, 0] = 2
+        seqs[r, 1:1 + n] = torch.randint(4, 10000, (n,), generator=g)
+        seqs[r, 1 + n] = 3
+        masks[r, :n + 2] = 1
+    total = masks[:, 1: T + 1].sum().reshape(1).to(DEV)
+    tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=DEV, seed=9, dropout=0.0, drop_prob_src=0.0)
+
+    def grads(lo, hi):
+        ws = tr._get_ws(hi - lo, 36, S, T, False)
+        tr.step_id = 1                      # same Philox stream base -> same Bernoulli masks for every shard
+        tr._wm_step = {}
+        tr.load_batch(ws, att[lo:hi].to(DEV), boxes[lo:hi].to(DEV), seqs[lo * S: hi * S], masks[lo * S: hi * S], None, total)
+        tr.forward(ws)
+        loss = tr.loss_and_backward(ws) * ws.inv_norm
+        torch.cuda.synchronize()
+        return float(loss), tr.flat_gw.clone(), tr.flat_gs.clone()
+
+    l_all, gw_all, gs_all = grads(0, B)
+    l_a, gw_a, gs_a = grads(0, 20)
+    l_b, gw_b, gs_b = grads(20, B)
+    assert abs(l_all - (l_a + l_b)) < 1e-4 * abs(l_all)
+    assert torch.isfinite(gw_all).all() and float(gw_all.abs().max()) > 0
+    # identical bf16 operands row by row; only the fp32 summation order over rows / split-K chunks differs
+    assert rel_err(gw_a + gw_b, gw_all) < 2e-3
+    assert rel_err(gs_a + gs_b, gs_all) < 2e-3
