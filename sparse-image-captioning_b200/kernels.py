@@ -370,7 +370,7 @@ def linear_dropout(x, w, bias=None, *, mask=None, mask_mode=MASK_NONE, uniforms=
              mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(bias), lib.ptr(residual), lib.ptr(out),
              lib.dtype_code(out.dtype), M, N, K, int(relu), tile_n, float(p), drop_seed, drop_stream, lib.stream(),
              meta=("gemm_bf16" if x.dtype == torch.bfloat16 else "gemm_f32", M, N, K, x.element_size(), w.element_size(),
-                   out.element_size(), mask is not None))
+                   out.element_size(), mask is not None, residual is not None, bool(relu), p > 0, tile_n))
     return out
 
 
