@@ -435,7 +435,7 @@ int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int l
                      float dropout_p, unsigned long long seed, unsigned long long stream_id, cudaStream_t stream) {
   int rc = check_common("sc_attention_fwd", G, Tq, Tk, h, dk);
   if (rc) return rc;
-  if (dtype == SC_BF16 && probs != nullptr) {
+  if (dtype == SC_BF16) {  // (probs may be NULL: the inference encoder uses the same kernel without saving them)
     rc = sc_attn_train_fwd_mma_launch(q, k, v, ldq, ldk, ldv, key_valid, bias, probs, out, ldo, G, Tq, Tk, h, dk, causal_T,
                                       dropout_p, seed, stream_id, stream);
     if (rc != SC_ERR_UNSUPPORTED) return rc;

@@ -231,6 +231,10 @@ class OrtEngine:
         self.wg_b_all = torch.cat([self.enc[u]["wg_b"] for u in self.enc], 0).contiguous()
         # tensor-path attention (mma tiles) serves bf16, d_k = 64, N <= 128; fp32 mode keeps the exact fused kernel
         self.split_box_attn = (adt == torch.bfloat16 and d // cfg.num_heads == 64)
+        import os
+        # CTA-per-(image, head) encoder attention (the training forward kernel without saved probabilities): 43 vs 50 us per
+        # launch, no difference on the whole step -> the warp-per-(image, head) kernel stays the default
+        self.enc_attn_cta = os.environ.get("SC_ENC_ATTN_CTA") == "1"
         # ---- decoder ----
         self.dec_uids = cfg.uids("dec")
         self.dec = {}
@@ -357,7 +361,12 @@ class OrtEngine:
                 e["n0"](ws.x, ws.xn)
                 e["qkv"](ws.xn, qkv)
             qo, ko, vo = e["offs"]
-            if ws.box_bias is not None:
+            if ws.box_bias is not None and self.enc_attn_cta:
+                # CTA = (image, head) with one warp per 16-query tile sharing the staged K / V (sc_attention_fwd's tensor path
+                # without saved probabilities): 3x the warps per SM of the warp-per-(image, head) kernel below
+                K.attention_fwd(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.att, None, G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=ld, ldk=ld,
+                                ldv=ld, ldo=d, key_valid=ws.att_mask, bias=ws.box_bias[self.enc_slot[u]])
+            elif ws.box_bias is not None:
                 K.bias_attention(qkv[:, qo:], qkv[:, ko:], qkv[:, vo:], ws.box_bias[self.enc_slot[u]], ws.att_mask, ws.att,
                                  B=B, N=N, h=h, dk=dk, ldq=ld, ldk=ld, ldv=ld, ldo=d)
             else:
