@@ -280,6 +280,7 @@ def main():
     ap.add_argument("--no-train-graph", action="store_true", help="diagnostic: eager launches instead of the captured training graph")
     ap.add_argument("--cpu-images", type=int, default=64)
     ap.add_argument("--ln-fold", action="store_true", help="LayerNorm folded into the consuming GEMMs (sc_linear_ln) instead of separate LayerNorm kernels")
+    ap.add_argument("--prefetch", action="store_true", help="e2e arm: H2D of the next batch on a copy stream underneath the previous decode of the same slot")
     ap.add_argument("--no-fuse-topk", action="store_true", help="diagnostic: materialise the logits (sc_linear + sc_beam_step) instead of the fused generator + beam row pass")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostic: disable programmatic dependent launch")
     ap.add_argument("--slots", type=int, default=0, help="batches in flight (pipeline slots: stream + workspaces + graphs each); 0 = 8 when the timed region is long enough "
@@ -398,7 +399,7 @@ def main():
     def e2e_step(i):
         att, boxes = host[i & 1]
         k = i % S
-        eng.submit(att, boxes, None, opt, slot=slots[k], out=(out_seq[k], out_lp[k]))
+        eng.submit(att, boxes, None, opt, slot=slots[k], out=(out_seq[k], out_lp[k]), prefetch=args.prefetch)
 
     for i in range(args.warmup):
         e2e_step(i)

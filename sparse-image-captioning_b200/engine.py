@@ -392,32 +392,33 @@ class OrtEngine:
     def encode(self, att_feats, boxes, att_masks=None, slot=0, prefetch=False):
         """Runs att_embed + encoder + cross K/V projections; returns the workspace holding memory K/V.
         ``slot`` selects an independent set of workspaces/graphs so that several batches can be in flight.
-        ``prefetch`` (host inputs): the H2D copy goes through a per-slot staging buffer on the slot's own copy stream, so it
-        overlaps the batch that is still decoding on this slot; the slot's compute stream then only does a device-to-device
-        copy.  Measured SLOWER with 5-8 slots in flight (7.08 vs 6.85 ms/step end to end: the other slots already hide the
-        copy, the extra 151 MB device copy and the burst of concurrent H2D requests cost more) - off by default."""
+        ``prefetch`` (host inputs): the H2D copy runs on the slot's own copy stream and only waits for the previous ENCODER on
+        this slot (the only reader of the input buffers), so it overlaps the batch that is still decoding on this slot.
+        Measured SLOWER with 5-8 slots in flight (7.10 vs 6.85 ms/step end to end; a variant through staging buffers: 7.08): the
+        other slots already hide the copy - off by default (bench.py --prefetch)."""
         B, N, F = att_feats.shape
         bf16_in = att_feats.dtype == torch.bfloat16 and self.adt == torch.bfloat16
         ws = self._get_enc_ws(B, N, att_masks is not None, slot, bf16_in)
         dst = ws.att_a if ws.bf16_in else ws.att_in
         src = att_feats.reshape(B * N, F)
         if prefetch and src.device.type == "cpu" and boxes.device.type == "cpu" and att_masks is None:
-            if getattr(ws, "stage", None) is None:
-                ws.stage, ws.stage_boxes = torch.empty_like(dst), torch.empty_like(ws.boxes)
-                ws.copy_stream, ws.stage_free = torch.cuda.Stream(self.dev), None
+            # the input buffers are only read by the encoder graph: the next batch's H2D may start as soon as the previous
+            # ENCODER on this slot is done (event), on the slot's copy stream, underneath the previous batch's decode
+            if getattr(ws, "copy_stream", None) is None:
+                ws.copy_stream, ws.enc_done = torch.cuda.Stream(self.dev), None
             cs, cur = ws.copy_stream, torch.cuda.current_stream(self.dev)
-            if ws.stage_free is not None:
-                cs.wait_event(ws.stage_free)  # the previous batch has been copied out of the staging buffers
+            if ws.enc_done is not None:
+                cs.wait_event(ws.enc_done)
             with torch.cuda.stream(cs):
-                ws.stage.copy_(src, non_blocking=True)
-                ws.stage_boxes.copy_(boxes, non_blocking=True)
+                dst.copy_(src, non_blocking=True)
+                ws.boxes.copy_(boxes, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(cs)
             cur.wait_event(ready)
-            dst.copy_(ws.stage, non_blocking=True)
-            ws.boxes.copy_(ws.stage_boxes, non_blocking=True)
-            ws.stage_free = torch.cuda.Event()
-            ws.stage_free.record(cur)
+            self.run_encoder(ws)
+            ws.enc_done = torch.cuda.Event()
+            ws.enc_done.record(cur)
+            return ws
         else:
             dst.copy_(src, non_blocking=True)
             ws.boxes.copy_(boxes, non_blocking=True)
