@@ -353,7 +353,8 @@ def main():
     cur = torch.cuda.current_stream(dev)
     encs = {}
     for s in slots:
-        eng.submit(host[s & 1][0], host[s & 1][1], None, opt, slot=s)
+        # inputs resident in HBM (fp32, as the data loader delivers them) -> the slot's workspaces + graphs
+        eng.submit(host[s & 1][0].to(dev), host[s & 1][1].to(dev), None, opt, slot=s)
         encs[s] = eng._get_enc_ws(B, N_BOX, False, s)
     eng.wait(host=True)
     torch.cuda.synchronize(dev)
@@ -401,7 +402,7 @@ def main():
         k = i % S
         eng.submit(att, boxes, None, opt, slot=slots[k], out=(out_seq[k], out_lp[k]), prefetch=args.prefetch)
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, S)):  # every slot's host-input path (its own workspaces / graphs with the fused ingest) is warm
         e2e_step(i)
     eng.wait()
     barrier()

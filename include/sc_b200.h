@@ -109,6 +109,9 @@ int sc_apply_mask(const float* w, const float* mask, int mask_mode, const float*
 int sc_mask_count(const float* logits, size_t n, unsigned long long* count_out, sc_stream_t stream);
 
 int sc_cast_f32_bf16(const float* x, void* y, size_t n, sc_stream_t stream);
+/* fused ingest (data/collate.py:107-112,196-216 -> device): y (bf16, device) = cast(pinned_host fp32), read over PCIe by the
+ * kernel itself (the pinned buffer must be mapped, as cudaHostAlloc / torch pin_memory buffers are); ctas <= 0: 64 CTAs */
+int sc_ingest_f32_bf16(const float* pinned_host, void* y, size_t n, int ctas, sc_stream_t stream);
 
 /* pack_wrapper zero-padding of padded regions (utils/model_utils.py:149-168): x[r,:] *= (mask[r] != 0) */
 int sc_mask_rows(float* x, const float* row_mask, int rows, int D, sc_stream_t stream);

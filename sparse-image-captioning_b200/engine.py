@@ -235,6 +235,11 @@ class OrtEngine:
         # CTA-per-(image, head) encoder attention (the training forward kernel without saved probabilities): 43 vs 50 us per
         # launch, no difference on the whole step -> the warp-per-(image, head) kernel stays the default
         self.enc_attn_cta = os.environ.get("SC_ENC_ATTN_CTA") == "1"
+        # > 0: fused ingest (sc_ingest_f32_bf16: the kernel reads the pinned fp32 features over PCIe and writes the bf16 operand,
+        # 51 GB/s vs 45.5 GB/s for cudaMemcpyAsync) with that many CTAs.  Off: with several slots in flight the ingest kernels of
+        # all slots share the link concurrently instead of queueing FIFO like DMA copies, so every batch's encoder starts late
+        # (9.1 vs 6.9 ms/step end to end); needs a dedicated ingest stream before it can be the default
+        self.zero_copy_ingest = int(os.environ.get("SC_INGEST_CTAS", "0"))
         # ---- decoder ----
         self.dec_uids = cfg.uids("dec")
         self.dec = {}
@@ -398,6 +403,16 @@ class OrtEngine:
         other slots already hide the copy - off by default (bench.py --prefetch)."""
         B, N, F = att_feats.shape
         bf16_in = att_feats.dtype == torch.bfloat16 and self.adt == torch.bfloat16
+        if (self.zero_copy_ingest and self.adt == torch.bfloat16 and att_feats.device.type == "cpu" and att_feats.dtype == torch.float32
+                and att_feats.is_pinned() and att_feats.is_contiguous() and (B * N * F) % 4 == 0):
+            # fused ingest: one kernel reads the pinned fp32 features over PCIe and writes the bf16 operand (no fp32 staging, no cast)
+            ws = self._get_enc_ws(B, N, att_masks is not None, slot, True)
+            K.ingest_f32_bf16(att_feats, ws.att_a.view(-1), ctas=self.zero_copy_ingest)
+            ws.boxes.copy_(boxes, non_blocking=True)
+            if att_masks is not None:
+                ws.att_mask.copy_(att_masks.float(), non_blocking=True)
+            self.run_encoder(ws)
+            return ws
         ws = self._get_enc_ws(B, N, att_masks is not None, slot, bf16_in)
         dst = ws.att_a if ws.bf16_in else ws.att_in
         src = att_feats.reshape(B * N, F)

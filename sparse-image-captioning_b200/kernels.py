@@ -168,6 +168,14 @@ def sell_spmm(x, sw, bias=None, *, residual=None, relu=False, out=None, out_dtyp
     return out
 
 
+def ingest_f32_bf16(host_pinned, out, ctas=0):
+    """out (device bf16) = cast(host_pinned fp32): the kernel reads the pinned host tensor over PCIe itself (sc_ingest_f32_bf16)."""
+    assert host_pinned.device.type == "cpu" and host_pinned.is_pinned() and host_pinned.dtype == torch.float32 and host_pinned.is_contiguous()
+    assert out.is_cuda and out.dtype == torch.bfloat16 and out.numel() == host_pinned.numel() and out.is_contiguous()
+    lib.call("sc_ingest_f32_bf16", host_pinned.data_ptr(), lib.ptr(out), host_pinned.numel(), int(ctas), lib.stream())
+    return out
+
+
 def layernorm(x, a, b, *, eps=1e-6, out=None, out_dtype=None):
     rows, D = x.shape
     _chk(x, "x")

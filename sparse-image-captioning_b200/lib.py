@@ -28,6 +28,7 @@ SIGNATURES = {
     "sc_apply_mask": [_p, _p, _i, _p, _u64, _u64, _p, _i, _sz, _p],
     "sc_mask_count": [_p, _sz, _p, _p],
     "sc_cast_f32_bf16": [_p, _p, _sz, _p],
+    "sc_ingest_f32_bf16": [_p, _p, _sz, _i, _p],
     "sc_mask_rows": [_p, _p, _i, _i, _p],
     "sc_box_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p],
     "sc_box_bias_all": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],

@@ -562,3 +562,12 @@ def test_sample_step_distribution(K):
     freq = torch.bincount(outs[0].long().cpu(), minlength=V).double() / R
     p = torch.softmax(row.double(), 0)
     assert float((freq - p).abs().max()) < 4 * float(torch.sqrt(p.max() * (1 - p.max()) / R)) + 2e-3
+
+
+def test_ingest_pinned_host_features(K):
+    """Fused ingest: the kernel reads pinned host fp32 over PCIe and writes bf16 - bit-identical to copy + cast."""
+    g = torch.Generator().manual_seed(51)
+    x = (torch.randn(37, 36, 2048, generator=g) * 3).pin_memory()
+    out = torch.zeros(x.numel(), device="cuda", dtype=torch.bfloat16)
+    K.ingest_f32_bf16(x, out, ctas=8)
+    assert torch.equal(out, x.cuda().bfloat16().view(-1))
