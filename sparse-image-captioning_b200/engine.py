@@ -236,9 +236,9 @@ class OrtEngine:
         # launch, no difference on the whole step -> the warp-per-(image, head) kernel stays the default
         self.enc_attn_cta = os.environ.get("SC_ENC_ATTN_CTA") == "1"
         # > 0: fused ingest (sc_ingest_f32_bf16: the kernel reads the pinned fp32 features over PCIe and writes the bf16 operand,
-        # 51 GB/s vs 45.5 GB/s for cudaMemcpyAsync) with that many CTAs.  Off: with several slots in flight the ingest kernels of
-        # all slots share the link concurrently instead of queueing FIFO like DMA copies, so every batch's encoder starts late
-        # (9.1 vs 6.9 ms/step end to end); needs a dedicated ingest stream before it can be the default
+        # 51 GB/s vs 45.5 GB/s for cudaMemcpyAsync) with that many CTAs, queued FIFO on one ingest stream.  Off: its CTAs sit on
+        # SMs for the ~3 ms a batch takes to cross PCIe, and an SM that hosts one cannot take a full-register GEMM CTA (end to end,
+        # ms/step: DMA copy + cast 6.84; ingest with 8 / 16 / 32 CTAs 7.05 / 7.31 / 7.66) - the copy engines are the better tool
         self.zero_copy_ingest = int(os.environ.get("SC_INGEST_CTAS", "0"))
         # ---- decoder ----
         self.dec_uids = cfg.uids("dec")
@@ -292,6 +292,7 @@ class OrtEngine:
         for name, val in hints.items():
             for e in self.dec.values():
                 e[name].tile_n = int(val)
+        self._ingest_stream = None
         self._sample_seed = torch.zeros(1, dtype=torch.int64, device=self.dev)  # re-seeds captured sampling graphs
         self._sample_count = 0
         self._enc_ws = {}
@@ -407,7 +408,17 @@ class OrtEngine:
                 and att_feats.is_pinned() and att_feats.is_contiguous() and (B * N * F) % 4 == 0):
             # fused ingest: one kernel reads the pinned fp32 features over PCIe and writes the bf16 operand (no fp32 staging, no cast)
             ws = self._get_enc_ws(B, N, att_masks is not None, slot, True)
-            K.ingest_f32_bf16(att_feats, ws.att_a.view(-1), ctas=self.zero_copy_ingest)
+            # one engine-wide ingest stream: the ingest kernels of all slots queue FIFO on the PCIe link like DMA copies would
+            # (launched on the slots' own streams they all share the link and every encoder starts late)
+            if self._ingest_stream is None:
+                self._ingest_stream = torch.cuda.Stream(self.dev)
+            ist, cur = self._ingest_stream, torch.cuda.current_stream(self.dev)
+            ist.wait_stream(cur)  # the previous batch of this slot is done with the operand buffer
+            with torch.cuda.stream(ist):
+                K.ingest_f32_bf16(att_feats, ws.att_a.view(-1), ctas=self.zero_copy_ingest)
+                ready = torch.cuda.Event()
+                ready.record(ist)
+            cur.wait_event(ready)
             ws.boxes.copy_(boxes, non_blocking=True)
             if att_masks is not None:
                 ws.att_mask.copy_(att_masks.float(), non_blocking=True)
