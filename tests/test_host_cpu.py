@@ -207,3 +207,36 @@ def test_radix_detokenisation_matches_reference_arithmetic():
                 assert int(n[b, k]) == len(want)
                 assert words[b, k, : len(want)].tolist() == want
                 assert bool((words[b, k, len(want):] == 0).all())
+
+
+def test_sell_weight_packing_roundtrip():
+    """Sliced-ELL packing (kernels.SellWeight, host-side tensor code): every non-zero lands at slab_ptr[s] + 32 i + lane with
+    its column and value, slab widths are multiples of 4, padding entries are (column 0, value 0)."""
+    import torch
+    from sparse_caption_b200.kernels import SellWeight
+    g = torch.Generator().manual_seed(0)
+    for dt in (torch.bfloat16, torch.float32):
+        N, Kd = 100, 72
+        w = torch.randn(N, Kd, generator=g) * (torch.rand(N, Kd, generator=g) > 0.9)
+        w[5] = 0
+        if dt == torch.bfloat16:
+            w = w.bfloat16().float()
+        sw = SellWeight(w, dt)
+        assert sw.nnz == int((w != 0).sum()) and sw.shape == (N, Kd)
+        slabs = (N + 31) // 32
+        assert sw.slab_ptr.numel() == slabs + 1 and int(sw.slab_ptr[0]) == 0
+        rec = torch.zeros(slabs * 32, Kd)
+        for s_ in range(slabs):
+            b, e = int(sw.slab_ptr[s_]), int(sw.slab_ptr[s_ + 1])
+            assert (e - b) % (32 * 4) == 0
+            ent = sw.entries[b:e]
+            if dt == torch.bfloat16:
+                u = ent.long() & 0xFFFFFFFF
+                cols = u >> 16
+                vals = (u & 0xFFFF).to(torch.int32).to(torch.int16).view(torch.bfloat16).float()
+            else:
+                cols = ent[:, 0].long()
+                vals = ent[:, 1].contiguous().view(torch.float32)
+            lane = torch.arange(e - b) % 32
+            rec.index_put_((s_ * 32 + lane, cols), vals, accumulate=True)
+        assert torch.equal(rec[:N], w)
