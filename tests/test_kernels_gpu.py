@@ -571,3 +571,26 @@ def test_ingest_pinned_host_features(K):
     out = torch.zeros(x.numel(), device="cuda", dtype=torch.bfloat16)
     K.ingest_f32_bf16(x, out, ctas=8)
     assert torch.equal(out, x.cuda().bfloat16().view(-1))
+
+
+def test_new_entry_points_reject_bad_arguments(K):
+    """Error behaviour of the entry points added this round: negative status -> RuntimeError with the library's message,
+    nothing launched."""
+    from sparse_caption_b200.engine import BeamState
+    x = torch.randn(16, 36, device="cuda").bfloat16()          # K = 36 is not a multiple of 8
+    w = torch.randn(40, 36) * (torch.rand(40, 36) > 0.5)
+    sw = K.SellWeight(w.cuda(), torch.bfloat16)
+    with pytest.raises(RuntimeError, match="sc_sell_spmm"):
+        K.sell_spmm(x, sw, None)
+    xb = torch.randn(8, 64, device="cuda").bfloat16()
+    wb = torch.randn(300, 64, device="cuda").bfloat16()
+    part = torch.empty(8, K.linear_topk_parts(300), 12, device="cuda")
+    with pytest.raises(RuntimeError, match="candidates"):
+        K.linear_topk(xb, wb, None, part, candidates=9)
+    st = BeamState(2, 7, 4, "cuda")
+    st.reset(2, 0)
+    with pytest.raises(RuntimeError, match="beam=7"):
+        K.beam_step_partials(torch.empty(14, 4, 12, device="cuda"), st, 0, B=2, beam=7, V=300, L=4, eos=3, pad=0)
+    with pytest.raises(RuntimeError, match="sc_ingest_f32_bf16"):
+        K.lib.call("sc_ingest_f32_bf16", torch.randn(16, device="cuda").data_ptr(), torch.empty(16, device="cuda", dtype=torch.bfloat16).data_ptr(),
+                   16, 0, K.lib.stream())                       # a device pointer is not pinned host memory
