@@ -51,6 +51,9 @@ struct GemmArgs {
   // folded LayerNorm (consumer) / residual-stream producer (ScGemmExtra)
   const float* ln_stats; const float* ln_c; float ln_eps;
   void* y2; float* stats_out;
+  // cluster2: CTAs are launched as clusters of 2 that work on two M blocks of the same N tile in lockstep; each CTA loads its
+  // own A tile and HALF of the shared B tile, multicast to both (L2 reads per CTA: 16 + 16 KB per k-block instead of 16 + 32)
+  int cluster2;
   int pdl_early;  // trigger the dependent launch as soon as this CTA's loads are in flight (else: implicit, at exit)
   // kEpi == 3 (generator fused with the beam step's row pass): no output tile; per (row, N tile, epilogue-warp half) one
   // record {max, sum exp(x - max), kTopK largest values, their columns} -> topk_part[row][tiles_n * 2][kTopKRec]
@@ -93,6 +96,26 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -360,6 +383,11 @@ template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false>
 __global__ void __launch_bounds__(32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0)),
                                   (!kMasked && kEpi != 2 && num_epilogue_warps(BLOCK_N, kStages) == 4) ? 2 : 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
+  // cluster2 mode: tma_b describes boxes of BLOCK_N / 2 rows (the half this CTA multicasts)
+  const bool c2 = args.cluster2 != 0;
+  const uint32_t crank = c2 ? cluster_ctarank() : 0u;
+  const int unit0 = c2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustride = c2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   using L = Smem<BLOCK_N, kStages>;
   constexpr int kNumEpilogueWarps = L::kNumEpilogueWarps;
   constexpr int kFirstTransformWarp = 4 + kNumEpilogueWarps;
@@ -384,7 +412,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], kMasked ? 1 + kNumTransformWarps : 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], c2 ? 2 : 1);  // cluster2: both CTAs' MMAs must have read the slot before it is refilled
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -399,6 +427,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (c2) cluster_sync_all();  // the peer's barriers are initialised before anything multicasts into / arrives on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -407,9 +436,9 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       sc::pdl_wait();  // A (and B) may be written by the previous kernel in the stream
       int it = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      for (int u = unit0; u < num_units; u += ustride) {
         const int tile = u / args.splits, split = u - tile * args.splits;
-        const int m0 = (tile / args.tiles_n) * BLOCK_M, n0 = (tile % args.tiles_n) * BLOCK_N;
+        const int m0 = (c2 ? (tile / args.tiles_n) * 2 + (int)crank : tile / args.tiles_n) * BLOCK_M, n0 = (tile % args.tiles_n) * BLOCK_N;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(kb0 + args.kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -427,7 +456,11 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes + hb * 8192, n0 + hb * 64, kb * BLOCK_K);
           } else {
             tma_load_2d(&tma_a, &full_bar[s], sa, kb * BLOCK_K, m0);
-            if (!kMasked) tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes, kb * BLOCK_K, n0);
+            if (!kMasked) {
+              if (c2) tma_load_2d_mc(&tma_b, &full_bar[s], sa + L::kABytes + crank * (L::kBBytes / 2), kb * BLOCK_K,
+                                     n0 + (int)crank * (BLOCK_N / 2), (uint16_t)3);
+              else tma_load_2d(&tma_b, &full_bar[s], sa + L::kABytes, kb * BLOCK_K, n0);
+            }
           }
         }
       }
@@ -438,7 +471,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, kMN ? 1 : 0);
       int it = 0, lt = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++lt) {
+      for (int u = unit0; u < num_units; u += ustride, ++lt) {
         const int split = u % args.splits;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(kb0 + args.kb_per_split, num_kb_total);
@@ -461,7 +494,8 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             const uint64_t adv = kMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
             umma_bf16(tmem_d, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          if (c2) tcgen05_commit_mc(&empty_bar[s], (uint16_t)3);
+          else tcgen05_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
         tcgen05_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
@@ -482,9 +516,9 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int et = threadIdx.x - 128;                    // 0..127 (4-warp configurations)
     const int jsw = lane & 7;  // swizzle key of this thread's own row (row-mapping: row = lane)
     int lt = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++lt) {
+    for (int u = unit0; u < num_units; u += ustride, ++lt) {
       const int tile = u / args.splits, split = u - tile * args.splits;
-      const int m0 = (tile / args.tiles_n) * BLOCK_M, n0 = (tile % args.tiles_n) * BLOCK_N;
+      const int m0 = (c2 ? (tile / args.tiles_n) * 2 + (int)crank : tile / args.tiles_n) * BLOCK_M, n0 = (tile % args.tiles_n) * BLOCK_N;
       const int buf = lt & 1;
       const int rbase = m0 + q * 32;
       float ln_rstd = 1.f, ln_mr = 0.f;
@@ -785,7 +819,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const sc::Philox philox(args.seed);
     constexpr int kPasses = BLOCK_N / 8;
     int it = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+    for (int u = unit0; u < num_units; u += ustride) {
       const int tile = u / args.splits, split = u - tile * args.splits;
       const int n0 = (tile % args.tiles_n) * BLOCK_N;
       const int kb0 = split * args.kb_per_split;
@@ -843,6 +877,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   tcgen05_fence_before();
   __syncthreads();
+  if (c2) cluster_sync_all();  // the peer may still arrive on this CTA's barriers / multicast into its smem until it is done too
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)));
@@ -918,6 +953,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   }
   a.tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
   a.num_tiles = a.tiles_n * ((a.M + BLOCK_M - 1) / BLOCK_M);
+  if (a.cluster2) a.num_tiles = a.tiles_n * (((a.M + BLOCK_M - 1) / BLOCK_M + 1) / 2);  // pairs of M blocks
   const int num_kb = (a.K + BLOCK_K - 1) / BLOCK_K;
   // split K (weight gradients only: few output tiles, thousands of tokens to contract) until the SMs are covered.
   // want_splits > 0: the caller (sc_linear_wgrad with a workspace) stores one fp32 partial product per split and
@@ -942,7 +978,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   const int units = a.num_tiles * a.splits;
   dim3 grid(min(units, per_sm * sm_count()));
   constexpr int threads = 32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0));
-  cudaError_t e = sc::launch_pdl(kern, grid, dim3(threads), (size_t)smem, stream, ta, tb, a);
+  cudaError_t e;
+  if (a.cluster2) {
+    const int clusters = min(units, sm_count() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (g_sc_pdl & 1) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+    cfg.attrs = at; cfg.numAttrs = na;
+    e = cudaLaunchKernelEx(&cfg, kern, ta, tb, a);
+  } else {
+    e = sc::launch_pdl(kern, grid, dim3(threads), (size_t)smem, stream, ta, tb, a);
+  }
   if (e != cudaSuccess) {
     sc_set_error("sc_gemm_bf16_kernel: launch failed: %s", cudaGetErrorString(e));
     return (int)e;
@@ -1023,6 +1078,12 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     block_n = 256;
   }
   const bool mn = ex && ex->mn_major;
+  // 2-CTA clusters with a multicast B tile (SC_GEMM_MULTICAST=1): the 128 x 256 tiles are bound by the bytes every SM pulls out
+  // of L2 (48 KB per k-block); sharing B between two M blocks cuts that to 32 KB
+  static int env_mc = -1;
+  if (env_mc < 0) { const char* e = getenv("SC_GEMM_MULTICAST"); env_mc = e ? atoi(e) : 0; }
+  const bool c2 = env_mc > 0 && block_n == 256 && !masked && !mn && !wgrad && !(ex && ex->partial_splits > 0) && force_splits == 0 &&
+                  mt >= 2 && !(ex && ex->hmask);
   CUtensorMap ta, tb;
   int rc;
   if (mn) {
@@ -1037,7 +1098,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     rc = make_tmap(&ta, x, M, K, BLOCK_M);
     if (rc) return rc;
     if (!masked) {
-      rc = make_tmap(&tb, w, N, K, block_n);
+      rc = make_tmap(&tb, w, N, K, c2 ? block_n / 2 : block_n);
       if (rc) return rc;
     } else {
       tb = ta;
@@ -1047,6 +1108,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K;
   a.pdl_early = (g_sc_pdl & 4) ? 1 : 0;
+  a.cluster2 = c2 ? 1 : 0;
   a.w32 = masked ? (const float*)w : nullptr;
   a.mask = mask; a.uniforms = uniforms; a.mask_mode = mask_mode;
   a.seed = seed; a.stream_id = stream_id;

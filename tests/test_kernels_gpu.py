@@ -594,3 +594,28 @@ def test_new_entry_points_reject_bad_arguments(K):
     with pytest.raises(RuntimeError, match="sc_ingest_f32_bf16"):
         K.lib.call("sc_ingest_f32_bf16", torch.randn(16, device="cuda").data_ptr(), torch.empty(16, device="cuda", dtype=torch.bfloat16).data_ptr(),
                    16, 0, K.lib.stream())                       # a device pointer is not pinned host memory
+
+
+def test_cluster_multicast_gemm_variant():
+    """SC_GEMM_MULTICAST=1 (2-CTA clusters, B tile multicast; read once per process, hence the subprocess): same results as
+    torch for an even and an odd number of M blocks."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import torch, sys
+sys.path.insert(0, %r)
+import sparse_caption_b200.kernels as K
+for (M, N, Kd) in ((1536, 1000, 512), (1400, 520, 136)):   # 12 and 11 M blocks (the last pair has a phantom block)
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, Kd, generator=g).bfloat16().cuda(); w = (torch.randn(N, Kd, generator=g) * 0.1).bfloat16().cuda(); b = torch.randn(N, generator=g).cuda()
+    out = torch.full((M, N), 7.0, device="cuda")
+    K.linear(x, w, b, out=out, tile_n=3256)
+    ref = x.float() @ w.float().t() + b
+    err = float((out - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, (M, N, Kd, err)
+print("multicast ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SC_GEMM_MULTICAST="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "multicast ok" in r.stdout, r.stdout + r.stderr
