@@ -109,6 +109,29 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) 
                "h"(mask)
                : "memory");
 }
+// ---- CTA-pair mode (cluster2 == 2): one tcgen05.mma.cta_group::2 of M = 256 spans both CTAs' TMEM; every CTA stages its own
+// 128 rows of A and its own HALF of the B tile (32 instead of 48 KB per k-block into each SM) ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load whose completion bytes are counted on a barrier of the pair's leader CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -156,6 +179,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
@@ -379,12 +412,16 @@ __device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, 
 // kStages: depth of the TMA->MMA smem ring.
 // kEpi: 0 = plain forward epilogue, 1 = full forward epilogue (dropout, folded LayerNorm, statistics), 2 = weight gradient
 // kMN: both operands are given transposed ([K, M] and [K, N] row-major, i.e. MN-major tiles): y = x^T w.
-template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false>
+// kPair: CTA-pair variant (launched as clusters of 2 with args.cluster2 == 2).  A separate instantiation: a kernel that contains
+// cta_group::2 instructions cannot be launched without a cluster.
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false, bool kPair = false>
 __global__ void __launch_bounds__(32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0)),
                                   (!kMasked && kEpi != 2 && num_epilogue_warps(BLOCK_N, kStages) == 4) ? 2 : 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
   // cluster2 mode: tma_b describes boxes of BLOCK_N / 2 rows (the half this CTA multicasts)
   const bool c2 = args.cluster2 != 0;
+  constexpr bool pair = kPair;  // one cta_group::2 MMA per CTA pair, issued by rank 0
+  if (pair) cluster_sync_all();  // both CTAs are resident before the pair-wide TMEM allocation
   const uint32_t crank = c2 ? cluster_ctarank() : 0u;
   const int unit0 = c2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int ustride = c2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -395,8 +432,12 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   if (smem - smem_raw > 768) __trap();  // the barrier block below would overlap the tiles (never with a 1 KB-aligned base)
   uint64_t* full_bar = (uint64_t*)(smem_raw + L::kTotal - 256);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;   // [2]
+  // pair mode stages 32 instead of 48 KB per k-block: the same ring bytes hold 3/2 as many stages (the main loop is bound by
+  // bytes in flight = ring bytes / TMA latency, so the deeper ring is where the pair mode gains)
+  const int nst = pair ? kStages * 3 / 2 : kStages;
+  const int stage_bytes = pair ? L::kABytes + L::kBBytes / 2 : L::kStageBytes;
+  uint64_t* empty_bar = full_bar + nst;
+  uint64_t* tmem_full_bar = empty_bar + nst;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty_bar + 2);
 
@@ -410,20 +451,27 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (!kMasked) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < nst; ++s) {
       mbar_init(&full_bar[s], kMasked ? 1 + kNumTransformWarps : 1);
-      mbar_init(&empty_bar[s], c2 ? 2 : 1);  // cluster2: both CTAs' MMAs must have read the slot before it is refilled
+      // multicast mode: both CTAs' MMAs must have read the slot before it is refilled; pair mode: one multicast commit
+      mbar_init(&empty_bar[s], (c2 && !pair) ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], kNumEpilogueWarps);
+      mbar_init(&tmem_empty_bar[b], pair ? 2 * kNumEpilogueWarps : kNumEpilogueWarps);  // pair: the peer's epilogue arrives here too
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                 "r"((uint32_t)(2 * BLOCK_N)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (pair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)(2 * BLOCK_N)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                   "r"((uint32_t)(2 * BLOCK_N)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -442,10 +490,18 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(kb0 + args.kb_per_split, num_kb_total);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = pair ? it % nst : it % kStages;
+          const uint32_t ph = (pair ? it / nst : it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * L::kStageBytes;
+          uint8_t* sa = smem + s * stage_bytes;
+          if (!kMasked && !kMN && pair) {
+            // both CTAs' bytes (A block + half of the B tile each) are counted on the leader's barrier
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0u);
+            if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * (L::kABytes + L::kBBytes / 2));
+            tma_load_2d_pair(&tma_a, fb, sa, kb * BLOCK_K, m0);
+            tma_load_2d_pair(&tma_b, fb, sa + L::kABytes, kb * BLOCK_K, n0 + (int)crank * (BLOCK_N / 2));
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], kMasked ? L::kABytes : L::kStageBytes);
           if (kMN) {
             // boxes of {64 MN-elements, 64 tokens}: coordinate 0 = position along M / N, coordinate 1 = token
@@ -468,8 +524,9 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0 && !(pair && crank != 0)) {
       constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, kMN ? 1 : 0);
+      constexpr uint32_t idesc_pair = make_idesc(2 * BLOCK_M, BLOCK_N, 0);
       int it = 0, lt = 0;
       for (int u = unit0; u < num_units; u += ustride, ++lt) {
         const int split = u % args.splits;
@@ -480,11 +537,11 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = pair ? it % nst : it % kStages;
+          const uint32_t ph = (pair ? it / nst : it / kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint64_t da = kMN ? make_smem_desc_mn(sa) : make_smem_desc(sa);
           const uint64_t db = kMN ? make_smem_desc_mn(sa + L::kABytes) : make_smem_desc(sa + L::kABytes);
 #pragma unroll
@@ -492,12 +549,15 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             // K-major: advance 32 B (16 bf16) along K inside the 128B swizzle row: +2 in 16-byte units;
             // MN-major: 16 tokens = two 1024-byte atoms: +128 units
             const uint64_t adv = kMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
-            umma_bf16(tmem_d, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (pair) umma_bf16_pair(tmem_d, da + adv, db + adv, idesc_pair, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da + adv, db + adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (c2) tcgen05_commit_mc(&empty_bar[s], (uint16_t)3);
+          if (pair) tcgen05_commit_pair(&empty_bar[s], (uint16_t)3);
+          else if (c2) tcgen05_commit_mc(&empty_bar[s], (uint16_t)3);
           else tcgen05_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        tcgen05_commit(&tmem_full_bar[buf]);  // accumulator complete
+        if (pair) tcgen05_commit_pair(&tmem_full_bar[buf], (uint16_t)3);  // both CTAs' epilogues
+        else tcgen05_commit(&tmem_full_bar[buf]);                          // accumulator complete
       }
     }
   } else if (warp >= 4 && warp < 4 + kNumEpilogueWarps) {
@@ -707,6 +767,33 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
             continue;
           }
+          if constexpr (!kDirect) {
+            // bf16 output of the throughput configurations: the thread's 64-byte row piece goes through the warp's staging
+            // tile (16-byte pieces XOR-swizzled by row pair) so that one store instruction writes 8 rows x 64 contiguous
+            // bytes (full sectors, 8 requests) instead of 32 rows x 16 bytes - the row-mapped stores cost 30 % of the
+            // GEMM's throughput by crowding the load path
+            if (args.y_bf16 && (args.N & 7) == 0 && col0 + 32 <= args.N) {
+              const int sw = (lane >> 1) & 3;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]), p1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]), p3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                uint4 o;
+                o.x = *(const uint32_t*)&p0; o.y = *(const uint32_t*)&p1; o.z = *(const uint32_t*)&p2; o.w = *(const uint32_t*)&p3;
+                *(uint4*)(stg + lane * 64 + ((j ^ sw) << 4)) = o;
+              }
+              __syncwarp();
+              __nv_bfloat16* yb = (__nv_bfloat16*)args.y + (size_t)split * args.split_stride + col0 + (lane & 3) * 8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rl = i * 8 + (lane >> 2);
+                const uint4 o = *(const uint4*)(stg + rl * 64 + (((lane & 3) ^ ((rl >> 1) & 3)) << 4));
+                if (rbase + rl < args.M) *(uint4*)(yb + (size_t)(rbase + rl) * args.N) = o;
+              }
+              __syncwarp();  // staging is rewritten by the next chunk
+              continue;
+            }
+          }
           if (row < args.M) epilogue_store_row<kEpi == 1>(args, f, row, col0, (size_t)split * args.split_stride);
           continue;
         }
@@ -808,7 +895,10 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (pair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[buf]), 0u));  // the leader's MMA warp owns both halves
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
     }
   } else if (kMasked && warp >= kFirstTransformWarp) {
     // ===== B transform: fp32 W (+ mask logits) -> masked bf16 operand tile (swizzled K-major) =====
@@ -880,7 +970,8 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (c2) cluster_sync_all();  // the peer may still arrive on this CTA's barriers / multicast into its smem until it is done too
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)));
+    if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BLOCK_N)));
   }
 }
 
@@ -941,9 +1032,10 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false>
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false, bool kPair = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_splits, cudaStream_t stream) {
-  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi, kMN>;
+  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi, kMN, kPair>;
+  SC_CHECK(kPair == (a.cluster2 == 2), SC_ERR_UNSUPPORTED, "CTA-pair mode reached an instantiation without it (cluster2 = %d)", a.cluster2);
   constexpr int smem = Smem<BLOCK_N, kStages>::kTotal;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1078,12 +1170,16 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
     block_n = 256;
   }
   const bool mn = ex && ex->mn_major;
-  // 2-CTA clusters with a multicast B tile (SC_GEMM_MULTICAST=1): the 128 x 256 tiles are bound by the bytes every SM pulls out
-  // of L2 (48 KB per k-block); sharing B between two M blocks cuts that to 32 KB
   static int env_mc = -1;
-  if (env_mc < 0) { const char* e = getenv("SC_GEMM_MULTICAST"); env_mc = e ? atoi(e) : 0; }
+  if (env_mc < 0) { const char* e = getenv("SC_GEMM_MULTICAST"); env_mc = e ? atoi(e) : 2; }
+  // SC_GEMM_MULTICAST: 0 = no clusters, 1 = 2-CTA clusters with a multicast B tile (two cta_group::1 MMAs; measured: no gain),
+  // 2 (default) / 3 = CTA pairs: one tcgen05.mma.cta_group::2 of M = 256, each CTA stages its A block and HALF of the B tile
+  // (+5..20 % on the encoder GEMMs together with the coalesced staged stores)
   const bool c2 = env_mc > 0 && block_n == 256 && !masked && !mn && !wgrad && !(ex && ex->partial_splits > 0) && force_splits == 0 &&
-                  mt >= 2 && !(ex && ex->hmask);
+                  mt >= 2 && !(ex && ex->hmask) && !(env_mc >= 2 && topk) &&
+                  // default (2): pairs for the many-wave problems (the encoder's M = 18432 GEMMs), where the main loop is what
+                  // bounds the launch; at M = 4250 / 1536 the whole step measured the same or slightly slower.  3 = every mt >= 2
+                  !(env_mc == 2 && mt < 64);
   CUtensorMap ta, tb;
   int rc;
   if (mn) {
@@ -1108,7 +1204,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K;
   a.pdl_early = (g_sc_pdl & 4) ? 1 : 0;
-  a.cluster2 = c2 ? 1 : 0;
+  a.cluster2 = c2 ? (env_mc >= 2 ? 2 : 1) : 0;  // 1: multicast B, two cta_group::1 MMAs; 2: one cta_group::2 MMA per pair (default)
   a.w32 = masked ? (const float*)w : nullptr;
   a.mask = mask; a.uniforms = uniforms; a.mask_mode = mask_mode;
   a.seed = seed; a.stream_id = stream_id;
@@ -1148,6 +1244,9 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   if (block_n == BN && stages == ST) {                                                                                \
     if (masked) return epi ? launch<BN, true, ST, 1>(ta, tb, a, force_splits, stream)                                 \
                            : launch<BN, true, ST, 0>(ta, tb, a, force_splits, stream);                                \
+    if (BN == 256 && a.cluster2 == 2 && epi != 2)                                                                     \
+      return epi == 1 ? launch<256, false, 3, 1, false, true>(ta, tb, a, force_splits, stream)                        \
+                      : launch<256, false, 3, 0, false, true>(ta, tb, a, force_splits, stream);                       \
     return epi == 2 ? launch<BN, false, ST, 2>(ta, tb, a, force_splits, stream)                                       \
          : epi == 1 ? launch<BN, false, ST, 1>(ta, tb, a, force_splits, stream)                                       \
                     : launch<BN, false, ST, 0>(ta, tb, a, force_splits, stream);                                      \

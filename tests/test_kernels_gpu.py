@@ -596,9 +596,12 @@ def test_new_entry_points_reject_bad_arguments(K):
                    16, 0, K.lib.stream())                       # a device pointer is not pinned host memory
 
 
-def test_cluster_multicast_gemm_variant():
-    """SC_GEMM_MULTICAST=1 (2-CTA clusters, B tile multicast; read once per process, hence the subprocess): same results as
-    torch for an even and an odd number of M blocks."""
+@pytest.mark.parametrize("mode", ["0", "1", "3"])
+def test_cluster_gemm_variants(mode):
+    """SC_GEMM_MULTICAST (read once per process, hence the subprocess): 0 = no clusters, 1 = 2-CTA clusters with a multicast B
+    tile, 3 = CTA pairs (tcgen05.mma.cta_group::2, the default for >= 64 M blocks) forced for every size.  Same results as
+    torch for an even and an odd number of M blocks, fp32 and bf16 (staged, coalesced stores) outputs, and a 72-block problem
+    that takes the pair path by default."""
     import os
     import subprocess
     import sys
@@ -606,16 +609,19 @@ def test_cluster_multicast_gemm_variant():
 import torch, sys
 sys.path.insert(0, %r)
 import sparse_caption_b200.kernels as K
-for (M, N, Kd) in ((1536, 1000, 512), (1400, 520, 136)):   # 12 and 11 M blocks (the last pair has a phantom block)
+for (M, N, Kd) in ((1536, 1000, 512), (1400, 520, 136), (9216, 1024, 512)):   # 12 / 11 (phantom block in the last pair) / 72 M blocks
     g = torch.Generator().manual_seed(M)
     x = torch.randn(M, Kd, generator=g).bfloat16().cuda(); w = (torch.randn(N, Kd, generator=g) * 0.1).bfloat16().cuda(); b = torch.randn(N, generator=g).cuda()
+    ref = x.float() @ w.float().t() + b
     out = torch.full((M, N), 7.0, device="cuda")
     K.linear(x, w, b, out=out, tile_n=3256)
-    ref = x.float() @ w.float().t() + b
     err = float((out - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, (M, N, Kd, err)
-print("multicast ok")
+    out16 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    K.linear(x, w, b, out=out16, tile_n=3256, relu=True)
+    assert torch.equal(out16, torch.relu(out).bfloat16()), (M, N, Kd, "bf16")
+print("variants ok")
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SC_GEMM_MULTICAST="1")
+    env = dict(os.environ, SC_GEMM_MULTICAST=mode)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and "multicast ok" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout + r.stderr
