@@ -794,6 +794,25 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               continue;
             }
           }
+          if constexpr (!kDirect && kEpi != 1) {
+            // fp32 output (e.g. the training logits, 170 MB per step): same idea with the full 4 KB staging tile - one store
+            // instruction writes 4 rows x 128 contiguous bytes
+            if (!args.y_bf16 && (args.N & 3) == 0 && col0 + 32 <= args.N) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *(float4*)(stg + lane * 128 + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              __syncwarp();
+              float* yf = (float*)args.y + (size_t)split * args.split_stride + col0 + (lane & 7) * 4;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rl = i * 4 + (lane >> 3);
+                const float4 o = *(const float4*)(stg + rl * 128 + (((lane & 7) ^ (rl & 7)) << 4));
+                if (rbase + rl < args.M) *(float4*)(yf + (size_t)(rbase + rl) * args.N) = o;
+              }
+              __syncwarp();  // staging is rewritten by the next chunk
+              continue;
+            }
+          }
           if (row < args.M) epilogue_store_row<kEpi == 1>(args, f, row, col0, (size_t)split * args.split_stride);
           continue;
         }
