@@ -156,7 +156,10 @@ int sc_decode_cross_attn_step(const void* q, int ldq, const void* mem_k, const v
  * penalty_kind: 0 "", 1 "wu_<alpha>", 2 "avg_<alpha>".  seq/lp/anc are ping-pong buffers [B*beam, L].
  * Two launches: one CTA per (image, beam) row reads its logits row once (log-softmax statistics + the row's top-`beam`
  * candidates by final score), then one small CTA per image merges the rows and does the bookkeeping.
- * workspace: sc_beam_step_workspace_bytes(B, beam) bytes of device scratch, 16-byte aligned. */
+ * workspace: sc_beam_step_workspace_bytes(B, beam) bytes of device scratch, 16-byte aligned.
+ * suppress_tok (optional int32 [B*beam], -1 = none): per-row token whose log-prob is -inf at this step (remove_bad_endings,
+ * caption_model.py:161-168); penalized_col (>= 0): column whose log-prob is lowered by 1000 (suppress_UNK, :169-170);
+ * both act after the normalisation, like the decoding constraint. */
 int sc_beam_step_workspace_bytes(int B, int beam);
 /* Generator fused with the row pass of the beam step (OutputEmbedding, models/transformer.py:405-413, + beam_step,
  * models/caption_model.py:56-111): the [M, N] logits are never written.  sc_linear_topk (bf16 x [M,K], bf16 w [N,K], fp32
@@ -174,7 +177,8 @@ int sc_beam_step_partials(const float* partials, int parts_per_row, int B, int b
                           float* done_lp, double* done_p, int* done_count, void* workspace, size_t workspace_bytes,
                           sc_stream_t stream);
 int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
-                 int decoding_constraint, int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out,
+                 int decoding_constraint, int penalty_kind, float penalty_alpha, const int* suppress_tok, int penalized_col,
+                 const int* seq_in, int* seq_out,
                  const float* lp_in, float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out,
                  int* done_seq, float* done_lp, double* done_p, int* done_count, void* workspace, size_t workspace_bytes,
                  sc_stream_t stream);
@@ -304,6 +308,14 @@ int sc_box_bias_fwd(const float* boxes, const float* wg_w, const float* wg_b, fl
                     float wave_len, sc_stream_t stream);
 int sc_box_bias_bwd(const float* boxes, const float* bias, const float* dbias, float* dwg_w, float* dwg_b, int B, int N, int h,
                     int trig, float wave_len, sc_stream_t stream);
+/* BoxRelationalEmbedding itself (relation_transformer.py:196-256) for callers of the static method: emb fp32 [B,N,N,64]
+ * (sin block, cos block) or [B,N,N,4] (the four log-deltas) when trig == 0. */
+int sc_box_embedding(const float* boxes, float* emb, int B, int N, int trig, float wave_len, sc_stream_t stream);
+/* out = log(max(x, lo)) (box_attention's additive term from the relu'd geometry weights, relation_transformer.py:283-286);
+ * with dy != NULL: out = dy / x where x > lo, else 0 (its gradient). */
+int sc_log_clamp(const float* x, const float* dy, float* out, size_t n, float lo, sc_stream_t stream);
+/* backward of a plain log_softmax (OutputEmbedding, transformer.py:405-413): dx = dy - exp(logprobs) * rowsum(dy) */
+int sc_logsoftmax_bwd(const float* logprobs, const float* dy, float* dx, int rows, int V, sc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -313,6 +313,46 @@ __global__ void __launch_bounds__(256) box_bias_fwd_kernel(const float* __restri
   }
 }
 
+// BoxRelationalEmbedding itself (relation_transformer.py:196-256), for callers of the static method: emb[b,i,j,:] =
+// [sin(100 * delta_c / wave^(f/8)) for c in (x,y,w,h), f in 0..7] ++ [cos(same)]  (dim_g = 64), or the 4 deltas (dim_g = 4).
+__global__ void __launch_bounds__(256) box_embedding_kernel(const float* __restrict__ boxes, float* __restrict__ emb, int B, int N,
+                                                            int trig, DimMat dm) {
+  const long total = (long)B * N * N;
+  for (long p = (long)blockIdx.x * 256 + threadIdx.x; p < total; p += (long)gridDim.x * 256) {
+    const int b = (int)(p / (N * N));
+    const int r = (int)(p - (long)b * N * N);
+    const int i = r / N, j = r - i * N;
+    float delta[4];
+    pair_deltas(boxes, b, N, i, j, delta);
+    if (trig) {
+      float* o = emb + (size_t)p * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float p100 = 100.0f * delta[c];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+          float sv, cv;
+          sincosf(p100 * dm.v[f], &sv, &cv);
+          o[c * 8 + f] = sv;
+          o[32 + c * 8 + f] = cv;
+        }
+      }
+    } else {
+      *(float4*)(emb + (size_t)p * 4) = make_float4(delta[0], delta[1], delta[2], delta[3]);
+    }
+  }
+}
+
+// box_attention's additive term from the relu'd geometry weights w_g: log(max(w_g, 1e-6)) (relation_transformer.py:283-286),
+// and its gradient d w_g = d bias / w_g where the clamp is inactive.
+__global__ void __launch_bounds__(256) log_clamp_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                        float* __restrict__ out, size_t n, float lo) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float v = x[i];
+    out[i] = dy ? (v > lo ? dy[i] / v : 0.f) : logf(fmaxf(v, lo));
+  }
+}
+
 // dWG[h,f] += sum_pairs dpre * emb_f ; db[h] += sum_pairs dpre, with dpre = dbias * exp(-bias) where the clamp/ReLU
 // were inactive (bias > log 1e-6).  CTA per (image, slice of pairs_per_cta pairs): one CTA per image left two thirds
 // of the SMs idle at 50 images; 32 pairs of embedding at a time in shared memory.
@@ -513,6 +553,25 @@ int sc_box_bias_bwd(const float* boxes, const float* bias, const float* dbias, f
   slices = (pairs + ppc - 1) / ppc;
   sc::launch_pdl_aux(box_bias_bwd_kernel, dim3(B, slices), dim3(256), 0, stream, boxes, bias, dbias, dwg_w, dwg_b, B, N, h, trig, make_dim_mat(wave_len), ppc);
   SC_LAUNCH_CHECK("sc_box_bias_bwd");
+  return SC_OK;
+}
+
+int sc_box_embedding(const float* boxes, float* emb, int B, int N, int trig, float wave_len, cudaStream_t stream) {
+  SC_CHECK(B > 0 && N > 0, SC_ERR_SHAPE, "sc_box_embedding: B=%d N=%d", B, N);
+  SC_CHECK(((uintptr_t)boxes & 15) == 0 && ((uintptr_t)emb & 15) == 0, SC_ERR_ALIGN, "sc_box_embedding: 16-byte alignment");
+  long blocks = ((long)B * N * N + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  box_embedding_kernel<<<(int)blocks, 256, 0, stream>>>(boxes, emb, B, N, trig, make_dim_mat(wave_len));
+  SC_LAUNCH_CHECK("sc_box_embedding");
+  return SC_OK;
+}
+
+int sc_log_clamp(const float* x, const float* dy, float* out, size_t n, float lo, cudaStream_t stream) {
+  SC_CHECK(n > 0 && x && out, SC_ERR_SHAPE, "sc_log_clamp: bad args");
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  log_clamp_kernel<<<(int)blocks, 256, 0, stream>>>(x, dy, out, n, lo);
+  SC_LAUNCH_CHECK("sc_log_clamp");
   return SC_OK;
 }
 

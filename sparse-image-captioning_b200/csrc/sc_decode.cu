@@ -328,6 +328,10 @@ struct BeamArgs {
   int* done_seq; float* done_lp; double* done_p; int* done_count;  // [B,beam,L] [B,beam,L] [B,beam] [B]
   // fused generator (sc_beam_step_partials): logits == nullptr; the raw logit of candidate j of row r is ws_raw[r*beam + j]
   const float* ws_raw;
+  // remove_bad_endings (caption_model.py:161-168): per-row token whose log-prob is -inf at this step (-1 = none), and
+  // suppress_UNK (:169-170): column whose log-prob is lowered by 1000 (-1 = none).  Both act AFTER the normalisation.
+  const int* suppress_tok;
+  int penalized_col;
 };
 
 __device__ __forceinline__ float block_max(float v, float* s_red) {
@@ -373,6 +377,8 @@ __global__ void __launch_bounds__(kBeamThreads, 4) beam_row_kernel(const BeamArg
   for (int i = 0; i < NB; ++i) { top[i].s = -INFINITY; top[i].idx = 0x7fffffff; }
   const float base = a.sum[r];
   const int prev = (a.constraint && a.t > 0) ? a.seq_in[(size_t)r * a.L + a.t - 1] : -1;
+  const int sup = (a.suppress_tok && a.t > 0) ? a.suppress_tok[r] : -1;
+  const int pen = a.penalized_col;
   float mx = -INFINITY, ls, mx2 = 0.f, ls2 = 0.f;
   if (kRegs) {
     // Register path (V <= 10240, V % 4 == 0): the row is read once with 16-byte loads.  The kernel used to be
@@ -398,6 +404,8 @@ __global__ void __launch_bounds__(kBeamThreads, 4) beam_row_kernel(const BeamArg
       float v[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
       mx = fmaxf(mx, fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])));
       if (prev >= c0 && prev < c0 + 4) v[prev - c0] = -INFINITY;  // decoding_constraint: never a candidate
+      if (sup >= c0 && sup < c0 + 4) v[sup - c0] = -INFINITY;
+      if (pen >= c0 && pen < c0 + 4) v[pen - c0] -= 1000.f * T;  // log-prob - 1000 (the final score is (x - mx - ls) / T ...)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (v[e] > rawtop[NB - 1].s) {  // ascending index order: strict '>' keeps the smaller index on ties
@@ -450,7 +458,8 @@ __global__ void __launch_bounds__(kBeamThreads, 4) beam_row_kernel(const BeamArg
     for (int i = tid; i < V; i += kBeamThreads) {
       float lp = (x[i] - mx) - ls;
       if (T != 1.0f) lp = (lp / T - mx2) - ls2;
-      if (i == prev) lp = -INFINITY;
+      if (i == prev || i == sup) lp = -INFINITY;
+      if (i == pen) lp -= 1000.f;
       Cand cd; cd.s = base + lp; cd.idx = k * V + i;
       topk_insert<NB>(top, cd);
     }
@@ -621,6 +630,7 @@ __global__ void __launch_bounds__(kMergeThreads) beam_merge_kernel(const BeamArg
       const float* st = ws_stats + ((size_t)b * NB + parent) * 4;
       float lp = (x - st[0]) - st[1];
       if (T != 1.0f) lp = (lp / T - st[2]) - st[3];
+      if (word == a.penalized_col) lp -= 1000.f;
       a.lp_out[dst] = lp;
       a.anc_out[dst] = b * NB + parent;
     } else {
@@ -877,7 +887,8 @@ size_t sc_beam_step_workspace_bytes_impl(int B, int beam) {
 }
 
 int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int eos, int pad, float temperature,
-                 int decoding_constraint, int penalty_kind, float penalty_alpha, const int* seq_in, int* seq_out,
+                 int decoding_constraint, int penalty_kind, float penalty_alpha, const int* suppress_tok, int penalized_col,
+                 const int* seq_in, int* seq_out,
                  const float* lp_in, float* lp_out, float* sum, const int* anc_in, int* anc_out, int* tokens_out,
                  int* done_seq, float* done_lp, double* done_p, int* done_count, void* workspace, size_t workspace_bytes,
                  cudaStream_t stream) {
@@ -893,6 +904,7 @@ int sc_beam_step(const float* logits, int B, int beam, int V, int L, int t, int 
   a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
   a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
   a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count; a.ws_raw = nullptr;
+  a.suppress_tok = suppress_tok; a.penalized_col = (penalized_col >= 0 && penalized_col < V) ? penalized_col : -1;
   float* ws_stats = (float*)workspace;
   Cand* ws_cand = (Cand*)(ws_stats + (size_t)B * beam * 4);
   const bool regs = V <= kBeamThreads * kBeamRegs && (V & 3) == 0 && ((uintptr_t)logits & 15) == 0;
@@ -936,6 +948,7 @@ int sc_beam_step_partials(const float* partials, int parts_per_row, int B, int b
   a.penalty_alpha = penalty_alpha; a.seq_in = seq_in; a.seq_out = seq_out; a.lp_in = lp_in; a.lp_out = lp_out;
   a.sum = sum; a.anc_in = anc_in; a.anc_out = anc_out; a.tokens_out = tokens_out; a.done_seq = done_seq;
   a.done_lp = done_lp; a.done_p = done_p; a.done_count = done_count;
+  a.suppress_tok = nullptr; a.penalized_col = -1;
   float* ws_stats = (float*)workspace;
   Cand* ws_cand = (Cand*)(ws_stats + (size_t)B * beam * 4);
   float* ws_raw = (float*)(ws_cand + (size_t)B * beam * beam);

@@ -660,6 +660,25 @@ __global__ void __launch_bounds__(256) logsoftmax_nll_kernel(const float* __rest
   }
 }
 
+// backward of a plain log_softmax (OutputEmbedding, transformer.py:405-413) for callers that take the loss outside
+// (LanguageModelCriterion / RewardCriterion on the returned log-probs): dx = dy - exp(lp) * sum(dy)
+__global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __restrict__ lp, const float* __restrict__ dy,
+                                                             float* __restrict__ dx, int V) {
+  __shared__ float s_red[8];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* g = dy + (size_t)r * V;
+  const float* l = lp + (size_t)r * V;
+  float s = 0.f;
+  for (int i = tid; i < V; i += 256) s += g[i];
+  s = sc::warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += s_red[w];
+  for (int i = tid; i < V; i += 256) dx[(size_t)r * V + i] = g[i] - expf(l[i]) * s;
+}
+
 __global__ void __launch_bounds__(128) embedding_bwd_kernel(const int* __restrict__ tokens, const float* __restrict__ dy,
                                                             float* __restrict__ dtable, int rows, int D, int V, float scale) {
   const int r = blockIdx.x;
@@ -882,6 +901,13 @@ int sc_logsoftmax_nll(const float* logits, const int* target, const float* weigh
     logsoftmax_nll_kernel<float><<<rows, 256, 0, stream>>>(logits, target, weight, inv_norm, loss_sum, (float*)dlogits, logprobs, V);
   else SC_CHECK(false, SC_ERR_DTYPE, "sc_logsoftmax_nll: bad dtype");
   SC_LAUNCH_CHECK("sc_logsoftmax_nll");
+  return SC_OK;
+}
+
+int sc_logsoftmax_bwd(const float* logprobs, const float* dy, float* dx, int rows, int V, cudaStream_t stream) {
+  SC_CHECK(rows > 0 && V > 0 && logprobs && dy && dx, SC_ERR_SHAPE, "sc_logsoftmax_bwd: rows=%d V=%d", rows, V);
+  logsoftmax_bwd_kernel<<<rows, 256, 0, stream>>>(logprobs, dy, dx, V);
+  SC_LAUNCH_CHECK("sc_logsoftmax_bwd");
   return SC_OK;
 }
 

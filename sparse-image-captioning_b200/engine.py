@@ -652,6 +652,29 @@ class OrtEngine:
             return st.seq.view(enc.B, 1, -1), st.lp.view(enc.B, 1, -1)
         return st.done_seq, st.done_lp
 
+    def teacher_force(self, enc, tokens, beam=1, out=None):
+        """Incremental (KV-cached) decoding along GIVEN token paths: row r = image r // beam feeds BOS, tokens[r, 0], ...,
+        tokens[r, L-2] and every step's full log-softmax is returned (fp32 [L, B*beam, V]).  Each row keeps its own KV
+        history (identity ancestors) and shares its image's cross K/V - the per-step arithmetic of ``decode`` without the
+        search, i.e. ``get_logprobs_state`` (relation_transformer.py:374-387) unrolled over a fixed path.  Used by the
+        parity tests at the BASELINE sizes and by ``get_logprobs_state``-style callers that score given captions."""
+        c = self.cfg
+        L, V = c.max_seq_length, c.vocab_size
+        R = enc.B * beam
+        tokens = tokens.to(self.dev).to(torch.int32).reshape(R, tokens.shape[-1])
+        ws = self._get_dec_ws(enc.B, beam, enc.N, True, enc.slot, tag="force")
+        st = ws.state
+        st.reset(c.bos_token_id, c.pad_token_id)
+        steps = min(L, tokens.shape[1] + 1)
+        if out is None:
+            out = torch.empty(steps, R, V, device=self.dev)
+        for t in range(steps):
+            if t > 0:
+                st.tokens.copy_(tokens[:, t - 1])
+            self._decode_step(ws, enc, t, st.anc)
+            K.logsoftmax_nll(ws.logits, logprobs=out[t])
+        return out
+
     # ---- batch pipelining: slot s owns a stream + workspaces + graphs; batches in different slots overlap on the GPU
     # (the decode loop is a chain of ~70 short dependent kernels per step that leaves most SMs idle; a second
     # batch fills them, and its H2D copy hides behind the first batch's compute) ----

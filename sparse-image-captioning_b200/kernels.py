@@ -282,11 +282,15 @@ def cross_attn_step(q, mem_k, mem_v, att_mask, out, *, B, beam, N, D, h, ldq, ld
     return out
 
 
-def beam_step(logits, st, t, *, B, beam, V, L, eos, pad, temperature=1.0, constraint=0, penalty_kind=0, penalty_alpha=0.0):
-    """``st``: BeamState.  Reads buffers ``t % 2`` and writes ``(t+1) % 2``."""
+def beam_step(logits, st, t, *, B, beam, V, L, eos, pad, temperature=1.0, constraint=0, penalty_kind=0, penalty_alpha=0.0,
+              suppress_tok=None, penalized_col=-1):
+    """``st``: BeamState.  Reads buffers ``t % 2`` and writes ``(t+1) % 2``.  ``suppress_tok`` (int32 [B*beam], -1 = none):
+    per-row token that cannot be chosen at this step (remove_bad_endings); ``penalized_col``: column whose log-prob is
+    lowered by 1000 (suppress_UNK)."""
     i, o = t & 1, (t + 1) & 1
+    assert suppress_tok is None or (suppress_tok.dtype == torch.int32 and suppress_tok.numel() == B * beam)
     lib.call("sc_beam_step", lib.ptr(logits), B, beam, V, L, t, eos, pad, float(temperature), int(constraint),
-             int(penalty_kind), float(penalty_alpha), lib.ptr(st.seq[i]), lib.ptr(st.seq[o]), lib.ptr(st.lp[i]),
+             int(penalty_kind), float(penalty_alpha), lib.ptr(suppress_tok), int(penalized_col), lib.ptr(st.seq[i]), lib.ptr(st.seq[o]), lib.ptr(st.lp[i]),
              lib.ptr(st.lp[o]), lib.ptr(st.sum), lib.ptr(st.anc[i]), lib.ptr(st.anc[o]), lib.ptr(st.tokens),
              lib.ptr(st.done_seq), lib.ptr(st.done_lp), lib.ptr(st.done_p), lib.ptr(st.done_count), lib.ptr(st.ws),
              st.ws.numel(), lib.stream())
@@ -546,3 +550,33 @@ def box_bias_fwd(boxes, wg_w, wg_b, bias, *, B, N, h, trig=True, wave_len=1000.0
 def box_bias_bwd(boxes, bias, dbias, dwg_w, dwg_b, *, B, N, h, trig=True, wave_len=1000.0):
     lib.call("sc_box_bias_bwd", lib.ptr(boxes), lib.ptr(bias), lib.ptr(dbias), lib.ptr(dwg_w), lib.ptr(dwg_b), B, N, h, int(trig),
              wave_len, lib.stream())
+
+
+def box_embedding(boxes, *, trig=True, wave_len=1000.0, out=None):
+    """BoxRelationalEmbedding (relation_transformer.py:196-256): boxes fp32 [B,N,4] -> fp32 [B,N,N,64] (or [B,N,N,4])."""
+    B, N = boxes.shape[:2]
+    _chk(boxes, "boxes")
+    assert boxes.dtype == torch.float32
+    if out is None:
+        out = torch.empty(B, N, N, 64 if trig else 4, device=boxes.device)
+    lib.call("sc_box_embedding", lib.ptr(boxes), lib.ptr(out), B, N, int(trig), float(wave_len), lib.stream())
+    return out
+
+
+def log_clamp(x, *, lo=1e-6, dy=None, out=None):
+    """out = log(max(x, lo)); with ``dy``: out = dy / x where x > lo else 0 (its gradient).  fp32."""
+    _chk(x, "x"), _chk(dy, "dy")
+    if out is None:
+        out = torch.empty_like(x)
+    lib.call("sc_log_clamp", lib.ptr(x), lib.ptr(dy), lib.ptr(out), x.numel(), float(lo), lib.stream())
+    return out
+
+
+def logsoftmax_bwd(logprobs, dy, out=None):
+    """dx = dy - exp(logprobs) * rowsum(dy): backward of log_softmax (sc_logsoftmax_bwd)."""
+    rows, V = logprobs.shape
+    _chk(logprobs, "logprobs"), _chk(dy, "dy")
+    if out is None:
+        out = torch.empty_like(logprobs)
+    lib.call("sc_logsoftmax_bwd", lib.ptr(logprobs), lib.ptr(dy), lib.ptr(out), rows, V, lib.stream())
+    return out

@@ -35,7 +35,7 @@ SIGNATURES = {
     "sc_bias_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "sc_decode_self_attn_step": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "sc_decode_cross_attn_step": [_p, _i, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "sc_beam_step": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
+    "sc_beam_step": [_p, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _f, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "sc_beam_step_workspace_bytes": [_i, _i],
     "sc_linear_hmask": [_p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
     "sc_linear_topk_parts": [_i],
@@ -65,6 +65,9 @@ SIGNATURES = {
     "sc_attention_bwd_bf16out": [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_box_bias_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     "sc_box_bias_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
+    "sc_box_embedding": [_p, _p, _i, _i, _i, _f, _p],
+    "sc_log_clamp": [_p, _p, _p, _sz, _f, _p],
+    "sc_logsoftmax_bwd": [_p, _p, _p, _i, _i, _p],
 }
 
 _lib = None
