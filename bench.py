@@ -171,7 +171,7 @@ def train_arm(args, dev, world, rank, dist_mod=None):
     from sparse_caption_b200 import distributed as D
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=0.0, device=dev)
     tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888,  # same mask seed on every rank
-                    use_graph=not args.no_train_graph)
+                    use_graph=not args.no_train_graph, fused_st=not (world > 1 and args.exchange == "sharded"))
     B, S, T = args.train_images, 5, 17
     g = torch.Generator().manual_seed(8888 + rank)
     att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank, pin=True)

@@ -287,6 +287,21 @@ int sc_adam_clip(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float eps, float weight_decay, float clip_value, float grad_scale, int step, const float* sigmoid_grad_coeff,
                  const float* dyn, sc_stream_t stream);
 
+/* Whole-model optimizer step in one launch with the straight-through epilogue of the masked weights inside it: the flat
+ * gradient buffer holds dWm = d loss / d (W . m) for masked tensors (what data-parallel ranks all-reduce - half the bytes of
+ * dW + dS) and ordinary gradients for unmasked parameters.  Per masked element the step's mask sample is regenerated
+ * (Philox(seed, stream_base + desc.stream, element) / uniforms / binarize / raw), dW = dWm * m, dS = dWm * W * sigmoid'(S)
+ * [+ coeff * sigmoid'(S)] (pruning/sampler.py:10-34, prune.py:249-258), then clip + Adam for both parameter groups
+ * (utils/optim.py:116-126,187-191; scripts/train_n_prune_transformer.py:67-82).
+ * descs: device int64 [n_desc][5] = {w_off, s_off (-1 = unmasked), n, stream, first block}; one CTA per
+ * sc_adam_clip_st_chunk() elements.  dyn (optional, device fp32) = {lr_w, 1 - b1^t, sqrt(1 - b2^t), lr_s}. */
+int sc_adam_clip_st_chunk(void);
+int sc_adam_clip_st(const void* descs, int n_desc, long total_blocks, float* w, const float* grad_wm, float* m_w, float* v_w, float* s,
+                    float* m_s, float* v_s, const float* uniforms, int mask_mode, int bypass_sigmoid_grad, int update_logits,
+                    unsigned long long seed, unsigned long long stream_base, float lr_w, float eps_w, float weight_decay_w, float lr_s,
+                    float eps_s, float beta1, float beta2, float clip_value, float grad_scale, int step,
+                    const float* sigmoid_grad_coeff, const float* dyn, sc_stream_t stream);
+
 /* teacher-forcing attention with saved probabilities + backward (decoder self: causal_T = T; cross: groups = images with
  * S*T query rows; encoder box attention: additive bias): transformer.py:230-295, relation_transformer.py:258-293 */
 int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* key_valid,

@@ -710,6 +710,111 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
   }
 }
 
+// Whole-model optimizer step in ONE launch, with the straight-through epilogue of the masked weights inside it.
+// The backward leaves dWm = d loss / d (W (.) m) in the flat gradient buffer (that is what a data-parallel run all-reduces:
+// half the bytes of dW and dS, which are both elementwise functions of dWm, W, S and the step's mask sample).  Per element
+// of a masked tensor:  m = mask sample regenerated from Philox(seed, stream, element) (sampler.py:10-34);
+//   dW = dWm * m ; dS = dWm * W * sigmoid'(S) (* 1 when bypass) + sparsity_coeff * sigmoid'(S)  (prune.py:249-258)
+// then clip_grad_value_ + Adam for the weight group AND the mask-logit group (utils/optim.py:116-126,187-191;
+// scripts/train_n_prune_transformer.py:67-82).  Unmasked parameters (biases, LayerNorm) take the plain update.
+// desc = {w_off, s_off (-1: unmasked), n, stream, blk_start} (5 x 64-bit words); CTA = a chunk of kStChunk elements.
+struct StDesc { long long w_off, s_off, n; unsigned long long stream; long long blk_start; };
+constexpr int kStChunk = 2048;
+
+struct StArgs {
+  float* w; const float* g; float* mw; float* vw;      // weight group, flat
+  float* s; float* ms; float* vs; const float* u;      // mask-logit group, flat (u: injected uniforms or NULL)
+  int mode, bypass, update_s;
+  unsigned long long seed, stream_base;
+  float lr_w, eps_w, wd_w, lr_s, eps_s, b1, b2, clip, grad_scale, bc1, bc2_sqrt;
+  const float* sig_coeff; const float* dyn;
+};
+
+__device__ __forceinline__ float adam_update(float p, float gi, float& m, float& v, float lr, float eps, float wd, float b1, float b2,
+                                             float clip, float bc1, float bc2_sqrt) {
+  if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+  if (wd != 0.f) gi += wd * p;
+  m = b1 * m + (1.f - b1) * gi;
+  v = b2 * v + (1.f - b2) * gi * gi;
+  return p - (lr / bc1) * (m / (sqrtf(v) / bc2_sqrt + eps));
+}
+
+__global__ void __launch_bounds__(256) adam_clip_st_kernel(const StDesc* __restrict__ descs, int n_desc, StArgs a) {
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].blk_start <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const StDesc d = descs[lo];
+  const long long e0 = ((long long)blockIdx.x - d.blk_start) * kStChunk;
+  float lr_w = a.lr_w, lr_s = a.lr_s, bc1 = a.bc1, bc2 = a.bc2_sqrt;
+  if (a.dyn) { lr_w = a.dyn[0]; bc1 = a.dyn[1]; bc2 = a.dyn[2]; lr_s = a.dyn[3]; }
+  const float spc = a.sig_coeff ? *a.sig_coeff : 0.f;
+  const sc::Philox ph(a.seed);
+  const unsigned long long stream = a.stream_base + d.stream;
+  const bool vec = ((d.w_off | d.n) & 3) == 0 && (d.s_off < 0 || (d.s_off & 3) == 0);
+  if (vec) {
+    for (long long e = e0 + (long long)threadIdx.x * 4; e < e0 + kStChunk && e < d.n; e += 256 * 4) {
+      const size_t iw = (size_t)(d.w_off + e);
+      float4 g4 = *(const float4*)(a.g + iw), w4 = *(const float4*)(a.w + iw), mw4 = *(const float4*)(a.mw + iw), vw4 = *(const float4*)(a.vw + iw);
+      float g[4] = {g4.x * a.grad_scale, g4.y * a.grad_scale, g4.z * a.grad_scale, g4.w * a.grad_scale};
+      float w[4] = {w4.x, w4.y, w4.z, w4.w}, mw[4] = {mw4.x, mw4.y, mw4.z, mw4.w}, vw[4] = {vw4.x, vw4.y, vw4.z, vw4.w};
+      if (d.s_off >= 0) {
+        const size_t is = (size_t)(d.s_off + e);
+        float4 s4 = *(const float4*)(a.s + is);
+        float sv[4] = {s4.x, s4.y, s4.z, s4.w}, m[4];
+        if (a.mode == SC_MASK_BERNOULLI) {
+          sc::bernoulli4(ph, (uint64_t)e >> 2, stream, sv, m);
+        } else {
+          float uv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (a.mode == SC_MASK_UNIFORM) { const float4 u4 = *(const float4*)(a.u + is); uv[0] = u4.x; uv[1] = u4.y; uv[2] = u4.z; uv[3] = u4.w; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j] = sc::mask_value(a.mode, sv[j], uv[j], ph, (size_t)e + j, stream);
+        }
+        float dw[4], ds[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sc::mask_grad_elem(a.mode, g[j], w[j], sv[j], m[j], a.bypass, spc, dw[j], ds[j]);
+        if (a.update_s) {
+          float4 ms4 = *(const float4*)(a.ms + is), vs4 = *(const float4*)(a.vs + is);
+          float ms[4] = {ms4.x, ms4.y, ms4.z, ms4.w}, vs[4] = {vs4.x, vs4.y, vs4.z, vs4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sv[j] = adam_update(sv[j], ds[j], ms[j], vs[j], lr_s, a.eps_s, 0.f, a.b1, a.b2, a.clip, bc1, bc2);
+          *(float4*)(a.s + is) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+          *(float4*)(a.ms + is) = make_float4(ms[0], ms[1], ms[2], ms[3]);
+          *(float4*)(a.vs + is) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = dw[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = adam_update(w[j], g[j], mw[j], vw[j], lr_w, a.eps_w, a.wd_w, a.b1, a.b2, a.clip, bc1, bc2);
+      *(float4*)(a.w + iw) = make_float4(w[0], w[1], w[2], w[3]);
+      *(float4*)(a.mw + iw) = make_float4(mw[0], mw[1], mw[2], mw[3]);
+      *(float4*)(a.vw + iw) = make_float4(vw[0], vw[1], vw[2], vw[3]);
+    }
+    return;
+  }
+  for (long long e = e0 + threadIdx.x; e < e0 + kStChunk && e < d.n; e += 256) {
+    const size_t iw = (size_t)(d.w_off + e);
+    float g = a.g[iw] * a.grad_scale, w = a.w[iw], mw = a.mw[iw], vw = a.vw[iw];
+    if (d.s_off >= 0) {
+      const size_t is = (size_t)(d.s_off + e);
+      float sv = a.s[is];
+      const float m = sc::mask_value(a.mode, sv, a.mode == SC_MASK_UNIFORM ? a.u[is] : 0.f, ph, (size_t)e, stream);
+      float dw, ds;
+      sc::mask_grad_elem(a.mode, g, w, sv, m, a.bypass, spc, dw, ds);
+      if (a.update_s) {
+        float ms = a.ms[is], vs = a.vs[is];
+        a.s[is] = adam_update(sv, ds, ms, vs, lr_s, a.eps_s, 0.f, a.b1, a.b2, a.clip, bc1, bc2);
+        a.ms[is] = ms; a.vs[is] = vs;
+      }
+      g = dw;
+    }
+    a.w[iw] = adam_update(w, g, mw, vw, lr_w, a.eps_w, a.wd_w, a.b1, a.b2, a.clip, bc1, bc2);
+    a.mw[iw] = mw; a.vw[iw] = vw;
+  }
+}
+
 // PruningMixin.compute_sparsity_loss (pruning/prune.py:228-269) from the binarized-mask count:
 //   out[0] = |target - sparsity| ; out[1] = d(scaled loss)/d(nnz) = sign(target - sparsity) / total * scale ; out[2] = sparsity
 __global__ void sparsity_coeff_kernel(const unsigned long long* count, double total, float target, float scale,
@@ -935,6 +1040,29 @@ int sc_adam_clip(float* param, const float* grad, float* exp_avg, float* exp_avg
   adam_clip_kernel<<<grid_for(n, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                          clip_value, grad_scale, bc1, bc2, sigmoid_grad_coeff, dyn);
   SC_LAUNCH_CHECK("sc_adam_clip");
+  return SC_OK;
+}
+
+int sc_adam_clip_st_chunk(void) { return kStChunk; }
+
+int sc_adam_clip_st(const void* descs, int n_desc, long total_blocks, float* w, const float* grad_wm, float* m_w, float* v_w, float* s,
+                    float* m_s, float* v_s, const float* uniforms, int mask_mode, int bypass_sigmoid_grad, int update_logits,
+                    unsigned long long seed, unsigned long long stream_base, float lr_w, float eps_w, float weight_decay_w, float lr_s,
+                    float eps_s, float beta1, float beta2, float clip_value, float grad_scale, int step,
+                    const float* sigmoid_grad_coeff, const float* dyn, cudaStream_t stream) {
+  SC_CHECK(descs != nullptr && n_desc > 0 && total_blocks > 0 && total_blocks < (1L << 31) && step >= 1, SC_ERR_SHAPE,
+           "sc_adam_clip_st: n_desc=%d blocks=%ld step=%d", n_desc, total_blocks, step);
+  SC_CHECK(mask_mode != SC_MASK_UNIFORM || uniforms != nullptr, SC_ERR_SHAPE, "sc_adam_clip_st: uniforms missing");
+  static_assert(sizeof(StDesc) == 40, "descriptor = 5 x 64-bit words");
+  StArgs a;
+  a.w = w; a.g = grad_wm; a.mw = m_w; a.vw = v_w; a.s = s; a.ms = m_s; a.vs = v_s; a.u = uniforms;
+  a.mode = mask_mode; a.bypass = bypass_sigmoid_grad; a.update_s = update_logits; a.seed = seed; a.stream_base = stream_base;
+  a.lr_w = lr_w; a.eps_w = eps_w; a.wd_w = weight_decay_w; a.lr_s = lr_s; a.eps_s = eps_s; a.b1 = beta1; a.b2 = beta2;
+  a.clip = clip_value; a.grad_scale = grad_scale;
+  a.bc1 = 1.f - powf(beta1, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  a.sig_coeff = sigmoid_grad_coeff; a.dyn = dyn;
+  adam_clip_st_kernel<<<(unsigned)total_blocks, 256, 0, stream>>>((const StDesc*)descs, n_desc, a);
+  SC_LAUNCH_CHECK("sc_adam_clip_st");
   return SC_OK;
 }
 

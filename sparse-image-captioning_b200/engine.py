@@ -179,7 +179,7 @@ class OrtEngine:
         lib.load()
         assert precision in ("bf16", "fp32")
         self.cfg = cfg
-        self.dev = torch.device(device)
+        self.dev = lib.resolve_device(device)
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.precision = precision
         self.use_graphs = use_graphs
@@ -572,16 +572,24 @@ class OrtEngine:
         st = ws.state
         st.reset(c.bos_token_id, c.pad_token_id)
         kind, alpha = _parse_penalty(opt.get("length_penalty", ""))
-        fused = (ws.topk_part is not None and float(opt.get("temperature", 1.0)) == 1.0 and not opt.get("decoding_constraint", 0))
+        bad = opt.get("bad_endings_ix")      # remove_bad_endings (caption_model.py:161-168): token 0 may not follow these
+        pen_col = int(opt.get("penalized_col", -1))  # suppress_UNK (:169-170)
+        bad_t = opt.get("_bad_t") if bad else None   # (device tensor made by decode() outside the graph capture)
+        fused = (ws.topk_part is not None and float(opt.get("temperature", 1.0)) == 1.0 and not opt.get("decoding_constraint", 0)
+                 and bad_t is None and pen_col < 0)
         for t in range(L):
             self._decode_step(ws, enc, t, st.anc[t & 1], fused_topk=fused)
+            sup = None
+            if bad_t is not None and t > 0:
+                # rows whose previous token (= the token just fed) is a bad ending: token 0 is suppressed at this step
+                sup = torch.where(torch.isin(st.tokens, bad_t), 0, -1).to(torch.int32)
             if fused:
                 K.beam_step_partials(ws.topk_part, st, t, B=ws.B, beam=ws.beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id,
                                      penalty_kind=kind, penalty_alpha=alpha)
             else:
                 K.beam_step(ws.logits, st, t, B=ws.B, beam=ws.beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id,
                             temperature=opt.get("temperature", 1.0), constraint=opt.get("decoding_constraint", 0),
-                            penalty_kind=kind, penalty_alpha=alpha)
+                            penalty_kind=kind, penalty_alpha=alpha, suppress_tok=sup, penalized_col=pen_col)
 
     def _greedy_body(self, ws, enc, opt):
         c = self.cfg
@@ -638,8 +646,10 @@ class OrtEngine:
         greedy = beam == 1
         assert beam <= self.cfg.vocab_size
         ws = self._get_dec_ws(enc.B, beam, enc.N, greedy, enc.slot)
-        body = (lambda: self._greedy_body(ws, enc, opt)) if greedy else (lambda: self._beam_body(ws, enc, opt))
         opt_key = (id(enc), tuple(sorted((k, str(v)) for k, v in opt.items())))
+        if opt.get("bad_endings_ix"):
+            opt = dict(opt, _bad_t=torch.tensor(sorted(opt["bad_endings_ix"]), dtype=torch.int32, device=self.dev))
+        body = (lambda: self._greedy_body(ws, enc, opt)) if greedy else (lambda: self._beam_body(ws, enc, opt))
         if not self.use_graphs:
             body()
         else:
@@ -673,6 +683,123 @@ class OrtEngine:
                 st.tokens.copy_(tokens[:, t - 1])
             self._decode_step(ws, enc, t, st.anc)
             K.logsoftmax_nll(ws.logits, logprobs=out[t])
+        return out
+
+    # ---- step-wise entry points (get_logprobs_state / batch_beam_search of the reference) over an explicit state ----
+    def _step_ws(self, R, N):
+        key = ("step", R, N)
+        ws = self._dec_ws.get(key)
+        if ws is None:
+            c, dev, adt = self.cfg, self.dev, self.adt
+            d, ff, L, V = c.d_model, c.dim_feedforward, c.max_seq_length, c.vocab_size
+            ws = type("StepWs", (), {})()
+            ws.B, ws.beam, ws.N, ws.R = R, 1, N, R   # every row carries its own memory K/V
+            ws.x = torch.zeros(R, d, device=dev)
+            ws.xn = torch.zeros(R, d, device=dev, dtype=adt)
+            ws.qkv = torch.zeros(R, 3 * d, device=dev, dtype=adt)
+            ws.att = torch.zeros(R, d, device=dev, dtype=adt)
+            ws.qc = torch.zeros(R, d, device=dev, dtype=adt)
+            ws.hid = torch.zeros(R, ff, device=dev, dtype=adt)
+            ws.logits = torch.zeros(R, V, device=dev)
+            ws.topk_part = None
+            if self.fold_dec:
+                ws.xb = torch.zeros(R, d, device=dev, dtype=adt)
+                ws.stats = torch.zeros(R, d // 32, 2, device=dev)
+            ws.state = type("Tok", (), {})()
+            ws.state.tokens = torch.zeros(R, dtype=torch.int32, device=dev)
+            ws.anc = torch.arange(R, dtype=torch.int32, device=dev).unsqueeze(1).expand(R, L * max(e["apps"] for e in self.dec.values())).contiguous()
+            self._dec_ws[key] = ws
+        return ws
+
+    def logprobs_step(self, it, memory, att_mask, caches, t):
+        """One ``get_logprobs_state`` step (relation_transformer.py:374-387).  ``it`` [R] tokens; ``memory`` [R, N, d] encoder
+        output (final norm applied); ``att_mask`` [R, 1, N] / [R, N] / None; ``caches`` None at t = 0 or, per unique decoder
+        layer, (self K [slots, R, d], self V [slots, R, d], cross K|V [1, R, N * ld]) - row dimension at dim 1, so the caller
+        may reorder / repeat beams with ``x[:, ix]``.  Returns (log-softmax fp32 [R, V], caches)."""
+        c = self.cfg
+        R = it.numel()
+        N = memory.shape[1]
+        d, L = c.d_model, c.max_seq_length
+        assert 0 <= t <= L, f"step {t} beyond max_seq_length {L}"
+        ws = self._step_ws(R, N)
+        uids = list(self.dec)
+        if caches is None:
+            mem = memory.reshape(-1, d)
+            mem = (K.cast_bf16(mem.float().contiguous()) if self.adt == torch.bfloat16 else mem.float().contiguous()) if mem.dtype != self.adt else mem.contiguous()
+            caches = []
+            for u in uids:
+                e = self.dec[u]
+                slots = L * e["apps"] + e["apps"]  # (+ one spare step: the reference calls the model once more after the last step)
+                ckv = torch.empty(1, memory.shape[0], N * e["ckv_ld"], device=self.dev, dtype=self.adt)
+                e["ckv"](mem, ckv.view(-1, e["ckv_ld"]))
+                caches += [torch.zeros(slots, memory.shape[0], d, device=self.dev, dtype=self.adt),
+                           torch.zeros(slots, memory.shape[0], d, device=self.dev, dtype=self.adt), ckv]
+        caches = list(caches)
+        rows = caches[0].shape[1]
+        if rows != R:  # first beam step: every cached row is repeated `beam` times (transformer.py:240-252)
+            assert R % rows == 0 and rows < R, (rows, R)
+            caches = [x.repeat_interleave(R // rows, 1) for x in caches]
+        caches = [x.contiguous() for x in caches]
+        enc = type("StepEnc", (), {})()
+        enc.memkv = {u: caches[3 * i + 2].view(R * N, self.dec[u]["ckv_ld"]) for i, u in enumerate(uids)}
+        m = None
+        if att_mask is not None:
+            m = att_mask.reshape(R, N).float().contiguous()
+            if bool((m != 0).all()):
+                m = None
+        enc.att_mask = m
+        ws.cache = {u: (caches[3 * i], caches[3 * i + 1]) for i, u in enumerate(uids)}
+        ws.state.tokens.copy_(it.reshape(-1).to(torch.int32))
+        self._decode_step(ws, enc, t, ws.anc)
+        out = torch.empty(R, c.vocab_size, device=self.dev)
+        K.logsoftmax_nll(ws.logits, logprobs=out)
+        return out, caches
+
+    def beam_search_stepwise(self, init_state, init_logprobs, args, opt, get_logprobs_state):
+        """``batch_beam_search`` (caption_model.py:30-226, group_size 1) driven step by step: sc_beam_step ranks the b*V
+        candidates, keeps the beam / finished-beam state on the device and yields the parent rows; the model state is reordered
+        with ``state[i][:, parents]`` and advanced through ``get_logprobs_state`` - the reference's own control flow.
+        Returns done_beams [B][beam] dicts."""
+        c = self.cfg
+        beam = int(opt.get("beam_size", 10))
+        L, V = c.max_seq_length, c.vocab_size
+        B = init_logprobs.shape[0]
+        st = BeamState(B, beam, L, self.dev)
+        st.reset(c.bos_token_id, c.pad_token_id)
+        kind, alpha = _parse_penalty(opt.get("length_penalty", ""))
+        bad = opt.get("bad_endings_ix")
+        bad_t = torch.tensor(sorted(bad), dtype=torch.int32, device=self.dev) if bad else None
+        pen_col = int(opt.get("penalized_col", -1))
+        temperature = float(opt.get("temperature", 1.0))
+        logits = torch.zeros(B * beam, V, device=self.dev)
+        logits.view(B, beam, V)[:, 0] = init_logprobs.float()   # t = 0: only beam 0 of an image is expanded
+        state = [x.clone() for x in init_state]
+        for t in range(L):
+            sup = None
+            if bad_t is not None and t > 0:
+                sup = torch.where(torch.isin(st.tokens, bad_t), 0, -1).to(torch.int32)
+            K.beam_step(logits, st, t, B=B, beam=beam, V=V, L=L, eos=c.eos_token_id, pad=c.pad_token_id, temperature=temperature,
+                        constraint=opt.get("decoding_constraint", 0), penalty_kind=kind, penalty_alpha=alpha, suppress_tok=sup,
+                        penalized_col=pen_col)
+            parents = st.anc[(t + 1) & 1][:, t].long()          # row each new beam descends from (b*beam + parent)
+            if t == 0:
+                parents = parents // beam                        # the first state holds one row per image
+            state = [x[:, parents] for x in state]
+            it = st.tokens.long()
+            logprobs, state = get_logprobs_state(it, *(list(args) + [state]))
+            logits = logprobs.contiguous()                       # (sc_beam_step re-normalises: log_softmax is idempotent)
+        done_seq, done_lp, done_p = st.done_seq.long().cpu(), st.done_lp.cpu(), st.done_p.cpu()
+        out = []
+        for b in range(B):
+            beams = []
+            for v in range(beam):
+                n = int((done_seq[b, v] != c.pad_token_id).sum())
+                eos = (done_seq[b, v] == c.eos_token_id).nonzero()
+                if eos.numel():
+                    n = int(eos[0]) + 1
+                beams.append({"seq": done_seq[b, v, :n].to(self.dev), "logps": done_lp[b, v, :n].to(self.dev),
+                              "unaug_p": float(done_lp[b, v, :n].sum()), "p": float(done_p[b, v])})
+            out.append(beams)
         return out
 
     # ---- batch pipelining: slot s owns a stream + workspaces + graphs; batches in different slots overlap on the GPU

@@ -511,6 +511,27 @@ def adam_clip(param, grad, m, v, *, lr, betas, eps, weight_decay, clip, grad_sca
              lib.ptr(sigmoid_grad_coeff), lib.ptr(dyn), lib.stream())
 
 
+def st_descriptors(segments, device):
+    """Descriptor table of sc_adam_clip_st.  segments: (w_off, s_off | -1, n, stream_id) in flat-buffer elements.
+    Returns (int64 device tensor [n, 5], total blocks)."""
+    chunk = int(lib.load().sc_adam_clip_st_chunk())
+    rows, start = [], 0
+    for w_off, s_off, n, sid in segments:
+        rows.append([int(w_off), int(s_off), int(n), int(sid), start])
+        start += (int(n) + chunk - 1) // chunk
+    return torch.tensor(rows, dtype=torch.int64).to(device), start
+
+
+def adam_clip_st(desc, blocks, w, g, m_w, v_w, s, m_s, v_s, *, uniforms, mask_mode, bypass, update_logits, seed, stream_base, lr, eps,
+                 weight_decay, mask_lr, mask_eps, betas, clip, grad_scale, step, sigmoid_grad_coeff=None, dyn=None):
+    """One-launch optimizer step over a descriptor table (sc_adam_clip_st): straight-through dW / dS from the exchanged dWm
+    with the mask sample regenerated, then clip + Adam for the weight and the mask-logit groups."""
+    lib.call("sc_adam_clip_st", lib.ptr(desc), desc.shape[0], blocks, lib.ptr(w), lib.ptr(g), lib.ptr(m_w), lib.ptr(v_w), lib.ptr(s),
+             lib.ptr(m_s), lib.ptr(v_s), lib.ptr(uniforms), int(mask_mode), int(bypass), int(update_logits), seed, stream_base,
+             float(lr), float(eps), float(weight_decay), float(mask_lr), float(mask_eps), float(betas[0]), float(betas[1]), float(clip),
+             float(grad_scale), int(step), lib.ptr(sigmoid_grad_coeff), lib.ptr(dyn), lib.stream())
+
+
 def sparsity_coeff(count, total, target, scale, out3, scale_dev=None):
     """out3 = [|target - sparsity|, d(scaled loss)/d(nnz), sparsity] from the device-side binarized-mask count."""
     lib.call("sc_sparsity_coeff", lib.ptr(count), float(total), float(target), float(scale), lib.ptr(scale_dev), lib.ptr(out3),

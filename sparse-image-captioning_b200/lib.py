@@ -60,6 +60,8 @@ SIGNATURES = {
     "sc_embedding_bwd": [_p, _p, _p, _i, _i, _i, _f, _p],
     "sc_adam_clip": [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p],
     "sc_sparsity_coeff": [_p, C.c_double, _f, _f, _p, _p, _p],
+    "sc_adam_clip_st_chunk": [],
+    "sc_adam_clip_st": [_p, _i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _u64, _u64, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p],
     "sc_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_attention_bwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
     "sc_attention_bwd_bf16out": [_p, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
@@ -102,6 +104,19 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def resolve_device(device):
+    """The kernels launch on the CURRENT device's current stream and cache function attributes / the SM count per process:
+    an engine or trainer therefore lives on the current CUDA device (one process per GPU; call torch.cuda.set_device first)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return dev  # (parameter-layout bookkeeping only, e.g. the CPU tier's bucket tests: every kernel wrapper rejects CPU tensors)
+    cur = torch.cuda.current_device()
+    if dev.index is not None and dev.index != cur:
+        raise RuntimeError(f"device {dev} is not the current CUDA device (cuda:{cur}): call torch.cuda.set_device({dev.index}) "
+                           f"first - kernels launch on the current device's stream")
+    return torch.device("cuda", cur)
 
 
 def dtype_code(dt):

@@ -9,7 +9,7 @@ import torch
 
 from . import kernels as K
 
-_state = {"seed": 0, "stream": 0}
+_state = {"seed": 0, "stream": 0, "drop": 0, "uniforms": None}
 
 
 def set_mask_seed(seed: int) -> None:
@@ -17,6 +17,26 @@ def set_mask_seed(seed: int) -> None:
     that they draw the same mask (the reference draws ONE mask per layer per step, masked_layer.py:97)."""
     _state["seed"] = int(seed)
     _state["stream"] = 0
+
+
+def next_dropout_stream():
+    """(seed, stream_id) of the next dropout site (activation / attention dropout of the module-level path); a stream
+    space disjoint from the mask streams."""
+    _state["drop"] += 1
+    return _state["seed"] + 1, (1 << 40) + _state["drop"]
+
+
+def inject_uniforms(mapping) -> None:
+    """Parity tests: ``{mask_logits Parameter: uniforms tensor}`` - train-mode supermasks then use ``u < sigmoid(S)`` with the
+    given uniforms instead of the Philox stream (the reference side patches torch.bernoulli the same way).  None clears."""
+    _state["uniforms"] = None if mapping is None else {id(k): v for k, v in mapping.items()}
+
+
+def injected_uniforms(logits):
+    u = _state["uniforms"]
+    if u is None or logits is None:
+        return None
+    return u.get(id(logits))
 
 
 def next_mask_stream():

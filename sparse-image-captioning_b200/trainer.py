@@ -27,11 +27,11 @@ def _round_up(n, m):
 class OrtTrainer:
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, mask_type: Optional[str] = "supermask",
                  precision="bf16", device="cuda", dropout=0.1 / 3, drop_prob_src=0.5, bypass_sigmoid_grad=False, seed=0,
-                 mask_init_value=5.0, uniforms: Optional[Dict[str, torch.Tensor]] = None, use_graph=False):
+                 mask_init_value=5.0, uniforms: Optional[Dict[str, torch.Tensor]] = None, use_graph=False, fused_st=True):
         assert cfg.share_att_encoder is None and cfg.share_att_decoder is None and not cfg.share_layer_encoder \
             and not cfg.share_layer_decoder, "ACORT weight sharing is an inference-side feature in this round"
         self.cfg = cfg
-        self.dev = torch.device(device)
+        self.dev = K.lib.resolve_device(device)
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.mask_type = mask_type
         self.p_drop, self.p_src = float(dropout), float(drop_prob_src)
@@ -43,6 +43,13 @@ class OrtTrainer:
         # everything that changes per step (Philox seeds, lr, Adam bias corrections, sparsity-loss scale) is read from
         # small device buffers that the host rewrites before each replay (sc_b200.h: seed pointers, `dyn`)
         self.use_graph = bool(use_graph)
+        # straight-through epilogue inside the optimizer kernel (sc_adam_clip_st): the backward leaves dWm = dL/d(W.m) in flat_gw,
+        # which is ALL a data-parallel run exchanges (half the bytes of dW + dS); dW = dWm.m and dS = dWm.W.sigmoid'(S) are formed
+        # per element inside the update with the step's mask sample regenerated.  False: the weight-gradient epilogue writes dW and
+        # dS (needed by the ZeRO-style ShardedExchange, whose shards cut through tensors).
+        self.fused_st = bool(fused_st)
+        self._materialized = False
+        self._st_desc = {}
         self._seeds_host = torch.zeros(3, dtype=torch.int64).pin_memory() if self.use_graph else None
         self._seeds_dev = torch.zeros(3, dtype=torch.int64, device=self.dev)
         self._dyn_host = torch.zeros(8, dtype=torch.float32).pin_memory() if self.use_graph else None
@@ -435,6 +442,8 @@ class OrtTrainer:
                 K.linear(gb, wT, None, residual=dx_residual, out=dx, tile_n=5128 if (N >= 8192 and Kd <= 512) else 0)  # generator dX
         gW = self._group(self.g, wname, count)
         gS = self._group(self.gs, wname, count) if S is not None else None
+        if self.fused_st:
+            S, gS, mode, U = None, None, K.MASK_NONE, None  # the weight gradient stays dWm; sc_adam_clip_st applies the mask
         if side:
             # fork after the gradient operand exists (the dX GEMM above only reads it), join before the optimizer
             main, st = torch.cuda.current_stream(self.dev), self._side_stream()
@@ -615,7 +624,7 @@ class OrtTrainer:
         ench = f"model.encoder.layers.{half}.self_attn.linears.0.weight"
         spans = {0: [(dech, lut), (gen, None)], 1: [(dec0, dech), (lut, gen)], 2: [(ench, dec0)], 3: [(self.names[0], ench)]}[phase]
         out = []
-        for flat, offs in ((self.flat_gw, self._offs_w), (self.flat_gs, self._offs_s) if self.masked else (None, None)):
+        for flat, offs in ((self.flat_gw, self._offs_w), (self.flat_gs, self._offs_s) if (self.masked and not self.fused_st) else (None, None)):
             if flat is None:
                 continue
             for first, last in spans:
@@ -638,6 +647,7 @@ class OrtTrainer:
         ws.side_used = False
         half = L // 2
         if phase == 0:
+            self._materialized = False
             # norm and bias gradients accumulate through atomics: one memset of the flat buffer (weights are overwritten)
             self.flat_gw.zero_()
             ws.loss_sum.zero_()
@@ -717,17 +727,22 @@ class OrtTrainer:
         if phase == 0:
             self._join_side(ws)
             return
-        # embedding: dropout mask is recoverable from the saved output (dropped entries are exact zeros)
+        # embedding: its dropout mask is regenerated from the forward's Philox stream (an exact zero in the saved output is
+        # not proof of a dropped element: sin(0) = 0 in the positional encoding, masked-out table entries)
         W, S_, mode, U, seed, stream = self._mask_args("model.tgt_embed.0.lut.weight")
         emb_g = ws.ga.view(-1)[: MD * d].view(MD, d)
         if pd > 0:
-            K.prep_grad(cur, h=ws.y[0], out=emb_g, scale=1.0 / (1.0 - pd))
+            K.prep_grad(cur, out=emb_g, p=pd, seed=self._sd(1), stream_id=self._drop_stream(2))
         else:
             emb_g = cur
-        ws.dtable.zero_()
-        K.embedding_bwd(ws.tokens, emb_g, ws.dtable, math.sqrt(d))
-        K.mask_grad(ws.dtable, W, S_, mode, self.g["model.tgt_embed.0.lut.weight"],
-                    self.gs.get("model.tgt_embed.0.lut.weight"), uniforms=U, seed=seed, stream_id=stream, bypass=self.bypass)
+        if self.fused_st:
+            # (flat_gw was zeroed at the start of the backward: the scatter-add lands directly in the table's gradient view)
+            K.embedding_bwd(ws.tokens, emb_g, self.g["model.tgt_embed.0.lut.weight"], math.sqrt(d))
+        else:
+            ws.dtable.zero_()
+            K.embedding_bwd(ws.tokens, emb_g, ws.dtable, math.sqrt(d))
+            K.mask_grad(ws.dtable, W, S_, mode, self.g["model.tgt_embed.0.lut.weight"],
+                        self.gs.get("model.tgt_embed.0.lut.weight"), uniforms=U, seed=seed, stream_id=stream, bypass=self.bypass)
         self._join_side(ws)
 
     def _join_side(self, ws):
@@ -778,14 +793,19 @@ class OrtTrainer:
                 K.attention_bwd(q[:, 0:], q[:, d:], q[:, 2 * d:], ws.e_probs[l], ga_a, gq[:, 0:], gq[:, d:], gq[:, 2 * d:], dtype=self.adt,
                                 G=B, Tq=N, Tk=N, h=h, dk=dk, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldd=d, ldgq=3 * d, ldgk=3 * d, ldgv=3 * d,
                                 dbias=ws.dbias, p=pd, seed=self._sd(2), stream_id=self._drop_stream(10 + l))
-            ws.dwg.zero_()
             gb_wg = self._group(self.g, f"{p}.self_attn.WGs.0.bias", h)
             gb_wg.zero_()
-            K.box_bias_bwd(ws.boxes, ws.e_bias[l], ws.dbias, ws.dwg, gb_wg, B=B, N=N, h=h, trig=trig)
-            Wg, Sg, mode, U, seed, stream = self._mask_args(f"{p}.self_attn.WGs.0.weight", h)
-            K.mask_grad(ws.dwg, Wg, Sg, mode, self._group(self.g, f"{p}.self_attn.WGs.0.weight", h),
-                        self._group(self.gs, f"{p}.self_attn.WGs.0.weight", h) if Sg is not None else None, uniforms=U, seed=seed,
-                        stream_id=stream, bypass=self.bypass)
+            if self.fused_st:
+                gw_wg = self._group(self.g, f"{p}.self_attn.WGs.0.weight", h)
+                gw_wg.zero_()
+                K.box_bias_bwd(ws.boxes, ws.e_bias[l], ws.dbias, gw_wg, gb_wg, B=B, N=N, h=h, trig=trig)
+            else:
+                ws.dwg.zero_()
+                K.box_bias_bwd(ws.boxes, ws.e_bias[l], ws.dbias, ws.dwg, gb_wg, B=B, N=N, h=h, trig=trig)
+                Wg, Sg, mode, U, seed, stream = self._mask_args(f"{p}.self_attn.WGs.0.weight", h)
+                K.mask_grad(ws.dwg, Wg, Sg, mode, self._group(self.g, f"{p}.self_attn.WGs.0.weight", h),
+                            self._group(self.gs, f"{p}.self_attn.WGs.0.weight", h) if Sg is not None else None, uniforms=U, seed=seed,
+                            stream_id=stream, bypass=self.bypass)
             ga_a2 = ws.ga.view(-1)[: ME * d].view(ME, d)
             self._lin_bwd(ws, f"{p}.self_attn.linears.0.weight", ws.e_xn1[l], gq, count=3, dx=ga_a2, pre=pre_qkv)
             pre = self._ln_bwd(f"{p}.sublayer.0.norm", x0, ga_a2, nxt, dres=cur, ws=ws,
@@ -812,6 +832,10 @@ class OrtTrainer:
         if not _dyn and part != "lo":
             self.opt_step += 1
         dyn = self._dyn_dev if _dyn else None
+        if self.fused_st and not self._materialized:
+            return self._optimizer_step_st(lr=lr, mask_lr=mask_lr, clip=clip, betas=betas, eps=eps, mask_eps=mask_eps,
+                                           weight_decay=weight_decay, grad_scale=grad_scale, sparsity_target=sparsity_target,
+                                           sparsity_weight=sparsity_weight, current_step=current_step, max_step=max_step, dyn=dyn, part=part)
         cut_w = self._offs_w["model.decoder.layers.0.self_attn.linears.0.weight"]
         lo_w, hi_w = {"all": (0, self.flat_w.numel()), "hi": (cut_w, self.flat_w.numel()), "lo": (0, cut_w)}[part]
         K.adam_clip(self.flat_w[lo_w:hi_w], self.flat_gw[lo_w:hi_w], self.m_w[lo_w:hi_w], self.v_w[lo_w:hi_w], lr=lr, betas=betas, eps=eps,
@@ -835,6 +859,74 @@ class OrtTrainer:
             if part != "hi" and self._s_pad_idx.numel():
                 self.flat_s.index_fill_(0, self._s_pad_idx, -1.0)
 
+    def _mask_groups(self):
+        """(first weight name, fused count) of every masked tensor exactly as the forward samples it (one Philox stream and one
+        element numbering per group): the linears of _premask_keys, the embedding table, the h geometry heads of each layer."""
+        h = self.cfg.num_heads
+        groups = list(self._premask_keys()) + [("model.tgt_embed.0.lut.weight", 1)]
+        groups += [(f"model.encoder.layers.{l}.self_attn.WGs.0.weight", h) for l in range(self.cfg.num_layers)]
+        return groups
+
+    def _st_table(self, part):
+        """Descriptor table of sc_adam_clip_st for "all" / "hi" (decoder, embedding, generator) / "lo" (att_embed, encoder)."""
+        if part not in self._st_desc:
+            first_of = {}
+            member = set()
+            if self.masked:
+                for wname, count in self._mask_groups():
+                    first_of[wname] = count
+                    i = self.names.index(wname)
+                    member.update(self.names[i + 1: i + count])  # (the fused members are consecutive names: [q;k;v], [k;v], WG heads)
+            cut = self.names.index("model.decoder.layers.0.self_attn.linears.0.weight")
+            names = {"all": self.names, "hi": self.names[cut:], "lo": self.names[:cut]}[part]
+            segs = []
+            for k in names:
+                if k in member:
+                    continue
+                if k in first_of:
+                    n = self._group(self.p, k, first_of[k]).numel()
+                    segs.append((self._offs_w[k], self._offs_s[k], n, self.stream_of[k]))
+                else:
+                    n = self._group(self.p, k, 1).numel() if k in self._pad_rows else self.p[k].numel()
+                    segs.append((self._offs_w[k], -1, n, 0))
+            self._st_desc[part] = K.st_descriptors(segs, self.dev)
+        return self._st_desc[part]
+
+    def _optimizer_step_st(self, *, lr, mask_lr, clip, betas, eps, mask_eps, weight_decay, grad_scale, sparsity_target, sparsity_weight,
+                           current_step, max_step, dyn, part):
+        supermask = bool(self.masked) and self.mask_type == "supermask"
+        coeff = None
+        if supermask and sparsity_target is not None and sparsity_weight:
+            if part != "lo":
+                anneal = (1.0 + math.cos(min(1.0, current_step / max_step) * math.pi)) / 2.0
+                self.sp_count.zero_()
+                K.lib.call("sc_mask_count", K.lib.ptr(self.flat_s), self.flat_s.numel(), K.lib.ptr(self.sp_count), K.lib.stream())
+                K.sparsity_coeff(self.sp_count, self.n_logits, sparsity_target, sparsity_weight * (1.0 - anneal), self.sp_out,
+                                 scale_dev=dyn[6:7] if dyn is not None else None)
+            coeff = self.sp_out[1:2]
+        desc, blocks = self._st_table(part)
+        mode = K.MASK_NONE  # the mask sample of the step being applied (train-mode forward)
+        if self.masked:
+            mode = (K.MASK_UNIFORM if self.flat_u is not None else K.MASK_BERNOULLI) if self.mask_type == "supermask" else K.MASK_RAW
+        K.adam_clip_st(desc, blocks, self.flat_w, self.flat_gw, self.m_w, self.v_w, self.flat_s, self.m_s, self.v_s, uniforms=self.flat_u,
+                       mask_mode=mode, bypass=self.bypass, update_logits=supermask, seed=self._sd(0), stream_base=self._step_base(),
+                       lr=lr, eps=eps, weight_decay=weight_decay, mask_lr=mask_lr, mask_eps=mask_eps, betas=betas, clip=clip,
+                       grad_scale=grad_scale, step=max(1, self.opt_step), sigmoid_grad_coeff=coeff, dyn=dyn)
+        if supermask and part != "hi" and self._s_pad_idx.numel():
+            self.flat_s.index_fill_(0, self._s_pad_idx, -1.0)
+
+    def materialize_grads(self):
+        """Reference ``.grad`` semantics for inspection: turns the dWm left by the backward into dW (in place, ``self.g``) and dS
+        (``self.gs``) with the step's mask sample; a following ``optimizer_step`` then runs the plain two-group update on them."""
+        if not self.fused_st or self._materialized or not self.masked:
+            self._materialized = True
+            return
+        for wname, count in self._mask_groups():
+            W, S, mode, U, seed, stream = self._mask_args(wname, count)
+            gW = self._group(self.g, wname, count)
+            K.mask_grad(gW, W, S, mode, gW, self._group(self.gs, wname, count), uniforms=U, seed=seed, stream_id=stream, bypass=self.bypass)
+        self._materialized = True
+
     def _sparsity_coeff(self, *, sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1, **_):
         """Device scalar d(sparsity loss)/d(nnz) from the CURRENT logits (must run before any logit is updated)."""
         if not (self.masked and self.mask_type == "supermask") or sparsity_target is None or not sparsity_weight:
@@ -849,6 +941,7 @@ class OrtTrainer:
         """Data-parallel step with the optimizer sharded over the ranks (distributed.ShardedExchange): after each backward
         phase the finished buckets go through reduce-scatter -> Adam on the owned shard -> all-gather on the exchange's
         stream while the next phase computes."""
+        assert not self.fused_st, "ShardedExchange cuts tensors into rank shards: build the trainer with fused_st=False"
         o = dict(mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0, grad_scale=1.0)
         o.update({k: v for k, v in opt.items() if k in o})
         coeff = self._sparsity_coeff(**opt)

@@ -124,3 +124,65 @@ def test_sharded_exchange_equals_allreduce_update(tmp_path):
     owned = sorted(c for r in range(world) for c in got[r]["calls"] if c[1] <= 399)
     assert owned == [(0, 133), (133, 266), (266, 399)]
     assert all((399, 400) in got[r]["calls"] and (400, 401) in got[r]["calls"] for r in range(world))
+
+
+def _dwm_worker(rank, world, port, out):
+    """Rank-local dWm = dL/d(W.m) (gradient with respect to the MASKED weight), summed over ranks; rank 0 then applies the
+    straight-through epilogue once - what OrtTrainer(fused_st=True) + sc_adam_clip_st do on the device."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle import ort_oracle as O
+    from sparse_caption_b200 import distributed as D
+    from tests import golden_io
+    z = golden_io.load("ort_prune_tiny")
+    cfg, full = z["cfg"], z["w"]
+    B = z["att_feats"].shape[0]
+    lo, hi = D.shard_range(B, rank, world)
+    T = z["seqs"].shape[1] - 1
+    denom = D.global_token_count(z["masks"][lo * 2: hi * 2], T)
+    keys = sorted(z["u"])
+    eff = {k: v.clone() for k, v in full.items() if not k.endswith("_pruning_mask")}
+    for k in keys:  # same Bernoulli sample on every rank (same uniforms / same Philox seed)
+        m = (z["u"][k] < torch.sigmoid(full[k + "_pruning_mask"])).float()
+        eff[k] = (m * full[k]).requires_grad_(True)
+    rows = slice(lo * 2, hi * 2)
+    lp = O.forward_tf(eff, cfg, z["att_feats"][lo:hi], z["boxes"][lo:hi], z["seqs"][rows], None)
+    loss = -(lp.gather(2, z["seqs"][rows, 1:].unsqueeze(2)).squeeze(2) * z["masks"][rows, 1:]).sum() / denom
+    loss.backward()
+    dwm = torch.cat([eff[k].grad.reshape(-1) for k in keys])
+    ar = D.make_all_reduce()
+    ar(dwm)                                                       # ONE buffer on the wire (vs dW and dS)
+    if rank == 0:
+        torch.save({"dwm": dwm}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dwm_exchange_equals_dw_and_ds_exchange(tmp_path):
+    """All-reducing dWm once and forming dW = dWm (.) m, dS = dWm (.) W (.) sigmoid'(S) afterwards equals all-reducing dW and
+    dS (both are linear in dWm with rank-independent factors): half the bytes, same update."""
+    out = str(tmp_path / "dwm.pt")
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_dwm_worker, args=(2, port, out), nprocs=2, join=True)
+    from tests import golden_io
+    z = golden_io.load("ort_prune_tiny")
+    keys = sorted(z["u"])
+    dwm = torch.load(out)["dwm"]
+    T = z["seqs"].shape[1] - 1
+    gw_ref, gs_ref = _grads(z, 0, z["att_feats"].shape[0], z["masks"][:, 1: T + 1].sum())
+    names = sorted(k for k, v in z["w"].items() if v.is_floating_point() and not k.endswith(".pe") and not k.endswith("_pruning_mask"))
+    ref_w = dict(zip(names, torch.split(gw_ref, [z["w"][k].numel() for k in names])))
+    ref_s = dict(zip(keys, torch.split(gs_ref, [z["w"][k].numel() for k in keys])))
+    off = 0
+    for k in keys:
+        n = z["w"][k].numel()
+        g = dwm[off: off + n].view(z["w"][k].shape)
+        off += n
+        S, W = z["w"][k + "_pruning_mask"], z["w"][k]
+        sig = torch.sigmoid(S)
+        m = (z["u"][k] < sig).float()
+        torch.testing.assert_close(g * m, ref_w[k].view(W.shape), rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(g * W * sig * (1 - sig), ref_s[k].view(W.shape), rtol=1e-4, atol=1e-7)

@@ -161,15 +161,18 @@ def test_gradient_buckets_partition_the_flat_buffers():
     for L in (1, 2, 3, 6):
         cfg = dict(d_model=32, dim_feedforward=64, num_layers=L, num_heads=4, max_seq_length=8, att_feat_size=48, vocab_size=37)
         sd = O.random_state_dict(O.Cfg(**cfg), seed=3, sparsity=0.0)
-        tr = OrtTrainer(sd, ModelCfg(cfg), mask_type="supermask", precision="fp32", device="cpu")
-        for flat in (tr.flat_gw, tr.flat_gs):
-            cover = torch.zeros(flat.numel(), dtype=torch.int32)
-            for phase in range(tr.N_PHASES):
-                for f, a, b in tr.grad_buckets(phase):
-                    if f is flat:
-                        assert 0 <= a < b <= flat.numel()
-                        cover[a:b] += 1
-            assert int(cover.min()) == 1 and int(cover.max()) == 1, (L, cover.unique())
+        for fused in (True, False):
+            # fused_st: only dWm (flat_gw) is exchanged - sc_adam_clip_st forms dW and dS; otherwise both flat buffers are
+            tr = OrtTrainer(sd, ModelCfg(cfg), mask_type="supermask", precision="fp32", device="cpu", fused_st=fused)
+            for flat in (tr.flat_gw, tr.flat_gs):
+                cover = torch.zeros(flat.numel(), dtype=torch.int32)
+                for phase in range(tr.N_PHASES):
+                    for f, a, b in tr.grad_buckets(phase):
+                        if f is flat:
+                            assert 0 <= a < b <= flat.numel()
+                            cover[a:b] += 1
+                want = 0 if (fused and flat is tr.flat_gs) else 1
+                assert int(cover.min()) == want and int(cover.max()) == want, (L, fused, cover.unique())
         # phase 0 must contain the generator, the last phase the first (att_embed) weight
         assert any(f is tr.flat_gw and b == tr.flat_gw.numel() for f, a, b in tr.grad_buckets(0))
         assert any(f is tr.flat_gw and a == 0 for f, a, b in tr.grad_buckets(tr.N_PHASES - 1))

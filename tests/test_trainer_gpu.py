@@ -29,6 +29,7 @@ def _run(tr, z, S=2):
     tr.load_batch(ws, z["att_feats"].to(DEV), z["boxes"].to(DEV), z["seqs"], z["masks"])
     logits = tr.forward(ws)[:, : tr.cfg.vocab_size]
     loss = tr.loss_and_backward(ws) * ws.inv_norm
+    tr.materialize_grads()  # dWm -> dW (tr.g) / dS (tr.gs): the reference's .grad tensors
     return ws, logits, loss
 
 
@@ -220,6 +221,7 @@ def test_d512_bf16_fused_paths_match_unfused():
         tr.load_batch(ws, data["att_feats"].to(DEV), data["boxes"].to(DEV), seqs, masks)
         tr.forward(ws)
         loss = float(tr.loss_and_backward(ws) * ws.inv_norm)
+        tr.materialize_grads()
         torch.cuda.synchronize()
         return tr, loss, tr.flat_gw.clone(), tr.flat_gs.clone()
 
@@ -287,6 +289,7 @@ def test_full_size_gradient_is_additive_over_image_shards():
         tr.load_batch(ws, att[lo:hi].to(DEV), boxes[lo:hi].to(DEV), seqs[lo * S: hi * S], masks[lo * S: hi * S], None, total)
         tr.forward(ws)
         loss = tr.loss_and_backward(ws) * ws.inv_norm
+        tr.materialize_grads()
         torch.cuda.synchronize()
         return float(loss), tr.flat_gw.clone(), tr.flat_gs.clone()
 
@@ -298,3 +301,32 @@ def test_full_size_gradient_is_additive_over_image_shards():
     # identical bf16 operands row by row; only the fp32 summation order over rows / split-K chunks differs
     assert rel_err(gw_a + gw_b, gw_all) < 2e-3
     assert rel_err(gs_a + gs_b, gs_all) < 2e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_straight_through_optimizer_matches_two_group_update(precision):
+    """sc_adam_clip_st (dWm in the gradient buffer; mask regenerated, dW / dS formed and both Adam groups updated in one launch)
+    against the path that materialises dW and dS in the weight-gradient epilogue and runs two sc_adam_clip launches: same
+    parameters, logits and moments after several steps, with injected uniforms and with the Philox sampler."""
+    z = golden_io.load("ort_prune_tiny")
+    from sparse_caption_b200.engine import ModelCfg
+    from sparse_caption_b200.trainer import OrtTrainer
+    for uniforms in (z["u"], None):
+        res = {}
+        for fused in (True, False):
+            tr = OrtTrainer(z["w"], ModelCfg(z["cfg_dict"]), mask_type="supermask", precision=precision, dropout=0.0, drop_prob_src=0.0,
+                            uniforms=uniforms, seed=17, fused_st=fused)
+            losses = []
+            for step in range(3):
+                losses.append(float(tr.train_step(z["att_feats"].to(DEV), z["boxes"].to(DEV), z["seqs"], z["masks"], seq_per_img=2, lr=1e-3,
+                                                  sparsity_target=0.9, sparsity_weight=5.0, current_step=step + 1, max_step=10)))
+            res[fused] = (losses, tr.flat_w.clone(), tr.flat_s.clone(), tr.m_s.clone(), tr.v_w.clone())
+        for a, b in zip(res[True][0], res[False][0]):
+            assert abs(a - b) <= 1e-5 * abs(b), (res[True][0], res[False][0])
+        # identical elementwise arithmetic; only atomics in the bias / LayerNorm sums may reorder -> tiny, sign-like Adam noise
+        for i in (1, 2, 3, 4):
+            assert float((res[True][i] - res[False][i]).abs().mean() / res[False][i].abs().mean().clamp_min(1e-12)) < 1e-3, i
+        # (the two kernels contract g * W * sigmoid'(S) + coeff * sigmoid'(S) into different fma sequences: last-bit differences
+        # are expected, real ones are not)
+        valid = ~tr._s_pad_mask
+        assert float(((res[True][2][valid] - res[False][2][valid]).abs() > 1e-3).float().mean()) < 0.01
