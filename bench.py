@@ -1,20 +1,26 @@
-"""Benchmark of the B200-native ORT captioning hot path (driver contract: one JSON line on stdout).
+"""Benchmark of the B200-native ORT / ACORT captioning hot path (driver contract: one JSON line on stdout).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--images B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config infer|train|acort|scst]
 
-Workload (BASELINE.json configs[2]): ORT 6x512, 95 % randomly pruned binarized-mask weights, beam-3 incremental
-decoding, max length 16, 36 regions x 2048-d synthetic features + boxes, 512 images per GPU per step.
-A "step" = one batch through encoder + 16 decode steps + beam bookkeeping.  N > 1: one process per GPU (torchrun),
-images sharded by rank, no collective on the data path (weak scaling).
+Workloads (BASELINE.json `configs`; synthetic 36-region x 2048-d features + boxes, random-init randomly pruned weights):
+  infer (default, configs[2]): ORT 6x512, 95 % sparse binarized-mask weights, beam-3 incremental decoding, L = 16, 512 images
+                               per GPU per step; the line also carries the SMP training arm (configs[1]) under "train".
+  train (configs[1]):          ORT supermask (SMP) training, bf16 GEMMs / fp32 master weights + logits, 50 images x 5 captions per
+                               GPU per step, Bernoulli masks + dropout + sparsity loss + clip + Adam; NCCL all-reduce of dWm at N > 1.
+  acort (configs[3]):          ACORT (2 unique layers x 3, share_att 'kv'), radix vocabulary 771, 99.1 % sparse, beam 5, L = 26.
+  scst  (configs[4]):          SCST rollouts for ORT: beam-5 + greedy baseline decode over ONE encoder pass, 1024 images per step.
+A "step" = one batch through encoder + all decode steps + beam bookkeeping (train: one full optimizer step).
+N > 1: one process per GPU (torchrun), images sharded by rank, no collective on the inference data path (weak scaling).
 
-  value : captions/s (one caption = the best beam of one image), inputs already resident in HBM.
-  e2e   : same through OrtEngine.sample() with pinned HOST fp32 features/boxes (H2D inside the timed region) and a
-          device->host read of the decoded tokens + log-probs every step.
-  roofline     : dominant kernel (the tcgen05 GEMM), algorithmic FLOPs / CUDA-event time of its launches in one
-                 instrumented (graph-less) step, against MEASURED_PEAKS.json.
+  value : metric with inputs already resident in HBM.
+  e2e   : same through OrtEngine.submit() with pinned HOST fp32 features / boxes (H2D inside the timed region) and a
+          device->host read of the decoded tokens + log-probs every step.  "e2e_bf16_host": same with bf16 pinned features.
+  roofline     : dominant kernel family (the tcgen05 GEMM): algorithmic FLOPs / in-graph CUDA-event time of every GEMM launch
+                 of one step, alone and with the timed region's concurrency, against MEASURED_PEAKS.json; "hbm_kernels": the
+                 HBM-bound decode kernels (cross / self attention, LayerNorm) as GB/s against the measured copy bandwidth.
   cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on this box's host cores, bounded sample.
   --impl reference : the same CPU arm alone (the reference is pure Python/PyTorch; its hot path restated in
-                 oracle/ort_oracle.py is what runs — /root/reference does not exist on the GPU box).
+                 oracle/ort_oracle.py is what runs - /root/reference does not exist on the GPU box).
 """
 import argparse
 import json
@@ -31,15 +37,23 @@ import torch  # noqa: E402
 
 CFG = dict(d_model=512, dim_feedforward=2048, num_layers=6, num_heads=8, max_seq_length=16, att_feat_size=2048,
            vocab_size=10000)
+ACORT_CFG = dict(CFG, vocab_size=771, max_seq_length=26, share_att_encoder="kv", share_att_decoder="kv",
+                 share_layer_encoder=(0, 0, 0, 1, 1, 1), share_layer_decoder=(0, 0, 0, 1, 1, 1), bos_token_id=769, eos_token_id=770)
 SPARSITY = 0.95
 BEAM = 3
 N_BOX = 36
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant GEMM shape (M=1536, N=512, K=512: 384 of the
-# 623 GEMM launches of a step), ncu --set full, profiles/r01b_ncu_full_summary.txt (inf_gemm64: 5.29 MB read, 0 written:
-# the 3 MB output tile stays in the 126 MB L2 for the next kernel)
-NCU_TRAFFIC_DOMINANT_GEMM = 5293312
-METRIC = "ort95_beam3_captions_per_sec"
-UNIT = "captions/s"
+WORKLOADS = {
+    "infer": dict(cfg=CFG, sparsity=0.95, decodes=[{"beam_size": 3}], images=512, metric="ort95_beam3_captions_per_sec", unit="captions/s",
+                  label="ORT 6x512 95%-sparse binarized-mask beam-3 inference, L=16, V=10000, 36x2048 features + boxes", idx=2),
+    "acort": dict(cfg=ACORT_CFG, sparsity=0.991, decodes=[{"beam_size": 5}], images=512, metric="acort991_beam5_captions_per_sec",
+                  unit="captions/s", label="ACORT (2 unique layers x 3, share_att kv) 99.1%-sparse radix-vocabulary (771) beam-5 "
+                  "incremental decoding, L=26, 36x2048 features + boxes", idx=3),
+    "scst": dict(cfg=CFG, sparsity=0.95, decodes=[{"beam_size": 5}, {"beam_size": 1}], images=1024, metric="scst_rollout_images_per_sec",
+                 unit="images/s", label="SCST rollout for ORT (fixed 0/1 masks): beam-5 rollout + greedy baseline decode over one encoder "
+                 "pass, L=16, V=10000 (CIDEr scoring excluded)", idx=4),
+}
+METRIC = WORKLOADS["infer"]["metric"]
+UNIT = WORKLOADS["infer"]["unit"]
 
 
 def load_peaks():
@@ -49,6 +63,13 @@ def load_peaks():
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each decode GEMM shape, from the committed ncu capture
+    (scripts/ncu_gemm_traffic.sh -> profiles/r02_gemm_traffic.json, keys "M,N,K,out_bytes,residual")."""
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 class ClockSampler(threading.Thread):
@@ -81,26 +102,115 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def cpu_arm(steps, warmup, images):
-    """Reference arm / cpu_baseline: the oracle port of the reference's PyTorch path on the host cores."""
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arms (reference arm / cpu_baseline): the oracle port of the reference's PyTorch path on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, images, wl=None):
+    from oracle import ort_oracle as O
+    from sparse_caption_b200.engine import ModelCfg
+    from sparse_caption_b200 import synthetic
+    wl = wl or WORKLOADS["infer"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = ModelCfg(wl["cfg"])
+    sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=wl["sparsity"])
+    ocfg = O.Cfg(**wl["cfg"])
+    att, boxes = synthetic.synthetic_inputs(images, N_BOX, wl["cfg"]["att_feat_size"], seed=8888)
+
+    def one(a, b):
+        memory, src_mask = O.encode(sd, ocfg, a, b, None)  # encoder once, every decode of the step shares it
+        for opt in wl["decodes"]:
+            if opt.get("beam_size", 1) > 1:
+                O.beam_search(sd, ocfg, memory, src_mask, opt)
+            else:
+                O.greedy_search(sd, ocfg, memory, src_mask, opt)
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            one(att[:8], boxes[:8])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one(att, boxes)
+        dt = time.perf_counter() - t0
+    return images * steps / dt, dt / steps, cores
+
+
+def _train_batch(B, S, T, V, rank):
+    from sparse_caption_b200 import synthetic
+    g = torch.Generator().manual_seed(8888 + rank)
+    att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank, pin=torch.cuda.is_available())
+    R = B * S
+    seqs = torch.zeros(R, T + 1, dtype=torch.long)
+    masks = torch.zeros(R, T + 1)
+    lens = torch.randint(6, T - 1, (R,), generator=g)
+    for r in range(R):
+        n = int(lens[r])
+        seqs[r, 0] = 2
+        seqs[r, 1:1 + n] = torch.randint(4, V, (n,), generator=g)
+        seqs[r, 1 + n] = 3
+        masks[r, :n + 2] = 1
+    return att, boxes, seqs, masks
+
+
+def cpu_train_arm(steps, warmup, images):
+    """SMP training step of the reference path on the host cores: supermask forward (sigmoid -> Bernoulli -> mul per masked
+    layer, masked_layer.py:84-110) + LanguageModelCriterion + backward through the straight-through estimators, fp32 autograd
+    over the oracle, clip + the two Adam groups over 110 M parameters included."""
     from oracle import ort_oracle as O
     from sparse_caption_b200.engine import ModelCfg
     from sparse_caption_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = ModelCfg(CFG)
-    sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=SPARSITY)
-    ocfg = O.Cfg(**CFG)
-    att, boxes = synthetic.synthetic_inputs(images, N_BOX, CFG["att_feat_size"], seed=8888)
-    opt = {"beam_size": BEAM}
-    with torch.no_grad():
-        for _ in range(warmup):
-            O.sample(sd, ocfg, att[:8], boxes[:8], None, opt)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            O.sample(sd, ocfg, att, boxes, None, opt)
-        dt = time.perf_counter() - t0
+    cfg_d = dict(CFG, max_seq_length=17)
+    ocfg = O.Cfg(**cfg_d)
+    sd = synthetic.random_state_dict(ModelCfg(cfg_d), seed=1234, sparsity=0.0)
+    W = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    keys = [k for k in sd if k.endswith(".weight") and sd[k].dim() == 2]
+    Sg = {k: torch.full_like(sd[k], 5.0).requires_grad_(True) for k in keys}
+    opt = torch.optim.Adam([{"params": list(W.values()), "lr": 3e-4, "betas": (0.9, 0.98), "eps": 1e-9},
+                            {"params": list(Sg.values()), "lr": 100.0, "betas": (0.9, 0.98), "eps": 1e-2}])
+    att, boxes, seqs, masks = _train_batch(images, 5, 17, CFG["vocab_size"], 0)
+
+    def step():
+        opt.zero_grad()
+        eff = dict(W)
+        for k in keys:
+            p = torch.sigmoid(Sg[k])
+            m = torch.bernoulli(p.detach())
+            eff[k] = (p + (m - p).detach()) * W[k]
+        lp = O.forward_tf(eff, ocfg, att, boxes, seqs, None)
+        loss = O.lm_criterion(lp, seqs[:, 1:], masks[:, 1:])
+        loss.backward()
+        for g in opt.param_groups:
+            torch.nn.utils.clip_grad_value_(g["params"], 0.1)
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
     return images * steps / dt, dt / steps, cores
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# in-graph kernel timing helpers (roofline legs)
+# ----------------------------------------------------------------------------------------------------------------------
+def _time_graph(run, dev, reps=40):
+    """us per launch of run(i): `reps` launches captured in one CUDA graph on the current stream, CUDA events around two replays."""
+    run(0)
+    torch.cuda.synchronize(dev)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for i in range(reps):
+            run(i)
+    gr.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); gr.replay(); gr.replay(); e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) * 1e3 / (2 * reps)
 
 
 def time_train_gemms(prof, dev):
@@ -114,17 +224,16 @@ def time_train_gemms(prof, dev):
         if meta and meta[0] == "gemm_bf16":
             key = (name,) + tuple(meta[1:])
             groups[key] = groups.get(key, 0) + 1
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tot_us, tot_fl = 0.0, 0.0
     for key, cnt in groups.items():
         name, d1, d2, d3 = key[:4]
         if name == "sc_linear_wgrad_rowmajor":
             N, Kd, M = d1, d2, d3
             dy = torch.randn(M, N, device=dev).bfloat16(); x = torch.randn(M, Kd, device=dev).bfloat16()
-            W = torch.randn(N, Kd, device=dev); S = torch.randn(N, Kd, device=dev)
-            gW, gS = torch.empty_like(W), torch.empty_like(S)
+            W = torch.randn(N, Kd, device=dev)
+            gW = torch.empty_like(W)
             wsb = torch.empty(4 * N * Kd, device=dev)
-            run = lambda i: KK.linear_wgrad_rowmajor(dy, x, W, S, KK.MASK_BERNOULLI, gW, gS, workspace=wsb, seed=3, stream_id=5)
+            run = lambda i: KK.linear_wgrad_rowmajor(dy, x, W, None, KK.MASK_NONE, gW, None, workspace=wsb)
             fl = 2.0 * M * N * Kd
         else:
             M, N, Kd = d1, d2, d3
@@ -144,27 +253,60 @@ def time_train_gemms(prof, dev):
                 has_res = key[8] if len(key) > 8 else False
                 res = torch.randn(M, N, device=dev) if has_res else None
                 run = lambda i: KK.linear(x, w, None, residual=res, out=outs[i % 2])
-        run(0)
-        torch.cuda.synchronize(dev)
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            for i in range(20):
-                run(i)
-        gr.replay()
-        torch.cuda.synchronize(dev)
-        e0.record(); gr.replay(); gr.replay(); e1.record()
-        torch.cuda.synchronize(dev)
-        tot_us += e0.elapsed_time(e1) * 1e3 / 40 * cnt
+        tot_us += _time_graph(run, dev, 20) * cnt
         tot_fl += fl * cnt
     return tot_us, tot_fl
 
 
-def train_arm(args, dev, world, rank, dist_mod=None):
-    """SMP training arm (BASELINE.json configs[1]): ORT supermask training, bf16 tensor-core GEMMs with fp32 master
-    weights + fp32 mask logits, 5 captions/image with the encoder run once, Bernoulli masks + dropout + sparsity
-    loss + clip + Adam inside the timed step.  Single-GPU here; the N-GPU variant adds the NCCL all-reduce of the
-    flat weight+logit gradient buffers (tests/test_ddp_cpu.py covers the sharding logic)."""
-    from sparse_caption_b200 import lib, synthetic
+def hbm_kernel_roofline(dev, B, beam, N, cfg, peaks):
+    """The HBM-bound decode kernels (K5 self attention at mid / last step, K6 cross attention, K9 LayerNorm) timed alone in a
+    CUDA graph over 4 rotating buffer sets (together larger than the 126 MB L2), algorithmic bytes / time against the measured
+    copy bandwidth."""
+    from sparse_caption_b200 import kernels as KK
+    d, h, L = cfg["d_model"], cfg["num_heads"], cfg["max_seq_length"]
+    R = B * beam
+    bf = dict(device=dev, dtype=torch.bfloat16)
+    out = []
+
+    def entry(name, run, nbytes):
+        us = _time_graph(run, dev)
+        gbs = nbytes / us / 1e3
+        out.append({"kernel": name, "us_per_launch": us, "algorithmic_bytes": nbytes, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm"]})
+
+    C = 4
+    qc = [torch.randn(R, d, **bf) for _ in range(C)]
+    mkv = [torch.randn(B * N, 2 * d, **bf) for _ in range(C)]
+    att = torch.empty(R, d, **bf)
+    entry("sc_decode_cross_attn_step", lambda i: KK.cross_attn_step(qc[i % C], mkv[i % C][:, 0:], mkv[i % C][:, d:], None, att, B=B, beam=beam,
+                                                                    N=N, D=d, h=h, ldq=d, ldm=2 * d, ldo=d),
+          B * N * 2 * d * 2 + 2 * R * d * 2)
+    qkv = [torch.randn(R, 3 * d, **bf) for _ in range(C)]
+    ck = [torch.randn(L, R, d, **bf) for _ in range(C)]
+    cv = [torch.randn(L, R, d, **bf) for _ in range(C)]
+    anc = torch.arange(R, device=dev, dtype=torch.int32).unsqueeze(1).expand(R, L).contiguous()
+    for t in (L // 2, L - 1):
+        entry(f"sc_decode_self_attn_step(t={t})",
+              lambda i, t=t: KK.self_attn_step(qkv[i % C][:, 0:], qkv[i % C][:, d:], qkv[i % C][:, 2 * d:], ck[i % C], cv[i % C], anc, att, R=R, D=d,
+                                               h=h, n_prev=t, write_slot=t, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldo=d, anc_ld=L, slot_div=1),
+              R * (t + 1) * 2 * d * 2 + R * 3 * d * 2 + 2 * R * d * 2 + R * d * 2)
+    rows = B * N  # the encoder-sized LayerNorm (the decode-sized one, R rows, moves 4.7 MB and is launch-latency bound)
+    x = [torch.randn(rows, d, device=dev) for _ in range(C)]
+    xn = torch.empty(rows, d, **bf)
+    a2, b2 = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    entry(f"sc_layernorm({rows} rows)", lambda i: KK.layernorm(x[i % C], a2, b2, out=xn), rows * d * 6)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SMP training arm (BASELINE.json configs[1])
+# ----------------------------------------------------------------------------------------------------------------------
+def train_arm(args, dev, world, rank, dist_mod=None, e2e=False):
+    """ORT supermask training, bf16 tensor-core GEMMs with fp32 master weights + fp32 mask logits, 5 captions/image with the
+    encoder run once, Bernoulli masks + dropout + sparsity loss + clip + Adam inside the timed step; at N > 1 the NCCL
+    all-reduce of the flat dWm buffer (tests/test_ddp_cpu.py covers the sharding logic)."""
+    from sparse_caption_b200 import lib
+    from sparse_caption_b200 import synthetic
     from sparse_caption_b200.engine import ModelCfg
     from sparse_caption_b200.trainer import OrtTrainer
     cfg = ModelCfg(dict(CFG, max_seq_length=17))
@@ -173,18 +315,7 @@ def train_arm(args, dev, world, rank, dist_mod=None):
     tr = OrtTrainer(sd, cfg, mask_type="supermask", precision="bf16", device=dev, seed=8888,  # same mask seed on every rank
                     use_graph=not args.no_train_graph, fused_st=not (world > 1 and args.exchange == "sharded"))
     B, S, T = args.train_images, 5, 17
-    g = torch.Generator().manual_seed(8888 + rank)
-    att, boxes = synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank, pin=True)
-    R = B * S
-    seqs = torch.zeros(R, T + 1, dtype=torch.long)
-    masks = torch.zeros(R, T + 1)
-    lens = torch.randint(6, T - 1, (R,), generator=g)
-    for r in range(R):
-        n = int(lens[r])
-        seqs[r, 0] = 2
-        seqs[r, 1:1 + n] = torch.randint(4, CFG["vocab_size"], (n,), generator=g)
-        seqs[r, 1 + n] = 3
-        masks[r, :n + 2] = 1
+    att, boxes, seqs, masks = _train_batch(B, S, T, CFG["vocab_size"], rank)
     seqs, masks = seqs.pin_memory(), masks.pin_memory()
     opt = dict(lr=3e-4, sparsity_target=0.95, sparsity_weight=30.0, current_step=100, max_step=1000)
     all_reduce = exchange = None
@@ -202,21 +333,35 @@ def train_arm(args, dev, world, rank, dist_mod=None):
             dist_mod.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(3):
+    for _ in range(max(3, args.warmup if e2e else 3)):
         step()
     barrier()
     before = lib.launch_count
+    n_steps = args.steps if e2e else args.train_steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.train_steps):
+    for _ in range(n_steps):
         loss = step()
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    ms_dev = e0.elapsed_time(e1)
+    launches = (lib.launch_count - before) // n_steps
+    # end to end: the same step with the loss read back to the host every step (the reference loop's loss.item(), :142,155)
+    host_loss = torch.zeros(1).pin_memory()
+    e0.record()
+    for _ in range(n_steps):
+        host_loss.copy_(step().reshape(1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    # every rank's loss is its share of the GLOBAL mean (normalised by the global token count): their sum is the loss
+    loss_g = loss.detach().double().reshape(1).clone()
     if dist_mod is not None:
         dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
-    ms = float(t[0]) / args.train_steps
-    launches = (lib.launch_count - before) // args.train_steps
+        dist_mod.all_reduce(loss_g, op=dist_mod.ReduceOp.SUM)
+    ms, ms_e = float(t[0]) / n_steps, float(t[1]) / n_steps
     if rank != 0:
         return None
     # GEMM share / tensor roofline from one instrumented step
@@ -236,18 +381,23 @@ def train_arm(args, dev, world, rank, dist_mod=None):
     except Exception as ex:  # diagnostics only: fall back to the event timing of the eager step
         print(f"in-graph training GEMM timing skipped: {ex}", file=sys.stderr)
         g_us, tf = None, tf_eager
+    h2d = att.numel() * 4 + boxes.numel() * 4 + seqs.numel() * 8 + masks.numel() * 4
     return {"metric": "smp_train_images_per_sec", "value": world * B / (ms / 1e3), "unit": "images/s", "n_gpus": world, "ms_per_step": ms,
+            "e2e": {"value": world * B / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e},
             "collective": "none (1 GPU)" if world == 1 else (
                 "per gradient bucket (4 backward phases): NCCL reduce-scatter -> Adam on the owned 1/N shard -> all-gather of the updated "
                 "weights + mask logits, on a side stream under the next phase" if exchange is not None else
-                "NCCL all-reduce(sum) of fp32 weight+logit gradient buckets, started after each of the 4 backward phases (overlaps the next phase)"),
+                "NCCL all-reduce(sum) of the fp32 dWm buckets (gradient w.r.t. the masked weights: 222 MB/step, half of dW + dS; the "
+                "straight-through dW / dS are formed inside the optimizer kernel), started after each of the 4 backward phases"),
             "images_per_gpu_per_step": B, "captions_per_image": S, "positions": T, "dtype": "bf16 GEMM / fp32 master+logits",
-            "loss": float(loss), "gpu_launches_per_step": launches, "h2d_bytes_per_step": att.numel() * 4 + boxes.numel() * 4 + seqs.numel() * 8 + masks.numel() * 4,
+            "loss": float(loss_g[0]), "loss_note": "global mean over all ranks' tokens (all-reduced)", "gpu_launches_per_step": launches,
+            "h2d_bytes_per_step": h2d,
             "includes": "H2D of the batch, Bernoulli masks, dropout, sparsity loss, clip + Adam (2 groups)",
             "algorithmic_gflop_per_step": gemm_fl / 1e9,
+            "step_tflops": gemm_fl / (ms / 1e3) / 1e12, "step_frac_of_sustained_peak": gemm_fl / (ms / 1e3) / 1e12 / peaks["tf_sus"],
             "roofline": {"kernel": "sc_gemm_bf16_kernel (fwd + dgrad + wgrad launches of one step, each through its own entry point)",
                          "bound": "tensor", "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"],
-                         "gemm_us_per_step_in_graph": g_us, "achieved_eager_events": tf_eager,
+                         "traffic": None, "gemm_us_per_step_in_graph": g_us, "achieved_eager_events": tf_eager,
                          "note": "in-graph timing per shape (20 launches, CUDA events); wgrad figures include the split-K reduction kernel",
                          "share_of_step": gemm_ms / tot_ms if tot_ms else None}}
 
@@ -269,51 +419,72 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--images", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--config", default="infer", choices=["infer", "train", "acort", "scst"],
+                    help="workload: BASELINE.json configs[2] (default; carries configs[1] under `train`), configs[1], configs[3], configs[4]")
+    ap.add_argument("--images", type=int, default=0, help="images per GPU per step (0 = the workload's own: 512 / 512 / 1024)")
     ap.add_argument("--backend", default="dense", choices=["dense", "csr", "sell", "auto"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the SMP training arm (BASELINE.json configs[1])")
     ap.add_argument("--train-images", type=int, default=50, help="images per GPU per training step (5 captions each)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--exchange", default="allreduce", choices=["sharded", "allreduce"],
-                    help="data-parallel gradient exchange of the training arm (2 GPUs measured: allreduce 6.05, sharded 6.18 ms/step)")
+                    help="data-parallel gradient exchange of the training arm")
     ap.add_argument("--no-train-graph", action="store_true", help="diagnostic: eager launches instead of the captured training graph")
     ap.add_argument("--cpu-images", type=int, default=64)
     ap.add_argument("--ln-fold", action="store_true", help="LayerNorm folded into the consuming GEMMs (sc_linear_ln) instead of separate LayerNorm kernels")
     ap.add_argument("--prefetch", action="store_true", help="e2e arm: H2D of the next batch on a copy stream underneath the previous decode of the same slot")
     ap.add_argument("--no-fuse-topk", action="store_true", help="diagnostic: materialise the logits (sc_linear + sc_beam_step) instead of the fused generator + beam row pass")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostic: disable programmatic dependent launch")
-    ap.add_argument("--slots", type=int, default=0, help="batches in flight (pipeline slots: stream + workspaces + graphs each); 0 = 8 when the timed region is long enough "
-                         "to amortise the pipeline's fill and drain (>= 24 steps), else 4")
+    ap.add_argument("--coalesce", type=int, default=0, help="queued batches the engine decodes as ONE device batch (dynamic batching: the decode "
+                         "GEMMs of G batches run as one M = G x rows GEMM); a timed step stays one batch of --images.  0 = the largest of "
+                         "5 / 4 / 2 that divides --steps (measured: scripts/gpu_dec_ab4.sh)")
+    ap.add_argument("--slots", type=int, default=0, help="device launches in flight (pipeline slots: stream + workspaces + graphs each); 0 = auto")
     args = ap.parse_args()
-    if args.slots <= 0:
-        # the K timed steps go round-robin over the slots; a slot count that divides K keeps every round of the pipeline
-        # full (K = 10 -> 5 slots: two full rounds instead of 4 + 4 + 2), long runs amortise fill / drain anyway
-        args.slots = 8 if args.steps >= 24 else next((sl for sl in (8, 7, 6, 5, 4) if args.steps % sl == 0), 4)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "ORT 6x512 95%-sparse binarized-mask beam-3 inference, L=16, V=10000, 36x2048 features + boxes "
-                          f"({args.images} images/GPU/step) [BASELINE.json configs[2]]",
-              "images_per_gpu_per_step": args.images, "beam": BEAM, "max_len": 16, "sparsity": SPARSITY,
+
+    if args.config == "train":
+        return train_main(args, out, rank, local_rank, world)
+
+    wl = WORKLOADS[args.config]
+    if args.images <= 0:
+        args.images = wl["images"]
+    if args.coalesce <= 0:
+        cands = (2,) if args.config == "scst" else (5, 4, 2)   # (scst: 1024 images and two decodes per step already)
+        args.coalesce = next((g for g in cands if args.steps % g == 0), 1)
+    if args.slots <= 0:
+        # the K / G device launches go round-robin over the slots (stream + workspaces + graphs each); a slot count that divides
+        # them keeps every round of the pipeline full, long runs amortise fill / drain anyway
+        launches = max(1, args.steps // max(1, args.coalesce))
+        args.slots = next((sl for sl in (4, 3, 2) if launches % sl == 0), min(4, launches)) if args.coalesce > 1 else (
+            8 if args.steps >= 24 else next((sl for sl in (8, 7, 6, 5, 4) if args.steps % sl == 0), 4))
+    cfgd = wl["cfg"]
+    L = cfgd["max_seq_length"]
+    beams = [int(o.get("beam_size", 1)) for o in wl["decodes"]]
+    config = {"workload": f"{wl['label']} ({args.images} images/GPU/step) [BASELINE.json configs[{wl['idx']}]]",
+              "images_per_gpu_per_step": args.images, "beam": beams if len(beams) > 1 else beams[0], "max_len": L, "sparsity": wl["sparsity"],
               "sharding": f"images by rank x{world}, no data-path collective", "decoder_gemm_backend": args.backend,
-              "batches_in_flight": args.slots,
-              "l2_policy": "inputs_larger_than_L2 (151 MB fresh fp32 features + ~0.7 GB of activations/KV per step vs 126 MB L2)"}
+              "batches_in_flight": args.slots * max(1, args.coalesce), "coalesced_batches_per_launch": max(1, args.coalesce),
+              "l2_policy": f"inputs_larger_than_L2 ({args.images * N_BOX * 2048 * 4 / 1e6:.0f} MB fresh fp32 features + ~0.7 GB of activations/KV per step vs 126 MB L2)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # K timed steps and W warm-up steps as asked; one step = a bounded sample (--cpu-images, default 64 images of the
-        # 512-image workload: ~0.6 s on 16 cores), so the default K=10 / W=3 run takes ~10 s
+        # K timed steps and W warm-up steps as asked; one step = a BOUNDED SAMPLE of the workload's step (--cpu-images images
+        # instead of --images: ~0.6 s on 16 cores) - stated in `config` - so the default K=10 / W=3 run takes ~10 s
         warm = max(1, args.warmup)
         steps = max(1, args.steps)
-        v, spp, cores = cpu_arm(steps, warm, args.cpu_images)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        v, spp, cores = cpu_arm(steps, warm, args.cpu_images, wl)
+        config = dict(config, images_per_gpu_per_step=args.cpu_images, sampled_from_images_per_step=args.images, batches_in_flight=1,
+                      coalesced_batches_per_launch=1,
+                      workload=config["workload"] + f" - reference arm: bounded sample of {args.cpu_images} images per step")
+        print(json.dumps({"impl": "reference", "metric": wl["metric"], "value": v, "unit": wl["unit"], "n_gpus": args.gpus, "steps": steps,
                           "warmup": warm, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                          "cpu_baseline": {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port",
                                            "sample": f"{steps} x {args.cpu_images} images, same model/beam/length, torch fp32 on host cores"},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out, flush=True)
+                          "e2e": {"value": v, "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out, flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
@@ -330,15 +501,20 @@ def main():
     if args.no_pdl:
         from sparse_caption_b200 import kernels as _K
         _K.set_pdl(False)
-    cfg = ModelCfg(CFG)
-    sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=SPARSITY, device=dev)
+    cfg = ModelCfg(cfgd)
+    sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=wl["sparsity"], device=dev)
+    G = max(1, args.coalesce)
+    assert args.steps % G == 0, "--steps must be a multiple of --coalesce"
     eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold,
                     fuse_topk=not args.no_fuse_topk,
-                    dec_tiles={"o": 3256, "co": 3256, "cq": 3128, "ff2": 3256} if args.slots >= 8 else None)
-    B = args.images
+                    # >= 8 batches in flight (throughput regime): 256-wide tiles, two tiles per persistent CTA (10^7 digit)
+                    dec_tiles=({k: 20003256 for k in ("qkv", "o", "cq", "co", "ff1", "ff2")}
+                               if args.slots * G >= 8 else None))
+    B = args.images * G      # device batch = G queued batches of --images
+    F = cfgd["att_feat_size"]
     # two distinct pinned host batches, alternated
-    host = [synthetic.synthetic_inputs(B, N_BOX, CFG["att_feat_size"], seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
-    opt = {"beam_size": BEAM}
+    host = [synthetic.synthetic_inputs(B, N_BOX, F, seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
+    opts = wl["decodes"]
 
     def barrier():
         if dist is not None:
@@ -346,26 +522,26 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---------------- device-resident arm: inputs already in HBM ----------------
-    # `slots` batches are in flight at once: slot s = its own stream, workspaces and CUDA graphs (engine.submit);
-    # every timed step is still one full batch (encoder + 16 decode steps + beam bookkeeping).
+    # `slots` device launches are in flight at once: slot s = its own stream, workspaces and CUDA graphs (engine.submit);
+    # every timed step is still one full batch of --images (encoder + all decode steps + beam bookkeeping).
     S = max(1, args.slots)
     slots = list(range(1, S + 1))
     cur = torch.cuda.current_stream(dev)
     encs = {}
     for s in slots:
         # inputs resident in HBM (fp32, as the data loader delivers them) -> the slot's workspaces + graphs
-        eng.submit(host[s & 1][0].to(dev), host[s & 1][1].to(dev), None, opt, slot=s)
+        eng.submit(host[s & 1][0].to(dev), host[s & 1][1].to(dev), None, opts, slot=s)
         encs[s] = eng._get_enc_ws(B, N_BOX, False, s)
     eng.wait(host=True)
     torch.cuda.synchronize(dev)
-    dws = eng._get_dec_ws(B, BEAM, N_BOX, False, slots[0])
-    launches_per_step = encs[slots[0]].launches + dws.launches
+    launches_per_call = encs[slots[0]].launches + sum(eng._get_dec_ws(B, b, N_BOX, b == 1, slots[0]).launches for b in beams)
 
     def dev_step(i):
         s = slots[i % S]
         with torch.cuda.stream(eng.stream(s)):
             eng.run_encoder(encs[s])
-            eng.decode(encs[s], opt)
+            for o in opts:
+                eng.decode(encs[s], o)
 
     def fork():
         for s in slots:
@@ -375,8 +551,9 @@ def main():
         for s in slots:
             cur.wait_stream(eng.stream(s))
 
+    n_warm, n_timed = max(1, -(-args.warmup // G)), args.steps // G   # device launches (each = G steps of --images images)
     fork()
-    for i in range(args.warmup):
+    for i in range(n_warm):
         dev_step(i)
     join()
     barrier()
@@ -386,7 +563,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     fork()
-    for i in range(args.steps):
+    for i in range(n_timed):
         dev_step(i)
     join()
     e1.record()
@@ -394,40 +571,47 @@ def main():
     ms_dev = e0.elapsed_time(e1)
 
     # ---------------- end-to-end arm: pinned host inputs -> tokens on the host ----------------
-    out_seq = [torch.empty(B, BEAM, 16, dtype=torch.int32).pin_memory() for _ in slots]
-    out_lp = [torch.empty(B, BEAM, 16, dtype=torch.float32).pin_memory() for _ in slots]
+    outs = [[(torch.empty(B, max(b, 1), L, dtype=torch.int32).pin_memory(), torch.empty(B, max(b, 1), L, dtype=torch.float32).pin_memory())
+             for b in beams] for _ in slots]
 
-    def e2e_step(i):
-        att, boxes = host[i & 1]
-        k = i % S
-        eng.submit(att, boxes, None, opt, slot=slots[k], out=(out_seq[k], out_lp[k]), prefetch=args.prefetch)
+    def e2e_run(batches):
+        def e2e_step(i):
+            att, boxes = batches[i & 1]
+            k = i % S
+            eng.submit(att, boxes, None, opts, slot=slots[k], out=outs[k], prefetch=args.prefetch)
+        for i in range(max(n_warm, S)):  # every slot's host-input path (its own workspaces / graphs) is warm
+            e2e_step(i)
+        eng.wait()
+        barrier()
+        e0.record()
+        for i in range(n_timed):
+            e2e_step(i)
+        eng.wait()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
 
-    for i in range(max(args.warmup, S)):  # every slot's host-input path (its own workspaces / graphs with the fused ingest) is warm
-        e2e_step(i)
-    eng.wait()
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    eng.wait()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = e2e_run(host)
+    # the same with bf16 pinned host features (half the H2D bytes; the engine lands them directly in the GEMM operand buffer)
+    host16 = [(a.to(torch.bfloat16).pin_memory(), b) for a, b in host]
+    ms_e2e16 = e2e_run(host16)
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
-    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
-    d2h = out_seq[0].numel() * 4 + out_lp[0].numel() * 4
+    h2d = (host[0][0].numel() * 4 + host[0][1].numel() * 4) // G   # per step of --images
+    h2d16 = (host[0][0].numel() * 2 + host[0][1].numel() * 4) // G
+    d2h = sum(o[0].numel() * 4 + o[1].numel() * 4 for o in outs[0]) // G
+    del host16
 
-    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_dev, ms_e2e, ms_e2e16], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
-    value = world * B * args.steps / (ms_dev / 1e3)
-    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    ms_dev, ms_e2e, ms_e2e16 = float(t[0]), float(t[1]), float(t[2])
+    per_s = lambda ms: world * args.images * args.steps / (ms / 1e3)
+    value, e2e_value = per_s(ms_dev), per_s(ms_e2e)
 
     train = None
-    if not args.no_train:
+    if not args.no_train and args.config == "infer":
         train = train_arm(args, dev, world, rank, dist_mod=dist)
 
     if rank != 0:
@@ -437,14 +621,19 @@ def main():
 
     # ---------------- roofline leg: one instrumented step without graphs ----------------
     peaks = load_peaks()
+    traffic = load_traffic()
+    Bp = args.images
+    att_p, box_p = host[0][0][:Bp], host[0][1][:Bp]
     eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False,
                      ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk)
-    enc2 = eng2.encode(host[0][0], host[0][1])
-    eng2.decode(enc2, opt)
+    enc2 = eng2.encode(att_p, box_p)
+    for o in opts:
+        eng2.decode(enc2, o)
     torch.cuda.synchronize(dev)
     lib.profile = []
     eng2.run_encoder(enc2)
-    eng2.decode(enc2, opt)
+    for o in opts:
+        eng2.decode(enc2, o)
     torch.cuda.synchronize(dev)
     prof, lib.profile = lib.profile, None
     by = {}
@@ -473,52 +662,37 @@ def main():
             key = tuple(meta[1:7]) + tuple(meta[8:10])
             shapes[key] = shapes.get(key, 0) + 1
     from sparse_caption_b200 import kernels as KK
-    gemm_us, gemm_fl, dom = 0.0, 0.0, None
-    for (M, N, Kd, xs, wsz, ys, has_res, relu), cnt in shapes.items():
+    topk_beam = max([b for b in beams if b > 1] or [3])
+
+    def make_run(M, N, Kd, ys, has_res, relu, nbuf):
         x = torch.randn(M, Kd, device=dev).bfloat16()
         w = torch.randn(N, Kd, device=dev).bfloat16()
         bias = torch.randn(N, device=dev)
         res = torch.randn(M, N, device=dev) if has_res else None
         if ys == 0:  # generator fused with the beam row pass: no output tile, 12-float records per (row, tile half)
             part = torch.empty(M, KK.linear_topk_parts(N), 12, device=dev)
-            run = lambda i: KK.linear_topk(x, w, bias, part, candidates=BEAM)
-        else:
-            outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(4)]
-            run = lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs[i % 4])
-        run(0)
-        torch.cuda.synchronize(dev)
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            for i in range(40):
-                run(i)
-        gr.replay()
-        torch.cuda.synchronize(dev)
-        e0.record(); gr.replay(); gr.replay(); e1.record()
-        torch.cuda.synchronize(dev)
-        us = e0.elapsed_time(e1) * 1e3 / 80
+            return lambda i: KK.linear_topk(x, w, bias, part, candidates=min(5, topk_beam))
+        outs_ = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(nbuf)]
+        return lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs_[i % nbuf])
+
+    gemm_us, gemm_fl, dom = 0.0, 0.0, None
+    for (M, N, Kd, xs, wsz, ys, has_res, relu), cnt in shapes.items():
+        us = _time_graph(make_run(M, N, Kd, ys, has_res, relu, 4), dev)
         gemm_us += us * cnt
         gemm_fl += 2.0 * M * N * Kd * cnt
         if dom is None or us * cnt > dom[0]:
-            dom = (us * cnt, M, N, Kd, us, cnt, xs * M * Kd + wsz * N * Kd + ys * M * N + (4 * M * N if has_res else 0))
-    # the same shapes with `slots` streams running them concurrently - the regime of the timed region (S batches in flight):
+            dom = (us * cnt, M, N, Kd, us, cnt, xs * M * Kd + wsz * N * Kd + ys * M * N + (4 * M * N if has_res else 0), ys, has_res)
+    # the same shapes with several streams running them concurrently - the regime of the timed region (launches in flight):
     # microseconds of wall time per GEMM = elapsed / (streams * launches)
     conc_us, conc_fl = 0.0, 0.0
+    CS = max(2, min(8, S * G))
     try:
-        streams = [torch.cuda.Stream(dev) for _ in range(S)]
+        streams = [torch.cuda.Stream(dev) for _ in range(CS)]
         cur_s = torch.cuda.current_stream(dev)
         for (M, N, Kd, xs, wsz, ys, has_res, relu), cnt in shapes.items():
             graphs = []
             for st in streams:
-                x = torch.randn(M, Kd, device=dev).bfloat16()
-                w = torch.randn(N, Kd, device=dev).bfloat16()
-                bias = torch.randn(N, device=dev)
-                res = torch.randn(M, N, device=dev) if has_res else None
-                if ys == 0:
-                    part = torch.empty(M, KK.linear_topk_parts(N), 12, device=dev)
-                    run = (lambda x, w, bias, part: (lambda i: KK.linear_topk(x, w, bias, part, candidates=BEAM)))(x, w, bias, part)
-                else:
-                    outs = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(2)]
-                    run = (lambda x, w, bias, res, outs: (lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs[i % 2])))(x, w, bias, res, outs)
+                run = make_run(M, N, Kd, ys, has_res, relu, 2)
                 run(0)
                 torch.cuda.synchronize(dev)
                 gr = torch.cuda.CUDAGraph()
@@ -539,7 +713,7 @@ def main():
             torch.cuda.synchronize(dev)
             e0.record(); go(); e1.record()
             torch.cuda.synchronize(dev)
-            us = e0.elapsed_time(e1) * 1e3 / (S * 40)
+            us = e0.elapsed_time(e1) * 1e3 / (CS * 40)
             conc_us += us * cnt
             conc_fl += 2.0 * M * N * Kd * cnt
             del graphs
@@ -548,14 +722,22 @@ def main():
     tf_conc = conc_fl / conc_us / 1e6 if conc_us else None
     tf = gemm_fl / gemm_us / 1e6 if gemm_us else 0.0
     tf_dom = 2.0 * dom[1] * dom[2] * dom[3] / dom[4] / 1e6 if dom else 0.0
+    dom_key = None if dom is None else f"{dom[1]},{dom[2]},{dom[3]},{dom[7]},{int(bool(dom[8]))}"
+    try:
+        hbm = hbm_kernel_roofline(dev, args.images, topk_beam, N_BOX, cfgd, peaks)
+    except Exception as ex:
+        print(f"HBM kernel timing skipped: {ex}", file=sys.stderr)
+        hbm = None
+    step_tf = gemm_fl / (ms_dev / args.steps / 1e3) / 1e12
     roofline = {"kernel": "sc_gemm_bf16_kernel (tcgen05/TMEM/TMA; every GEMM launch of one step)", "bound": "tensor", "achieved": tf,
                 "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"],
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant shape, ncu --set full
-                # (profiles/r01b_ncu_full_summary.txt); cold-cache capture, one launch
-                "traffic": NCU_TRAFFIC_DOMINANT_GEMM,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of THE SHAPE REPORTED as dominant, from the committed ncu
+                # capture keyed by shape (profiles/r02_gemm_traffic.json; cold-cache capture, one launch) - null when not captured
+                "traffic": traffic.get(dom_key) if dom_key else None, "traffic_key": dom_key,
                 "peak_source": f"{peaks['src']} MEASURED_PEAKS.json bf16_tflops (burst: shapes timed alone, in-graph)",
                 "achieved_in_flight": tf_conc, "frac_in_flight": (tf_conc / peaks["tf_sus"]) if tf_conc else None,
-                "in_flight_note": f"same shapes, {S} streams concurrently (the timed region's regime), wall time per GEMM; vs sustained peak",
+                "in_flight_note": f"same shapes, {CS} streams concurrently (the timed region's regime), wall time per GEMM; vs sustained peak",
+                "whole_step_tflops": step_tf, "whole_step_frac_of_sustained_peak": step_tf / peaks["tf_sus"],
                 "launches": g["n"], "avg_launch_us": gemm_us / max(1, g["n"]),
                 "algorithmic_gflop_per_step": gemm_fl / 1e9,
                 "dominant_shape": None if dom is None else {"M": dom[1], "N": dom[2], "K": dom[3], "launches": dom[5], "us_per_launch": dom[4],
@@ -563,25 +745,85 @@ def main():
                                                             "hbm_floor_us": dom[6] / (peaks["hbm"] * 1e3)},
                 "share_of_step": g["ms"] / total_ms if total_ms else None,
                 "share_source": "per-launch CUDA events of one un-graphed step (host launch gaps included); the ncu launch list "
-                                "profiles/r01b_infer_launches_summary.txt gives the same share",
-                "kernel_time_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])}}
+                                "profiles/r01c_infer_launches_summary.txt gives the same share",
+                "kernel_time_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])},
+                "hbm_kernels": hbm}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # (rank 0 at N = 1 only; at N > 1 the driver reads it from the N = 1 line)
         # bounded sample of ~10-20 s of CPU work: rate from one 64-image pass, then one pass sized from it
-        v0, _, cores = cpu_arm(1, 1, args.cpu_images)
+        v0, _, cores = cpu_arm(1, 1, args.cpu_images, wl)
         n_img = int(min(1024, max(args.cpu_images, 32 * round(v0 * 12 / 32))))
-        v, spp, cores = cpu_arm(1, 0, n_img)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "seconds": spp,
-               "sample": f"1 x {n_img} images (same model, beam 3, L=16; sized for ~12 s), torch fp32 oracle port of the reference path on host cores"}
+        v, spp, cores = cpu_arm(1, 0, n_img, wl)
+        cpu = {"value": v, "unit": wl["unit"], "cores": cores, "kind": "port", "seconds": spp,
+               "sample": f"1 x {n_img} images (same model, beams {beams}, L={L}; sized for ~12 s), torch fp32 oracle port of the reference path on host cores"}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": wl["metric"], "value": value, "unit": wl["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps, "clocks": sampler.summary(), "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": wl["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "host_features": "fp32 pinned (the reference loader's dtype)"},
+            "e2e_bf16_host": {"value": per_s(ms_e2e16), "unit": wl["unit"], "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h,
+                              "ms_per_step": ms_e2e16 / args.steps, "host_features": "bf16 pinned"},
+            "gpu_launches": launches_per_call * n_timed, "clocks": sampler.summary(), "roofline": roofline,
             "cpu_baseline": cpu, "train": train}
+    print(json.dumps(line), file=out, flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def train_main(args, out, rank, local_rank, world):
+    """--config train: the SMP training arm (BASELINE.json configs[1]) as the line's own metric."""
+    config = {"workload": f"ORT 6x512 supermask (SMP) training, bf16 GEMMs / fp32 master weights + mask logits, {args.train_images} images x 5 "
+                          f"captions per GPU per step, T=17, V=10000, encoder once per image [BASELINE.json configs[1]]",
+              "images_per_gpu_per_step": args.train_images, "captions_per_image": 5, "positions": 17,
+              "sharding": (f"images by rank x{world}; NCCL all-reduce of dWm (the weights' and mask logits' gradients follow from it)"
+                           if world > 1 else "1 GPU"),
+              "l2_policy": "inputs_larger_than_L2 (443 MB of weights + logits, 0.9 GB of saved activations per step vs 126 MB L2)"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_img = min(args.train_images, 10)
+        steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
+        v, spp, cores = cpu_train_arm(steps, warm, n_img)
+        config = dict(config, images_per_gpu_per_step=n_img, sampled_from_images_per_step=args.train_images,
+                      workload=config["workload"] + f" - reference arm: bounded sample of {n_img} images per step")
+        print(json.dumps({"impl": "reference", "metric": "smp_train_images_per_sec", "value": v, "unit": "images/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": warm, "ms_per_step": spp * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                           "sample": f"{steps} x {n_img} images x 5 captions, forward + backward + clip + Adam, torch fp32 autograd over the oracle"},
+                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=out, flush=True)
+        return
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from sparse_caption_b200 import lib
+    lib.load()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    tr = train_arm(args, dev, world, rank, dist_mod=dist, e2e=True)
+    sampler.stop_flag = True
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    sampler.join(timeout=2)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, spp, cores = cpu_train_arm(3, 1, 10)
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "seconds": spp * 3,
+               "sample": "3 x 10 images x 5 captions (forward + backward + clip + Adam), torch fp32 autograd over the oracle port on host cores"}
+    line = {"metric": tr["metric"], "value": tr["value"], "unit": tr["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tr["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config, "e2e": tr["e2e"], "gpu_launches": tr["gpu_launches_per_step"] * args.steps,
+            "clocks": sampler.summary(), "roofline": tr["roofline"], "cpu_baseline": cpu,
+            "train_detail": {k: v for k, v in tr.items() if k not in ("roofline", "e2e")}}
     print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -32,6 +32,7 @@ __host__ __device__ constexpr int num_epilogue_warps(int block_n, int stages) { 
 struct GemmArgs {
   int M, N, K;
   int tiles_n, num_tiles, splits, kb_per_split;  // persistent schedule: unit u -> (tile = u / splits, split = u % splits)
+  int tiles_per_cta;     // host only: > 1 caps the persistent grid at ceil(units / tiles_per_cta) CTAs
   size_t split_stride;   // split-K partial products: split s stores its fp32 tile at y + s * split_stride (0: single output)
   const float* w32;      // kMasked: fp32 weights [N,K]
   const float* mask;     // kMasked: fp32 logits / raw mask / nullptr
@@ -1087,7 +1088,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   // over two tiles (the small configurations still leave room for CTAs of other streams)
   const int per_sm = env_per_sm > 0 ? env_per_sm : 1;
   const int units = a.num_tiles * a.splits;
-  dim3 grid(min(units, per_sm * sm_count()));
+  // a.tiles_per_cta > 1 (throughput regime: several independent GEMM chains in flight): fewer persistent CTAs, each looping
+  // over that many tiles - the barrier / TMEM / tensor-map prologue is paid once and the epilogue of a tile runs under the
+  // main loop of the next (double-buffered accumulators) instead of holding an SM
+  int want = min(units, per_sm * sm_count());
+  if (a.tiles_per_cta > 1 && !a.cluster2) want = min(want, (units + a.tiles_per_cta - 1) / a.tiles_per_cta);
+  dim3 grid(want);
   constexpr int threads = 32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0));
   cudaError_t e;
   if (a.cluster2) {
@@ -1166,7 +1172,13 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   }
   const int sms = sm_count();
   const long mt = (M + 127) / 128;
-  int force_stages = 0, force_splits = 0;
+  int force_stages = 0, force_splits = 0, tiles_per_cta = 0;
+  {
+    static int env_tpc = -1;
+    if (env_tpc < 0) { const char* e = getenv("SC_GEMM_TPC"); env_tpc = e ? atoi(e) : 0; }
+    if (block_n >= 10000000) { tiles_per_cta = block_n / 10000000; block_n %= 10000000; }  // hint: + 10^7 * tiles per CTA
+    else if (env_tpc > 1 && mt <= 24) tiles_per_cta = env_tpc;                                // diagnostic: decode-sized problems
+  }
   if (block_n >= 100000) {  // tuning hook: tile_n = 100000 * splits + 1000 * stages + block_n
     force_splits = block_n / 100000;
     block_n %= 100000;
@@ -1223,6 +1235,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K;
   a.pdl_early = (g_sc_pdl & 4) ? 1 : 0;
+  a.tiles_per_cta = tiles_per_cta;
   a.cluster2 = c2 ? (env_mc >= 2 ? 2 : 1) : 0;  // 1: multicast B, two cta_group::1 MMAs; 2: one cta_group::2 MMA per pair (default)
   a.w32 = masked ? (const float*)w : nullptr;
   a.mask = mask; a.uniforms = uniforms; a.mask_mode = mask_mode;

@@ -808,22 +808,29 @@ class OrtEngine:
     def submit(self, att_feats, boxes, att_masks=None, opt=None, slot=0, out=None, prefetch=False):
         """Enqueue encode + decode of one batch on slot `slot` without waiting.  ``out``: optional pinned host tensors
         (seq int32 [B,b,L], lp fp32 [B,b,L]) that receive the result asynchronously.  Returns (seq, lp) device views
-        that are valid after ``wait(slot)``."""
-        opt = dict(opt or {})
+        that are valid after ``wait(slot)``.  ``opt`` may be a LIST of option dicts: several decodes over ONE encoder pass
+        (SCST: a beam / multinomial rollout plus the greedy baseline, utils/training.py:216-237); ``out`` and the result are
+        then lists."""
+        many = isinstance(opt, (list, tuple))
+        opts = [dict(o or {}) for o in (opt if many else [opt])]
+        outs = out if many else [out]
         cur = torch.cuda.current_stream(self.dev)
         st = self.stream(slot)
         if st is not cur:
             st.wait_stream(cur)
+        res = []
         with torch.cuda.stream(st):
             enc = self.encode(att_feats, boxes, att_masks, slot=slot, prefetch=prefetch)
-            seq, lp = self.decode(enc, opt)
-            if out is not None:
-                out[0].copy_(seq, non_blocking=True)
-                out[1].copy_(lp, non_blocking=True)
+            for i, o in enumerate(opts):
+                seq, lp = self.decode(enc, o)
+                if outs is not None and outs[i] is not None:
+                    outs[i][0].copy_(seq, non_blocking=True)
+                    outs[i][1].copy_(lp, non_blocking=True)
+                res.append((seq, lp))
             ev = torch.cuda.Event()
             ev.record(st)
         self._done[slot] = ev
-        return seq, lp
+        return res if many else res[0]
 
     def wait(self, slot=None, host=False):
         """Make the current stream (or the host when ``host``) wait for slot `slot` (all slots when None)."""
