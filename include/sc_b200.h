@@ -302,6 +302,17 @@ int sc_adam_clip_st(const void* descs, int n_desc, long total_blocks, float* w, 
                     float eps_s, float beta1, float beta2, float clip_value, float grad_scale, int step,
                     const float* sigmoid_grad_coeff, const float* dyn, sc_stream_t stream);
 
+/* CIDEr-D reward of SCST on the device (scst/cider/pyciderevalcap/ciderD/ciderD_scorer.py:133-212 as used by
+ * scst/scorers.py:47-114): one score per hypothesis (word ids [H, L], words = ids before the first <eos>, pads dropped) against
+ * the references of image hyp_img[h].  n-grams (n <= 4, ids < 65536) are exact 64-bit keys (id_j << 16 j).
+ * df_keys ascending with df_log = log(max(1, df)); ref_len = log(#documents); references of image b are
+ * [img_ref_off[b], img_ref_off[b+1]), reference r owns n-gram entries [ref_ng_off[r], ref_ng_off[r+1]) of ref_keys (ascending)
+ * / ref_vec (tf-idf), ref_norm [R,4], ref_length [R] (the scorer's bigram count).  Double precision, reference summation order. */
+int sc_ciderd_score(const int* hyp, int H, int L, const int* hyp_img, int eos, int pad, const unsigned long long* df_keys,
+                    const double* df_log, long n_df, double ref_len, double sigma, const long* img_ref_off, const long* ref_ng_off,
+                    const unsigned long long* ref_keys, const double* ref_vec, const double* ref_norm, const int* ref_length,
+                    double* out, sc_stream_t stream);
+
 /* teacher-forcing attention with saved probabilities + backward (decoder self: causal_T = T; cross: groups = images with
  * S*T query rows; encoder box attention: additive bias): transformer.py:230-295, relation_transformer.py:258-293 */
 int sc_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int dtype, const float* key_valid,
