@@ -84,6 +84,13 @@ int sc_csr_spmm(const void* x, int dtype, const int* row_ptr, const unsigned sho
  * x bf16: entries uint32 = (column << 16) | bf16 bits; x fp32: entries {uint32 column, fp32 value}.  K <= 6400. */
 int sc_sell_spmm(const void* x, int dtype, const int* slab_ptr, const void* entries, const float* bias,
                  const float* residual, void* y, int y_dtype, int M, int N, int K, int relu, sc_stream_t stream);
+/* K3b'' - the same product on the TENSOR CORES by gather (bf16 x [M, ldx], fp32 accumulate): per K chunk of 512 columns and group of
+ * 8 output features, grp_ptr [chunks][groups + 1] points at 16-entry MMA steps of words (col_in_chunk << 19) | (feature_in_group
+ * << 16) | bf16 bits (zero-valued padding words allowed).  The x slab is staged transposed in shared memory; ldmatrix gathers the
+ * columns of a step as the A operand, the B operand (one non-zero per k slot) is built in registers.  Roofline: shared-memory
+ * bandwidth, nnz x M x 2 bytes. */
+int sc_gspmm(const void* x, int ldx, const int* grp_ptr, const void* entries, const float* bias, const float* residual, void* y,
+             int y_dtype, int M, int N, int K, int relu, sc_stream_t stream);
 
 /* K9 — LayerNorm a*(x-mean)/(std_unbiased+eps)+b (models/transformer.py:329-341).  x fp32 [rows,D]. */
 int sc_layernorm(const float* x, const float* a, const float* b, void* y, int y_dtype, int rows, int D, float eps,

@@ -79,9 +79,14 @@ class _Lin:
         # ("K3a vs K3b"); its X tile [K][8] fp32 must fit in shared memory
         use_sell = (backend == "sell" or (backend == "auto" and self.sparsity >= csr_threshold)) and self.K * 32 <= 200 * 1024 \
             and self.K % 8 == 0
+        # "gs": gather SpMM on the tensor cores (sc_gspmm, bf16); "auto": from `csr_threshold` sparsity up (measured winner table:
+        # DESIGN.md "K3a vs K3b")
+        use_gs = (backend == "gs" or (backend == "auto" and self.sparsity >= csr_threshold)) and adt == torch.bfloat16 and self.K % 8 == 0
+        use_sell = use_sell and not use_gs
         self.csr = K.CsrWeight(w, adt) if use_csr else None
         self.sell = K.SellWeight(w, adt) if use_sell else None
-        use_csr = use_csr or use_sell  # "not on the dense path"
+        self.gs = K.GsWeight(w) if use_gs else None
+        use_csr = use_csr or use_sell or use_gs  # "not on the dense path"
         self.w = None
         if not use_csr:
             self.w = K.cast_bf16(w) if adt == torch.bfloat16 else w
@@ -101,6 +106,8 @@ class _Lin:
         return K.linear_ln(x, self.w, self.bias, residual=residual, relu=relu, out=out, out_bf16=out_bf16, stats_out=stats)
 
     def __call__(self, x, out, residual=None, relu=False):
+        if self.gs is not None:
+            return K.gspmm(x, self.gs, self.bias, residual=residual, relu=relu, out=out)
         if self.sell is not None:
             return K.sell_spmm(x, self.sell, self.bias, residual=residual, relu=relu, out=out)
         if self.csr is not None:

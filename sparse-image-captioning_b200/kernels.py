@@ -168,6 +168,91 @@ def sell_spmm(x, sw, bias=None, *, residual=None, relu=False, out=None, out_dtyp
     return out
 
 
+class GsWeight:
+    """Gather-SpMM form of a pruned [N, K] weight for sc_gspmm (tensor-core SpMM, bf16): per K chunk of 512 columns and per
+    group of 8 output features, the group's non-zeros as 32-bit words ``(col_in_chunk << 19) | (feature_in_group << 16) | bf16
+    bits``, padded with zero-valued words to a multiple of 16 (one m16n8k16 MMA step).  Inside a step the two octets are
+    ordered so that their columns differ mod 8 wherever the group's columns allow it: the eight ldmatrix row pointers of an
+    octet then fall into eight different shared-memory bank groups.  Built once from the dense (already masked) tensor or the
+    reference's COO ``to_sparse()`` tensors (pruning/prune.py:200-221)."""
+
+    KC = 512
+
+    def __init__(self, w):
+        import numpy as np
+        if w.is_sparse:
+            w = w.to_dense()
+        dev = w.device
+        wn = w.detach().float().cpu()
+        N, K = wn.shape
+        assert K % 8 == 0
+        bits_all = (wn.to(torch.bfloat16).view(torch.int16).to(torch.int32) & 0xFFFF).numpy()
+        nzmask = (wn != 0).numpy()
+        ngroups, nchunks = (N + 7) // 8, (K + self.KC - 1) // self.KC
+        ptr = np.zeros((nchunks, ngroups + 1), dtype=np.int32)
+        words, off = [], 0
+        for c in range(nchunks):
+            k0, k1 = c * self.KC, min(K, (c + 1) * self.KC)
+            for g in range(ngroups):
+                ptr[c, g] = off
+                sub = nzmask[g * 8: (g + 1) * 8, k0:k1]
+                f, col = np.nonzero(sub)
+                if f.size:
+                    val = bits_all[g * 8 + f, k0 + col]
+                    ent = ((col.astype(np.int64) << 19) | (f.astype(np.int64) << 16) | val.astype(np.int64))
+                    ent = self._order(ent, col)
+                    words.append(ent)
+                    off += ent.size
+            ptr[c, ngroups] = off
+        ent = np.concatenate(words) if words else np.zeros(16, dtype=np.int64)
+        ent = np.where(ent >= (1 << 31), ent - (1 << 32), ent).astype(np.int32)
+        self.entries = torch.from_numpy(ent).to(dev).contiguous()
+        self.grp_ptr = torch.from_numpy(ptr.reshape(-1)).to(dev).contiguous()
+        self.shape = (N, K)
+        self.nnz = int(nzmask.sum())
+        self.padded = int(off)
+
+    @staticmethod
+    def _order(ent, col):
+        """Entries of one (chunk, group) -> ceil(n / 8) octets (no octet of padding is ever added: shared-memory traffic is the
+        kernel's bound) with the columns of every residue class mod 8 spread evenly over the octets, so that as few ldmatrix
+        phases as the column set allows see two rows in one bank group; the tail is padded with zero-valued words to 16."""
+        import numpy as np
+        n = ent.size
+        n_oct = (n + 7) // 8
+        octets = [[] for _ in range(n_oct)]
+        per_res = [[0] * 8 for _ in range(n_oct)]
+        res = (col & 7)
+        for r in sorted(range(8), key=lambda r: -int((res == r).sum())):
+            for e in ent[res == r]:
+                k = min((o for o in range(n_oct) if len(octets[o]) < 8), key=lambda o: (per_res[o][r], len(octets[o])))
+                octets[k].append(int(e))
+                per_res[k][r] += 1
+        out = []
+        for o in range(n_oct):
+            free = [r for r in range(8) if per_res[o][r] == 0]
+            while len(octets[o]) < 8:
+                octets[o].append((free.pop() if free else 0) << 19)   # zero-valued padding word (column r < 8 of the chunk)
+            out += octets[o]
+        if len(out) % 16:
+            out += [r << 19 for r in range(8)]
+        return np.array(out, dtype=np.int64)
+
+
+def gspmm(x, gw, bias=None, *, residual=None, relu=False, out=None, out_dtype=None):
+    """y = act(x W^T + b) + residual with W in gather-SpMM form (sc_gspmm: mma.sync over gathered activation columns)."""
+    M, K = x.shape
+    N = gw.shape[0]
+    assert gw.shape[1] == K and x.dtype == torch.bfloat16 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype or torch.float32)
+    _chk(out, "out")
+    lib.call("sc_gspmm", lib.ptr(x), x.stride(0), lib.ptr(gw.grp_ptr), lib.ptr(gw.entries), lib.ptr(bias), lib.ptr(residual),
+             lib.ptr(out), lib.dtype_code(out.dtype), M, N, K, int(relu), lib.stream(),
+             meta=("gspmm", M, N, K, 2, gw.nnz, out.element_size()))
+    return out
+
+
 def ingest_f32_bf16(host_pinned, out, ctas=0):
     """out (device bf16) = cast(host_pinned fp32): the kernel reads the pinned host tensor over PCIe itself (sc_ingest_f32_bf16)."""
     assert host_pinned.device.type == "cpu" and host_pinned.is_pinned() and host_pinned.dtype == torch.float32 and host_pinned.is_contiguous()

@@ -22,6 +22,7 @@ SIGNATURES = {
     "sc_set_pdl": [_i],
     "sc_csr_spmm": [_p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "sc_sell_spmm": [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "sc_gspmm": [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "sc_layernorm": [_p, _p, _p, _p, _i, _i, _i, _f, _p],
     "sc_embed_pe": [_p, _p, _p, _i, _p, _u64, _u64, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p],
     "sc_embed_pe_stats": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],

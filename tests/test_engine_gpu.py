@@ -53,7 +53,7 @@ def _medium(seed=0, **kw):
     return cfg, ocfg, sd
 
 
-@pytest.mark.parametrize("backend", ["dense", "csr", "sell"])
+@pytest.mark.parametrize("backend", ["dense", "csr", "sell", "gs"])
 def test_bf16_engine_close_to_oracle(backend):
     """bf16 tensor-core path vs fp32 CPU oracle: greedy step-0 log-probs within 2e-2, captions mostly identical."""
     cfg, ocfg, sd = _medium()

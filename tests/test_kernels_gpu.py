@@ -387,6 +387,37 @@ def test_sell_spmm(K, dt, shape):
     assert rel_err(y2, torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double())) < 2e-5
 
 
+@pytest.mark.parametrize("shape", [(1536, 512, 512, 0.95), (100, 771, 512, 0.99), (300, 512, 2048, 0.9), (20, 64, 96, 0.5),
+                                   (130, 10000, 512, 0.95), (2560, 2048, 512, 0.991), (257, 512, 1024, 0.8)])
+def test_gspmm(K, shape):
+    """Gather SpMM on the tensor cores (K3b''): ragged feature groups, an empty feature row, N not a multiple of 8, M not a
+    multiple of the 128-row slab, K chunks (K > 512) with accumulators carried across them, x with a leading dimension > K;
+    bf16 operands, fp32 accumulation -> 2e-5 against the fp64 product of the same bf16 values."""
+    M, N, Kd, sp = shape
+    x, w, s, u, b, r = _mk(M, N, Kd, seed=4)
+    w = w * (torch.rand(N, Kd) >= sp)
+    w[min(3, N - 1)] = 0  # an empty row
+    dev = "cuda"
+    dt = torch.bfloat16
+    gw = K.GsWeight(w.to(dt).float().to(dev))
+    assert gw.nnz == int((w.to(dt) != 0).sum()) and gw.padded % 16 == 0
+    xb = x.to(dt).to(dev)
+    ref0 = torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double(), b.double())
+    for out_dt in (torch.float32, torch.bfloat16):
+        y = K.gspmm(xb, gw, b.to(dev), residual=r.to(dev), relu=True, out_dtype=out_dt)
+        assert rel_err(y.float(), torch.relu(ref0) + r.double()) < (2e-5 if out_dt == torch.float32 else 1e-2)
+    y2 = K.gspmm(xb, gw, None)
+    assert rel_err(y2, torch.nn.functional.linear(x.to(dt).double(), w.to(dt).double())) < 2e-5
+    # activations inside a wider buffer (the fused q|k|v projection output): leading dimension 2 * K
+    wide = torch.zeros(M, 2 * Kd, device=dev, dtype=dt)
+    wide[:, Kd:] = xb
+    y3 = K.gspmm(wide[:, Kd:], gw, b.to(dev))
+    assert rel_err(y3, ref0) < 2e-5
+    # the COO tensors of state_dict_sparse pack to the same words
+    gw2 = K.GsWeight(w.to(dt).float().to_sparse().to(dev))
+    assert torch.equal(gw2.entries, gw.entries) and torch.equal(gw2.grp_ptr, gw.grp_ptr)
+
+
 def _beam_ref(logits, B, beam, V, L, eos, opt):
     """Drive oracle.beam_select + the bookkeeping of oracle.beam_search on a fixed logits sequence."""
     pen = O.length_penalty(opt.get("length_penalty", ""))
