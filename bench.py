@@ -439,6 +439,9 @@ def main():
                          "GEMMs of G batches run as one M = G x rows GEMM); a timed step stays one batch of --images.  0 = the largest of "
                          "5 / 4 / 2 that divides --steps (measured: scripts/gpu_dec_ab4.sh)")
     ap.add_argument("--slots", type=int, default=0, help="device launches in flight (pipeline slots: stream + workspaces + graphs each); 0 = auto")
+    ap.add_argument("--e2e-coalesce", type=int, default=0, help="--coalesce of the end-to-end arm (0 = 2 when --steps is even: smaller device batches "
+                         "start their H2D copies earlier, so the pipeline of copy -> encode -> decode fills faster)")
+    ap.add_argument("--e2e-slots", type=int, default=0, help="--slots of the end-to-end arm (0 = auto)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -571,36 +574,45 @@ def main():
     ms_dev = e0.elapsed_time(e1)
 
     # ---------------- end-to-end arm: pinned host inputs -> tokens on the host ----------------
-    outs = [[(torch.empty(B, max(b, 1), L, dtype=torch.int32).pin_memory(), torch.empty(B, max(b, 1), L, dtype=torch.float32).pin_memory())
-             for b in beams] for _ in slots]
+    # its own batching: a launch cannot start before its H2D copy, so smaller coalesced batches on more slots fill the
+    # copy -> encode -> decode pipeline sooner (measured: scripts/gpu_dec_ab4.sh)
+    Ge = args.e2e_coalesce if args.e2e_coalesce > 0 else (2 if args.steps % 2 == 0 else 1)
+    assert args.steps % Ge == 0, "--steps must be a multiple of --e2e-coalesce"
+    ne_timed = args.steps // Ge
+    Se = args.e2e_slots if args.e2e_slots > 0 else next((sl for sl in (5, 4, 3, 2) if ne_timed % sl == 0), min(4, ne_timed))
+    Be = args.images * Ge
+    eslots = list(range(101, 101 + Se))
+    ehost = [(a[:Be], b[:Be]) for a, b in host] if Be <= B else [synthetic.synthetic_inputs(Be, N_BOX, F, seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
+    outs = [[(torch.empty(Be, max(b, 1), L, dtype=torch.int32).pin_memory(), torch.empty(Be, max(b, 1), L, dtype=torch.float32).pin_memory())
+             for b in beams] for _ in eslots]
 
     def e2e_run(batches):
         def e2e_step(i):
             att, boxes = batches[i & 1]
-            k = i % S
-            eng.submit(att, boxes, None, opts, slot=slots[k], out=outs[k], prefetch=args.prefetch)
-        for i in range(max(n_warm, S)):  # every slot's host-input path (its own workspaces / graphs) is warm
+            k = i % Se
+            eng.submit(att, boxes, None, opts, slot=eslots[k], out=outs[k], prefetch=args.prefetch)
+        for i in range(max(-(-args.warmup // Ge), Se)):  # every slot's host-input path (its own workspaces / graphs) is warm
             e2e_step(i)
         eng.wait()
         barrier()
         e0.record()
-        for i in range(n_timed):
+        for i in range(ne_timed):
             e2e_step(i)
         eng.wait()
         e1.record()
         barrier()
         return e0.elapsed_time(e1)
 
-    ms_e2e = e2e_run(host)
+    ms_e2e = e2e_run(ehost)
     # the same with bf16 pinned host features (half the H2D bytes; the engine lands them directly in the GEMM operand buffer)
-    host16 = [(a.to(torch.bfloat16).pin_memory(), b) for a, b in host]
+    host16 = [(a.to(torch.bfloat16).pin_memory(), b) for a, b in ehost]
     ms_e2e16 = e2e_run(host16)
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
-    h2d = (host[0][0].numel() * 4 + host[0][1].numel() * 4) // G   # per step of --images
-    h2d16 = (host[0][0].numel() * 2 + host[0][1].numel() * 4) // G
-    d2h = sum(o[0].numel() * 4 + o[1].numel() * 4 for o in outs[0]) // G
+    h2d = (ehost[0][0].numel() * 4 + ehost[0][1].numel() * 4) // Ge   # per step of --images
+    h2d16 = (ehost[0][0].numel() * 2 + ehost[0][1].numel() * 4) // Ge
+    d2h = sum(o[0].numel() * 4 + o[1].numel() * 4 for o in outs[0]) // Ge
     del host16
 
     t = torch.tensor([ms_dev, ms_e2e, ms_e2e16], device=dev, dtype=torch.float64)
@@ -762,7 +774,8 @@ def main():
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": wl["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "host_features": "fp32 pinned (the reference loader's dtype)"},
+                    "ms_per_step": ms_e2e / args.steps, "host_features": "fp32 pinned (the reference loader's dtype)",
+                    "coalesced_batches_per_launch": Ge, "launches_in_flight": Se},
             "e2e_bf16_host": {"value": per_s(ms_e2e16), "unit": wl["unit"], "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h,
                               "ms_per_step": ms_e2e16 / args.steps, "host_features": "bf16 pinned"},
             "gpu_launches": launches_per_call * n_timed, "clocks": sampler.summary(), "roofline": roofline,
