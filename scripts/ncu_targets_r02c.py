@@ -1,0 +1,50 @@
+"""ncu targets (round 2, session c): one warm launch each of the kernels under work, at the coalesced device batch
+(2560 images, beam 3): fused generator GEMM, the o-shaped residual GEMM, cross-attention step, encoder attention, box bias."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import sparse_caption_b200.kernels as K
+from sparse_caption_b200 import lib
+lib.load()
+dev = "cuda"
+B, beam, N, d, h, V, ff = 2560, 3, 36, 512, 8, 10000, 2048
+R = B * beam
+bf = dict(device=dev, dtype=torch.bfloat16)
+which = set((os.environ.get("SC_TARGETS") or "topk,o,cross,enc,box,ff2,self").split(","))
+reps = int(os.environ.get("SC_REPS", "1"))
+if "topk" in which:
+    xn = torch.randn(R, d, **bf); wg = torch.randn(V, d, **bf); bg = torch.randn(V, device=dev)
+    part = torch.empty(R, K.linear_topk_parts(V), 12, device=dev)
+    for _ in range(reps):
+        K.linear_topk(xn, wg, bg, part, candidates=beam)
+if "o" in which:
+    x = torch.randn(R, d, **bf); w = torch.randn(d, d, **bf); b = torch.randn(d, device=dev); x32 = torch.randn(R, d, device=dev)
+    for hint in (20003256, 3256):
+        for _ in range(reps):
+            K.linear(x, w, b, residual=x32, out=x32, tile_n=hint)
+if "ff2" in which:
+    x = torch.randn(R, ff, **bf); w = torch.randn(d, ff, **bf); b = torch.randn(d, device=dev); x32 = torch.randn(R, d, device=dev)
+    for _ in range(reps):
+        K.linear(x, w, b, residual=x32, out=x32, tile_n=20003256)
+if "cross" in which:
+    qc = torch.randn(R, d, **bf); mkv = torch.randn(B * N, 2 * d, **bf); att = torch.empty(R, d, **bf)
+    for _ in range(reps):
+        K.cross_attn_step(qc, mkv[:, 0:], mkv[:, d:], None, att, B=B, beam=beam, N=N, D=d, h=h, ldq=d, ldm=2 * d, ldo=d)
+if "self" in which:
+    L = 16
+    qkv = torch.randn(R, 3 * d, **bf); ck = torch.randn(L, R, d, **bf); cv = torch.randn(L, R, d, **bf); att = torch.empty(R, d, **bf)
+    anc = torch.arange(R, device=dev, dtype=torch.int32).unsqueeze(1).expand(R, L).contiguous()
+    for _ in range(reps):
+        K.self_attn_step(qkv[:, 0:], qkv[:, d:], qkv[:, 2 * d:], ck, cv, anc, att, R=R, D=d, h=h, n_prev=8, write_slot=8, ldq=3 * d, ldk=3 * d,
+                         ldv=3 * d, ldo=d, anc_ld=L, slot_div=1)
+if "enc" in which or "box" in which:
+    boxes = torch.rand(B, N, 4, device=dev); boxes[..., 2:] += boxes[..., :2]
+    wgw = torch.randn(6 * h, 64, device=dev) * 0.1; wgb = torch.rand(6 * h, device=dev)
+    bias = torch.empty(6, B, h, N, N, device=dev)
+    for _ in range(reps):
+        K.box_bias_all(boxes, wgw, wgb, bias, B=B, N=N, layers=6, h=h)
+    qkv = torch.randn(B * N, 3 * d, **bf); out = torch.empty(B * N, d, **bf)
+    if "enc" in which:
+        for _ in range(reps):
+            K.bias_attention(qkv[:, 0:], qkv[:, d:], qkv[:, 2 * d:], bias[0], None, out, B=B, N=N, h=h, dk=64, ldq=3 * d, ldk=3 * d, ldv=3 * d, ldo=d)
+torch.cuda.synchronize()

@@ -62,6 +62,7 @@ struct GemmArgs {
   // dX GEMM that prepares the NEXT linear's gradient operand (kEpi == 4, bf16 output, no residual): y = acc * hscale where
   // the saved post-ReLU/dropout activation hmask[row, col] != 0, else 0; colsum[col] += column sums of the bf16 values
   const __nv_bfloat16* hmask; float hscale; float* colsum;
+  int dbg;  // diagnostics (SC_GEMM_DBG): 1 = top-k epilogue without the insertion, 2 = without the exp-sum as well
 };
 
 constexpr int kTopK = 5;                 // candidates kept per record (beam sizes up to 5 use the fused path)
@@ -204,6 +205,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// two chunks in flight before one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, uint32_t (&v)[32], uint32_t tb, uint32_t (&w)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]),
+        "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]),
+        "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]),
+        "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+      : "r"(tb));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
@@ -407,6 +431,132 @@ __device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, 
   }
 }
 
+// ---- kEpi == 3 / 5: generator GEMM fused with the beam step's row pass ----------------------------------------------------
+// Per thread (= accumulator row) and chunk of 32 columns: running max, sum exp(x - max) (log2 domain: FFMA + MUFU.EX2 + FADD per
+// element) and the kTK largest (value, column) pairs by a branch-free sorted insertion (a divergent `if (candidate)` ran for
+// nearly every element: some lane of the 32 independent rows always had one).  The insertion is 3 FSETP + 10 SEL per element on
+// the half-rate ALU pipe and a serial chain through the kTK slots: the thread therefore runs TWO independent chains (chunk pairs)
+// whose instructions interleave, and merges them once per tile.
+template <int kTK>
+struct TopkState {
+  float m, s;
+  float v[kTK];
+  int i[kTK];
+  __device__ __forceinline__ void init() {
+    m = -INFINITY; s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kTK; ++k) { v[k] = -INFINITY; i[k] = 0x7fffffff; }
+  }
+  // columns arrive in ascending order: strict '>' keeps the earlier (smaller) column on ties
+  __device__ __forceinline__ void insert(float x, int col) {
+    bool pgt[kTK];
+#pragma unroll
+    for (int k = 0; k < kTK; ++k) pgt[k] = x > v[k];
+#pragma unroll
+    for (int k = kTK - 1; k >= 1; --k) {
+      v[k] = pgt[k - 1] ? v[k - 1] : (pgt[k] ? x : v[k]);
+      i[k] = pgt[k - 1] ? i[k - 1] : (pgt[k] ? col : i[k]);
+    }
+    v[0] = pgt[0] ? x : v[0];
+    i[0] = pgt[0] ? col : i[0];
+  }
+  // any column order (merging the second chain): equal values rank by the smaller column
+  __device__ __forceinline__ void insert_any(float x, int col) {
+    bool pgt[kTK];
+#pragma unroll
+    for (int k = 0; k < kTK; ++k) pgt[k] = x > v[k] || (x == v[k] && col < i[k]);
+#pragma unroll
+    for (int k = kTK - 1; k >= 1; --k) {
+      v[k] = pgt[k - 1] ? v[k - 1] : (pgt[k] ? x : v[k]);
+      i[k] = pgt[k - 1] ? i[k - 1] : (pgt[k] ? col : i[k]);
+    }
+    v[0] = pgt[0] ? x : v[0];
+    i[0] = pgt[0] ? col : i[0];
+  }
+};
+
+__device__ __forceinline__ float max32(const float (&f)[32]) {
+  float c[4] = {f[0], f[1], f[2], f[3]};
+#pragma unroll
+  for (int j = 4; j < 32; ++j) c[j & 3] = fmaxf(c[j & 3], f[j]);
+  return fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one chunk (kTwo: two chunks, instruction streams interleaved) of 32 accumulator columns + bias into the running statistics
+template <int kTK, bool kTwo>
+__device__ __forceinline__ void topk_absorb(TopkState<kTK>& A, float (&fa)[32], int cola, const float* ba, TopkState<kTK>& B,
+                                            float (&fb)[32], int colb, const float* bb, int N, int dbg) {
+  constexpr float kL2E = 1.4426950408889634f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 x = *(const float4*)(ba + 4 * j);
+    fa[4 * j] += x.x; fa[4 * j + 1] += x.y; fa[4 * j + 2] += x.z; fa[4 * j + 3] += x.w;
+    if (kTwo) {
+      const float4 y = *(const float4*)(bb + 4 * j);
+      fb[4 * j] += y.x; fb[4 * j + 1] += y.y; fb[4 * j + 2] += y.z; fb[4 * j + 3] += y.w;
+    }
+  }
+  if (cola + 32 > N) {  // warp-uniform: only the tail chunk of the last N tile has columns to blank
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (cola + j >= N) fa[j] = -INFINITY;
+  }
+  if (kTwo && colb + 32 > N) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (colb + j >= N) fb[j] = -INFINITY;
+  }
+  const float cma = max32(fa);
+  if (cma > A.m) { A.s *= __expf(A.m - cma); A.m = cma; }  // first chunk: 0 * exp(-inf) = 0
+  const float nma = -A.m * kL2E;
+  float nmb = 0.f;
+  if (kTwo) {
+    const float cmb = max32(fb);
+    if (cmb > B.m) { B.s *= __expf(B.m - cmb); B.m = cmb; }
+    nmb = -B.m * kL2E;
+  }
+  float pa[4] = {0.f, 0.f, 0.f, 0.f}, pb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (dbg >= 2) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    pa[j & 3] += ex2_approx(fmaf(fa[j], kL2E, nma));
+    if (kTwo) pb[j & 3] += ex2_approx(fmaf(fb[j], kL2E, nmb));
+  }
+  A.s += (pa[0] + pa[1]) + (pa[2] + pa[3]);
+  if (kTwo) B.s += (pb[0] + pb[1]) + (pb[2] + pb[3]);
+  if (dbg >= 1) return;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    A.insert(fa[j], cola + j);
+    if (kTwo) B.insert(fb[j], colb + j);
+  }
+}
+
+// The fp32 residual chunk (32 columns x 32 rows of one epilogue warp) in the COALESCED mapping: lane = 16-byte piece (lane & 7) of
+// rows (lane >> 3) + 4 i.  Requested one chunk ahead of its use (the first one before the accumulator is awaited): the global
+// latency (an L2 / HBM round trip per chunk, 4-8 chunks per tile) used to sit between every tcgen05.ld and its stores.
+__device__ __forceinline__ void load_residual8(const GemmArgs& args, int rbase, int lane, int col, float4 (&r)[8]) {
+  const bool vec = (args.N & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int row = rbase + i * 4 + (lane >> 3);
+    if (row < args.M && col < args.N) {
+      const float* rp = args.residual + (size_t)row * args.N + col;  // plain loads: written by the predecessor
+      if (vec) r[i] = *(const float4*)rp;
+      else {
+        r[i].x = rp[0];
+        if (col + 1 < args.N) r[i].y = rp[1];
+        if (col + 2 < args.N) r[i].z = rp[2];
+        if (col + 3 < args.N) r[i].w = rp[3];
+      }
+    }
+  }
+}
+
 // Persistent kernel: CTA c processes work units c, c + gridDim.x, ...  (unit = output tile x K split; N-tiles of one
 // M block are adjacent units so that concurrently running CTAs share the A tile through L2).  The accumulator is
 // double-buffered in TMEM (2 x BLOCK_N columns): the epilogue of unit i overlaps the TMA/MMA main loop of unit i+1.
@@ -415,7 +565,10 @@ __device__ __forceinline__ void epilogue_wgrad4(const GemmArgs& args, float4 f, 
 // kMN: both operands are given transposed ([K, M] and [K, N] row-major, i.e. MN-major tiles): y = x^T w.
 // kPair: CTA-pair variant (launched as clusters of 2 with args.cluster2 == 2).  A separate instantiation: a kernel that contains
 // cta_group::2 instructions cannot be launched without a cluster.
-template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false, bool kPair = false>
+// kResCo: the coalesced fp32-residual epilogue of the 8-epilogue-warp configurations is compiled in (launched when there IS a
+// residual).  A separate instantiation because its register footprint (a prefetched residual chunk + two base pointers live
+// across the chunk loop) cost the residual-free epilogues of the same kernel 13-15 % (same-box A/B, decode GEMMs).
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false, bool kPair = false, bool kResCo = false>
 __global__ void __launch_bounds__(32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0)),
                                   (!kMasked && kEpi != 2 && num_epilogue_warps(BLOCK_N, kStages) == 4) ? 2 : 1)
 sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmArgs args) {
@@ -639,26 +792,81 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
+      // coalesced-path residual, software-pipelined one chunk ahead (see load_residual8)
+      constexpr bool kPipeRes = !kDirect && kEpi != 2 && kResCo;
+      const bool pipe_res = kPipeRes && args.residual != nullptr;
+      float4 rnext[kPipeRes ? 8 : 1];
+      // fast tile: the warp's 32 rows and the whole N tile lie inside the matrix, rows are 16-byte aligned, plain fp32 output -
+      // every chunk is straight-line code from two per-lane base pointers (the generic path spends ~700 instructions per 32 x 32
+      // chunk on bounds checks, dtype branches and 64-bit address arithmetic for 64 useful FADDs: it made the fp32-residual
+      // epilogue, not the MMAs, the long pole of the N = d_model GEMMs)
+      const bool fast_tile = pipe_res && !args.y_bf16 && !(kEpi == 1 && args.y2) && (args.N & 3) == 0 && rbase + 32 <= args.M &&
+                             n0 + BLOCK_N <= args.N;
+      const size_t lane_off = (size_t)(rbase + (lane >> 3)) * args.N + n0 + (lane & 7) * 4;
+      const size_t row4 = (size_t)4 * args.N;  // this lane's next row (4 rows down)
+      const float* res_lane = args.residual + lane_off;
+      float* y_lane = (float*)args.y + (size_t)split * args.split_stride + lane_off;
+      if constexpr (kPipeRes) {
+        if (fast_tile) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rnext[i] = *(const float4*)(res_lane + half * 32 + i * row4);
+        } else if (pipe_res && rbase < args.M && n0 + half * 32 < args.N) {
+          load_residual8(args, rbase, lane, n0 + half * 32 + (lane & 7) * 4, rnext);
+        }
+      }
       mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
       if (kPrefetchRes) asm volatile("cp.async.wait_group 0;" ::: "memory");
       // kEpi == 3 / 5: running log-sum-exp statistics and top-kTK (5 / 3) of this thread's row over the warp's chunks of the
-      // tile.  The insertion is warp-divergent (it runs whenever ANY lane has a new candidate, i.e. for most elements), so
-      // the depth matters: beam <= 3 uses the top-3 variant.
+      // tile (beam <= 3 uses the top-3 variant: the depth of the insertion is what the epilogue costs)
       constexpr bool kTopkEpi = (kEpi == 3 || kEpi == 5);
       constexpr int kTK = (kEpi == 5) ? 3 : kTopK;
-      float tk_m = -INFINITY, tk_s = 0.f;
-      float tk_v[kTopkEpi ? kTK : 1];
-      int tk_i[kTopkEpi ? kTK : 1];
       if constexpr (kTopkEpi) {
+        TopkState<kTK> sa, sb2;
+        sa.init(); sb2.init();
+        if (rbase < args.M) {
+#pragma unroll 1
+          for (int c = half; c < BLOCK_N / 32; c += 2 * kChunkStep) {
+            const int cola = n0 + c * 32, colb = cola + kChunkStep * 32;
+            if (cola >= args.N) break;  // warp-uniform
+            const uint32_t ta_ = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32);
+            uint32_t va[32];
+            float fa[32], fb[32];
+            if (c + kChunkStep < BLOCK_N / 32 && colb < args.N) {
+              uint32_t vb[32];
+              tmem_ld32x2(ta_, va, ta_ + (uint32_t)(kChunkStep * 32), vb);
 #pragma unroll
-        for (int i = 0; i < kTK; ++i) { tk_v[i] = -INFINITY; tk_i[i] = 0x7fffffff; }
+              for (int j = 0; j < 32; ++j) { fa[j] = __uint_as_float(va[j]); fb[j] = __uint_as_float(vb[j]); }
+              topk_absorb<kTK, true>(sa, fa, cola, sbias + c * 32, sb2, fb, colb, sbias + (c + kChunkStep) * 32, args.N, args.dbg);
+            } else {
+              tmem_ld32(ta_, va);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) fa[j] = __uint_as_float(va[j]);
+              topk_absorb<kTK, false>(sa, fa, cola, sbias + c * 32, sb2, fb, colb, sbias, args.N, args.dbg);
+            }
+          }
+          // merge the second chain (its columns interleave with the first one's: full (value, column) order)
+          const float mm = fmaxf(sa.m, sb2.m);
+          if (mm > -INFINITY) sa.s = sa.s * __expf(sa.m - mm) + sb2.s * __expf(sb2.m - mm);
+          sa.m = mm;
+#pragma unroll
+          for (int k = 0; k < kTK; ++k) sa.insert_any(sb2.v[k], sb2.i[k]);
+        }
+        if (rbase + lane < args.M) {
+          float* rec = args.topk_part + ((size_t)(rbase + lane) * (args.tiles_n * kChunkStep) + (size_t)(tile % args.tiles_n) * kChunkStep + half) * kTopKRec;
+          rec[0] = sa.m; rec[1] = sa.s;
+#pragma unroll
+          for (int k = 0; k < kTopK; ++k) {
+            rec[2 + k] = k < kTK ? sa.v[k < kTK ? k : 0] : -INFINITY;
+            rec[2 + kTopK + k] = __int_as_float(k < kTK ? sa.i[k < kTK ? k : 0] : 0x7fffffff);
+          }
+        }
       }
 #pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += kChunkStep) {
+      for (int c = half; c < (kTopkEpi ? 0 : BLOCK_N / 32); c += kChunkStep) {
         const int col0 = n0 + c * 32;
         if (col0 >= args.N || rbase >= args.M) continue;  // warp-uniform
-        if (kDirect || (kEpi != 2 && args.residual == nullptr)) {
+        if (kDirect || (kEpi != 2 && (!kResCo || args.residual == nullptr))) {
           // (the throughput configurations only take the transposed path below for fp32 residual streams: without a
           // residual to read, storing the row straight from registers measured faster)
           const int row = rbase + lane;
@@ -736,38 +944,6 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               }
             }
           }
-          if constexpr (kTopkEpi) {
-            // columns are visited in ascending order: strict '>' keeps the smaller column on ties
-            float cm = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j >= args.N) f[j] = -INFINITY;
-              cm = fmaxf(cm, f[j]);
-            }
-            if (cm > tk_m) { tk_s *= __expf(tk_m - cm); tk_m = cm; }  // first chunk: 0 * exp(-inf) = 0
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              tk_s += __expf(f[j] - tk_m);
-              // branch-free sorted insertion (a divergent `if (new candidate)` ran for almost every element: some lane of the
-              // warp always had one): slot i takes the old slot i-1 when the value beats that one, else the value itself
-              // when it beats slot i; strict '>' keeps the earlier (smaller) column on ties
-              {
-                const float v = f[j];
-                const int cidx = col0 + j;
-                bool pgt[kTK];
-#pragma unroll
-                for (int i = 0; i < kTK; ++i) pgt[i] = v > tk_v[i];
-#pragma unroll
-                for (int i = kTK - 1; i >= 1; --i) {
-                  tk_v[i] = pgt[i - 1] ? tk_v[i - 1] : (pgt[i] ? v : tk_v[i]);
-                  tk_i[i] = pgt[i - 1] ? tk_i[i - 1] : (pgt[i] ? cidx : tk_i[i]);
-                }
-                tk_v[0] = pgt[0] ? v : tk_v[0];
-                tk_i[0] = pgt[0] ? cidx : tk_i[0];
-              }
-            }
-            continue;
-          }
           if constexpr (!kDirect) {
             // bf16 output of the throughput configurations: the thread's 64-byte row piece goes through the warp's staging
             // tile (16-byte pieces XOR-swizzled by row pair) so that one store instruction writes 8 rows x 64 contiguous
@@ -820,25 +996,49 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // coalesced mapping: lane handles 16-byte piece (lane & 7) of rows (lane >> 3) + 4 i, i = 0..7
         const int pj = lane & 7;
         const int col = col0 + pj * 4;
-        // the residual chunk is requested (coalesced, 8 rows in flight per lane) before the accumulator is awaited
-        float4 rres[8];
-        const bool has_res = kEpi != 2 && args.residual != nullptr;
-        if (has_res) {
-          const bool vec = (args.N & 3) == 0;
+        if constexpr (kPipeRes) {
+          if (fast_tile) {
+            // staging offsets: row rl = 4 i + (lane >> 3), piece pj ^ (rl & 7); (rl & 7) = (lane >> 3) + 4 (i & 1)
+            uint8_t* stc = stg + (lane >> 3) * 128;
+            const uint32_t sw0 = (uint32_t)((pj ^ (lane >> 3)) << 4);
+            uint8_t* str_ = stg + lane * 128;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            rres[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int row = rbase + i * 4 + (lane >> 3);
-            if (row < args.M && col < args.N) {
-              const float* rp = args.residual + (size_t)row * args.N + col;  // plain loads: written by the predecessor
-              if (vec) rres[i] = *(const float4*)rp;
-              else {
-                rres[i].x = rp[0];
-                if (col + 1 < args.N) rres[i].y = rp[1];
-                if (col + 2 < args.N) rres[i].z = rp[2];
-                if (col + 3 < args.N) rres[i].w = rp[3];
-              }
+            for (int i = 0; i < 8; ++i) *(float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6))) = rnext[i];
+            __syncwarp();
+            float res[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r4 = *(const float4*)(str_ + ((j ^ jsw) << 4));
+              res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w;
             }
+            __syncwarp();
+            if (c + kChunkStep < BLOCK_N / 32) {  // next chunk of this warp: in flight underneath the rest of this one
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rnext[i] = *(const float4*)(res_lane + (c + kChunkStep) * 32 + i * row4);
+            }
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *(float4*)(str_ + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *(float4*)(y_lane + c * 32 + i * row4) = *(const float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6)));
+            __syncwarp();  // staging is rewritten by the next chunk
+            continue;
+          }
+        }
+        // the residual chunk was requested one chunk ago (the tile's first one before the accumulator was awaited)
+        float4 rres[8];
+        const bool has_res = kEpi != 2 && kResCo && args.residual != nullptr;
+        if constexpr (kPipeRes) {
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rres[i] = rnext[i];
           }
         }
         // weight gradient: W, logits (and injected uniforms) of the 8 rows this lane serves, all in flight together
@@ -856,14 +1056,13 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           }
         }
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
-        if (kEpi != 2) {
-          float f[32], res[32];
+        // residual: coalesced mapping -> staging -> row mapping (16-byte piece p of row r sits at piece p ^ (r & 7)), done BEFORE the
+        // accumulator load so that the next chunk's request is in flight underneath the tcgen05.ld, the element-wise stage and the stores
+        float res[kEpi != 2 ? 32 : 1];
+        if constexpr (kEpi != 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v[j]); res[j] = 0.f; }
+          for (int j = 0; j < 32; ++j) res[j] = 0.f;
           if (has_res) {
-            // residual: coalesced mapping -> staging -> row mapping (16-byte piece p of row r sits at piece p ^ (r & 7))
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rl = i * 4 + (lane >> 3);
@@ -876,7 +1075,18 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w;
             }
             __syncwarp();
+            if constexpr (kPipeRes) {
+              const int cn = c + kChunkStep;  // next chunk of this warp
+              if (cn < BLOCK_N / 32 && n0 + cn * 32 < args.N) load_residual8(args, rbase, lane, n0 + cn * 32 + pj * 4, rnext);
+            }
           }
+        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+        if constexpr (kEpi != 2) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -903,15 +1113,6 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
         __syncwarp();  // staging is rewritten by the next chunk
-      }
-      if constexpr (kTopkEpi) if (rbase + lane < args.M) {
-        float* rec = args.topk_part + ((size_t)(rbase + lane) * (args.tiles_n * kChunkStep) + (size_t)(tile % args.tiles_n) * kChunkStep + half) * kTopKRec;
-        rec[0] = tk_m; rec[1] = tk_s;
-#pragma unroll
-        for (int i = 0; i < kTopK; ++i) {
-          rec[2 + i] = i < kTK ? tk_v[i < kTK ? i : 0] : -INFINITY;
-          rec[2 + kTopK + i] = __int_as_float(i < kTK ? tk_i[i < kTK ? i : 0] : 0x7fffffff);
-        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -1052,9 +1253,11 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false, bool kPair = false>
+template <int BLOCK_N, bool kMasked, int kStages, int kEpi, bool kMN = false, bool kPair = false, bool kResCo = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_splits, cudaStream_t stream) {
-  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi, kMN, kPair>;
+  auto kern = sc_gemm_bf16_kernel<BLOCK_N, kMasked, kStages, kEpi, kMN, kPair, kResCo>;
+  SC_CHECK(kResCo || a.residual == nullptr || num_epilogue_warps(BLOCK_N, kStages) == 4 || kEpi == 2, SC_ERR_UNSUPPORTED,
+           "fp32 residual reached an 8-epilogue-warp instantiation without the coalesced residual epilogue");
   SC_CHECK(kPair == (a.cluster2 == 2), SC_ERR_UNSUPPORTED, "CTA-pair mode reached an instantiation without it (cluster2 = %d)", a.cluster2);
   constexpr int smem = Smem<BLOCK_N, kStages>::kTotal;
   static bool attr_set = false;
@@ -1121,6 +1324,36 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   }
   SC_LAUNCH_CHECK("sc_gemm_bf16_kernel");
   return SC_OK;
+}
+
+// (block_n, stages) -> instantiation: masked / plain weights, epilogue kind, CTA pairs, and - for the 8-epilogue-warp
+// configurations only - the variant with the coalesced fp32-residual epilogue when the call has a residual
+template <int BN, int ST>
+int dispatch_case(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, bool masked, int epi, int force_splits, cudaStream_t stream) {
+  constexpr bool kWide = num_epilogue_warps(BN, ST) == 8;
+  if constexpr (kWide) {
+    if (a.residual != nullptr && epi != 2) {
+      if (masked) return epi ? launch<BN, true, ST, 1, false, false, true>(ta, tb, a, force_splits, stream)
+                             : launch<BN, true, ST, 0, false, false, true>(ta, tb, a, force_splits, stream);
+      if constexpr (BN == 256) {
+        if (a.cluster2 == 2)
+          return epi == 1 ? launch<256, false, 3, 1, false, true, true>(ta, tb, a, force_splits, stream)
+                          : launch<256, false, 3, 0, false, true, true>(ta, tb, a, force_splits, stream);
+      }
+      return epi == 1 ? launch<BN, false, ST, 1, false, false, true>(ta, tb, a, force_splits, stream)
+                      : launch<BN, false, ST, 0, false, false, true>(ta, tb, a, force_splits, stream);
+    }
+  }
+  if (masked) return epi ? launch<BN, true, ST, 1>(ta, tb, a, force_splits, stream)
+                         : launch<BN, true, ST, 0>(ta, tb, a, force_splits, stream);
+  if constexpr (BN == 256) {
+    if (a.cluster2 == 2 && epi != 2)
+      return epi == 1 ? launch<256, false, 3, 1, false, true>(ta, tb, a, force_splits, stream)
+                      : launch<256, false, 3, 0, false, true>(ta, tb, a, force_splits, stream);
+  }
+  return epi == 2 ? launch<BN, false, ST, 2>(ta, tb, a, force_splits, stream)
+       : epi == 1 ? launch<BN, false, ST, 1>(ta, tb, a, force_splits, stream)
+                  : launch<BN, false, ST, 0>(ta, tb, a, force_splits, stream);
 }
 
 }  // namespace
@@ -1235,6 +1468,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K;
   a.pdl_early = (g_sc_pdl & 4) ? 1 : 0;
+  { static int env_dbg = -1; if (env_dbg < 0) { const char* e = getenv("SC_GEMM_DBG"); env_dbg = e ? atoi(e) : 0; } a.dbg = env_dbg; }
   a.tiles_per_cta = tiles_per_cta;
   a.cluster2 = c2 ? (env_mc >= 2 ? 2 : 1) : 0;  // 1: multicast B, two cta_group::1 MMAs; 2: one cta_group::2 MMA per pair (default)
   a.w32 = masked ? (const float*)w : nullptr;
@@ -1273,16 +1507,7 @@ int sc_gemm_bf16_launch(const void* x, const void* w, int w_dtype, const float* 
                           : launch<64, false, 3, 0, true>(ta, tb, a, force_splits, stream);
   }
 #define SC_GEMM_CASE(BN, ST)                                                                                          \
-  if (block_n == BN && stages == ST) {                                                                                \
-    if (masked) return epi ? launch<BN, true, ST, 1>(ta, tb, a, force_splits, stream)                                 \
-                           : launch<BN, true, ST, 0>(ta, tb, a, force_splits, stream);                                \
-    if (BN == 256 && a.cluster2 == 2 && epi != 2)                                                                     \
-      return epi == 1 ? launch<256, false, 3, 1, false, true>(ta, tb, a, force_splits, stream)                        \
-                      : launch<256, false, 3, 0, false, true>(ta, tb, a, force_splits, stream);                       \
-    return epi == 2 ? launch<BN, false, ST, 2>(ta, tb, a, force_splits, stream)                                       \
-         : epi == 1 ? launch<BN, false, ST, 1>(ta, tb, a, force_splits, stream)                                       \
-                    : launch<BN, false, ST, 0>(ta, tb, a, force_splits, stream);                                      \
-  }
+  if (block_n == BN && stages == ST) return dispatch_case<BN, ST>(ta, tb, a, masked, epi, force_splits, stream);
   int stages = force_stages;
   if (stages == 0) stages = (block_n == 128 && (long)mt * ((N + 127) / 128) > 2L * sms) ? 5 : 3;  // 128x5: multi-wave throughput config
   SC_GEMM_CASE(64, 3); SC_GEMM_CASE(64, 4); SC_GEMM_CASE(64, 6);

@@ -42,30 +42,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *(uint32_t*)&t;
 }
 
-// rows [0, rows_pad) of a [*, 64] bf16 slice (row stride ld elements) -> smem rows of kPitch bytes; rows >= n zeroed
-__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, size_t ld, int n, int rows_pad,
-                                           unsigned char* dst, int lane) {
-  for (int idx = lane; idx < rows_pad * 8; idx += 32) {
+// rows [0, n) of a [*, 64] bf16 slice (row stride ld elements) -> smem rows of kPitch bytes.  Only the REAL rows are staged:
+// the ldmatrix row addresses of the padding rows (up to the next multiple of 16) point at one shared all-zero row instead
+// (36 boxes: 36 instead of 48 rows per tile -> a third more warps per SM for these latency-bound kernels).
+__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ src, size_t ld, int n, unsigned char* dst, int lane) {
+  for (int idx = lane; idx < n * 8; idx += 32) {
     const int r = idx >> 3, c = idx & 7;
-    void* d = dst + r * kPitch + c * 16;
-    if (r < n) cp_async16(d, src + (size_t)r * ld + c * 8);
-    else *(uint4*)d = make_uint4(0u, 0u, 0u, 0u);
+    cp_async16(dst + r * kPitch + c * 16, src + (size_t)r * ld + c * 8);
   }
 }
 
 // One m-tile (16 query rows starting at m0) of softmax(bias + mask(Q K^T / 8)) V for one warp.
-// sQ/sK/sV: this warp's staged tiles.  Result rows are written back over the Q rows of the m-tile (bf16, kPitch rows).
+// sQ/sK/sV: this warp's staged tiles (nq / nk real rows); zrow: shared-memory address of a zeroed kPitch-byte row that stands in
+// for the padding rows.  Result rows < nq are written back over the Q rows of the m-tile (bf16, kPitch rows).
 template <int NT>
 __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned char* sK, const unsigned char* sV, int m0,
                                            int nq, int nk, const float* __restrict__ bias, int bias_ld,
-                                           const float* __restrict__ key_mask, int lane) {
+                                           const float* __restrict__ key_mask, int lane, uint32_t zrow) {
   const int g = lane >> 2, t = lane & 3;
   // ---- S = Q K^T ----
   float s[2 * NT][4];
 #pragma unroll
   for (int n = 0; n < 2 * NT; ++n) { s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f; }
-  const uint32_t qbase = smem_u32(sQ) + (uint32_t)((m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 16);
-  const uint32_t kbase = smem_u32(sK) + (uint32_t)(((lane & 7) + (lane >> 4) * 8) * kPitch + ((lane >> 3) & 1) * 16);
+  const int qrow = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const uint32_t qbase = qrow < nq ? smem_u32(sQ) + (uint32_t)(qrow * kPitch + (lane >> 4) * 16) : zrow + (uint32_t)((lane >> 4) * 16);
+  const int krow = (lane & 7) + (lane >> 4) * 8;  // + 16 np
+  uint32_t kaddr[NT];
+#pragma unroll
+  for (int np = 0; np < NT; ++np)
+    kaddr[np] = krow + 16 * np < nk ? smem_u32(sK) + (uint32_t)((krow + 16 * np) * kPitch + ((lane >> 3) & 1) * 16) : zrow + (uint32_t)(((lane >> 3) & 1) * 16);
 #pragma unroll
   for (int ks = 0; ks < kDk / 16; ++ks) {
     uint32_t a[4];
@@ -73,7 +78,7 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
 #pragma unroll
     for (int np = 0; np < NT; ++np) {
       uint32_t b[4];
-      ldsm_x4(kbase + np * 16 * kPitch + ks * 32, b);
+      ldsm_x4(kaddr[np] + ks * 32, b);
       mma_bf16(s[2 * np], a, b[0], b[1]);
       mma_bf16(s[2 * np + 1], a, b[2], b[3]);
     }
@@ -119,7 +124,7 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
   float o[kDk / 8][4];
 #pragma unroll
   for (int n = 0; n < kDk / 8; ++n) { o[n][0] = 0.f; o[n][1] = 0.f; o[n][2] = 0.f; o[n][3] = 0.f; }
-  const uint32_t vbase = smem_u32(sV) + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + (lane >> 4) * 16);
+  const int vrow = (lane & 7) + ((lane >> 3) & 1) * 8;  // + 16 kk
 #pragma unroll
   for (int kk = 0; kk < NT; ++kk) {
     uint32_t a[4];
@@ -127,10 +132,11 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
     a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
     a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
     a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    const uint32_t vaddr = vrow + 16 * kk < nk ? smem_u32(sV) + (uint32_t)((vrow + 16 * kk) * kPitch + (lane >> 4) * 16) : zrow + (uint32_t)((lane >> 4) * 16);
 #pragma unroll
     for (int dp = 0; dp < kDk / 16; ++dp) {
       uint32_t b[4];
-      ldsm_x4_trans(vbase + kk * 16 * kPitch + dp * 32, b);
+      ldsm_x4_trans(vaddr + dp * 32, b);
       mma_bf16(o[2 * dp], a, b[0], b[1]);
       mma_bf16(o[2 * dp + 1], a, b[2], b[3]);
     }
@@ -139,8 +145,8 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
   __syncwarp();
 #pragma unroll
   for (int n = 0; n < kDk / 8; ++n) {
-    *(uint32_t*)(sQ + (m0 + g) * kPitch + (n * 8 + 2 * t) * 2) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
-    *(uint32_t*)(sQ + (m0 + g + 8) * kPitch + (n * 8 + 2 * t) * 2) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
+    if (r0 < nq) *(uint32_t*)(sQ + r0 * kPitch + (n * 8 + 2 * t) * 2) = pack_bf16(o[n][0] * inv0, o[n][1] * inv0);
+    if (r1 < nq) *(uint32_t*)(sQ + r1 * kPitch + (n * 8 + 2 * t) * 2) = pack_bf16(o[n][2] * inv1, o[n][3] * inv1);
   }
 }
 
@@ -165,24 +171,29 @@ __global__ void __launch_bounds__(128) enc_attn_mma_kernel(const EncAttnArgs a) 
   extern __shared__ __align__(16) unsigned char smem_x[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * a.warps + warp;
+  // smem: [zero row][warp 0: Q K V (N rows each)][warp 1: ...]
+  if (threadIdx.x < kPitch / 16) *(uint4*)(smem_x + threadIdx.x * 16) = make_uint4(0u, 0u, 0u, 0u);
   sc::pdl_launch();
   sc::pdl_wait();
-  if (w >= a.B * a.h) return;
-  const int b = w / a.h, hh = w - b * a.h;
-  constexpr int kRows = 16 * NT;
-  unsigned char* sQ = smem_x + (size_t)warp * 3 * kRows * kPitch;
-  unsigned char* sK = sQ + kRows * kPitch;
-  unsigned char* sV = sK + kRows * kPitch;
   const int N = a.N;
+  const bool live = w < a.B * a.h;
+  const int b = live ? w / a.h : 0, hh = live ? w - b * a.h : 0;
+  unsigned char* sQ = smem_x + kPitch + (size_t)warp * 3 * N * kPitch;
+  unsigned char* sK = sQ + N * kPitch;
+  unsigned char* sV = sK + N * kPitch;
   const size_t row0 = (size_t)b * N;
-  stage_tile(a.q + row0 * a.ldq + hh * kDk, a.ldq, N, kRows, sQ, lane);
-  stage_tile(a.k + row0 * a.ldk + hh * kDk, a.ldk, N, kRows, sK, lane);
-  stage_tile(a.v + row0 * a.ldv + hh * kDk, a.ldv, N, kRows, sV, lane);
+  if (live) {
+    stage_tile(a.q + row0 * a.ldq + hh * kDk, a.ldq, N, sQ, lane);
+    stage_tile(a.k + row0 * a.ldk + hh * kDk, a.ldk, N, sK, lane);
+    stage_tile(a.v + row0 * a.ldv + hh * kDk, a.ldv, N, sV, lane);
+  }
   cp_async_wait_all();
-  __syncwarp();
+  __syncthreads();  // (the zero row is shared by the CTA's warps)
+  if (!live) return;
   const float* bias = a.bias + ((size_t)b * a.h + hh) * N * N;
   const float* km = a.att_mask ? a.att_mask + (size_t)b * N : nullptr;
-  for (int m0 = 0; m0 < N; m0 += 16) attn_mtile<NT>(sQ, sK, sV, m0, N, N, bias, N, km, lane);
+  const uint32_t zrow = smem_u32(smem_x);
+  for (int m0 = 0; m0 < N; m0 += 16) attn_mtile<NT>(sQ, sK, sV, m0, N, N, bias, N, km, lane, zrow);
   __syncwarp();
   store_rows(sQ, N, a.out + row0 * a.ldo + hh * kDk, a.ldo, lane);
 }
@@ -200,22 +211,26 @@ __global__ void __launch_bounds__(256) cross_attn_mma_kernel(const CrossAttnArgs
   extern __shared__ __align__(16) unsigned char smem_x[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * a.warps + warp;
+  // smem: [zero row][warp 0: Q (beam rows) K V (N rows each)][warp 1: ...]
+  if (threadIdx.x < kPitch / 16) *(uint4*)(smem_x + threadIdx.x * 16) = make_uint4(0u, 0u, 0u, 0u);
   sc::pdl_launch();
   sc::pdl_wait();
-  if (w >= a.B * a.h) return;
-  const int b = w / a.h, hh = w - b * a.h;
-  constexpr int kRows = 16 * NT;
-  unsigned char* sQ = smem_x + (size_t)warp * (2 * kRows + 16) * kPitch;
-  unsigned char* sK = sQ + 16 * kPitch;
-  unsigned char* sV = sK + kRows * kPitch;
   const int N = a.N;
-  stage_tile(a.q + (size_t)b * a.NB * a.ldq + hh * kDk, a.ldq, a.NB, 16, sQ, lane);
-  stage_tile(a.mk + (size_t)b * N * a.ldm + hh * kDk, a.ldm, N, kRows, sK, lane);
-  stage_tile(a.mv + (size_t)b * N * a.ldm + hh * kDk, a.ldm, N, kRows, sV, lane);
+  const bool live = w < a.B * a.h;
+  const int b = live ? w / a.h : 0, hh = live ? w - b * a.h : 0;
+  unsigned char* sQ = smem_x + kPitch + (size_t)warp * (2 * N + a.NB) * kPitch;
+  unsigned char* sK = sQ + a.NB * kPitch;
+  unsigned char* sV = sK + N * kPitch;
+  if (live) {
+    stage_tile(a.q + (size_t)b * a.NB * a.ldq + hh * kDk, a.ldq, a.NB, sQ, lane);
+    stage_tile(a.mk + (size_t)b * N * a.ldm + hh * kDk, a.ldm, N, sK, lane);
+    stage_tile(a.mv + (size_t)b * N * a.ldm + hh * kDk, a.ldm, N, sV, lane);
+  }
   cp_async_wait_all();
-  __syncwarp();
+  __syncthreads();  // (the zero row is shared by the CTA's warps)
+  if (!live) return;
   const float* km = a.att_mask ? a.att_mask + (size_t)b * N : nullptr;
-  attn_mtile<NT>(sQ, sK, sV, 0, a.NB, N, nullptr, 0, km, lane);
+  attn_mtile<NT>(sQ, sK, sV, 0, a.NB, N, nullptr, 0, km, lane, smem_u32(smem_x));
   __syncwarp();
   store_rows(sQ, a.NB, a.out + (size_t)b * a.NB * a.ldo + hh * kDk, a.ldo, lane);
 }
@@ -326,11 +341,12 @@ int sc_bias_attention_fwd(const void* q, const void* k, const void* v, int ldq, 
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.bias = bias; a.att_mask = att_mask; a.out = (__nv_bfloat16*)out; a.ldo = ldo;
   a.B = B; a.N = N; a.h = h;
   const int NT = (N + 15) / 16;
-  const size_t per_warp = (size_t)3 * 16 * NT * kPitch;
-  int warps = (int)((200 * 1024) / per_warp);
+  const size_t per_warp = (size_t)3 * N * kPitch;  // only the real rows are staged (see stage_tile)
+  int warps = (int)((200 * 1024 - kPitch) / per_warp);
   if (warps > 4) warps = 4;
+  SC_CHECK(warps >= 1, SC_ERR_UNSUPPORTED, "sc_bias_attention_fwd: N=%d does not fit in shared memory", N);
   a.warps = warps;
-  const size_t smem = per_warp * warps;
+  const size_t smem = per_warp * warps + kPitch;
   const int blocks = (B * h + warps - 1) / warps;
 #define ENC_CASE(NTV)                                                                                              \
   case NTV: {                                                                                                      \
@@ -362,12 +378,13 @@ int sc_cross_attn_mma_launch(const void* q, int ldq, const void* mem_k, const vo
   a.q = (const __nv_bfloat16*)q; a.ldq = ldq; a.mk = (const __nv_bfloat16*)mem_k; a.mv = (const __nv_bfloat16*)mem_v; a.ldm = ldm;
   a.att_mask = att_mask; a.out = (__nv_bfloat16*)out; a.ldo = ldo; a.B = B; a.NB = beam; a.N = N; a.h = h;
   const int NT = (N + 15) / 16;
-  const size_t per_warp = (size_t)(2 * 16 * NT + 16) * kPitch;
-  int warps = (int)((100 * 1024) / per_warp);
+  const size_t per_warp = (size_t)(2 * N + beam) * kPitch;  // only the real rows are staged (see stage_tile)
+  // 6 warps x 10.8 KB (36 boxes, beam 3): three CTAs = 18 warps per SM keep ~170 KB of K / V requests in flight
+  int warps = (int)((72 * 1024 - kPitch) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) return SC_ERR_UNSUPPORTED;
   a.warps = warps;
-  const size_t smem = per_warp * warps;
+  const size_t smem = per_warp * warps + kPitch;
   const int blocks = (B * h + warps - 1) / warps;
 #define X_CASE(NTV)                                                                                                \
   case NTV: {                                                                                                      \

@@ -8,7 +8,8 @@ import os
 import torch  # noqa: F401  (loads libcudart into the process before our library)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsc_b200.so")
+# SC_LIB_PATH: diagnostic override (same-box A/B of two builds of the library, scripts/); the product path is the in-tree build
+LIB_PATH = os.environ.get("SC_LIB_PATH") or os.path.join(_HERE, "csrc", "libsc_b200.so")
 
 F32, BF16 = 0, 1
 MASK_NONE, MASK_ROUND, MASK_BERNOULLI, MASK_RAW, MASK_UNIFORM = 0, 1, 2, 3, 4
