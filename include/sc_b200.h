@@ -138,6 +138,13 @@ int sc_box_attention_fwd(const void* q, const void* k, const void* v, int ldq, i
 int sc_box_bias_all(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int layers,
                     int h, int trig, float wave_len, sc_stream_t stream);
 
+/* Same bias on the tensor cores (the bf16 inference path's encoder): [16 pairs, layers*h] = emb[16, 64] . WG^T as mma.sync tiles
+ * with both operands split into bf16 hi + lo parts (three products, fp32 accumulation: ~1e-5 absolute on WG . emb), sin / cos /
+ * log through the SFU after range reduction.  Trigonometric embedding only, layers*h a multiple of 8 (<= 64).  The exact kernel
+ * above stays the fp32 verification / training path. */
+int sc_box_bias_all_tc(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int layers,
+                       int h, float wave_len, sc_stream_t stream);
+
 /* K4 (inference split) — box_attention given the bias of one layer (models/relation_transformer.py:258-293):
  * out = softmax(bias + masked_fill(QK^T/sqrt(dk), mask==0, -1e9)) V.  bf16, d_k = 64, N <= 128; one warp per
  * (image, head) on mma.sync tiles.  bias fp32 [B, h, N, N]; att_mask fp32 [B,N] or NULL. */

@@ -43,6 +43,7 @@ if "enc" in which or "box" in which:
     bias = torch.empty(6, B, h, N, N, device=dev)
     for _ in range(reps):
         K.box_bias_all(boxes, wgw, wgb, bias, B=B, N=N, layers=6, h=h)
+        K.box_bias_all(boxes, wgw, wgb, bias, B=B, N=N, layers=6, h=h, tensor_cores=True)
     qkv = torch.randn(B * N, 3 * d, **bf); out = torch.empty(B * N, d, **bf)
     if "enc" in which:
         for _ in range(reps):

@@ -60,10 +60,31 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
                                            int nq, int nk, const float* __restrict__ bias, int bias_ld,
                                            const float* __restrict__ key_mask, int lane, uint32_t zrow) {
   const int g = lane >> 2, t = lane & 3;
-  // ---- S = Q K^T ----
+  const int r0 = m0 + g, r1 = r0 + 8;
+  // ---- S = Q K^T, accumulated on top of the geometry bias: its loads (the only global reads of the m-tile) are requested
+  // before the MMAs instead of between them and the softmax ----
   float s[2 * NT][4];
 #pragma unroll
   for (int n = 0; n < 2 * NT; ++n) { s[n][0] = 0.f; s[n][1] = 0.f; s[n][2] = 0.f; s[n][3] = 0.f; }
+  float bv[2 * NT][4];
+  if (bias) {
+    const bool vec2 = (bias_ld & 1) == 0 && (((uintptr_t)bias) & 7) == 0;
+#pragma unroll
+    for (int n = 0; n < 2 * NT; ++n) {
+      const int col = n * 8 + 2 * t;
+      bv[n][0] = bv[n][1] = bv[n][2] = bv[n][3] = 0.f;
+      if (vec2 && col + 1 < nk) {
+        if (r0 < nq) { const float2 b2 = *(const float2*)(bias + (size_t)r0 * bias_ld + col); bv[n][0] = b2.x; bv[n][1] = b2.y; }
+        if (r1 < nq) { const float2 b2 = *(const float2*)(bias + (size_t)r1 * bias_ld + col); bv[n][2] = b2.x; bv[n][3] = b2.y; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (col + c < nk && r0 < nq) bv[n][c] = bias[(size_t)r0 * bias_ld + col + c];
+          if (col + c < nk && r1 < nq) bv[n][2 + c] = bias[(size_t)r1 * bias_ld + col + c];
+        }
+      }
+    }
+  }
   const int qrow = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
   const uint32_t qbase = qrow < nq ? smem_u32(sQ) + (uint32_t)(qrow * kPitch + (lane >> 4) * 16) : zrow + (uint32_t)((lane >> 4) * 16);
   const int krow = (lane & 7) + (lane >> 4) * 8;  // + 16 np
@@ -84,7 +105,6 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
     }
   }
   // ---- scale, mask, bias, softmax (rows g and g+8 of the tile; a row lives in the 4 lanes of a quad) ----
-  const int r0 = m0 + g, r1 = r0 + 8;
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int n = 0; n < 2 * NT; ++n) {
@@ -94,10 +114,7 @@ __device__ __forceinline__ void attn_mtile(unsigned char* sQ, const unsigned cha
       float v0 = s[n][c] * 0.125f, v1 = s[n][2 + c] * 0.125f;  // / sqrt(64)
       if (col < nk) {
         if (key_mask && key_mask[col] == 0.f) { v0 = -1e9f; v1 = -1e9f; }
-        if (bias) {
-          if (r0 < nq) v0 += bias[(size_t)r0 * bias_ld + col];
-          if (r1 < nq) v1 += bias[(size_t)r1 * bias_ld + col];
-        }
+        if (bias) { v0 += bv[n][c]; v1 += bv[n][2 + c]; }
       } else {
         v0 = -INFINITY; v1 = -INFINITY;
       }
@@ -302,6 +319,135 @@ __global__ void __launch_bounds__(128) box_bias_all_kernel(const float* __restri
   }
 }
 
+// ---- the same bias on the tensor cores (bf16 inference path): D[16 pairs, LH] = emb[16, 64] . WG^T[64, LH] on mma.sync tiles ----
+// The fp32 kernel above spends 3072 FFMAs + 768 shared-memory weight loads per box pair (1.07 ms for 2560 images: 14 % of an encoder
+// pass).  Here a warp owns tiles of 16 consecutive pairs: every lane evaluates exactly the 16 sin/cos pairs its A fragments need
+// (rows g / g + 8, frequencies 2t / 2t + 1 of each of the 4 deltas: no value is computed twice in the warp) and 4 x LH/8 x 3
+// m16n8k16 MMAs replace the FFMA loop.  Both operands are split into bf16 hi + lo parts (x = hi + lo to 2^-17) and the product
+// is hi.hi + lo.hi + hi.lo (fp32 accumulation): ~1e-5 absolute on the pre-activation, i.e. fp32-grade - the tensor cores buy
+// speed here, not a precision trade.  The remaining approximations: sin / cos by two-term Cody-Waite reduction + MUFU (abs 1e-6),
+// log by MUFU.LG2 (the exact kernel stays the fp32 verification / training path).  WG^T fragments (hi | lo) sit in shared memory
+// in per-lane order (one conflict-free LDS.128 per (k-step, n-tile)).
+__device__ __forceinline__ void fast_sincos(float x, float& sn, float& cs) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);   // 2 pi = 6.2831854820251465 - 1.7484556e-7
+  r = fmaf(k, 1.7484556e-7f, r);
+  sn = __sinf(r); cs = __cosf(r);
+}
+// (x0, x1) -> packed bf16 hi pair and packed bf16 residual pair
+__device__ __forceinline__ void split_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h2);
+  const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *(const uint32_t*)&h2; lo = *(const uint32_t*)&l2;
+}
+
+template <int NT>  // NT = LH / 8 output tiles of 8 (layer, head) columns
+__global__ void __launch_bounds__(128) box_bias_all_tc_kernel(const float* __restrict__ boxes, const float* __restrict__ wg_w,
+                                                              const float* __restrict__ wg_b, float* __restrict__ bias,
+                                                              int B, int N, int h, DimMat8 dm) {
+  __shared__ uint4 s_b[4 * NT * 32];  // [ks][nt][lane]: {b0 hi, b1 hi, b0 lo, b1 lo}
+  __shared__ float s_dm[8];
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // B fragment of WG^T (k x n) for m16n8k16: b0 = W[n = 8 nt + g][k = 16 ks + 2t, + 1], b1 = W[n][k + 8, + 9]
+  for (int idx = threadIdx.x; idx < 4 * NT * 32; idx += blockDim.x) {
+    const int ln = idx & 31, nt = (idx >> 5) % NT, ks = idx / (32 * NT);
+    const float* w = wg_w + (size_t)(nt * 8 + (ln >> 2)) * 64 + ks * 16 + 2 * (ln & 3);
+    uint4 o;
+    split_bf16(w[0], w[1], o.x, o.z);
+    split_bf16(w[8], w[9], o.y, o.w);
+    s_b[idx] = o;
+  }
+  if (threadIdx.x < 8) s_dm[threadIdx.x] = dm.v[threadIdx.x];
+  __syncthreads();
+  float wb[NT][2];
+  uint32_t lh_off[NT][2];  // byte offset of the (layer, head) plane of this lane's two columns of each n tile (image 0; host: < 2^32)
+  const int pairs = N * N;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int lh = nt * 8 + 2 * t + e;
+      wb[nt][e] = __ldg(wg_b + lh);
+      lh_off[nt][e] = (uint32_t)((((size_t)(lh / h) * B * h + lh % h) * pairs) * sizeof(float));
+    }
+  const int total = B * pairs;  // (host: < 2^31)
+  const int tiles = (total + 15) / 16;
+  // a warp walks a CONTIGUOUS range of tiles: its boxes stay in L1 and (image, pair) advance without divisions
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int per_warp = (tiles + warps_total - 1) / warps_total;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int tile0 = w * per_warp, tile1 = min(tile0 + per_warp, tiles);
+  const float f0 = s_dm[2 * t], f1 = s_dm[2 * t + 1];
+  const float inv_n = 1.0f / (float)N;
+  int bb0 = tile0 < tiles ? (tile0 * 16) / pairs : 0;
+  int rr0 = tile0 * 16 - bb0 * pairs;  // first pair of the tile inside image bb0
+  for (int tile = tile0; tile < tile1; ++tile) {
+    // A fragments (hi | lo) of rows g and g + 8: k-step ks covers the columns of deltas 2 ks, 2 ks + 1; ks < 2: sin, ks >= 2: cos
+    uint32_t ah[4][4], al[4][4];
+    bool ok[2];
+    uint32_t out_r[2];  // byte offset of (image, head 0, pair) of the lane's two rows
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      int rr = rr0 + g + 8 * r, bb = bb0;
+      if (rr >= pairs) { rr -= pairs; ++bb; }  // (a tile spans at most two images: pairs >= 16 is checked by the host)
+      ok[r] = bb < B;
+      if (!ok[r]) { bb = B - 1; }
+      out_r[r] = (uint32_t)(((size_t)bb * h * pairs + rr) * sizeof(float));
+      const int i = (int)(((float)rr + 0.5f) * inv_n);  // exact for rr < 2^22
+      const int j = rr - i * N;
+      // the quad's lane t evaluates delta[t] (one log + one division), the other three arrive by shuffle
+      const float4 bi = __ldg((const float4*)(boxes + ((size_t)bb * N + i) * 4));
+      const float4 bj = __ldg((const float4*)(boxes + ((size_t)bb * N + j) * 4));
+      const bool xdir = (t & 1) == 0;  // t = 0: dx / w, 1: dy / h, 2: w / w, 3: h / h
+      const float lo_i = xdir ? bi.x : bi.y, hi_i = xdir ? bi.z : bi.w, lo_j = xdir ? bj.x : bj.y, hi_j = xdir ? bj.z : bj.w;
+      const float ci = (lo_i + hi_i) * 0.5f, cj = (lo_j + hi_j) * 0.5f, si = (hi_i - lo_i) + 1.0f, sj = (hi_j - lo_j) + 1.0f;
+      const float mine = logf(t < 2 ? fmaxf(fabsf((ci - cj) / si), 1e-3f) : si / sj);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float p100 = 100.0f * __shfl_sync(0xffffffffu, mine, (lane & ~3) | c);
+        float s0, c0, s1, c1;
+        fast_sincos(p100 * f0, s0, c0);
+        fast_sincos(p100 * f1, s1, c1);
+        // delta c -> k-step c / 2 (sin) and 2 + c / 2 (cos); register r (+ 2 for the odd delta: columns + 8)
+        split_bf16(s0, s1, ah[c >> 1][r + 2 * (c & 1)], al[c >> 1][r + 2 * (c & 1)]);
+        split_bf16(c0, c1, ah[2 + (c >> 1)][r + 2 * (c & 1)], al[2 + (c >> 1)][r + 2 * (c & 1)]);
+      }
+    }
+    rr0 += 16;
+    if (rr0 >= pairs) { rr0 -= pairs; ++bb0; }
+    float d[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { d[nt][0] = 0.f; d[nt][1] = 0.f; d[nt][2] = 0.f; d[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint4 bw[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) bw[nt] = s_b[(ks * NT + nt) * 32 + lane];
+      // small terms first; consecutive MMAs go to different accumulators
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_bf16(d[nt], al[ks], bw[nt].x, bw[nt].y);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_bf16(d[nt], ah[ks], bw[nt].z, bw[nt].w);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_bf16(d[nt], ah[ks], bw[nt].x, bw[nt].y);
+    }
+    // D: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1) of each n tile; column = layer * h + head
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e >> 1;
+        if (ok[r]) {  // log(max(relu(x), 1e-6)); the argument is never denormal: plain MUFU.LG2
+          float l2;
+          asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaxf(d[nt][e] + wb[nt][e & 1], 1e-6f)));
+          *(float*)((char*)bias + (out_r[r] + lh_off[nt][e & 1])) = l2 * 0.6931471805599453f;
+        }
+      }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -324,6 +470,33 @@ int sc_box_bias_all(const float* boxes, const float* wg_w, const float* wg_b, fl
   const long total = (long)B * N * N;
   box_bias_all_kernel<<<(unsigned)((total + 127) / 128), 128, smem, stream>>>(boxes, wg_w, wg_b, bias, B, N, LH, h, trig, dm);
   SC_LAUNCH_CHECK("sc_box_bias_all");
+  return SC_OK;
+}
+
+int sc_box_bias_all_tc(const float* boxes, const float* wg_w, const float* wg_b, float* bias, int B, int N, int layers, int h,
+                       float wave_len, cudaStream_t stream) {
+  SC_CHECK(B > 0 && N > 0 && layers >= 1 && h >= 1, SC_ERR_SHAPE, "sc_box_bias_all_tc: B=%d N=%d layers=%d h=%d", B, N, layers, h);
+  SC_CHECK(((uintptr_t)boxes & 15) == 0, SC_ERR_ALIGN, "sc_box_bias_all_tc: boxes must be 16-byte aligned");
+  const int LH = layers * h;
+  SC_CHECK(LH % 8 == 0 && LH <= 64, SC_ERR_UNSUPPORTED, "sc_box_bias_all_tc: layers * h = %d must be a multiple of 8, at most 64 (use sc_box_bias_all)", LH);
+  SC_CHECK(N >= 4 && N <= 2048 && (long)B * N * N < (1L << 31) - 16, SC_ERR_UNSUPPORTED,
+           "sc_box_bias_all_tc: N=%d in [4, 2048] and B*N*N < 2^31 (use sc_box_bias_all)", N);
+  SC_CHECK((size_t)LH * B * N * N * sizeof(float) < ((size_t)1 << 32), SC_ERR_UNSUPPORTED,
+           "sc_box_bias_all_tc: the bias tensor must stay below 4 GB (32-bit byte offsets; use sc_box_bias_all or split the batch)");
+  DimMat8 dm;
+  for (int f = 0; f < 8; ++f) dm.v[f] = 1.0f / powf(wave_len, (float)f / 8.0f);
+  const long tiles = ((long)B * N * N + 15) / 16;
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  long blocks = (tiles + 3) / 4;
+  if (blocks > (long)sms * 8) blocks = (long)sms * 8;
+#define TC_CASE(NTV) case NTV: box_bias_all_tc_kernel<NTV><<<(unsigned)blocks, 128, 0, stream>>>(boxes, wg_w, wg_b, bias, B, N, h, dm); break
+  switch (LH / 8) {
+    TC_CASE(1); TC_CASE(2); TC_CASE(3); TC_CASE(4); TC_CASE(5); TC_CASE(6); TC_CASE(7); TC_CASE(8);
+    default: SC_CHECK(false, SC_ERR_UNSUPPORTED, "sc_box_bias_all_tc: LH=%d", LH);
+  }
+#undef TC_CASE
+  SC_LAUNCH_CHECK("sc_box_bias_all_tc");
   return SC_OK;
 }
 

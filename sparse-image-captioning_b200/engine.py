@@ -363,7 +363,8 @@ class OrtEngine:
             K.mask_rows(ws.x, ws.att_mask.view(-1))
         trig = not c.no_box_trigonometric_embedding
         if ws.box_bias is not None:
-            K.box_bias_all(ws.boxes, self.wg_w_all, self.wg_b_all, ws.box_bias, B=B, N=N, layers=len(self.enc), h=h, trig=trig)
+            K.box_bias_all(ws.boxes, self.wg_w_all, self.wg_b_all, ws.box_bias, B=B, N=N, layers=len(self.enc), h=h, trig=trig,
+                           tensor_cores=True)  # (bf16 path only: ws.box_bias exists when split_box_attn)
         for u in self.enc_uids:
             e = self.enc[u]
             ld = e["ld"]

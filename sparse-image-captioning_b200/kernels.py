@@ -339,8 +339,15 @@ def box_attention(q, k, v, boxes, wg_w, wg_b, att_mask, out, *, B, N, h, dk, ldq
     return out
 
 
-def box_bias_all(boxes, wg_w, wg_b, out, *, B, N, layers, h, trig=True, wave_len=1000.0):
-    """Geometry bias of every encoder layer at once: out fp32 [layers, B, h, N, N] (sc_box_bias_all)."""
+def box_bias_all(boxes, wg_w, wg_b, out, *, B, N, layers, h, trig=True, wave_len=1000.0, tensor_cores=False):
+    """Geometry bias of every encoder layer at once: out fp32 [layers, B, h, N, N] (sc_box_bias_all).
+    ``tensor_cores``: the TF32 mma variant of the bf16 inference path (sc_box_bias_all_tc) when the shape is served."""
+    if (tensor_cores and trig and (layers * h) % 8 == 0 and layers * h <= 64 and 4 <= N <= 2048
+            and layers * h * B * N * N * 4 < 2 ** 32):
+        for t, n in ((boxes, "boxes"), (wg_w, "wg_w"), (wg_b, "wg_b"), (out, "out")):
+            _chk(t, n)
+        lib.call("sc_box_bias_all_tc", lib.ptr(boxes), lib.ptr(wg_w), lib.ptr(wg_b), lib.ptr(out), B, N, layers, h, wave_len, lib.stream())
+        return out
     lib.call("sc_box_bias_all", lib.ptr(boxes), lib.ptr(wg_w), lib.ptr(wg_b), lib.ptr(out), B, N, layers, h, int(trig),
              wave_len, lib.stream())
     return out

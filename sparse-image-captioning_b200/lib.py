@@ -34,6 +34,7 @@ SIGNATURES = {
     "sc_mask_rows": [_p, _p, _i, _i, _p],
     "sc_box_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p],
     "sc_box_bias_all": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "sc_box_bias_all_tc": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     "sc_bias_attention_fwd": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "sc_decode_self_attn_step": [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "sc_decode_cross_attn_step": [_p, _i, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -323,6 +323,32 @@ def test_box_bias_all_and_tensor_attention(K, cfg, masked):
         assert rel_err(out.float(), ref) < 2e-2, l
 
 
+@pytest.mark.parametrize("cfg", [(3, 36, 8, 6), (2, 47, 8, 2), (1, 100, 8, 1), (2, 17, 4, 2), (5, 36, 8, 3)])
+def test_box_bias_all_tensor_cores(K, cfg):
+    """sc_box_bias_all_tc (mma.sync tiles over bf16 hi + lo operand splits, SFU sin / cos / log: the bf16 engine's encoder) vs the
+    fp64 geometry weights of the oracle embedding: the attention multiplier g = exp(bias) within 2e-4 absolute - the bound the
+    exact fp32 kernel is held to (the 100x angles amplify fp32 rounding where WG.emb crosses 0) - and bias within 2e-3 wherever
+    g >= 1e-2; non-multiple-of-16 pair counts and ragged tiles covered by N = 47 / 17."""
+    B, N, h, layers = cfg
+    g = torch.Generator().manual_seed(23)
+    boxes = O.synthetic_inputs(B, N, 8, seed=31)["boxes"]
+    wg_w = torch.randn(layers * h, 64, generator=g) * 0.3
+    wg_b = torch.randn(layers * h, generator=g) * 0.3
+    bias = torch.full((layers, B, h, N, N), float("nan"), device="cuda")
+    K.box_bias_all(boxes.cuda(), wg_w.cuda(), wg_b.cuda(), bias, B=B, N=N, layers=layers, h=h, tensor_cores=True)
+    exact = torch.zeros_like(bias)
+    K.box_bias_all(boxes.cuda(), wg_w.cuda(), wg_b.cuda(), exact, B=B, N=N, layers=layers, h=h)
+    emb = O.box_relational_embedding(boxes).double()
+    gw = torch.relu(torch.einsum("bijf,lhf->lbhij", emb, wg_w.double().view(layers, h, 64)) + wg_b.double().view(layers, 1, h, 1, 1))
+    ref = torch.log(torch.clamp(gw, min=1e-6))
+    got = bias.cpu().double()
+    assert torch.isfinite(got).all()
+    assert float((got.exp() - ref.exp()).abs().max()) < 2e-4
+    big = gw >= 1e-2
+    assert float((got - ref)[big].abs().max()) < 2e-3
+    assert float((got.exp() - exact.cpu().double().exp()).abs().max()) < 2e-4
+
+
 @pytest.mark.parametrize("cfg", [(5, 3, 36, 8), (3, 5, 47, 4), (2, 1, 100, 8), (4, 8, 7, 2)])
 def test_cross_attention_tensor_path(K, cfg):
     """K6 on the mma.sync path (bf16, d_k = 64): the beam rows of an image share one read of its memory K/V."""
