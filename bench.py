@@ -508,11 +508,10 @@ def main():
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=wl["sparsity"], device=dev)
     G = max(1, args.coalesce)
     assert args.steps % G == 0, "--steps must be a multiple of --coalesce"
+    # >= 8 batches in flight (throughput regime): 256-wide tiles, two tiles per persistent CTA (10^7 digit)
+    dec_tiles = {k: 20003256 for k in ("qkv", "o", "cq", "co", "ff1", "ff2")} if args.slots * G >= 8 else None
     eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold,
-                    fuse_topk=not args.no_fuse_topk,
-                    # >= 8 batches in flight (throughput regime): 256-wide tiles, two tiles per persistent CTA (10^7 digit)
-                    dec_tiles=({k: 20003256 for k in ("qkv", "o", "cq", "co", "ff1", "ff2")}
-                               if args.slots * G >= 8 else None))
+                    fuse_topk=not args.no_fuse_topk, dec_tiles=dec_tiles)
     B = args.images * G      # device batch = G queued batches of --images
     F = cfgd["att_feat_size"]
     # two distinct pinned host batches, alternated
@@ -634,10 +633,11 @@ def main():
     # ---------------- roofline leg: one instrumented step without graphs ----------------
     peaks = load_peaks()
     traffic = load_traffic()
-    Bp = args.images
+    # the DEVICE batch of the timed region (G coalesced batches of --images): the roofline is quoted on the shapes that were launched
+    Bp = B
     att_p, box_p = host[0][0][:Bp], host[0][1][:Bp]
     eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False,
-                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk)
+                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk, dec_tiles=dec_tiles)
     enc2 = eng2.encode(att_p, box_p)
     for o in opts:
         eng2.decode(enc2, o)
@@ -671,25 +671,26 @@ def main():
     shapes = {}
     for name, meta, a, b in prof:
         if meta and meta[0] == "gemm_bf16":
-            key = tuple(meta[1:7]) + tuple(meta[8:10])
+            key = tuple(meta[1:7]) + tuple(meta[8:10]) + ((meta[10] if len(meta) > 10 else 0),)   # (+ the engine's tile hint)
             shapes[key] = shapes.get(key, 0) + 1
     from sparse_caption_b200 import kernels as KK
     topk_beam = max([b for b in beams if b > 1] or [3])
 
-    def make_run(M, N, Kd, ys, has_res, relu, nbuf):
+    def make_run(M, N, Kd, ys, has_res, relu, tile, nbuf):
         x = torch.randn(M, Kd, device=dev).bfloat16()
         w = torch.randn(N, Kd, device=dev).bfloat16()
         bias = torch.randn(N, device=dev)
-        res = torch.randn(M, N, device=dev) if has_res else None
         if ys == 0:  # generator fused with the beam row pass: no output tile, 12-float records per (row, tile half)
             part = torch.empty(M, KK.linear_topk_parts(N), 12, device=dev)
             return lambda i: KK.linear_topk(x, w, bias, part, candidates=min(5, topk_beam))
         outs_ = [torch.empty(M, N, device=dev, dtype=torch.bfloat16 if ys == 2 else torch.float32) for _ in range(nbuf)]
-        return lambda i: KK.linear(x, w, bias, residual=res, relu=relu, out=outs_[i % nbuf])
+        if has_res:  # the engine's residual GEMMs update the fp32 residual stream in place
+            return lambda i: KK.linear(x, w, bias, residual=outs_[i % nbuf], relu=relu, out=outs_[i % nbuf], tile_n=tile)
+        return lambda i: KK.linear(x, w, bias, relu=relu, out=outs_[i % nbuf], tile_n=tile)
 
     gemm_us, gemm_fl, dom = 0.0, 0.0, None
-    for (M, N, Kd, xs, wsz, ys, has_res, relu), cnt in shapes.items():
-        us = _time_graph(make_run(M, N, Kd, ys, has_res, relu, 4), dev)
+    for (M, N, Kd, xs, wsz, ys, has_res, relu, tile), cnt in shapes.items():
+        us = _time_graph(make_run(M, N, Kd, ys, has_res, relu, tile, 4), dev)
         gemm_us += us * cnt
         gemm_fl += 2.0 * M * N * Kd * cnt
         if dom is None or us * cnt > dom[0]:
@@ -697,14 +698,14 @@ def main():
     # the same shapes with several streams running them concurrently - the regime of the timed region (launches in flight):
     # microseconds of wall time per GEMM = elapsed / (streams * launches)
     conc_us, conc_fl = 0.0, 0.0
-    CS = max(2, min(8, S * G))
+    CS = max(2, min(8, S if G > 1 else S * G))   # device launches in flight in the timed region
     try:
         streams = [torch.cuda.Stream(dev) for _ in range(CS)]
         cur_s = torch.cuda.current_stream(dev)
-        for (M, N, Kd, xs, wsz, ys, has_res, relu), cnt in shapes.items():
+        for (M, N, Kd, xs, wsz, ys, has_res, relu, tile), cnt in shapes.items():
             graphs = []
             for st in streams:
-                run = make_run(M, N, Kd, ys, has_res, relu, 2)
+                run = make_run(M, N, Kd, ys, has_res, relu, tile, 2)
                 run(0)
                 torch.cuda.synchronize(dev)
                 gr = torch.cuda.CUDAGraph()
@@ -736,11 +737,11 @@ def main():
     tf_dom = 2.0 * dom[1] * dom[2] * dom[3] / dom[4] / 1e6 if dom else 0.0
     dom_key = None if dom is None else f"{dom[1]},{dom[2]},{dom[3]},{dom[7]},{int(bool(dom[8]))}"
     try:
-        hbm = hbm_kernel_roofline(dev, args.images, topk_beam, N_BOX, cfgd, peaks)
+        hbm = hbm_kernel_roofline(dev, Bp, topk_beam, N_BOX, cfgd, peaks)
     except Exception as ex:
         print(f"HBM kernel timing skipped: {ex}", file=sys.stderr)
         hbm = None
-    step_tf = gemm_fl / (ms_dev / args.steps / 1e3) / 1e12
+    step_tf = (gemm_fl / G) / (ms_dev / args.steps / 1e3) / 1e12   # (gemm_fl covers one device launch = G steps)
     roofline = {"kernel": "sc_gemm_bf16_kernel (tcgen05/TMEM/TMA; every GEMM launch of one step)", "bound": "tensor", "achieved": tf,
                 "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of THE SHAPE REPORTED as dominant, from the committed ncu
@@ -750,8 +751,10 @@ def main():
                 "achieved_in_flight": tf_conc, "frac_in_flight": (tf_conc / peaks["tf_sus"]) if tf_conc else None,
                 "in_flight_note": f"same shapes, {CS} streams concurrently (the timed region's regime), wall time per GEMM; vs sustained peak",
                 "whole_step_tflops": step_tf, "whole_step_frac_of_sustained_peak": step_tf / peaks["tf_sus"],
+                "device_batch_images": Bp, "steps_per_device_launch": G,
                 "launches": g["n"], "avg_launch_us": gemm_us / max(1, g["n"]),
-                "algorithmic_gflop_per_step": gemm_fl / 1e9,
+                "launches_note": "GEMM launches of ONE device launch (G coalesced steps), timed at the shapes and tile hints the timed region uses",
+                "algorithmic_gflop_per_step": gemm_fl / G / 1e9,
                 "dominant_shape": None if dom is None else {"M": dom[1], "N": dom[2], "K": dom[3], "launches": dom[5], "us_per_launch": dom[4],
                                                             "tflops": tf_dom, "algorithmic_bytes": dom[6],
                                                             "hbm_floor_us": dom[6] / (peaks["hbm"] * 1e3)},

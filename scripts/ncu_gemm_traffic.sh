@@ -1,10 +1,12 @@
 #!/bin/bash
-# dram bytes per launch of every decode GEMM shape (ncu, cold operands) -> profiles/r02_gemm_traffic.json keyed "M,N,K,out_bytes,residual"
+# dram bytes per launch of every GEMM shape of configs[2] (ncu, cold operands) -> profiles/r02_gemm_traffic.json keyed "M,N,K,out_bytes,residual"
 mkdir -p gpurun_out
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
     --kernel-name regex:sc_gemm_bf16_kernel --log-file gpurun_out/gemm_traffic.csv python scripts/gemm_shapes_once.py > gpurun_out/gemm_traffic.log 2>&1
 python - <<'PY'
-import csv, json, io
+import csv, json, io, sys
+sys.path.insert(0, "scripts")
+from gemm_shapes_once import SHAPES
 rows = [l for l in open("gpurun_out/gemm_traffic.csv") if l.startswith('"')]
 rd = list(csv.DictReader(io.StringIO("".join(rows))))
 # launches alternate warm-up / measured per shape, 3 metric rows per launch
@@ -12,16 +14,16 @@ by_id = {}
 for r in rd:
     by_id.setdefault(int(r["ID"]), {})[r["Metric Name"]] = (float(r["Metric Value"].replace(",", "")), r["Metric Unit"])
 ids = sorted(by_id)
-SHAPES = [(1536, 512, 2, 0), (512, 512, 4, 1), (512, 512, 2, 0), (2048, 512, 2, 0), (512, 2048, 4, 1), (10000, 512, 0, 0)]
 unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out, detail = {}, {}
-for i, (N, K, ys, res) in enumerate(SHAPES):
+for i, (M, N, K, ys, res, relu, tile) in enumerate(SHAPES):
     m = by_id[ids[2 * i + 1]]  # the second (cold-operand) launch of the shape
     rdb = m["dram__bytes_read.sum"][0] * unit[m["dram__bytes_read.sum"][1]]
     wrb = m["dram__bytes_write.sum"][0] * unit[m["dram__bytes_write.sum"][1]]
-    key = f"1536,{N},{K},{ys},{res}"
+    key = f"{M},{N},{K},{ys},{res}"
     out[key] = int(rdb + wrb)
-    detail[key] = {"dram_read": int(rdb), "dram_write": int(wrb), "time": m["gpu__time_duration.sum"]}
+    detail[key] = {"dram_read": int(rdb), "dram_write": int(wrb), "time": m["gpu__time_duration.sum"],
+                   "algorithmic_bytes": 2 * M * K + 2 * N * K + ys * M * N + (4 * M * N if res else 0)}
 json.dump(out, open("gpurun_out/r02_gemm_traffic.json", "w"), indent=1)
 json.dump(detail, open("gpurun_out/r02_gemm_traffic_detail.json", "w"), indent=1)
 print(json.dumps(detail, indent=1))

@@ -35,7 +35,7 @@ def linear(x, w, bias=None, *, mask=None, mask_mode=MASK_NONE, uniforms=None, se
              mask_mode, lib.ptr(uniforms), seed, stream_id, lib.ptr(bias), lib.ptr(residual), lib.ptr(out),
              lib.dtype_code(out.dtype), M, N, K, int(relu), tile_n, lib.stream(),
              meta=("gemm_bf16" if x.dtype == torch.bfloat16 else "gemm_f32", M, N, K, x.element_size(), w.element_size(),
-                   out.element_size(), mask is not None, residual is not None, bool(relu)))
+                   out.element_size(), mask is not None, residual is not None, bool(relu), tile_n))
     return out
 
 
