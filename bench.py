@@ -253,7 +253,10 @@ def time_train_gemms(prof, dev):
                 has_res = key[8] if len(key) > 8 else False
                 res = torch.randn(M, N, device=dev) if has_res else None
                 run = lambda i: KK.linear(x, w, None, residual=res, out=outs[i % 2])
-        tot_us += _time_graph(run, dev, 20) * cnt
+        us = _time_graph(run, dev, 20)
+        if os.environ.get("SC_BENCH_VERBOSE") == "1":
+            print(f"  train gemm {name:26s} {str(key[1:4]):22s} x{cnt:3d}  {us:7.2f} us  {fl / us / 1e6:6.0f} TF/s  flags {key[4:]}", file=sys.stderr)
+        tot_us += us * cnt
         tot_fl += fl * cnt
     return tot_us, tot_fl
 
@@ -442,6 +445,7 @@ def main():
     ap.add_argument("--e2e-coalesce", type=int, default=0, help="--coalesce of the end-to-end arm (0 = 2 when --steps is even: smaller device batches "
                          "start their H2D copies earlier, so the pipeline of copy -> encode -> decode fills faster)")
     ap.add_argument("--e2e-slots", type=int, default=0, help="--slots of the end-to-end arm (0 = auto)")
+    ap.add_argument("--e2e-schedule", default="", help="queued batches per launch of the end-to-end arm, e.g. 2,2,4,4,4,4 (sums to --steps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -573,24 +577,35 @@ def main():
     ms_dev = e0.elapsed_time(e1)
 
     # ---------------- end-to-end arm: pinned host inputs -> tokens on the host ----------------
-    # its own batching: a launch cannot start before its H2D copy, so smaller coalesced batches on more slots fill the
-    # copy -> encode -> decode pipeline sooner (measured: scripts/gpu_dec_ab4.sh)
-    Ge = args.e2e_coalesce if args.e2e_coalesce > 0 else (2 if args.steps % 2 == 0 else 1)
-    assert args.steps % Ge == 0, "--steps must be a multiple of --e2e-coalesce"
-    ne_timed = args.steps // Ge
-    Se = args.e2e_slots if args.e2e_slots > 0 else next((sl for sl in (5, 4, 3, 2) if ne_timed % sl == 0), min(4, ne_timed))
-    Be = args.images * Ge
+    # --e2e-coalesce 0 (default): 4 queued batches per launch when --steps allows it (else 2 / 1).  The H2D copy of a launch's
+    # batches paces its start (3 ms per batch over PCIe): measured schedules for 20 steps (scripts/gpu_e2e_sched.sh, ms/step):
+    # 10 x 2: 6.00, 5 x 4: 5.89, 2,2,4,4,4,4: 5.87, 2,3,5,5,5: 5.85, 4 x 5: 5.97, ramp 1,1,2,4,4,4,4: 6.54 (its single-batch
+    # launches are latency-bound chains that leave the SMs idle)
+    if args.e2e_schedule:
+        sched = [int(g) for g in args.e2e_schedule.split(",")]
+        assert sum(sched) == args.steps, "--e2e-schedule must sum to --steps"
+    else:
+        ge = args.e2e_coalesce if args.e2e_coalesce > 0 else next(g for g in (4, 2, 1) if args.steps % g == 0 and g <= max(1, G))
+        assert args.steps % ge == 0, "--steps must be a multiple of --e2e-coalesce"
+        sched = [ge] * (args.steps // ge)
+    Ge = max(sched)
+    ne_timed = len(sched)
+    Se = args.e2e_slots if args.e2e_slots > 0 else min(5, ne_timed)
     eslots = list(range(101, 101 + Se))
-    ehost = [(a[:Be], b[:Be]) for a, b in host] if Be <= B else [synthetic.synthetic_inputs(Be, N_BOX, F, seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
-    outs = [[(torch.empty(Be, max(b, 1), L, dtype=torch.int32).pin_memory(), torch.empty(Be, max(b, 1), L, dtype=torch.float32).pin_memory())
-             for b in beams] for _ in eslots]
+    Bmax = args.images * Ge
+    big = host if Bmax <= B else [synthetic.synthetic_inputs(Bmax, N_BOX, F, seed=8888 + rank + 100 * i, pin=True) for i in range(2)]
+    outs = {}   # (slot index, batches in the launch) -> pinned result buffers per decode
 
     def e2e_run(batches):
         def e2e_step(i):
+            g = sched[i]
             att, boxes = batches[i & 1]
             k = i % Se
-            eng.submit(att, boxes, None, opts, slot=eslots[k], out=outs[k], prefetch=args.prefetch)
-        for i in range(max(-(-args.warmup // Ge), Se)):  # every slot's host-input path (its own workspaces / graphs) is warm
+            if (k, g) not in outs:
+                outs[(k, g)] = [(torch.empty(args.images * g, max(b, 1), L, dtype=torch.int32).pin_memory(),
+                                 torch.empty(args.images * g, max(b, 1), L, dtype=torch.float32).pin_memory()) for b in beams]
+            eng.submit(att[: args.images * g], boxes[: args.images * g], None, opts, slot=eslots[k], out=outs[(k, g)], prefetch=args.prefetch)
+        for i in range(ne_timed):  # one untimed pass of the schedule: every (slot, batch size) pair's workspaces / graphs are warm
             e2e_step(i)
         eng.wait()
         barrier()
@@ -602,16 +617,17 @@ def main():
         barrier()
         return e0.elapsed_time(e1)
 
-    ms_e2e = e2e_run(ehost)
+    ms_e2e = e2e_run(big)
     # the same with bf16 pinned host features (half the H2D bytes; the engine lands them directly in the GEMM operand buffer)
-    host16 = [(a.to(torch.bfloat16).pin_memory(), b) for a, b in ehost]
+    host16 = [(a.to(torch.bfloat16).pin_memory(), b) for a, b in big]
     ms_e2e16 = e2e_run(host16)
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
-    h2d = (ehost[0][0].numel() * 4 + ehost[0][1].numel() * 4) // Ge   # per step of --images
-    h2d16 = (ehost[0][0].numel() * 2 + ehost[0][1].numel() * 4) // Ge
-    d2h = sum(o[0].numel() * 4 + o[1].numel() * 4 for o in outs[0]) // Ge
+    per_img = big[0][0][0].numel()
+    h2d = args.images * (per_img * 4 + N_BOX * 4 * 4)     # per step of --images: fp32 features + boxes
+    h2d16 = args.images * (per_img * 2 + N_BOX * 4 * 4)
+    d2h = sum(args.images * max(b, 1) * L * 8 for b in beams)   # tokens (int32) + log-probs (fp32)
     del host16
 
     t = torch.tensor([ms_dev, ms_e2e, ms_e2e16], device=dev, dtype=torch.float64)
@@ -778,7 +794,7 @@ def main():
             "dtype": "bf16", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": wl["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "host_features": "fp32 pinned (the reference loader's dtype)",
-                    "coalesced_batches_per_launch": Ge, "launches_in_flight": Se},
+                    "batches_per_launch_schedule": sched, "launches_in_flight": Se},
             "e2e_bf16_host": {"value": per_s(ms_e2e16), "unit": wl["unit"], "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h,
                               "ms_per_step": ms_e2e16 / args.steps, "host_features": "bf16 pinned"},
             "gpu_launches": launches_per_call * n_timed, "clocks": sampler.summary(), "roofline": roofline,

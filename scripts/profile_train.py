@@ -17,8 +17,8 @@ if "SC_WGRAD_RING" in os.environ:
     tr.wgrad_ring = int(os.environ["SC_WGRAD_RING"])
 if "SC_PDL_MASK" in os.environ:
     tr.pdl_mask = int(os.environ["SC_PDL_MASK"])
-if "SC_PREMASK_OVERLAP" in os.environ:
-    tr.premask_overlap = os.environ["SC_PREMASK_OVERLAP"] == "1"
+if os.environ.get("SC_SKIP_WGRAD") == "1":
+    tr._diag_skip_wgrad = True   # (wrong gradients: timing of the main chain alone)
 S, T = 5, 17
 g = torch.Generator().manual_seed(8888)
 att, boxes = synthetic.synthetic_inputs(B, 36, 2048, seed=8888, pin=True)

@@ -800,8 +800,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // every chunk is straight-line code from two per-lane base pointers (the generic path spends ~700 instructions per 32 x 32
       // chunk on bounds checks, dtype branches and 64-bit address arithmetic for 64 useful FADDs: it made the fp32-residual
       // epilogue, not the MMAs, the long pole of the N = d_model GEMMs)
-      const bool fast_tile = pipe_res && !args.y_bf16 && !(kEpi == 1 && args.y2) && (args.N & 3) == 0 && rbase + 32 <= args.M &&
-                             n0 + BLOCK_N <= args.N;
+      const bool fast_tile = pipe_res && !args.y_bf16 && (args.N & 3) == 0 && rbase + 32 <= args.M && n0 + BLOCK_N <= args.N;
       const size_t lane_off = (size_t)(rbase + (lane >> 3)) * args.N + n0 + (lane & 7) * 4;
       const size_t row4 = (size_t)4 * args.N;  // this lane's next row (4 rows down)
       const float* res_lane = args.residual + lane_off;
@@ -1027,7 +1026,18 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               *(float4*)(str_ + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *(float4*)(y_lane + c * 32 + i * row4) = *(const float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6)));
+            for (int i = 0; i < 8; ++i) {
+              const float4 o = *(const float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6)));
+              *(float4*)(y_lane + c * 32 + i * row4) = o;
+              if constexpr (kEpi == 1) {
+                if (args.y2) {  // bf16 copy of the residual stream (LayerNorm-folding consumers read it as their A operand)
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                  uint2 pk;
+                  pk.x = *(const uint32_t*)&lo; pk.y = *(const uint32_t*)&hi;
+                  *(uint2*)((__nv_bfloat16*)args.y2 + lane_off + c * 32 + i * row4) = pk;
+                }
+              }
+            }
             __syncwarp();  // staging is rewritten by the next chunk
             continue;
           }

@@ -99,11 +99,12 @@ class _Lin:
 
     def ln(self, xb, stats, out, relu=False):
         """out = act(LayerNorm(x) W^T + b) from the bf16 copy of x and its chunk statistics."""
-        return K.linear_ln(xb, self.wf, self.bias_f, out=out, relu=relu, ln_stats=stats, ln_c=self.ln_c)
+        return K.linear_ln(xb, self.wf, self.bias_f, out=out, relu=relu, ln_stats=stats, ln_c=self.ln_c, tile_n=self.tile_n)
 
     def produce(self, x, out, out_bf16, stats, residual=None, relu=False):
         """out (fp32 residual stream) = act(x W^T + b) + residual, plus its bf16 copy and chunk statistics."""
-        return K.linear_ln(x, self.w, self.bias, residual=residual, relu=relu, out=out, out_bf16=out_bf16, stats_out=stats)
+        return K.linear_ln(x, self.w, self.bias, residual=residual, relu=relu, out=out, out_bf16=out_bf16, stats_out=stats,
+                           tile_n=self.tile_n)
 
     def __call__(self, x, out, residual=None, relu=False):
         if self.gs is not None:
@@ -517,7 +518,7 @@ class OrtEngine:
         """The fused generator + beam row pass serves the dense bf16 tensor path, beam <= 5 (options are checked per call)."""
         g = self.generator
         return (self.fuse_topk and self.adt == torch.bfloat16 and g.w is not None and g.w.dtype == torch.bfloat16 and beam <= 5
-                and g.K % 8 == 0 and not self.fold_dec)
+                and g.K % 8 == 0)
 
     def _decode_step(self, ws, enc, t, anc, fused_topk=False):
         c = self.cfg
@@ -565,14 +566,13 @@ class OrtEngine:
                 e["n2"](ws.x, ws.xn)
                 e["ff1"](ws.xn, ws.hid, relu=True)
                 e["ff2"](ws.hid, ws.x, residual=ws.x)
-        if fold:
-            self.generator.ln(ws.xb, ws.stats, ws.logits)
+        # (the final norm stays a kernel also when the layers' norms are folded: the fused generator + top-k epilogue has no
+        # folded-LayerNorm variant, and one LayerNorm per step is 1/19 of them)
+        self.dec_norm(ws.x, ws.xn)
+        if fused_topk:
+            K.linear_topk(ws.xn, self.generator.w, self.generator.bias, ws.topk_part, candidates=ws.beam)
         else:
-            self.dec_norm(ws.x, ws.xn)
-            if fused_topk:
-                K.linear_topk(ws.xn, self.generator.w, self.generator.bias, ws.topk_part, candidates=ws.beam)
-            else:
-                self.generator(ws.xn, ws.logits)
+            self.generator(ws.xn, ws.logits)
 
     def _beam_body(self, ws, enc, opt):
         c = self.cfg

@@ -154,6 +154,9 @@ class OrtTrainer:
         self.premask = True   # False: mask inside the GEMM operand prologue (K1 fused variant)
         self._wm, self._wmT, self._wm_step = {}, {}, {}
         self._premask_desc = None
+        # timing diagnostic (scripts/profile_train.py SC_SKIP_WGRAD=1: wrong gradients): the main chain alone - measured 4.95 of the
+        # 5.35 ms step, i.e. the weight-gradient side stream costs 0.4 ms and the step is bound by the ~290 dependent launches
+        self._diag_skip_wgrad = False
         self.pdl_mask = 3            # sc_set_pdl mask while the step is launched / captured (see train_step)
         self.wgrad_ring = 4          # 1: weight gradients stay on the main stream
         import os
@@ -451,8 +454,9 @@ class OrtTrainer:
             ev.record(main)
             st.wait_event(ev)
             with torch.cuda.stream(st):
-                K.linear_wgrad_rowmajor(gb, x_saved, W, S, mode, gW, gS, workspace=ws.wgrad_ws, uniforms=U, seed=seed,
-                                        stream_id=stream, bypass=self.bypass)
+                if not self._diag_skip_wgrad:
+                    K.linear_wgrad_rowmajor(gb, x_saved, W, S, mode, gW, gS, workspace=ws.wgrad_ws, uniforms=U, seed=seed,
+                                            stream_id=stream, bypass=self.bypass)
                 if slot is not None:
                     ws.gb_free[slot] = torch.cuda.Event()
                     ws.gb_free[slot].record(st)
