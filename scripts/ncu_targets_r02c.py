@@ -22,6 +22,13 @@ if "o" in which:
     for hint in (20003256, 3256):
         for _ in range(reps):
             K.linear(x, w, b, residual=x32, out=x32, tile_n=hint)
+if "obig" in which:   # encoder-size residual GEMM, many tiles per persistent CTA (run with SC_GEMM_MULTICAST=0 for the single-CTA kernel)
+    Mb = 92160
+    x = torch.randn(Mb, d, **bf); w = torch.randn(d, d, **bf); b = torch.randn(d, device=dev); x32 = torch.randn(Mb, d, device=dev)
+    y16 = torch.empty(Mb, d, **bf)
+    for _ in range(reps):
+        K.linear(x, w, b, residual=x32, out=x32, tile_n=3256)
+        K.linear(x, w, b, out=y16, tile_n=3256)
 if "ff2" in which:
     x = torch.randn(R, ff, **bf); w = torch.randn(d, ff, **bf); b = torch.randn(d, device=dev); x32 = torch.randn(R, d, device=dev)
     for _ in range(reps):

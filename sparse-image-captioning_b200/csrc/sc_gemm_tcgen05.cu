@@ -264,7 +264,10 @@ struct Smem {
 // dropout / LayerNorm / row-statistics code.
 template <bool kFull>
 __device__ __forceinline__ void epilogue_row(const GemmArgs& args, float (&f)[32], const float (&res)[32], int row, int col0,
-                                             float ln_rstd, float ln_mr, const float* sb, const float* sc) {
+                                             float ln_rstd, float ln_mr, const float* sb, const float* sc,
+                                             const uint8_t* res_stage = nullptr, int res_sw = 0) {
+  // res_stage: the thread's residual row piece still sits in the warp's (XOR-swizzled) staging tile and is added from there -
+  // 32 registers less than a separate res[] array (the fast residual tile spilled its base pointers without this)
   // sb / sc: this chunk's 32 bias / ln_c values in shared memory (zero-filled beyond N; staged once per tile so that no
   // global latency sits between the accumulator load and the stores)
   if (kFull && args.ln_stats) {
@@ -304,8 +307,16 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& args, float (&f)[32
     }
   }
   if (args.residual) {
+    if (res_stage != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] += res[j];
+      for (int j = 0; j < 8; ++j) {
+        const float4 r4 = *(const float4*)(res_stage + ((j ^ res_sw) << 4));
+        f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] += res[j];
+    }
   }
   if (kFull && args.stats_out) {
     // (sum, M2 about the chunk mean) of this row's 32-column chunk; the LayerNorm consumer merges the N/32 chunks
@@ -1004,13 +1015,6 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 8; ++i) *(float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6))) = rnext[i];
             __syncwarp();
-            float res[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r4 = *(const float4*)(str_ + ((j ^ jsw) << 4));
-              res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w;
-            }
-            __syncwarp();
             if (c + kChunkStep < BLOCK_N / 32) {  // next chunk of this warp: in flight underneath the rest of this one
 #pragma unroll
               for (int i = 0; i < 8; ++i) rnext[i] = *(const float4*)(res_lane + (c + kChunkStep) * 32 + i * row4);
@@ -1020,7 +1024,9 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
+            // (the residual row piece is added straight from the staging tile: no res[] registers)
+            epilogue_row<kEpi == 1>(args, f, f, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32, str_, jsw);
+            __syncwarp();  // every lane has read its residual piece: the tile may take the results
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *(float4*)(str_ + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -1068,21 +1074,13 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         // residual: coalesced mapping -> staging -> row mapping (16-byte piece p of row r sits at piece p ^ (r & 7)), done BEFORE the
         // accumulator load so that the next chunk's request is in flight underneath the tcgen05.ld, the element-wise stage and the stores
-        float res[kEpi != 2 ? 32 : 1];
+        // (the residual row piece is then added straight from the staging tile inside epilogue_row: no res[] registers)
         if constexpr (kEpi != 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) res[j] = 0.f;
           if (has_res) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rl = i * 4 + (lane >> 3);
               *(float4*)(stg + rl * 128 + ((pj ^ (rl & 7)) << 4)) = rres[i];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r4 = *(const float4*)(stg + lane * 128 + ((j ^ jsw) << 4));
-              res[4 * j] = r4.x; res[4 * j + 1] = r4.y; res[4 * j + 2] = r4.z; res[4 * j + 3] = r4.w;
             }
             __syncwarp();
             if constexpr (kPipeRes) {
@@ -1097,7 +1095,9 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          epilogue_row<kEpi == 1>(args, f, res, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32);
+          epilogue_row<kEpi == 1>(args, f, f, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32,
+                                  has_res ? stg + lane * 128 : nullptr, jsw);
+          __syncwarp();  // every lane has read its residual piece: the tile may take the results
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *(float4*)(stg + lane * 128 + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
