@@ -550,7 +550,13 @@ class _OrtBase(nn.Module):
         """The fused training engine bound to a COPY of this module's parameters (rebuilt when they change).
         ``trainer().train_step(...)`` replaces loss.backward() + clip_gradient + optimizer.step() of the reference
         loop (scripts/train_n_prune_transformer.py:136-153); ``sync_from_trainer()`` copies the result back."""
-        from .trainer import OrtTrainer
+        from .trainer import ModuleTrainer, OrtTrainer
+        c = self.cfg
+        if c.share_att_encoder or c.share_att_decoder or c.share_layer_encoder or c.share_layer_decoder:
+            # ACORT weight sharing: the module tree under autograd + the fused clip / Adam kernel (trainer.ModuleTrainer)
+            if not isinstance(self._trainer, ModuleTrainer):
+                self._trainer = ModuleTrainer(self)
+            return self._trainer
         key = self._param_key()
         if self._trainer is None or self._trainer_key != key:
             self._trainer = OrtTrainer(self.state_dict(), self.cfg, mask_type=self.mask_type if self.MASKED else None,
@@ -561,6 +567,9 @@ class _OrtBase(nn.Module):
 
     @torch.no_grad()
     def sync_from_trainer(self):
+        from .trainer import ModuleTrainer
+        if isinstance(self._trainer, ModuleTrainer):
+            return  # (it updates this module's parameters in place)
         self.load_state_dict(self._trainer.state_dict(), strict=False)
         self._trainer_key = self._param_key()  # the trainer's parameters ARE the module's now
 

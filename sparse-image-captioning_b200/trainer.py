@@ -29,7 +29,7 @@ class OrtTrainer:
                  precision="bf16", device="cuda", dropout=0.1 / 3, drop_prob_src=0.5, bypass_sigmoid_grad=False, seed=0,
                  mask_init_value=5.0, uniforms: Optional[Dict[str, torch.Tensor]] = None, use_graph=False, fused_st=True):
         assert cfg.share_att_encoder is None and cfg.share_att_decoder is None and not cfg.share_layer_encoder \
-            and not cfg.share_layer_decoder, "ACORT weight sharing is an inference-side feature in this round"
+            and not cfg.share_layer_decoder, "the fused engine lays out the ORT stack; ACORT weight sharing trains through ModuleTrainer (model.trainer() picks it)"
         self.cfg = cfg
         self.dev = K.lib.resolve_device(device)
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
@@ -1120,3 +1120,61 @@ class OrtTrainer:
         sd = {k: v.clone() for k, v in self.p.items()}
         sd.update({k + "_pruning_mask": v.clone() for k, v in self.s.items()})
         return sd
+
+
+class ModuleTrainer:
+    """``train_step`` for the configurations the fused engine does not lay out - ACORT weight sharing (``share_att_*`` /
+    ``share_layer_*``, models/relation_transformer.py:80-89,162-176): the kernel-backed module tree under autograd (every
+    forward / backward is a kernel, autograd accumulates the applications of a shared layer and draws a fresh Bernoulli mask per
+    application like the reference), LanguageModelCriterion (utils/losses.py:32-43) + sparsity loss (pruning/prune.py:228-269),
+    then clip_gradient + Adam for the two parameter groups (scripts/train_n_prune_transformer.py:67-82, utils/optim.py:116-126)
+    as one ``sc_adam_clip`` launch per tensor.  It updates the module's own parameters (nothing to sync back)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.opt_step = 0
+        self._mv = {}
+
+    def train_step(self, att_feats, boxes, seqs, masks, att_masks=None, *, seq_per_img, lr, all_reduce=None, global_tokens=None,
+                   mask_lr=100.0, clip=0.1, betas=(0.9, 0.98), eps=1e-9, mask_eps=1e-2, weight_decay=0.0, grad_scale=1.0,
+                   sparsity_target=None, sparsity_weight=0.0, current_step=0, max_step=1):
+        m = self.model
+        dev = m._device()
+        m.train()
+        params = [(n, p) for n, p in m.named_parameters() if p.requires_grad]
+        for _, p in params:
+            p.grad = None
+        seqs_d, masks_d = seqs.to(dev), masks.to(dev).float()
+        assert seqs_d.shape[0] == att_feats.shape[0] * seq_per_img, (seqs_d.shape, att_feats.shape, seq_per_img)
+        out = m(att_feats=att_feats.to(dev), boxes=boxes.to(dev), seqs=seqs_d, att_masks=None if att_masks is None else att_masks.to(dev))
+        T = out.shape[1]
+        target, w = seqs_d[:, 1: T + 1], masks_d[:, 1: T + 1]
+        denom = w.sum() if global_tokens is None else global_tokens
+        loss = -(out.gather(2, target.unsqueeze(2)).squeeze(2) * w).sum() / denom
+        total = loss
+        if getattr(m, "MASKED", False) and m.mask_type == "supermask" and sparsity_target is not None and sparsity_weight:
+            total = total + m.compute_sparsity_loss(sparsity_target, sparsity_weight, current_step, max_step)
+        total.backward()
+        if all_reduce is not None:  # data parallel: sum the gradients of every rank (the loss is normalised by the global token count)
+            flat = torch._utils._flatten_dense_tensors([p.grad for _, p in params])
+            h = all_reduce(flat)
+            if h is not None:
+                h.wait()
+            for (_, p), g in zip(params, torch._utils._unflatten_dense_tensors(flat, [p.grad for _, p in params])):
+                p.grad.copy_(g)
+        self.opt_step += 1
+        with torch.no_grad():
+            for n, p in params:
+                is_logit = n.endswith("_pruning_mask")
+                if n not in self._mv:
+                    self._mv[n] = (torch.zeros_like(p, dtype=torch.float32).view(-1), torch.zeros_like(p, dtype=torch.float32).view(-1))
+                mom, var = self._mv[n]
+                g = p.grad.contiguous().view(-1)
+                K.adam_clip(p.data.view(-1), g, mom, var, lr=mask_lr if is_logit else lr, betas=betas, eps=mask_eps if is_logit else eps,
+                            weight_decay=0.0 if is_logit else weight_decay, clip=clip, grad_scale=grad_scale, step=self.opt_step)
+                torch.autograd.graph.increment_version(p)  # (written through raw pointers: cached engines must notice)
+        return loss.detach()
+
+    def state_dict(self):
+        return self.model.state_dict()
+

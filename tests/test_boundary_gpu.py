@@ -356,3 +356,44 @@ def test_scst_style_rollout_in_train_mode_draws_bernoulli_masks():
     e1, _ = m(att_feats=att, boxes=boxes, opt={"beam_size": 2}, mode="sample")
     e2, _ = m(att_feats=att, boxes=boxes, opt={"beam_size": 2}, mode="sample")
     assert torch.equal(e1, e2)
+
+
+def test_acort_trainer_step_matches_reference_recipe():
+    """``model.trainer()`` of an ACORT configuration (shared attention projections + shared layers, pruned class): one
+    ``train_step`` = the reference recipe (loss.backward() -> clip_gradient(0.1) -> Adam with the two parameter groups of
+    scripts/train_n_prune_transformer.py:67-82) applied to the gradients the kernel-backed module tree produced; shared layers
+    stay shared; the loss of a repeated batch goes down."""
+    from sparse_caption_b200.trainer import ModuleTrainer
+    z = golden_io.load("acort_tiny")
+    import sparse_caption_b200.relation_transformer as R
+    m = R.get_model("relation_transformer_prune")(dict(z["cfg_dict"])).to(DEV)
+    m.precision = "fp32"
+    tr = m.trainer()
+    assert isinstance(tr, ModuleTrainer) and m.trainer() is tr
+
+    def shared_ok():
+        for stack, share in ((m.model.encoder, m.cfg.share_layer_encoder), (m.model.decoder, m.cfg.share_layer_decoder)):
+            for i, u in enumerate(share):
+                for j, v in enumerate(share):
+                    if (stack.layers[i] is stack.layers[j]) != (u == v):
+                        return False
+        return True
+    assert m.cfg.share_layer_encoder and m.cfg.share_layer_decoder and shared_ok()
+    named = [(n, p) for n, p in m.named_parameters() if p.requires_grad]
+    before = {n: p.detach().clone() for n, p in named}
+    S = z["seqs"].shape[0] // z["att_feats"].shape[0]
+    kw = dict(seq_per_img=S, lr=1e-3, mask_lr=10.0, sparsity_target=0.9, sparsity_weight=1.0, current_step=500, max_step=1000)
+    loss0 = float(tr.train_step(z["att_feats"], z["boxes"], z["seqs"], z["masks"], **kw))
+    # the same update with torch: clip_gradient (clamp to +-0.1, utils/optim.py:187-191) then Adam, first step
+    for n, p in named:
+        g = p.grad.clamp(-0.1, 0.1)
+        logit = n.endswith("_pruning_mask")
+        lr, eps = (10.0, 1e-2) if logit else (1e-3, 1e-9)
+        mhat, vhat = g, g * g                          # (1 - b) g / (1 - b^1) = g
+        ref = before[n] - lr * mhat / (vhat.sqrt() + eps)
+        assert rel_err(p.detach(), ref) < 1e-5, n
+    assert shared_ok()
+    losses = [float(tr.train_step(z["att_feats"], z["boxes"], z["seqs"], z["masks"], **kw)) for _ in range(12)]
+    assert math.isfinite(loss0) and min(losses[-3:]) < loss0, (loss0, losses)
+    m.sync_from_trainer()  # no-op for the module trainer
+
