@@ -740,6 +740,11 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     float4* pre = (float4*)(smem + L::kStagingOffset);  // residual prefetch: piece j of epilogue thread t at [j * 128 + t]
     const int et = threadIdx.x - 128;                    // 0..127 (4-warp configurations)
     const int jsw = lane & 7;  // swizzle key of this thread's own row (row-mapping: row = lane)
+    // coalesced-path residual, software-pipelined TWO chunks ahead (two register buffers; see load_residual8) and across tiles:
+    // the first two chunks of the NEXT tile are requested while the last two of this one are processed
+    constexpr bool kPipeRes = !kDirect && kEpi != 2 && kResCo;
+    float4 rnext[kPipeRes ? 8 : 1], rnext2[kPipeRes ? 8 : 1];
+    bool pre_tile = false;  // rnext / rnext2 already hold the requests of this tile's first chunks
     int lt = 0;
     for (int u = unit0; u < num_units; u += ustride, ++lt) {
       const int tile = u / args.splits, split = u - tile * args.splits;
@@ -803,10 +808,7 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      // coalesced-path residual, software-pipelined one chunk ahead (see load_residual8)
-      constexpr bool kPipeRes = !kDirect && kEpi != 2 && kResCo;
       const bool pipe_res = kPipeRes && args.residual != nullptr;
-      float4 rnext[kPipeRes ? 8 : 1];
       // fast tile: the warp's 32 rows and the whole N tile lie inside the matrix, rows are 16-byte aligned, plain fp32 output -
       // every chunk is straight-line code from two per-lane base pointers (the generic path spends ~700 instructions per 32 x 32
       // chunk on bounds checks, dtype branches and 64-bit address arithmetic for 64 useful FADDs: it made the fp32-residual
@@ -816,13 +818,21 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const size_t row4 = (size_t)4 * args.N;  // this lane's next row (4 rows down)
       const float* res_lane = args.residual + lane_off;
       float* y_lane = (float*)args.y + (size_t)split * args.split_stride + lane_off;
+      constexpr int kWarpChunks = BLOCK_N / 32 / kChunkStep;  // chunks of a tile per epilogue warp
       if constexpr (kPipeRes) {
         if (fast_tile) {
+          if (!pre_tile) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rnext[i] = *(const float4*)(res_lane + half * 32 + i * row4);
+            for (int i = 0; i < 8; ++i) rnext[i] = *(const float4*)(res_lane + half * 32 + i * row4);
+            if constexpr (kWarpChunks > 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rnext2[i] = *(const float4*)(res_lane + (half + kChunkStep) * 32 + i * row4);
+            }
+          }
         } else if (pipe_res && rbase < args.M && n0 + half * 32 < args.N) {
           load_residual8(args, rbase, lane, n0 + half * 32 + (lane & 7) * 4, rnext);
         }
+        pre_tile = false;
       }
       mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
       tcgen05_fence_after();
@@ -872,8 +882,75 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
         }
       }
+      bool fast_done = false;
+      if constexpr (kPipeRes) {
+        if (fast_tile) {
+          // staging offsets: row rl = 4 i + (lane >> 3), piece pj ^ (rl & 7); (rl & 7) = (lane >> 3) + 4 (i & 1)
+          const int pj = lane & 7;
+          uint8_t* stc = stg + (lane >> 3) * 128;
+          const uint32_t sw0 = (uint32_t)((pj ^ (lane >> 3)) << 4);
+          uint8_t* str_ = stg + lane * 128;
+          // the next unit of this CTA: its first chunks are requested underneath the last chunks of this tile
+          const float* res_nt = nullptr;
+          {
+            const int un = u + ustride;
+            if (un < num_units) {
+              const int tn = un / args.splits;
+              const int m0n = (c2 ? (tn / args.tiles_n) * 2 + (int)crank : tn / args.tiles_n) * BLOCK_M, n0n = (tn % args.tiles_n) * BLOCK_N;
+              if (m0n + q * 32 + 32 <= args.M && n0n + BLOCK_N <= args.N)
+                res_nt = args.residual + (size_t)(m0n + q * 32 + (lane >> 3)) * args.N + n0n + pj * 4;
+            }
+          }
+          // one chunk: residual (requested earlier into rb) -> staging; request `reload` into rb; accumulator; element-wise stage
+          // with the residual added straight from the staging tile; results -> staging -> coalesced stores
+          auto fast_chunk = [&](int c, float4 (&rb)[8], const float* reload) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *(float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6))) = rb[i];
+            __syncwarp();
+            if (reload != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rb[i] = *(const float4*)(reload + i * row4);
+            }
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            epilogue_row<kEpi == 1>(args, f, f, rbase + lane, n0 + c * 32, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32, str_, jsw);
+            __syncwarp();  // every lane has read its residual piece: the tile may take the results
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *(float4*)(str_ + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 o = *(const float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6)));
+              *(float4*)(y_lane + c * 32 + i * row4) = o;
+              if constexpr (kEpi == 1) {
+                if (args.y2) {  // bf16 copy of the residual stream (LayerNorm-folding consumers read it as their A operand)
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                  uint2 pk;
+                  pk.x = *(const uint32_t*)&lo; pk.y = *(const uint32_t*)&hi;
+                  *(uint2*)((__nv_bfloat16*)args.y2 + lane_off + c * 32 + i * row4) = pk;
+                }
+              }
+            }
+            __syncwarp();  // staging is rewritten by the next chunk
+          };
+#pragma unroll
+          for (int k = 0; k < kWarpChunks; k += 2) {
+            const int c = half + k * kChunkStep;
+            fast_chunk(c, rnext, k + 2 < kWarpChunks ? res_lane + (c + 2 * kChunkStep) * 32 : (res_nt ? res_nt + half * 32 : nullptr));
+            if (k + 1 < kWarpChunks)
+              fast_chunk(c + kChunkStep, rnext2,
+                         k + 3 < kWarpChunks ? res_lane + (c + 3 * kChunkStep) * 32 : (res_nt ? res_nt + (half + kChunkStep) * 32 : nullptr));
+          }
+          pre_tile = res_nt != nullptr;
+          fast_done = true;
+        }
+      }
 #pragma unroll 1
-      for (int c = half; c < (kTopkEpi ? 0 : BLOCK_N / 32); c += kChunkStep) {
+      for (int c = half; c < ((kTopkEpi || fast_done) ? 0 : BLOCK_N / 32); c += kChunkStep) {
         const int col0 = n0 + c * 32;
         if (col0 >= args.N || rbase >= args.M) continue;  // warp-uniform
         if (kDirect || (kEpi != 2 && (!kResCo || args.residual == nullptr))) {
@@ -1006,48 +1083,6 @@ sc_gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         // coalesced mapping: lane handles 16-byte piece (lane & 7) of rows (lane >> 3) + 4 i, i = 0..7
         const int pj = lane & 7;
         const int col = col0 + pj * 4;
-        if constexpr (kPipeRes) {
-          if (fast_tile) {
-            // staging offsets: row rl = 4 i + (lane >> 3), piece pj ^ (rl & 7); (rl & 7) = (lane >> 3) + 4 (i & 1)
-            uint8_t* stc = stg + (lane >> 3) * 128;
-            const uint32_t sw0 = (uint32_t)((pj ^ (lane >> 3)) << 4);
-            uint8_t* str_ = stg + lane * 128;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) *(float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6))) = rnext[i];
-            __syncwarp();
-            if (c + kChunkStep < BLOCK_N / 32) {  // next chunk of this warp: in flight underneath the rest of this one
-#pragma unroll
-              for (int i = 0; i < 8; ++i) rnext[i] = *(const float4*)(res_lane + (c + kChunkStep) * 32 + i * row4);
-            }
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), v);
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            // (the residual row piece is added straight from the staging tile: no res[] registers)
-            epilogue_row<kEpi == 1>(args, f, f, rbase + lane, col0, ln_rstd, ln_mr, sbias + c * 32, slnc + c * 32, str_, jsw);
-            __syncwarp();  // every lane has read its residual piece: the tile may take the results
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *(float4*)(str_ + ((j ^ jsw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 o = *(const float4*)(stc + i * 512 + (sw0 ^ ((i & 1) << 6)));
-              *(float4*)(y_lane + c * 32 + i * row4) = o;
-              if constexpr (kEpi == 1) {
-                if (args.y2) {  // bf16 copy of the residual stream (LayerNorm-folding consumers read it as their A operand)
-                  const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                  uint2 pk;
-                  pk.x = *(const uint32_t*)&lo; pk.y = *(const uint32_t*)&hi;
-                  *(uint2*)((__nv_bfloat16*)args.y2 + lane_off + c * 32 + i * row4) = pk;
-                }
-              }
-            }
-            __syncwarp();  // staging is rewritten by the next chunk
-            continue;
-          }
-        }
         // the residual chunk was requested one chunk ago (the tile's first one before the accumulator was awaited)
         float4 rres[8];
         const bool has_res = kEpi != 2 && kResCo && args.residual != nullptr;
