@@ -776,7 +776,7 @@ def main():
                                                             "hbm_floor_us": dom[6] / (peaks["hbm"] * 1e3)},
                 "share_of_step": g["ms"] / total_ms if total_ms else None,
                 "share_source": "per-launch CUDA events of one un-graphed step (host launch gaps included); the ncu launch list "
-                                "profiles/r01c_infer_launches_summary.txt gives the same share",
+                                "profiles/r02c_infer_launches_summary.txt (kernels of the same command) gives the same share",
                 "kernel_time_breakdown_ms": {k: round(v["ms"], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1]["ms"])},
                 "hbm_kernels": hbm}
 
