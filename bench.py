@@ -512,10 +512,11 @@ def main():
     sd = synthetic.random_state_dict(cfg, seed=1234, sparsity=wl["sparsity"], device=dev)
     G = max(1, args.coalesce)
     assert args.steps % G == 0, "--steps must be a multiple of --coalesce"
-    # >= 8 batches in flight (throughput regime): 256-wide tiles, two tiles per persistent CTA (10^7 digit)
-    dec_tiles = {k: 20003256 for k in ("qkv", "o", "cq", "co", "ff1", "ff2")} if args.slots * G >= 8 else None
+    # >= 8 batches in flight (throughput regime): the decode GEMMs run 256-wide tiles on persistent grids of ~48 CTAs (qkv, ff1:
+    # 8 - 10 tiles per CTA) / ~60 CTAs (the N = d_model GEMMs), sized per workspace by the engine (OrtEngine dec_ctas)
+    dec_ctas = (48, 60) if args.slots * G >= 8 else None
     eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold,
-                    fuse_topk=not args.no_fuse_topk, dec_tiles=dec_tiles)
+                    fuse_topk=not args.no_fuse_topk, dec_ctas=dec_ctas)
     B = args.images * G      # device batch = G queued batches of --images
     F = cfgd["att_feat_size"]
     # two distinct pinned host batches, alternated
@@ -653,7 +654,7 @@ def main():
     Bp = B
     att_p, box_p = host[0][0][:Bp], host[0][1][:Bp]
     eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False,
-                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk, dec_tiles=dec_tiles)
+                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk, dec_ctas=dec_ctas)
     enc2 = eng2.encode(att_p, box_p)
     for o in opts:
         eng2.decode(enc2, o)

@@ -1339,13 +1339,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, int want_s
   // a.tiles_per_cta > 1 (throughput regime: several independent GEMM chains in flight): fewer persistent CTAs, each looping
   // over that many tiles - the barrier / TMEM / tensor-map prologue is paid once and the epilogue of a tile runs under the
   // main loop of the next (double-buffered accumulators) instead of holding an SM
-  int want = min(units, per_sm * sm_count());
+  // SC_GEMM_MAX_CTAS (diagnostic): cap on the persistent grid - leaves SMs to the HBM-bound kernels of other streams
+  static int env_cap_ctas = -1;
+  if (env_cap_ctas < 0) { const char* e = getenv("SC_GEMM_MAX_CTAS"); env_cap_ctas = e ? atoi(e) : 0; }
+  const int sm_budget = env_cap_ctas > 0 ? min(env_cap_ctas, sm_count()) : sm_count();
+  int want = min(units, per_sm * sm_budget);
   if (a.tiles_per_cta > 1 && !a.cluster2) want = min(want, (units + a.tiles_per_cta - 1) / a.tiles_per_cta);
   dim3 grid(want);
   constexpr int threads = 32 * (4 + num_epilogue_warps(BLOCK_N, kStages) + (kMasked ? kNumTransformWarps : 0));
   cudaError_t e;
   if (a.cluster2) {
-    const int clusters = min(units, sm_count() / 2);
+    int clusters = min(units, sm_budget / 2);
+    if (a.tiles_per_cta > 1) clusters = min(clusters, max(1, (units + a.tiles_per_cta - 1) / a.tiles_per_cta));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
     cudaLaunchAttribute at[2];

@@ -97,23 +97,24 @@ class _Lin:
             self.ln_c = self.wf.float().sum(1).contiguous()
             self.bias_f = (w @ b2.float() + (self.bias if self.bias is not None else 0.0)).contiguous()
 
-    def ln(self, xb, stats, out, relu=False):
+    def ln(self, xb, stats, out, relu=False, tile_n=None):
         """out = act(LayerNorm(x) W^T + b) from the bf16 copy of x and its chunk statistics."""
-        return K.linear_ln(xb, self.wf, self.bias_f, out=out, relu=relu, ln_stats=stats, ln_c=self.ln_c, tile_n=self.tile_n)
+        return K.linear_ln(xb, self.wf, self.bias_f, out=out, relu=relu, ln_stats=stats, ln_c=self.ln_c,
+                           tile_n=self.tile_n if tile_n is None else tile_n)
 
-    def produce(self, x, out, out_bf16, stats, residual=None, relu=False):
+    def produce(self, x, out, out_bf16, stats, residual=None, relu=False, tile_n=None):
         """out (fp32 residual stream) = act(x W^T + b) + residual, plus its bf16 copy and chunk statistics."""
         return K.linear_ln(x, self.w, self.bias, residual=residual, relu=relu, out=out, out_bf16=out_bf16, stats_out=stats,
-                           tile_n=self.tile_n)
+                           tile_n=self.tile_n if tile_n is None else tile_n)
 
-    def __call__(self, x, out, residual=None, relu=False):
+    def __call__(self, x, out, residual=None, relu=False, tile_n=None):
         if self.gs is not None:
             return K.gspmm(x, self.gs, self.bias, residual=residual, relu=relu, out=out)
         if self.sell is not None:
             return K.sell_spmm(x, self.sell, self.bias, residual=residual, relu=relu, out=out)
         if self.csr is not None:
             return K.csr_spmm(x, self.csr, self.bias, residual=residual, relu=relu, out=out)
-        return K.linear(x, self.w, self.bias, residual=residual, relu=relu, out=out, tile_n=self.tile_n)
+        return K.linear(x, self.w, self.bias, residual=residual, relu=relu, out=out, tile_n=self.tile_n if tile_n is None else tile_n)
 
 
 class _Norm:
@@ -181,7 +182,7 @@ class OrtEngine:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ModelCfg, *, precision="bf16", sparse_backend="dense",
                  csr_threshold=0.995, device="cuda", use_graphs=True, no_history=False, ln_fold=False, fuse_topk=True,
-                 dec_tiles=None):
+                 dec_tiles=None, dec_ctas=None):
         if not torch.cuda.is_available():
             raise RuntimeError("OrtEngine needs a CUDA device: the B200 path has no CPU fallback")
         lib.load()
@@ -300,6 +301,12 @@ class OrtEngine:
         for name, val in hints.items():
             for e in self.dec.values():
                 e[name].tile_n = int(val)
+        # throughput regime (several device launches in flight): ``dec_ctas = (wide, narrow)`` sizes the persistent grids of the
+        # decode GEMMs per workspace - ~wide CTAs for N > d_model (qkv, ff1), ~narrow for the N = d_model GEMMs with the fp32
+        # residual epilogue - by giving each CTA ceil(tiles / target) tiles.  Measured (scripts/gpu_cap_ab*.sh): the 360- / 480-tile
+        # GEMMs on 148 CTAs monopolise the SMs for their whole duration; on ~48 CTAs (8 - 10 tiles each, epilogues hidden under the
+        # next main loops) the GEMMs of the other launches and their HBM-bound attention kernels run beside them: 4.95 -> 4.75 ms/step
+        self.dec_ctas = tuple(dec_ctas) if dec_ctas else None
         self._ingest_stream = None
         self._sample_seed = torch.zeros(1, dtype=torch.int64, device=self.dev)  # re-seeds captured sampling graphs
         self._sample_count = 0
@@ -509,10 +516,28 @@ class OrtEngine:
         ws.cache = {u: (torch.zeros(L * e["apps"], R, d, device=dev, dtype=adt),
                         torch.zeros(L * e["apps"], R, d, device=dev, dtype=adt)) for u, e in self.dec.items()}
         ws.state = GreedyState(R, L, dev) if greedy else BeamState(B, beam, L, dev)
+        ws.tile = self._dec_hints(R)
         ws.graph = None
         ws.opt_key = None
         self._dec_ws[key] = ws
         return ws
+
+    def _dec_hints(self, R):
+        """{(unique layer, linear): tile hint} of the decode GEMMs at R rows (None: the linear's own hint); see ``dec_ctas``."""
+        hints = {}
+        if not self.dec_ctas:
+            return hints
+        for u, e in self.dec.items():
+            for name in ("qkv", "o", "cq", "co", "ff1", "ff2"):
+                lin = e[name]
+                if lin.w is None or lin.tile_n:   # sparse backends / an explicit hint win
+                    continue
+                tiles = -(-R // 128) * -(-lin.N // 256)
+                target = self.dec_ctas[1] if lin.N <= self.cfg.d_model else self.dec_ctas[0]
+                tpc = -(-tiles // target)
+                if tpc >= 2:
+                    hints[(u, name)] = min(tpc, 200) * 10000000 + 3256
+        return hints
 
     def _topk_ok(self, beam):
         """The fused generator + beam row pass serves the dense bf16 tensor path, beam <= 5 (options are checked per call)."""
@@ -529,15 +554,17 @@ class OrtEngine:
         else:
             K.embed_pe(ws.state.tokens, self.table, self.pe, T=1, pos0=t, out=ws.x)
         used = {u: 0 for u in self.dec}
+        tiles = getattr(ws, "tile", None) or {}
         for u in self.dec_uids:
             e = self.dec[u]
+            tl = lambda name, u=u: tiles.get((u, name))   # per-workspace grid sizing of the decode GEMMs (dec_ctas)
             ld = e["ld"]
             qkv = ws.qkv.view(-1)[: R * ld].view(R, ld)
             if fold:
-                e["qkv"].ln(ws.xb, ws.stats, qkv)
+                e["qkv"].ln(ws.xb, ws.stats, qkv, tile_n=tl("qkv"))
             else:
                 e["n0"](ws.x, ws.xn)
-                e["qkv"](ws.xn, qkv)
+                e["qkv"](ws.xn, qkv, tile_n=tl("qkv"))
             qo, ko, vo = e["offs"]
             apps = e["apps"]
             slot = t * apps + used[u]
@@ -547,25 +574,25 @@ class OrtEngine:
                              n_prev=0 if self.no_history else slot, write_slot=-1 if self.no_history else slot,
                              ldq=ld, ldk=ld, ldv=ld, ldo=d, anc_ld=anc.shape[1], slot_div=apps)
             if fold:
-                e["o"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x)
-                e["cq"].ln(ws.xb, ws.stats, ws.qc)
+                e["o"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x, tile_n=tl("o"))
+                e["cq"].ln(ws.xb, ws.stats, ws.qc, tile_n=tl("cq"))
             else:
-                e["o"](ws.att, ws.x, residual=ws.x)
+                e["o"](ws.att, ws.x, residual=ws.x, tile_n=tl("o"))
                 e["n1"](ws.x, ws.xn)
-                e["cq"](ws.xn, ws.qc)
+                e["cq"](ws.xn, ws.qc, tile_n=tl("cq"))
             mkv = enc.memkv[u]
             ko2, vo2 = e["ckv_offs"]
             K.cross_attn_step(ws.qc, mkv[:, ko2:], mkv[:, vo2:], enc.att_mask, ws.att, B=ws.B, beam=ws.beam, N=N, D=d, h=h,
                               ldq=d, ldm=e["ckv_ld"], ldo=d)
             if fold:
-                e["co"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x)
-                e["ff1"].ln(ws.xb, ws.stats, ws.hid, relu=True)
-                e["ff2"].produce(ws.hid, ws.x, ws.xb, ws.stats, residual=ws.x)
+                e["co"].produce(ws.att, ws.x, ws.xb, ws.stats, residual=ws.x, tile_n=tl("co"))
+                e["ff1"].ln(ws.xb, ws.stats, ws.hid, relu=True, tile_n=tl("ff1"))
+                e["ff2"].produce(ws.hid, ws.x, ws.xb, ws.stats, residual=ws.x, tile_n=tl("ff2"))
             else:
-                e["co"](ws.att, ws.x, residual=ws.x)
+                e["co"](ws.att, ws.x, residual=ws.x, tile_n=tl("co"))
                 e["n2"](ws.x, ws.xn)
-                e["ff1"](ws.xn, ws.hid, relu=True)
-                e["ff2"](ws.hid, ws.x, residual=ws.x)
+                e["ff1"](ws.xn, ws.hid, relu=True, tile_n=tl("ff1"))
+                e["ff2"](ws.hid, ws.x, residual=ws.x, tile_n=tl("ff2"))
         # (the final norm stays a kernel also when the layers' norms are folded: the fused generator + top-k epilogue has no
         # folded-LayerNorm variant, and one LayerNorm per step is 1/19 of them)
         self.dec_norm(ws.x, ws.xn)
