@@ -445,6 +445,8 @@ def main():
     ap.add_argument("--e2e-coalesce", type=int, default=0, help="--coalesce of the end-to-end arm (0 = 2 when --steps is even: smaller device batches "
                          "start their H2D copies earlier, so the pipeline of copy -> encode -> decode fills faster)")
     ap.add_argument("--e2e-slots", type=int, default=0, help="--slots of the end-to-end arm (0 = auto)")
+    ap.add_argument("--dec-ctas", default="48,60", help="persistent-grid targets of the decode GEMMs in the throughput regime: CTAs for the wide "
+                         "(qkv, ff1) and for the N = d_model GEMMs (OrtEngine dec_ctas); 0,0 = one CTA per SM / two tiles per CTA as before")
     ap.add_argument("--e2e-schedule", default="", help="queued batches per launch of the end-to-end arm, e.g. 2,2,4,4,4,4 (sums to --steps)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -514,9 +516,12 @@ def main():
     assert args.steps % G == 0, "--steps must be a multiple of --coalesce"
     # >= 8 batches in flight (throughput regime): the decode GEMMs run 256-wide tiles on persistent grids of ~48 CTAs (qkv, ff1:
     # 8 - 10 tiles per CTA) / ~60 CTAs (the N = d_model GEMMs), sized per workspace by the engine (OrtEngine dec_ctas)
-    dec_ctas = (48, 60) if args.slots * G >= 8 else None
+    dec_ctas = tuple(int(v) for v in args.dec_ctas.split(",")) if args.slots * G >= 8 else None
+    dec_tiles = None
+    if dec_ctas is not None and not any(dec_ctas):   # (the round-2 start configuration, kept for A/B runs)
+        dec_ctas, dec_tiles = None, {k: 20003256 for k in ("qkv", "o", "cq", "co", "ff1", "ff2")}
     eng = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, ln_fold=args.ln_fold,
-                    fuse_topk=not args.no_fuse_topk, dec_ctas=dec_ctas)
+                    fuse_topk=not args.no_fuse_topk, dec_ctas=dec_ctas, dec_tiles=dec_tiles)
     B = args.images * G      # device batch = G queued batches of --images
     F = cfgd["att_feat_size"]
     # two distinct pinned host batches, alternated
@@ -654,7 +659,7 @@ def main():
     Bp = B
     att_p, box_p = host[0][0][:Bp], host[0][1][:Bp]
     eng2 = OrtEngine(sd, cfg, precision="bf16", sparse_backend=args.backend, device=dev, use_graphs=False,
-                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk, dec_ctas=dec_ctas)
+                     ln_fold=args.ln_fold, fuse_topk=not args.no_fuse_topk, dec_ctas=dec_ctas, dec_tiles=dec_tiles)
     enc2 = eng2.encode(att_p, box_p)
     for o in opts:
         eng2.decode(enc2, o)
