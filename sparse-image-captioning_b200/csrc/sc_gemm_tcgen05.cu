@@ -1414,12 +1414,13 @@ int sc_gemm_wgrad_splits(int N, int K, int M, int max_splits) {
   const int bn = (t128 >= sm_count() / 4) ? 128 : 64;
   const long tiles = (long)((N + 127) / 128) * ((K + bn - 1) / bn);
   const int num_kb = (M + BLOCK_K - 1) / BLOCK_K;
-  // as many splits as keep all work units in ONE wave, at most 4 (the reduction re-reads every partial product):
-  // measured with scripts/wgrad_sweep.py, e.g. 64 tiles: 2 splits 16.4 us, 3 splits 20.4 us
+  // as many splits as keep all work units in ONE wave, at most 2: alone, up to 4 splits are faster for the smallest weights
+  // (scripts/wgrad_sweep.py), but the weight gradients run on a side stream BESIDE the backward's dX chain - fewer, longer CTAs
+  // leave that chain its SMs (whole SMP step, SC_WGRAD_MAX_SPLITS = 4 / 3 / 2 / 1: 5.35 / 5.33 / 5.28 / 5.49 ms)
   static int env_cap = -1;
   if (env_cap < 0) { const char* e = getenv("SC_WGRAD_MAX_SPLITS"); env_cap = e ? atoi(e) : 0; }
   int splits = (int)(sm_count() / tiles);
-  splits = max(1, min(splits, env_cap > 0 ? env_cap : 4));
+  splits = max(1, min(splits, env_cap > 0 ? env_cap : 2));
   splits = max(1, min(splits, num_kb / 4 > 0 ? num_kb / 4 : 1));
   splits = min(splits, max(1, max_splits));
   const int per = (num_kb + splits - 1) / splits;
