@@ -532,11 +532,9 @@ class OrtEngine:
                 lin = e[name]
                 if lin.w is None or lin.tile_n:   # sparse backends / an explicit hint win
                     continue
-                tiles = -(-R // 128) * -(-lin.N // 256)
-                target = self.dec_ctas[1] if lin.N <= self.cfg.d_model else self.dec_ctas[0]
-                tpc = -(-tiles // target)
-                if tpc >= 2:
-                    hints[(u, name)] = min(tpc, 200) * 10000000 + 3256
+                hint = decode_grid_hint(R, lin.N, self.cfg.d_model, self.dec_ctas)
+                if hint:
+                    hints[(u, name)] = hint
         return hints
 
     def _topk_ok(self, beam):
@@ -887,6 +885,17 @@ class OrtEngine:
         enc = self.encode(att_feats, boxes, att_masks)
         seq, lp = self.decode(enc, opt)
         return seq.long(), lp.clone()
+
+
+def decode_grid_hint(rows, n_out, d_model, dec_ctas):
+    """Tile hint (10^7 * tiles per persistent CTA + 3256: 256-wide tiles) that holds the persistent grid of a decode GEMM with
+    ``rows`` x ``n_out`` outputs to about ``dec_ctas[0]`` CTAs (N > d_model: qkv, ff1) or ``dec_ctas[1]`` (the N <= d_model GEMMs
+    with the fp32 residual epilogue); 0 when one tile per CTA already stays below the target (small batches: the kernel's own
+    heuristic)."""
+    tiles = -(-rows // 128) * -(-n_out // 256)
+    target = dec_ctas[1] if n_out <= d_model else dec_ctas[0]
+    tpc = -(-tiles // max(1, target))
+    return min(tpc, 200) * 10000000 + 3256 if tpc >= 2 else 0
 
 
 def _parse_penalty(s):

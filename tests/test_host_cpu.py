@@ -243,3 +243,23 @@ def test_sell_weight_packing_roundtrip():
             lane = torch.arange(e - b) % 32
             rec.index_put_((s_ * 32 + lane, cols), vals, accumulate=True)
         assert torch.equal(rec[:N], w)
+
+
+def test_decode_grid_hint():
+    """Grid sizing of the decode GEMMs in the throughput regime (engine.decode_grid_hint): tiles per persistent CTA so that the
+    wide GEMMs land on ~48 CTAs and the N = d_model ones on ~60; small batches keep the kernel's own heuristic."""
+    from sparse_caption_b200.engine import decode_grid_hint
+    dc = (48, 60)
+    # 5 coalesced batches x 512 images x beam 3 = 7680 rows: qkv 60 x 6 = 360 tiles, ff1 480, N = 512 GEMMs 120
+    assert decode_grid_hint(7680, 1536, 512, dc) == 8 * 10000000 + 3256
+    assert decode_grid_hint(7680, 2048, 512, dc) == 10 * 10000000 + 3256
+    assert decode_grid_hint(7680, 512, 512, dc) == 2 * 10000000 + 3256
+    for rows, n in ((7680, 1536), (7680, 2048), (7680, 512), (12800, 1024), (30720, 2048)):
+        hint = decode_grid_hint(rows, n, 512, dc)
+        tiles = -(-rows // 128) * -(-n // 256)
+        ctas = -(-tiles // (hint // 10000000))
+        assert ctas <= (60 if n <= 512 else 48) and hint % 10000000 == 3256
+    # one batch of 16 images: 1 M block, nothing to cap
+    assert decode_grid_hint(48, 1536, 512, dc) == 0 and decode_grid_hint(1536, 512, 512, dc) == 0
+    assert decode_grid_hint(10 ** 7, 2048, 512, dc) // 10000000 == 200   # (the hint's tiles-per-CTA digit is capped)
+
