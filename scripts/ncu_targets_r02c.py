@@ -29,6 +29,13 @@ if "obig" in which:   # encoder-size residual GEMM, many tiles per persistent CT
     for _ in range(reps):
         K.linear(x, w, b, residual=x32, out=x32, tile_n=3256)
         K.linear(x, w, b, out=y16, tile_n=3256)
+if "sized" in which:   # the decode GEMMs on the sized persistent grids of the throughput regime (OrtEngine dec_ctas=(48, 60))
+    x = torch.randn(R, d, **bf); x32 = torch.randn(R, d, device=dev)
+    for (Nn, hint, res) in ((3 * d, 80003256, False), (ff, 100003256, False), (d, 20003256, True)):
+        w = torch.randn(Nn, d, **bf); b = torch.randn(Nn, device=dev)
+        y = x32 if res else torch.empty(R, Nn, **bf)
+        for _ in range(reps):
+            K.linear(x, w, b, residual=x32 if res else None, relu=(Nn == ff), out=y, tile_n=hint)
 if "ff2" in which:
     x = torch.randn(R, ff, **bf); w = torch.randn(d, ff, **bf); b = torch.randn(d, device=dev); x32 = torch.randn(R, d, device=dev)
     for _ in range(reps):
