@@ -263,3 +263,17 @@ def test_decode_grid_hint():
     assert decode_grid_hint(48, 1536, 512, dc) == 0 and decode_grid_hint(1536, 512, 512, dc) == 0
     assert decode_grid_hint(10 ** 7, 2048, 512, dc) // 10000000 == 200   # (the hint's tiles-per-CTA digit is capped)
 
+
+def test_acort_trainer_refuses_cpu():
+    """``model.trainer()`` of an ACORT configuration hands out the module trainer; like every other entry of the path it fails
+    loudly on a CPU model instead of falling back."""
+    import sparse_caption_b200.relation_transformer as R
+    from sparse_caption_b200.trainer import ModuleTrainer
+    z = golden_io.load("acort_tiny")
+    m = R.get_model("relation_transformer_prune")(dict(z["cfg_dict"]))
+    tr = m.trainer()
+    assert isinstance(tr, ModuleTrainer) and m.trainer() is tr
+    S = z["seqs"].shape[0] // z["att_feats"].shape[0]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tr.train_step(z["att_feats"], z["boxes"], z["seqs"], z["masks"], seq_per_img=S, lr=1e-3)
+
